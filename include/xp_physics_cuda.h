@@ -1,0 +1,191 @@
+/*
+ * xp_physics_cuda.h -- C ABI of the B200-native (sm_100a) replacement for the xp_physics
+ * swept-sphere vs triangle collision path of bjrnmrtns/xp-game-engine.
+ *
+ * The reference has NO FFI today: its boundary is the Rust crate's public fn API
+ * (xp_physics/src/lib.rs:9-15,17,29).  Each entry point below names the reference item it
+ * replaces; INTEGRATION.md shows the Rust `extern "C"` block a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns XP_OK (0) or a negative XP_E* code; nothing unwinds across the ABI;
+ *   - the reference's panics become per-sphere status bits (XP_ST_*);
+ *   - plain pointers + sizes only; `*_dev` variants take device pointers on the scene's device
+ *     and are asynchronous on the scene's stream, the others take host pointers, copy, and
+ *     return after the results are back in the caller's buffers;
+ *   - one xp_scene per device; calls on one scene are serialised by the caller (the reference
+ *     is single-threaded); different scenes are independent;
+ *   - there is no CPU fallback: without a usable CUDA device every call fails with XP_ECUDA.
+ *
+ * All arithmetic is IEEE binary32.  XP_ARITH_EXACT (default) evaluates the reference's
+ * operations in the reference's order without fused multiply-add and is bit-identical to
+ * the Rust code's results; XP_ARITH_FAST lets the compiler contract a*b+c (<= 1e-5 relative).
+ */
+#ifndef XP_PHYSICS_CUDA_H
+#define XP_PHYSICS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- value types: byte-for-byte the reference's structs with nalgebra Vec3 = 3 x f32 ---- */
+typedef struct { float x, y, z; } xp_vec3;                              /* nalgebra_glm::Vec3            */
+typedef struct { xp_vec3 c; float r; } xp_sphere;                       /* xp_physics/src/sphere.rs:4-7   16 B */
+typedef struct { xp_vec3 v0, v1, v2; } xp_triangle;                     /* xp_physics/src/triangle.rs:4-8 36 B */
+typedef struct { xp_sphere sphere; xp_vec3 movement; } xp_response;     /* xp_physics/src/response.rs:5-8 28 B */
+typedef struct { float time_to, distance_to;
+                 xp_vec3 position, intersection; } xp_collision;        /* xp_physics/src/collision.rs:5-10 32 B */
+
+typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + workspaces */
+
+/* ---- error codes ---- */
+#define XP_OK        0
+#define XP_EINVAL   -1   /* bad argument (null pointer, n_vec3 % 3 != 0 like lib.rs:19-24, ...) */
+#define XP_ECUDA    -2   /* CUDA runtime error; xp_last_cuda_error() has the text               */
+#define XP_ENOMEM   -3   /* device or host allocation failed                                     */
+#define XP_ESTATE   -4   /* scene not built / no triangles set                                   */
+#define XP_ECAP     -5   /* output capacity too small (xp_broadphase_pairs)                      */
+
+/* ---- per-sphere status bits (where the reference panics) ---- */
+#define XP_ST_RADIUS_NE_1          1u  /* assert_eq!(sphere.r, 1.0)  collision_detect.rs:161   */
+#define XP_ST_ASSERT_NEG_DISTANCE  2u  /* assert!(d >= 0.0)          collision_response.rs:22  */
+#define XP_ST_ITER_CAP             4u  /* iteration cap reached; the reference loop (lib.rs:32) has none */
+
+/* ---- horizon_mode: the broadphase query volume ---- */
+#define XP_HORIZON_INF   0u  /* ray t in [0,+inf): reference-faithful (hits at any t>0, collision_detect.rs:201-202) */
+#define XP_HORIZON_UNIT  1u  /* ray t in [0,1]: Fauerby-correct, NOT what the reference computes */
+
+/* ---- scene options (xp_scene_set_option) ---- */
+#define XP_OPT_ARITH      1  /* XP_ARITH_*                                      */
+#define XP_OPT_METHOD     2  /* XP_METHOD_*                                     */
+#define XP_OPT_TIMING     3  /* 1: record CUDA events around every kernel stage */
+#define XP_OPT_SORT_SPHERES 4 /* 1: process spheres in Morton order of their centre (default 1) */
+#define XP_OPT_MAX_PAIRS  5  /* capacity (pairs) of the two-stage candidate buffer per chunk */
+#define XP_OPT_PRUNE      6  /* BVH_FUSED only. 0 (default): evaluate detect on EVERY pair passing P, so
+                                narrowphase_tests == |P| and the candidate set is the bit-exact one;
+                                1: skip subtrees whose entry time exceeds the best t found so far
+                                (same closest collision, fewer tests) */
+
+#define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical */
+#define XP_ARITH_FAST     1  /* FMA contraction allowed                          */
+
+#define XP_METHOD_BVH_FUSED  0  /* default. One kernel: per-lane stack traversal feeds a warp-shared candidate queue in
+                                   shared memory; the warp drains it 32 pairs at a time through the narrowphase */
+#define XP_METHOD_BVH_PAIRS  1  /* two kernels: traversal emits every pair passing P to HBM; narrowphase over the pairs */
+#define XP_METHOD_BRUTE      2  /* the reference's literal algorithm: every triangle for every sphere (lib.rs:33-35) */
+
+/* ---- statistics of the last detect / response call on a scene ---- */
+#define XP_STAGE_COUNT 12
+typedef struct {
+    uint64_t narrowphase_tests;   /* (sphere,triangle) pairs on which detect was evaluated          */
+    uint64_t broadphase_pairs;    /* pairs passing P (BVH_PAIRS) */
+    uint64_t node_visits;         /* internal LBVH nodes fetched */
+    uint32_t kernel_launches;     /* kernels of this library launched by the call                    */
+    uint32_t iterations_run;      /* outer response iterations executed (max over spheres)           */
+    float    stage_ms[XP_STAGE_COUNT]; /* XP_OPT_TIMING=1: CUDA-event ms per stage, see XP_STAGE_*   */
+} xp_stats;
+
+#define XP_STAGE_BUILD_BOUNDS   0
+#define XP_STAGE_BUILD_MORTON   1
+#define XP_STAGE_BUILD_SORT     2
+#define XP_STAGE_BUILD_PACK     3
+#define XP_STAGE_BUILD_TREE     4
+#define XP_STAGE_BUILD_REFIT    5
+#define XP_STAGE_RAY_SETUP      6
+#define XP_STAGE_TRAVERSE       7   /* broadphase traversal (BVH_PAIRS) or fused traversal+narrowphase */
+#define XP_STAGE_NARROWPHASE    8   /* narrowphase over pairs / brute force                            */
+#define XP_STAGE_RESPONSE       9
+#define XP_STAGE_FINALIZE      10
+#define XP_STAGE_SPHERE_SORT   11
+
+/* ---- scene lifetime ---- */
+int  xp_scene_create(int device, xp_scene **out);
+void xp_scene_destroy(xp_scene *s);
+/* cudaStream_t (as void*) every later call on this scene is enqueued on; NULL = default stream. */
+int  xp_scene_set_stream(xp_scene *s, void *cuda_stream);
+int  xp_scene_set_option(xp_scene *s, int option, int64_t value);
+int  xp_scene_get_stats(const xp_scene *s, xp_stats *out);
+
+/* The `&[Triangle]` argument of collision_response (lib.rs:29): uploaded ONCE instead of
+ * being walked on every call.  Copies; the caller keeps ownership. */
+int  xp_scene_set_triangles(xp_scene *s, const xp_triangle *aos, uint64_t n);
+int  xp_scene_set_triangles_dev(xp_scene *s, const xp_triangle *d_aos, uint64_t n);
+/* The `&[Vec3]` argument of collision_response_non_trianulated (lib.rs:17-25): every three
+ * consecutive Vec3 form one triangle; n_vec3 % 3 != 0 -> XP_EINVAL (the reference panics). */
+int  xp_scene_set_positions(xp_scene *s, const xp_vec3 *soup, uint64_t n_vec3);
+/* (Re)build the device LBVH: per-triangle normal / plane constant / inflated AABB, 30-bit
+ * Morton codes, radix sort, Karras hierarchy, bottom-up refit.  New: the reference has no
+ * broadphase (lib.rs:33-35 walks every triangle). */
+int  xp_scene_build(xp_scene *s);
+uint64_t xp_scene_triangle_count(const xp_scene *s);
+
+/* ---- a11 + the min_by of lib.rs:33-42: closest collision of each sphere against the scene.
+ * out[i] is written only where hit[i] != 0; tri_index (nullable) is the index, in upload
+ * order, of the triangle the reference's min_by would return (ties -> later triangle), or
+ * 0xFFFFFFFF; status (nullable) carries XP_ST_RADIUS_NE_1. */
+int  xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                     xp_collision *out, uint8_t *hit, uint32_t *tri_index, uint32_t *status);
+int  xp_detect_batch_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                         xp_collision *d_out, uint8_t *d_hit, uint32_t *d_tri_index,
+                         uint32_t *d_status);
+
+/* ---- a16: collision_response (lib.rs:29-62) for a batch of independent spheres.
+ * max_iter == 0: unbounded like the reference (an internal guard of 65536 iterations sets
+ * XP_ST_ITER_CAP).  out[i] = the Response the reference returns; where a panic site is hit
+ * the sphere stops, the status bit is set and out[i] is the Response current at that point.
+ * iterations / status / last_slide_normal (collision_response.rs:16) are nullable. */
+int  xp_collision_response_batch(xp_scene *s, const xp_response *in, uint64_t n,
+                                 uint32_t max_iter, uint32_t horizon_mode, xp_response *out,
+                                 uint32_t *iterations, uint32_t *status,
+                                 xp_vec3 *last_slide_normal);
+int  xp_collision_response_batch_dev(xp_scene *s, const xp_response *d_in, uint64_t n,
+                                     uint32_t max_iter, uint32_t horizon_mode,
+                                     xp_response *d_out, uint32_t *d_iterations,
+                                     uint32_t *d_status, xp_vec3 *d_last_slide_normal);
+
+/* ---- the 1-sphere calls with the reference's exact shapes (host pointers) ----
+ * sphere_triangle_detect_collision (collision_detect.rs:155): returns 1 = Some, 0 = None,
+ * XP_EINVAL where the reference panics on r != 1.  Evaluated on the device. */
+int  xp_sphere_triangle_detect_collision(int device, const xp_response *response,
+                                         const xp_triangle *triangle, xp_collision *out);
+/* sphere_triangle_calculate_response (collision_response.rs:6): returns 0, or 1 where
+ * assert!(d >= 0) would fire.  Evaluated on the device. */
+int  xp_sphere_triangle_calculate_response(int device, const xp_response *response,
+                                           const xp_collision *collision, xp_response *out);
+
+/* ---- broadphase candidate set, for the bit-exact check against predicate P ----
+ * Writes the (sphere, triangle-upload-index) pairs whose triangle AABB, inflated by
+ * 1 + 1e-4, is hit by the ray c + t*m over the horizon.  Order unspecified.  If more than
+ * cap pairs exist, *count still receives the total and XP_ECAP is returned. */
+int  xp_broadphase_pairs(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                         uint64_t cap, uint32_t *sphere_idx, uint32_t *tri_idx, uint64_t *count);
+
+/* ---- LBVH introspection for tests (host buffers, nullable) ----
+ * sorted_tri[j]  = upload index of the triangle stored in leaf j (Morton order)
+ * morton[j]      = its 30-bit code
+ * node_child[2i], node_child[2i+1] = children of internal node i (>= 0 internal, < 0 leaf ~c)
+ * node_lo/hi[i]  = AABB of internal node i. */
+int  xp_scene_debug_tree(xp_scene *s, uint32_t *sorted_tri, uint32_t *morton, int32_t *node_child,
+                         xp_vec3 *node_lo, xp_vec3 *node_hi);
+
+/* ---- contact record for the multi-GPU allgather ----
+ * 40 B per sphere: the 32 B collision + tri_index + (hit | status << 8 | iterations << 16). */
+typedef struct { xp_collision col; uint32_t tri_index; uint32_t flags; } xp_contact;
+/* Closest collision per sphere written as xp_contact records straight into a (send) buffer,
+ * e.g. this rank's slot of the NCCL allgather buffer.  Device pointers. */
+int  xp_detect_contacts_dev(xp_scene *s, const xp_response *d_in, uint64_t n,
+                            uint32_t horizon_mode, xp_contact *d_out);
+
+/* ---- measurement helpers ---- */
+/* Dependent-free FFMA loop on every SM: the fp32 CUDA-core peak used as roofline denominator. */
+int  xp_probe_fp32_peak(int device, double *tflops);
+int  xp_device_count(int *count);
+const char *xp_strerror(int code);
+const char *xp_last_cuda_error(void);
+const char *xp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XP_PHYSICS_CUDA_H */

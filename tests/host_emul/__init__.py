@@ -1,0 +1,27 @@
+"""Test-only host build of the device narrowphase header (see emul.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libxp_emul.so")
+_SRC = os.path.join(_HERE, "emul.cpp")
+_HDR = os.path.normpath(os.path.join(_HERE, "..", "..", "xp-game-engine_b200", "csrc", "xp_narrowphase.cuh"))
+
+
+def lib():
+    stale = (not os.path.exists(_SO)) or max(os.path.getmtime(_SRC), os.path.getmtime(_HDR)) > os.path.getmtime(_SO)
+    if stale:
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                        "-fno-math-errno", "-o", _SO, _SRC], check=True, capture_output=True)
+    L = C.CDLL(_SO)
+    vp = C.c_void_p
+    L.emul_detect.argtypes = [vp, vp, vp, C.c_int]
+    L.emul_detect.restype = C.c_int
+    L.emul_respond.argtypes = [vp, vp, vp, vp]
+    L.emul_respond.restype = C.c_int
+    L.emul_broadphase.argtypes = [vp, vp, C.c_float]
+    L.emul_broadphase.restype = C.c_int
+    L.emul_detect_many.argtypes = [vp, vp, C.c_long, vp, vp]
+    L.emul_detect_many.restype = None
+    return L

@@ -1,0 +1,78 @@
+// TEST-ONLY host build of the product's device header (xp_narrowphase.cuh compiles as plain C++
+// when __CUDACC__ is absent).  It lets the CPU test-suite check that the GPU's RE-ORGANISED
+// formulas (cached normal / plane constant, shared vertex terms, running minimum, branch-free
+// slab test) are bit-identical to the oracle's line-by-line restatement, before any GPU time is
+// spent.  Nothing in the product links this; the product has no CPU path.
+// Build: g++ -O2 -ffp-contract=off -fno-fast-math -shared -fPIC (see tests/host_emul/__init__.py)
+#include <cstring>
+#include "../../xp-game-engine_b200/csrc/xp_narrowphase.cuh"
+
+using namespace xp;
+
+extern "C" {
+
+// resp: 7 floats (c, r, m); tri: 9 floats; out: 8 floats (collision). returns 1/0/-1
+int emul_detect(const float *resp, const float *tri, float *out, int fast) {
+    if (!(resp[3] == 1.0f)) return -1;
+    V3 c = {resp[0], resp[1], resp[2]}, m = {resp[4], resp[5], resp[6]};
+    V3 v0 = {tri[0], tri[1], tri[2]}, v1 = {tri[3], tri[4], tri[5]}, v2 = {tri[6], tri[7], tri[8]};
+    TriDerived d = xp_tri_derive(v0, v1, v2);
+    (void)fast;
+    Ray ray = xp_ray_setup<ExactOps>(c, m);
+    float t;
+    if (!xp_detect<ExactOps>(ray, v0, v1, v2, d.n, d.pc, t)) return 0;
+    Contact k = xp_make_collision<ExactOps>(ray, t);
+    out[0] = k.time_to; out[1] = k.distance_to;
+    out[2] = k.position.x; out[3] = k.position.y; out[4] = k.position.z;
+    out[5] = k.intersection.x; out[6] = k.intersection.y; out[7] = k.intersection.z;
+    return 1;
+}
+
+// returns 0 ok / 1 assert
+int emul_respond(const float *resp, const float *col, float *out, float *normal) {
+    V3 nc, nm, sn;
+    bool ok = xp_respond<ExactOps>(V3{resp[0], resp[1], resp[2]}, V3{resp[4], resp[5], resp[6]},
+                                   V3{col[2], col[3], col[4]}, V3{col[5], col[6], col[7]}, nc, nm, sn);
+    normal[0] = sn.x; normal[1] = sn.y; normal[2] = sn.z;
+    if (!ok) return 1;
+    out[0] = nc.x; out[1] = nc.y; out[2] = nc.z; out[3] = 1.0f; out[4] = nm.x; out[5] = nm.y; out[6] = nm.z;
+    return 0;
+}
+
+// the branch-free slab form used by the traversal kernel (inv = 1/m even when m == 0)
+static bool slab_branchfree(V3 c, V3 inv, float horizon, V3 lo, V3 hi) {
+    float tmin = 0.0f, tmax = horizon;
+    const float cs[3] = {c.x, c.y, c.z}, is[3] = {inv.x, inv.y, inv.z};
+    const float ls[3] = {lo.x, lo.y, lo.z}, hs[3] = {hi.x, hi.y, hi.z};
+    for (int k = 0; k < 3; ++k) {
+        const float a = (ls[k] - cs[k]) * is[k], b = (hs[k] - cs[k]) * is[k];
+        const float nr = (is[k] > 0.0f) ? a : b, fr = (is[k] > 0.0f) ? b : a;
+        if (nr > tmin) tmin = nr;
+        if (fr < tmax) tmax = fr;
+    }
+    return tmin <= tmax;
+}
+
+// returns bit0 = header form (explicit m==0 branch), bit1 = branch-free kernel form
+int emul_broadphase(const float *resp, const float *tri, float horizon) {
+    V3 c = {resp[0], resp[1], resp[2]}, m = {resp[4], resp[5], resp[6]};
+    V3 v0 = {tri[0], tri[1], tri[2]}, v1 = {tri[3], tri[4], tri[5]}, v2 = {tri[6], tri[7], tri[8]};
+    V3 lo, hi;
+    xp_tri_aabb(v0, v1, v2, lo, hi);
+    SlabRay s = xp_slab_setup(c, m, horizon);
+    float tn;
+    int r = xp_slab_hit(s, lo, hi, tn) ? 1 : 0;
+    if (slab_branchfree(c, s.inv, s.horizon, lo, hi)) r |= 2;
+    return r;
+}
+
+void emul_detect_many(const float *resp, const float *tris, long n_tris, float *out_t, int *out_hit) {
+    for (long j = 0; j < n_tris; ++j) {
+        float col[8];
+        int r = emul_detect(resp, tris + 9 * j, col, 0);
+        out_hit[j] = r;
+        out_t[j] = (r == 1) ? col[0] : 0.0f;
+    }
+}
+
+}

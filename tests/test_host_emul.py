@@ -1,0 +1,145 @@
+"""CPU check that the RE-ORGANISED device formulas (xp_narrowphase.cuh, compiled for the host by
+tests/host_emul) are bit-identical to the oracle's line-by-line restatement of the reference.
+This does not replace the GPU parity tests; it finds formula bugs before GPU time is spent."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests.conftest import assert_bits_equal, bits
+from tests.host_emul import lib as emul_lib
+from xp_physics_cuda import scenes
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _emul_detect(E, resp, tri):
+    out = np.zeros(8, np.float32)
+    r = E.emul_detect(_p(resp), _p(tri), _p(out), 0)
+    return r, out
+
+
+def _cases(seed, n):
+    rng = np.random.default_rng(seed)
+    for _ in range(n):
+        kind = rng.integers(0, 6)
+        tri = rng.uniform(-3, 3, (3, 3)).astype(np.float32)
+        c = rng.uniform(-4, 4, 3).astype(np.float32)
+        m = rng.uniform(-1, 1, 3).astype(np.float32)
+        if kind == 1:      # sphere above a roughly horizontal triangle, moving down
+            tri[:, 1] = rng.uniform(-0.2, 0.2, 3)
+            c[1] = rng.uniform(1.0, 3.0)
+            m[1] = -abs(m[1]) - 0.05
+        elif kind == 2:    # axis-aligned movement (zeros in m)
+            m[rng.integers(0, 3)] = 0.0
+        elif kind == 3:    # integer lattice: lots of exact ties and zeros
+            tri = rng.integers(-3, 4, (3, 3)).astype(np.float32)
+            c = rng.integers(-4, 5, 3).astype(np.float32)
+            m = rng.integers(-2, 3, 3).astype(np.float32)
+        elif kind == 4:    # degenerate triangle (quirk B10)
+            tri[2] = tri[1]
+        elif kind == 5:    # already touching / embedded (|sd| < 1)
+            c = (tri.mean(axis=0) + rng.uniform(-0.8, 0.8, 3)).astype(np.float32)
+        yield c, m, np.ascontiguousarray(tri)
+
+
+def test_detect_lean_equals_oracle_bitwise(oracle):
+    E = emul_lib()
+    n_hit = 0
+    for c, m, tri in _cases(11, 30000):
+        resp = oracle.make_responses([c], [m])
+        want = oracle.detect(resp, tri)
+        r, got = _emul_detect(E, resp, tri)
+        assert (want is not None) == (r == 1), (c, m, tri)
+        if want is not None:
+            n_hit += 1
+            w = np.concatenate([[want["time_to"], want["distance_to"]], want["position"], want["intersection"]])
+            assert_bits_equal(got, w.astype(np.float32), "collision fields")
+    assert n_hit > 1000
+
+
+def test_detect_lean_equals_oracle_on_terrain(oracle):
+    E = emul_lib()
+    tris, h = scenes.sine_terrain(24, 24, seed=3)
+    resps = scenes.terrain_spheres(h, 64, seed=5)
+    out_t = np.zeros(len(tris), np.float32)
+    out_hit = np.zeros(len(tris), np.int32)
+    flat = np.ascontiguousarray(tris.reshape(-1, 9))
+    total_hits = 0
+    for i in range(len(resps)):
+        E.emul_detect_many(_p(resps[i:i + 1]), _p(flat), len(tris), _p(out_t), _p(out_hit))
+        for j in range(len(tris)):
+            w = oracle.detect(resps[i:i + 1], tris[j])
+            assert (w is not None) == (out_hit[j] == 1)
+            if w is not None:
+                total_hits += 1
+                assert bits(np.float32(w["time_to"])) == bits(out_t[j])
+    assert total_hits > 200
+
+
+def test_respond_equals_oracle_bitwise(oracle):
+    E = emul_lib()
+    rng = np.random.default_rng(7)
+    n_ok = n_assert = 0
+    for c, m, tri in _cases(13, 20000):
+        m = (m * rng.uniform(0.2, 1.5)).astype(np.float32)
+        resp = oracle.make_responses([c], [m])
+        col = oracle.detect(resp, tri)
+        if col is None:
+            continue
+        want, wn = oracle.respond(resp, np.array([col]))
+        out = np.zeros(7, np.float32)
+        nrm = np.zeros(3, np.float32)
+        r = E.emul_respond(_p(resp), _p(np.array([col])), _p(out), _p(nrm))
+        assert_bits_equal(nrm, wn, "slide normal")
+        if want is None:
+            assert r == 1
+            n_assert += 1
+        else:
+            assert r == 0
+            n_ok += 1
+            assert_bits_equal(out, np.concatenate([want["c"], [want["r"]], want["movement"]]).astype(np.float32), "response")
+    assert n_ok > 500 and n_assert > 10
+
+
+def test_slab_forms_agree_with_predicate_P(oracle):
+    """header form (explicit m==0 branch) == branch-free kernel form == oracle's P, incl. boundary cases."""
+    E = emul_lib()
+    rng = np.random.default_rng(17)
+    n_acc = 0
+    for it in range(40000):
+        tri = rng.integers(-3, 4, (3, 3)).astype(np.float32) if it % 2 else rng.uniform(-3, 3, (3, 3)).astype(np.float32)
+        c = rng.integers(-5, 6, 3).astype(np.float32) if it % 3 == 0 else rng.uniform(-5, 5, 3).astype(np.float32)
+        m = rng.uniform(-1, 1, 3).astype(np.float32)
+        for k in range(3):
+            if rng.random() < 0.25:
+                m[k] = 0.0 if rng.random() < 0.5 else -0.0
+        if it % 5 == 0:      # centre exactly on an inflated face of the box
+            lo, hi = oracle.triangle_aabbs(tri[None])
+            k = rng.integers(0, 3)
+            c[k] = lo[0, k] if rng.random() < 0.5 else hi[0, k]
+        resp = oracle.make_responses([c], [m])
+        for horizon in (np.inf, 1.0):
+            want = oracle.lib().xpo_broadphase_accept(_p(resp), _p(np.ascontiguousarray(tri)), horizon)
+            got = E.emul_broadphase(_p(resp), _p(np.ascontiguousarray(tri)), horizon)
+            assert got == (3 if want else 0), (c, m, tri, horizon, want, got)
+            n_acc += want
+    assert n_acc > 5000
+
+
+def test_P_is_conservative(oracle):
+    """every (sphere, triangle) with detect != None satisfies P(horizon = inf)."""
+    tris, h = scenes.sine_terrain(32, 32, seed=9)
+    resps = scenes.terrain_spheres(h, 200, seed=10)
+    si, ti = oracle.broadphase_pairs(resps, tris)
+    P = set(zip(si.tolist(), ti.tolist()))
+    hits = 0
+    for i in range(len(resps)):
+        for j in range(len(tris)):
+            if oracle.detect(resps[i:i + 1], tris[j]) is not None:
+                hits += 1
+                assert (i, j) in P
+    assert hits > 1000
+    assert len(P) < 0.2 * len(resps) * len(tris)

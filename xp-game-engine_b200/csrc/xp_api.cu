@@ -1,0 +1,366 @@
+// xp_api.cu -- the C ABI declared in include/xp_physics_cuda.h (scene lifetime, host<->device
+// staging, option handling).  No arithmetic of the path happens on the host: every entry point
+// that computes launches kernels, and fails with XP_ECUDA when no CUDA device is usable.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "xp_internal.h"
+
+namespace xp {
+
+static thread_local char g_cuda_err[256] = "";
+
+static int fail_cuda(cudaError_t e) {
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    cudaGetLastError();   // clear the sticky-free error state
+    return e == cudaErrorMemoryAllocation ? XP_ENOMEM : XP_ECUDA;
+}
+
+StageTimer::StageTimer(xp_scene *scene, int st) : s(scene), stage(st) {
+    if (!s->timing) return;
+    if (!s->ev_created) {
+        for (int i = 0; i < 2 * XP_STAGE_COUNT; ++i) cudaEventCreate(&s->ev[i]);
+        s->ev_created = true;
+    }
+    cudaEventRecord(s->ev[2 * stage], s->stream);
+}
+StageTimer::~StageTimer() {
+    if (!s->timing) return;
+    cudaEventRecord(s->ev[2 * stage + 1], s->stream);
+    cudaEventSynchronize(s->ev[2 * stage + 1]);
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, s->ev[2 * stage], s->ev[2 * stage + 1]) == cudaSuccess)
+        s->stats.stage_ms[stage] += ms;
+}
+
+static void reset_stats(xp_scene *s) { memset(&s->stats, 0, sizeof s->stats); }
+
+}  // namespace xp
+
+using namespace xp;
+
+#define XP_API_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail_cuda(_e); } while (0)
+#define XP_BIND(s) do { cudaError_t _e = cudaSetDevice((s)->device); if (_e != cudaSuccess) return fail_cuda(_e); } while (0)
+
+extern "C" {
+
+int xp_device_count(int *count) {
+    if (!count) return XP_EINVAL;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail_cuda(e); }
+    *count = n;
+    return XP_OK;
+}
+
+int xp_scene_create(int device, xp_scene **out) {
+    if (!out) return XP_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    XP_API_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return XP_EINVAL;
+    XP_API_TRY(cudaSetDevice(device));
+    XP_API_TRY(cudaFree(0));
+    xp_scene *s = new (std::nothrow) xp_scene();
+    if (!s) return XP_ENOMEM;
+    s->device = device;
+    reset_stats(s);
+    *out = s;
+    return XP_OK;
+}
+
+void xp_scene_destroy(xp_scene *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_lo, &s->node_hi, &s->leaf_lo, &s->leaf_hi,
+                      &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
+                      &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->rays, &s->best, &s->active_a,
+                      &s->active_b, &s->pairs, &s->counters, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
+                      &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
+    for (DevBuf *b : bufs) b->release();
+    if (s->ev_created)
+        for (int i = 0; i < 2 * XP_STAGE_COUNT; ++i) cudaEventDestroy(s->ev[i]);
+    delete s;
+}
+
+int xp_scene_set_stream(xp_scene *s, void *cuda_stream) {
+    if (!s) return XP_EINVAL;
+    s->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return XP_OK;
+}
+
+int xp_scene_set_option(xp_scene *s, int option, int64_t value) {
+    if (!s) return XP_EINVAL;
+    switch (option) {
+    case XP_OPT_ARITH:
+        if (value != XP_ARITH_EXACT && value != XP_ARITH_FAST) return XP_EINVAL;
+        s->arith = (int)value; return XP_OK;
+    case XP_OPT_METHOD:
+        if (value < XP_METHOD_BVH_FUSED || value > XP_METHOD_BRUTE) return XP_EINVAL;
+        s->method = (int)value; return XP_OK;
+    case XP_OPT_TIMING: s->timing = value ? 1 : 0; return XP_OK;
+    case XP_OPT_SORT_SPHERES: s->sort_spheres = value ? 1 : 0; return XP_OK;
+    case XP_OPT_MAX_PAIRS:
+        if (value < 4096) return XP_EINVAL;
+        s->max_pairs = (uint64_t)value; return XP_OK;
+    case XP_OPT_PRUNE: s->prune = value ? 1 : 0; return XP_OK;
+    default: return XP_EINVAL;
+    }
+}
+
+int xp_scene_get_stats(const xp_scene *s, xp_stats *out) {
+    if (!s || !out) return XP_EINVAL;
+    *out = s->stats;
+    return XP_OK;
+}
+
+uint64_t xp_scene_triangle_count(const xp_scene *s) { return s ? s->n_tris : 0; }
+
+int xp_scene_set_triangles(xp_scene *s, const xp_triangle *aos, uint64_t n) {
+    if (!s || (!aos && n)) return XP_EINVAL;
+    XP_BIND(s);
+    s->built = false;
+    s->n_tris = 0;
+    if (n) {
+        XP_API_TRY(s->tris_aos.reserve(n * sizeof(xp_triangle)));
+        XP_API_TRY(cudaMemcpyAsync(s->tris_aos.p, aos, n * sizeof(xp_triangle), cudaMemcpyHostToDevice, s->stream));
+        XP_API_TRY(cudaStreamSynchronize(s->stream));
+    }
+    s->n_tris = n;
+    return XP_OK;
+}
+
+int xp_scene_set_triangles_dev(xp_scene *s, const xp_triangle *d_aos, uint64_t n) {
+    if (!s || (!d_aos && n)) return XP_EINVAL;
+    XP_BIND(s);
+    s->built = false;
+    s->n_tris = 0;
+    if (n) {
+        XP_API_TRY(s->tris_aos.reserve(n * sizeof(xp_triangle)));
+        XP_API_TRY(cudaMemcpyAsync(s->tris_aos.p, d_aos, n * sizeof(xp_triangle), cudaMemcpyDeviceToDevice, s->stream));
+    }
+    s->n_tris = n;
+    return XP_OK;
+}
+
+int xp_scene_set_positions(xp_scene *s, const xp_vec3 *soup, uint64_t n_vec3) {
+    if (n_vec3 % 3 != 0) return XP_EINVAL;     // lib.rs:19-24: chunks(3) then vs[2] panics
+    // Vec3 triples are exactly the Triangle layout (lib.rs:20-24), so this is one upload
+    return xp_scene_set_triangles(s, reinterpret_cast<const xp_triangle *>(soup), n_vec3 / 3);
+}
+
+int xp_scene_build(xp_scene *s) {
+    if (!s) return XP_EINVAL;
+    XP_BIND(s);
+    reset_stats(s);
+    XP_API_TRY(build_lbvh(s));
+    XP_API_TRY(cudaStreamSynchronize(s->stream));
+    return XP_OK;
+}
+
+static int check_query(xp_scene *s, const void *in, uint64_t n) {
+    if (!s || (!in && n)) return XP_EINVAL;
+    if (!s->built) return XP_ESTATE;
+    return XP_OK;
+}
+
+int xp_detect_batch_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                        xp_collision *d_out, uint8_t *d_hit, uint32_t *d_tri_index, uint32_t *d_status) {
+    int rc = check_query(s, d_in, n);
+    if (rc) return rc;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    QueryOut q = {d_out, d_hit, d_tri_index, d_status, nullptr};
+    XP_API_TRY(detect_dev(s, d_in, n, horizon_mode, q));
+    return XP_OK;
+}
+
+int xp_detect_contacts_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                           xp_contact *d_out) {
+    int rc = check_query(s, d_in, n);
+    if (rc) return rc;
+    if (!d_out && n) return XP_EINVAL;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    XP_API_TRY(s->io_status.reserve(n * 4));
+    QueryOut q = {nullptr, nullptr, nullptr, s->io_status.as<uint32_t>(), d_out};
+    XP_API_TRY(detect_dev(s, d_in, n, horizon_mode, q));
+    return XP_OK;
+}
+
+int xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                    xp_collision *out, uint8_t *hit, uint32_t *tri_index, uint32_t *status) {
+    int rc = check_query(s, in, n);
+    if (rc) return rc;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    cudaStream_t st = s->stream;
+    XP_API_TRY(s->io_in.reserve(n * sizeof(xp_response)));
+    XP_API_TRY(s->io_col.reserve(n * sizeof(xp_collision)));
+    XP_API_TRY(s->io_hit.reserve(n));
+    XP_API_TRY(s->io_tri.reserve(n * 4));
+    XP_API_TRY(s->io_status.reserve(n * 4));
+    XP_API_TRY(cudaMemcpyAsync(s->io_in.p, in, n * sizeof(xp_response), cudaMemcpyHostToDevice, st));
+    if (out) XP_API_TRY(cudaMemsetAsync(s->io_col.p, 0, n * sizeof(xp_collision), st));
+    QueryOut q = {out ? s->io_col.as<xp_collision>() : nullptr, s->io_hit.as<uint8_t>(),
+                  tri_index ? s->io_tri.as<uint32_t>() : nullptr, s->io_status.as<uint32_t>(), nullptr};
+    XP_API_TRY(detect_dev(s, s->io_in.as<xp_response>(), n, horizon_mode, q));
+    if (out) XP_API_TRY(cudaMemcpyAsync(out, s->io_col.p, n * sizeof(xp_collision), cudaMemcpyDeviceToHost, st));
+    if (hit) XP_API_TRY(cudaMemcpyAsync(hit, s->io_hit.p, n, cudaMemcpyDeviceToHost, st));
+    if (tri_index) XP_API_TRY(cudaMemcpyAsync(tri_index, s->io_tri.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if (status) XP_API_TRY(cudaMemcpyAsync(status, s->io_status.p, n * 4, cudaMemcpyDeviceToHost, st));
+    XP_API_TRY(cudaStreamSynchronize(st));
+    return XP_OK;
+}
+
+int xp_collision_response_batch_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t max_iter,
+                                    uint32_t horizon_mode, xp_response *d_out, uint32_t *d_iterations,
+                                    uint32_t *d_status, xp_vec3 *d_last_slide_normal) {
+    int rc = check_query(s, d_in, n);
+    if (rc) return rc;
+    if (!d_out && n) return XP_EINVAL;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    XP_API_TRY(response_dev(s, d_in, n, max_iter, horizon_mode, d_out, d_iterations, d_status, d_last_slide_normal));
+    return XP_OK;
+}
+
+int xp_collision_response_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t max_iter,
+                                uint32_t horizon_mode, xp_response *out, uint32_t *iterations,
+                                uint32_t *status, xp_vec3 *last_slide_normal) {
+    int rc = check_query(s, in, n);
+    if (rc) return rc;
+    if (!out && n) return XP_EINVAL;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    cudaStream_t st = s->stream;
+    XP_API_TRY(s->io_out.reserve(n * sizeof(xp_response)));
+    XP_API_TRY(s->io_iter.reserve(n * 4));
+    XP_API_TRY(s->io_status.reserve(n * 4));
+    XP_API_TRY(s->io_normal.reserve(n * sizeof(xp_vec3)));
+    // the current Response of every sphere lives in io_out and is updated in place
+    XP_API_TRY(cudaMemcpyAsync(s->io_out.p, in, n * sizeof(xp_response), cudaMemcpyHostToDevice, st));
+    XP_API_TRY(response_dev(s, s->io_out.as<xp_response>(), n, max_iter, horizon_mode, s->io_out.as<xp_response>(),
+                            s->io_iter.as<uint32_t>(), s->io_status.as<uint32_t>(),
+                            last_slide_normal ? s->io_normal.as<xp_vec3>() : nullptr));
+    XP_API_TRY(cudaMemcpyAsync(out, s->io_out.p, n * sizeof(xp_response), cudaMemcpyDeviceToHost, st));
+    if (iterations) XP_API_TRY(cudaMemcpyAsync(iterations, s->io_iter.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if (status) XP_API_TRY(cudaMemcpyAsync(status, s->io_status.p, n * 4, cudaMemcpyDeviceToHost, st));
+    if (last_slide_normal)
+        XP_API_TRY(cudaMemcpyAsync(last_slide_normal, s->io_normal.p, n * sizeof(xp_vec3), cudaMemcpyDeviceToHost, st));
+    XP_API_TRY(cudaStreamSynchronize(st));
+    return XP_OK;
+}
+
+int xp_broadphase_pairs(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode, uint64_t cap,
+                        uint32_t *sphere_idx, uint32_t *tri_idx, uint64_t *count) {
+    int rc = check_query(s, in, n);
+    if (rc) return rc;
+    if (!count || (cap && (!sphere_idx || !tri_idx))) return XP_EINVAL;
+    XP_BIND(s);
+    reset_stats(s);
+    *count = 0;
+    if (n == 0) return XP_OK;
+    if (n > (1ull << 24)) return XP_EINVAL;     // introspection call: bounded batch
+    cudaStream_t st = s->stream;
+    XP_API_TRY(s->io_in.reserve(n * sizeof(xp_response)));
+    XP_API_TRY(s->io_tri.reserve((cap ? cap : 1) * 4));
+    XP_API_TRY(s->io_iter.reserve((cap ? cap : 1) * 4));
+    XP_API_TRY(cudaMemcpyAsync(s->io_in.p, in, n * sizeof(xp_response), cudaMemcpyHostToDevice, st));
+    uint64_t total = 0;
+    XP_API_TRY(pairs_dev(s, s->io_in.as<xp_response>(), n, horizon_mode, cap, s->io_iter.as<uint32_t>(),
+                         s->io_tri.as<uint32_t>(), &total));
+    *count = total;
+    const uint64_t k = total < cap ? total : cap;
+    if (k) {
+        XP_API_TRY(cudaMemcpyAsync(sphere_idx, s->io_iter.p, k * 4, cudaMemcpyDeviceToHost, st));
+        XP_API_TRY(cudaMemcpyAsync(tri_idx, s->io_tri.p, k * 4, cudaMemcpyDeviceToHost, st));
+    }
+    XP_API_TRY(cudaStreamSynchronize(st));
+    return total > cap ? XP_ECAP : XP_OK;
+}
+
+int xp_scene_debug_tree(xp_scene *s, uint32_t *sorted_tri, uint32_t *morton, int32_t *node_child,
+                        xp_vec3 *node_lo, xp_vec3 *node_hi) {
+    if (!s) return XP_EINVAL;
+    if (!s->built) return XP_ESTATE;
+    XP_BIND(s);
+    const uint64_t n = s->n_tris;
+    if (n == 0) return XP_OK;
+    XP_API_TRY(cudaStreamSynchronize(s->stream));
+    if (sorted_tri) XP_API_TRY(cudaMemcpy(sorted_tri, s->vals_a.p, n * 4, cudaMemcpyDeviceToHost));
+    if (morton) XP_API_TRY(cudaMemcpy(morton, s->keys_a.p, n * 4, cudaMemcpyDeviceToHost));
+    const uint64_t ni = n > 1 ? n - 1 : 1;
+    if (node_child) {
+        Node *h = new (std::nothrow) Node[ni];
+        if (!h) return XP_ENOMEM;
+        cudaError_t e = cudaMemcpy(h, s->nodes.p, ni * sizeof(Node), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            for (uint64_t i = 0; i < ni; ++i) { node_child[2 * i] = h[i].link.x; node_child[2 * i + 1] = h[i].link.y; }
+        delete[] h;
+        if (e != cudaSuccess) return fail_cuda(e);
+    }
+    if (node_lo || node_hi) {
+        float4 *h = new (std::nothrow) float4[ni];
+        if (!h) return XP_ENOMEM;
+        for (int pass = 0; pass < 2; ++pass) {
+            xp_vec3 *dst = pass ? node_hi : node_lo;
+            if (!dst) continue;
+            cudaError_t e = cudaMemcpy(h, pass ? s->node_hi.p : s->node_lo.p, ni * sizeof(float4), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { delete[] h; return fail_cuda(e); }
+            for (uint64_t i = 0; i < ni; ++i) { dst[i].x = h[i].x; dst[i].y = h[i].y; dst[i].z = h[i].z; }
+        }
+        delete[] h;
+    }
+    return XP_OK;
+}
+
+int xp_sphere_triangle_detect_collision(int device, const xp_response *response, const xp_triangle *triangle,
+                                        xp_collision *out) {
+    if (!response || !triangle || !out) return XP_EINVAL;
+    XP_API_TRY(cudaSetDevice(device));
+    int result = 0;
+    XP_API_TRY(single_detect_dev(response, triangle, out, &result));
+    return result < 0 ? XP_EINVAL : result;
+}
+
+int xp_sphere_triangle_calculate_response(int device, const xp_response *response, const xp_collision *collision,
+                                          xp_response *out) {
+    if (!response || !collision || !out) return XP_EINVAL;
+    XP_API_TRY(cudaSetDevice(device));
+    int result = 0;
+    XP_API_TRY(single_respond_dev(response, collision, out, &result));
+    return result;
+}
+
+int xp_probe_fp32_peak(int device, double *tflops) {
+    if (!tflops) return XP_EINVAL;
+    XP_API_TRY(cudaSetDevice(device));
+    XP_API_TRY(probe_fp32(tflops));
+    return XP_OK;
+}
+
+const char *xp_strerror(int code) {
+    switch (code) {
+    case XP_OK: return "ok";
+    case XP_EINVAL: return "invalid argument";
+    case XP_ECUDA: return "CUDA error (see xp_last_cuda_error)";
+    case XP_ENOMEM: return "out of memory";
+    case XP_ESTATE: return "scene not built";
+    case XP_ECAP: return "output capacity too small";
+    default: return "unknown error";
+    }
+}
+
+const char *xp_last_cuda_error(void) { return g_cuda_err; }
+
+const char *xp_version(void) { return "xp_physics_cuda 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,498 @@
+// xp_build.cu -- device LBVH construction over the uploaded triangle soup (sm_100a).
+//
+// New relative to the reference, which has no broadphase: collision_response walks every
+// triangle on every iteration (/root/reference/xp_physics/src/lib.rs:33-35).  The per-triangle
+// quantities cached here are the ones collision_detect.rs:162,171 recomputes on every test
+// (Triangle::normal, triangle.rs:44-46; Triangle::plane_constant, triangle.rs:47-50).
+//
+// Stages (all HBM-bound; bytes per triangle in DESIGN.md):
+//   K0 bounds   AABB of the triangle-box centres (ordered-int atomics, block-reduced)
+//   K2 morton   30-bit Morton code of each centre
+//   K3 sort     CUB-free LSD radix sort, 8 bits x 4 passes, stable (histogram / scan / scatter)
+//   K1 pack     TriRec + inflated leaf AABB written in Morton order
+//   K4 tree     Karras 2012 hierarchy emission (one thread per internal node)
+//   K5 refit    bottom-up AABB refit with per-node arrival counters; writes the 64 B nodes
+#include <cstdio>
+
+#include "xp_internal.h"
+#include "xp_narrowphase.cuh"
+
+namespace xp {
+
+// ------------------------------------------------------------------------------------------
+// ordered-int encoding so float min/max can use integer atomics
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned enc_f(float f) {
+    unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f(unsigned e) {
+    unsigned b = (e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e;
+    return __uint_as_float(b);
+}
+
+__device__ __forceinline__ void load_tri(const float *__restrict__ aos, uint64_t i, V3 &v0, V3 &v1, V3 &v2) {
+    const float *p = aos + i * 9;
+    v0 = {__ldg(p + 0), __ldg(p + 1), __ldg(p + 2)};
+    v1 = {__ldg(p + 3), __ldg(p + 4), __ldg(p + 5)};
+    v2 = {__ldg(p + 6), __ldg(p + 7), __ldg(p + 8)};
+}
+
+__device__ __forceinline__ V3 box_centre(V3 lo, V3 hi) {
+    return {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+}
+
+// K0 -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bounds(const float *__restrict__ aos, uint64_t n,
+                                                unsigned *__restrict__ bounds) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        V3 v0, v1, v2, lo, hi;
+        load_tri(aos, i, v0, v1, v2);
+        xp_tri_aabb(v0, v1, v2, lo, hi);
+        V3 c = box_centre(lo, hi);
+        mn[0] = fminf(mn[0], c.x); mn[1] = fminf(mn[1], c.y); mn[2] = fminf(mn[2], c.z);
+        mx[0] = fmaxf(mx[0], c.x); mx[1] = fmaxf(mx[1], c.y); mx[2] = fmaxf(mx[2], c.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&bounds[k], enc_f(mn[k]));
+            atomicMax(&bounds[3 + k], enc_f(mx[k]));
+        }
+    }
+}
+
+__global__ void k_bounds_init(unsigned *bounds) {
+    if (threadIdx.x < 3) bounds[threadIdx.x] = 0xFFFFFFFFu;
+    else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
+}
+
+// K2 -----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned expand_bits10(unsigned v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ unsigned morton30(V3 c, const unsigned *__restrict__ bounds) {
+    float q[3] = {c.x, c.y, c.z};
+    unsigned code = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float lo = dec_f(bounds[k]), hi = dec_f(bounds[3 + k]);
+        float ext = hi - lo;
+        float u = (ext > 0.0f) ? (q[k] - lo) / ext : 0.0f;
+        u = fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f);
+        code |= expand_bits10((unsigned)u) << (2 - k);
+    }
+    return code;
+}
+
+__global__ void __launch_bounds__(256) k_morton_tris(const float *__restrict__ aos, uint64_t n,
+                                                     const unsigned *__restrict__ bounds,
+                                                     uint32_t *__restrict__ keys,
+                                                     uint32_t *__restrict__ vals) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 v0, v1, v2, lo, hi;
+    load_tri(aos, i, v0, v1, v2);
+    xp_tri_aabb(v0, v1, v2, lo, hi);
+    keys[i] = morton30(box_centre(lo, hi), bounds);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k_morton_spheres(const xp_response *__restrict__ in, uint64_t n,
+                                                        const unsigned *__restrict__ bounds,
+                                                        uint32_t *__restrict__ keys,
+                                                        uint32_t *__restrict__ vals) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = reinterpret_cast<const float *>(in) + i * 7;
+    V3 c = {__ldg(p + 0), __ldg(p + 1), __ldg(p + 2)};
+    keys[i] = morton30(c, bounds);
+    vals[i] = (uint32_t)i;
+}
+
+// K3: radix sort -------------------------------------------------------------------------------
+static constexpr int RS_THREADS = 256;
+static constexpr int RS_ITEMS = 16;
+static constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 keys per block
+static constexpr int RS_WARPS = RS_THREADS / 32;
+static constexpr int RS_SEG = RS_TILE / RS_WARPS;       // 512 consecutive keys per warp
+
+// per-tile digit histogram, stored digit-major so one flat exclusive scan yields the bases
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t *__restrict__ keys, uint64_t n,
+                                                        int shift, uint32_t *__restrict__ hist,
+                                                        unsigned num_tiles) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        uint64_t idx = base + (uint64_t)c * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(uint64_t)threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// stable scatter: warp w owns keys [w*512, (w+1)*512) of the tile, processed in chunks of 32
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__restrict__ keys_in,
+                                                           const uint32_t *__restrict__ vals_in,
+                                                           uint32_t *__restrict__ keys_out,
+                                                           uint32_t *__restrict__ vals_out, uint64_t n,
+                                                           int shift, const uint32_t *__restrict__ scanned,
+                                                           unsigned num_tiles) {
+    __shared__ unsigned cnt[RS_WARPS][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)w * RS_SEG;
+    uint32_t k[RS_ITEMS], v[RS_ITEMS];
+    // pass A: per-warp digit counts
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        const uint64_t idx = base + (uint64_t)c * 32 + lane;
+        const bool valid = idx < n;
+        k[c] = valid ? keys_in[idx] : 0u;
+        v[c] = valid ? vals_in[idx] : 0u;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned d = (k[c] >> shift) & 255u;
+            const unsigned peers = __match_any_sync(vm, d);
+            if (lane == (31 - __clz(peers))) cnt[w][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive prefix over warps, seeded with this tile's global base for the digit
+        const unsigned d = threadIdx.x;
+        unsigned run = scanned[(uint64_t)d * num_tiles + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) {
+            unsigned t = cnt[ww][d];
+            cnt[ww][d] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    // pass B: ranks in original order -> stable
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        const uint64_t idx = base + (uint64_t)c * 32 + lane;
+        const bool valid = idx < n;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        unsigned d = 0, peers = 0;
+        if (valid) {
+            d = (k[c] >> shift) & 255u;
+            peers = __match_any_sync(vm, d);
+            const unsigned pos = cnt[w][d] + __popc(peers & ((1u << lane) - 1u));
+            keys_out[pos] = k[c];
+            vals_out[pos] = v[c];
+        }
+        __syncwarp();
+        if (valid && lane == (31 - __clz(peers))) cnt[w][d] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+// exclusive scan of a uint32 array (hierarchical: 2048 elements per block) -------------------
+static constexpr int SC_THREADS = 256;
+static constexpr int SC_ITEMS = 8;
+static constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_local(uint32_t *__restrict__ data, uint64_t n,
+                                                           uint32_t *__restrict__ sums) {
+    __shared__ unsigned warp_tot[SC_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+    unsigned x[SC_ITEMS], tot = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        x[i] = (base + i < n) ? data[base + i] : 0u;
+        tot += x[i];
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned t = (lane < SC_THREADS / 32) ? warp_tot[lane] : 0u;
+        unsigned ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += y;
+        }
+        if (lane < SC_THREADS / 32) warp_tot[lane] = ti - t;   // exclusive
+        if (lane == SC_THREADS / 32 - 1 && sums) sums[blockIdx.x] = ti;
+    }
+    __syncthreads();
+    unsigned run = warp_tot[w] + (inc - tot);
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        if (base + i < n) data[base + i] = run;
+        run += x[i];
+    }
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_add(uint32_t *__restrict__ data, uint64_t n,
+                                                         const uint32_t *__restrict__ sums) {
+    const unsigned add = sums[blockIdx.x];
+    const uint64_t base = (uint64_t)blockIdx.x * SC_TILE + (uint64_t)threadIdx.x * SC_ITEMS;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i)
+        if (base + i < n) data[base + i] += add;
+}
+
+// scratch must hold ceil(n/2048) + ceil(that/2048) + ... uint32
+static cudaError_t exclusive_scan_u32(uint32_t *data, uint64_t n, uint32_t *scratch, cudaStream_t st,
+                                      unsigned *launches) {
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = grid_for(n, SC_TILE);
+    k_scan_local<<<blocks, SC_THREADS, 0, st>>>(data, n, blocks > 1 ? scratch : nullptr);
+    ++*launches;
+    if (blocks > 1) {
+        cudaError_t e = exclusive_scan_u32(scratch, blocks, scratch + blocks, st, launches);
+        if (e != cudaSuccess) return e;
+        k_scan_add<<<blocks, SC_THREADS, 0, st>>>(data, n, scratch);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb,
+                             uint64_t n, int bits, bool *in_a) {
+    *in_a = true;
+    if (n == 0) return cudaSuccess;
+    const unsigned tiles = grid_for(n, RS_TILE);
+    const uint64_t hist_n = (uint64_t)tiles * 256;
+    // histogram + scan scratch (geometric series of block sums: < hist_n/2047 + 64)
+    cudaError_t e = s->hist.reserve((hist_n + hist_n / 1024 + 4096) * sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    uint32_t *hist = s->hist.as<uint32_t>();
+    uint32_t *scratch = hist + hist_n;
+    uint32_t *ki = ka, *ko = kb, *vi = va, *vo = vb;
+    for (int shift = 0; shift < bits; shift += 8) {
+        k_rs_hist<<<tiles, RS_THREADS, 0, s->stream>>>(ki, n, shift, hist, tiles);
+        ++s->stats.kernel_launches;
+        e = exclusive_scan_u32(hist, hist_n, scratch, s->stream, &s->stats.kernel_launches);
+        if (e != cudaSuccess) return e;
+        k_rs_scatter<<<tiles, RS_THREADS, 0, s->stream>>>(ki, vi, ko, vo, n, shift, hist, tiles);
+        ++s->stats.kernel_launches;
+        uint32_t *t = ki; ki = ko; ko = t;
+        t = vi; vi = vo; vo = t;
+        *in_a = !*in_a;
+    }
+    return cudaGetLastError();
+}
+
+// K1 -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uint64_t n,
+                                              const uint32_t *__restrict__ sorted_idx,
+                                              TriRec *__restrict__ recs, float4 *__restrict__ leaf_lo,
+                                              float4 *__restrict__ leaf_hi) {
+    uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t i = sorted_idx[j];
+    V3 v0, v1, v2, lo, hi;
+    load_tri(aos, i, v0, v1, v2);
+    const TriDerived d = xp_tri_derive(v0, v1, v2);
+    xp_tri_aabb(v0, v1, v2, lo, hi);
+    TriRec r;
+    r.q0 = make_float4(v0.x, v0.y, v0.z, d.n.x);
+    r.q1 = make_float4(v1.x, v1.y, v1.z, d.n.y);
+    r.q2 = make_float4(v2.x, v2.y, v2.z, d.n.z);
+    r.q3 = make_float4(d.pc, 0.0f, 0.0f, __uint_as_float(i));
+    recs[j] = r;
+    leaf_lo[j] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+    leaf_hi[j] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+}
+
+// K4: Karras 2012 ------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint32_t *__restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __clz((unsigned)i ^ (unsigned)j);   // tie-break on the index
+    return __clz(a ^ b);
+}
+
+__global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ keys, int n,
+                                                Node *__restrict__ nodes, int *__restrict__ parent_internal,
+                                                int *__restrict__ parent_leaf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int sft = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (sft + t) * d) > dnode) sft += t;
+    } while (t > 1);
+    const int gamma = i + sft * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    int c0, c1;
+    if (lo == gamma) { c0 = ~gamma; parent_leaf[gamma] = i; } else { c0 = gamma; parent_internal[gamma] = i; }
+    if (hi == gamma + 1) { c1 = ~(gamma + 1); parent_leaf[gamma + 1] = i; } else { c1 = gamma + 1; parent_internal[gamma + 1] = i; }
+    if (i == 0) parent_internal[0] = -1;
+    nodes[i].link = make_int4(c0, c1, 0, 0);
+}
+
+// K5: refit --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_refit(int n, Node *__restrict__ nodes,
+                                               const int *__restrict__ parent_internal,
+                                               const int *__restrict__ parent_leaf,
+                                               const float4 *__restrict__ leaf_lo,
+                                               const float4 *__restrict__ leaf_hi, float4 *node_lo,
+                                               float4 *node_hi, unsigned *__restrict__ flags) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int cur = parent_leaf[j];
+    while (cur >= 0) {
+        if (atomicAdd(&flags[cur], 1u) == 0u) return;     // first arrival: the sibling finishes
+        const int4 link = nodes[cur].link;
+        float4 lo0, hi0, lo1, hi1;
+        if (link.x < 0) { lo0 = leaf_lo[~link.x]; hi0 = leaf_hi[~link.x]; }
+        else { lo0 = __ldcg(&node_lo[link.x]); hi0 = __ldcg(&node_hi[link.x]); }
+        if (link.y < 0) { lo1 = leaf_lo[~link.y]; hi1 = leaf_hi[~link.y]; }
+        else { lo1 = __ldcg(&node_lo[link.y]); hi1 = __ldcg(&node_hi[link.y]); }
+        nodes[cur].q0 = make_float4(lo0.x, lo0.y, lo0.z, hi0.x);
+        nodes[cur].q1 = make_float4(hi0.y, hi0.z, lo1.x, lo1.y);
+        nodes[cur].q2 = make_float4(lo1.z, hi1.x, hi1.y, hi1.z);
+        __stcg(&node_lo[cur], make_float4(fminf(lo0.x, lo1.x), fminf(lo0.y, lo1.y), fminf(lo0.z, lo1.z), 0.0f));
+        __stcg(&node_hi[cur], make_float4(fmaxf(hi0.x, hi1.x), fmaxf(hi0.y, hi1.y), fmaxf(hi0.z, hi1.z), 0.0f));
+        __threadfence();
+        cur = parent_internal[cur];
+    }
+}
+
+// a scene with one triangle: root = (leaf 0, empty); the empty box (+inf,-inf) can never be hit
+__global__ void k_single_root(Node *nodes, const float4 *leaf_lo, const float4 *leaf_hi,
+                              float4 *node_lo, float4 *node_hi) {
+    const float4 lo = leaf_lo[0], hi = leaf_hi[0];
+    const float inf = INFINITY;
+    nodes[0].q0 = make_float4(lo.x, lo.y, lo.z, hi.x);
+    nodes[0].q1 = make_float4(hi.y, hi.z, inf, inf);
+    nodes[0].q2 = make_float4(inf, -inf, -inf, -inf);
+    nodes[0].link = make_int4(~0, ~0, 0, 0);
+    node_lo[0] = lo; node_hi[0] = hi;
+}
+
+#define XP_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
+
+cudaError_t build_lbvh(xp_scene *s) {
+    const uint64_t n = s->n_tris;
+    s->built = false;
+    if (n == 0) { s->built = true; return cudaSuccess; }
+    if (n >= (1ull << 27)) return cudaErrorInvalidValue;   // leaf index must fit 27 bits (queue packing)
+    cudaStream_t st = s->stream;
+    const float *aos = s->tris_aos.as<float>();
+    XP_TRY(s->bounds.reserve(8 * sizeof(unsigned)));
+    XP_TRY(s->keys_a.reserve(n * 4)); XP_TRY(s->keys_b.reserve(n * 4));
+    XP_TRY(s->vals_a.reserve(n * 4)); XP_TRY(s->vals_b.reserve(n * 4));
+    XP_TRY(s->recs.reserve(n * sizeof(TriRec)));
+    XP_TRY(s->nodes.reserve((n > 1 ? n - 1 : 1) * sizeof(Node)));
+    XP_TRY(s->node_lo.reserve(n * 16)); XP_TRY(s->node_hi.reserve(n * 16));
+    XP_TRY(s->leaf_lo.reserve(n * 16)); XP_TRY(s->leaf_hi.reserve(n * 16));
+    XP_TRY(s->parent_internal.reserve(n * 4)); XP_TRY(s->parent_leaf.reserve(n * 4));
+    XP_TRY(s->refit_flags.reserve(n * 4));
+    unsigned *bounds = s->bounds.as<unsigned>();
+    {
+        StageTimer t(s, XP_STAGE_BUILD_BOUNDS);
+        k_bounds_init<<<1, 32, 0, st>>>(bounds);
+        unsigned blocks = grid_for(n, 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_bounds<<<blocks, 256, 0, st>>>(aos, n, bounds);
+        s->stats.kernel_launches += 2;
+    }
+    {
+        StageTimer t(s, XP_STAGE_BUILD_MORTON);
+        k_morton_tris<<<grid_for(n, 256), 256, 0, st>>>(aos, n, bounds, s->keys_a.as<uint32_t>(),
+                                                       s->vals_a.as<uint32_t>());
+        ++s->stats.kernel_launches;
+    }
+    bool in_a = true;
+    {
+        StageTimer t(s, XP_STAGE_BUILD_SORT);
+        XP_TRY(radix_sort_pairs(s, s->keys_a.as<uint32_t>(), s->keys_b.as<uint32_t>(),
+                                s->vals_a.as<uint32_t>(), s->vals_b.as<uint32_t>(), n, 32, &in_a));
+    }
+    if (!in_a) {   // keep the sorted arrays in *_a (scene invariant used by debug_tree and queries)
+        xp::DevBuf t = s->keys_a; s->keys_a = s->keys_b; s->keys_b = t;
+        t = s->vals_a; s->vals_a = s->vals_b; s->vals_b = t;
+    }
+    const uint32_t *keys = s->keys_a.as<uint32_t>();
+    const uint32_t *vals = s->vals_a.as<uint32_t>();
+    {
+        StageTimer t(s, XP_STAGE_BUILD_PACK);
+        k_pack<<<grid_for(n, 256), 256, 0, st>>>(aos, n, vals, s->recs.as<TriRec>(),
+                                                s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>());
+        ++s->stats.kernel_launches;
+    }
+    if (n == 1) {
+        k_single_root<<<1, 1, 0, st>>>(s->nodes.as<Node>(), s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>(),
+                                       s->node_lo.as<float4>(), s->node_hi.as<float4>());
+        ++s->stats.kernel_launches;
+    } else {
+        {
+            StageTimer t(s, XP_STAGE_BUILD_TREE);
+            k_karras<<<grid_for(n - 1, 256), 256, 0, st>>>(keys, (int)n, s->nodes.as<Node>(),
+                                                          s->parent_internal.as<int>(),
+                                                          s->parent_leaf.as<int>());
+            ++s->stats.kernel_launches;
+        }
+        {
+            StageTimer t(s, XP_STAGE_BUILD_REFIT);
+            XP_TRY(cudaMemsetAsync(s->refit_flags.p, 0, n * 4, st));
+            k_refit<<<grid_for(n, 256), 256, 0, st>>>((int)n, s->nodes.as<Node>(),
+                                                     s->parent_internal.as<int>(), s->parent_leaf.as<int>(),
+                                                     s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>(),
+                                                     s->node_lo.as<float4>(), s->node_hi.as<float4>(),
+                                                     s->refit_flags.as<unsigned>());
+            ++s->stats.kernel_launches;
+        }
+    }
+    XP_TRY(cudaGetLastError());
+    // scene bounds on the host too (sphere ordering falls back to identity if degenerate)
+    s->built = true;
+    return cudaSuccess;
+}
+
+cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order) {
+    StageTimer t(s, XP_STAGE_SPHERE_SORT);
+    XP_TRY(s->active_a.reserve(n * 4)); XP_TRY(s->active_b.reserve(n * 4));
+    XP_TRY(s->sort_ka.reserve(n * 4)); XP_TRY(s->sort_kb.reserve(n * 4));
+    uint32_t *ka = s->sort_ka.as<uint32_t>(), *kb = s->sort_kb.as<uint32_t>();
+    uint32_t *va = s->active_a.as<uint32_t>(), *vb = s->active_b.as<uint32_t>();
+    k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va);
+    ++s->stats.kernel_launches;
+    bool in_a = true;
+    XP_TRY(radix_sort_pairs(s, ka, kb, va, vb, n, 32, &in_a));
+    if (!in_a) { xp::DevBuf tmp = s->active_a; s->active_a = s->active_b; s->active_b = tmp; }
+    *order = s->active_a.as<uint32_t>();
+    return cudaGetLastError();
+}
+
+}  // namespace xp

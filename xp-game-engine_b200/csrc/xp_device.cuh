@@ -1,0 +1,89 @@
+// xp_device.cuh -- device data layouts and the scene object shared by the .cu files.
+//
+// HBM layout (all fp32, 16-byte aligned float4 planes so every access is one LDG.128):
+//   TriRec[T]  64 B  leaf j (Morton order): q0=(v0, n.x) q1=(v1, n.y) q2=(v2, n.z)
+//                    q3=(plane_constant, 0, 0, bits(upload index))
+//   Node[T-1]  64 B  internal node i: both child AABBs (already inflated by 1+1e-4) and the two
+//                    child links (>= 0 internal, < 0 leaf ~c); node 0 is the root
+//   RayRec[S]  64 B  per sphere per sweep: q0=(c, |m|) q1=(m, |m|^2) q2=(m/|m|, horizon)
+//                    q3=(1/m.x, 1/m.y, 1/m.z, bits(flags))
+//   best[S]     8 B  (bits(t) << 32) | ~upload_index, all ones = no hit; atomicMin gives the
+//                    reference's min_by with ties going to the later triangle (lib.rs:33-42)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/xp_physics_cuda.h"
+
+namespace xp {
+
+struct __align__(16) TriRec { float4 q0, q1, q2, q3; };
+struct __align__(16) Node { float4 q0, q1, q2; int4 link; };
+struct __align__(16) RayRec { float4 q0, q1, q2, q3; };
+
+static constexpr unsigned long long BEST_NONE = 0xFFFFFFFFFFFFFFFFull;
+static constexpr uint32_t RAY_VALID = 1u;
+static constexpr uint32_t HARD_ITER_CAP = 65536u;
+
+// Growable device buffer (never shrinks; freed with the scene).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct DeviceCounters {           // one small block of device memory, zeroed per call
+    unsigned long long tests;
+    unsigned long long pairs;
+    unsigned long long node_visits;
+    unsigned int next_active;
+    unsigned int stack_overflow;
+    unsigned int pad[2];
+};
+
+}  // namespace xp
+
+struct xp_scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // options
+    int arith = XP_ARITH_EXACT;
+    int method = XP_METHOD_BVH_FUSED;
+    int prune = 0;
+    int timing = 0;
+    int sort_spheres = 1;
+    uint64_t max_pairs = 1ull << 26;
+    // geometry
+    uint64_t n_tris = 0;
+    bool built = false;
+    xp::DevBuf tris_aos;      // xp_triangle[T], upload order
+    xp::DevBuf recs;          // TriRec[T], Morton order
+    xp::DevBuf nodes;         // Node[max(T-1,1)]
+    xp::DevBuf node_lo, node_hi, leaf_lo, leaf_hi;   // float4 boxes used by the refit
+    xp::DevBuf parent_internal, parent_leaf, refit_flags;
+    xp::DevBuf keys_a, keys_b, vals_a, vals_b;       // radix sort ping-pong (triangles / spheres)
+    xp::DevBuf hist;          // radix histograms + scan scratch
+    xp::DevBuf bounds;        // 6 ordered-int floats: scene AABB of triangle centres
+    float h_bounds[6] = {0, 0, 0, 0, 0, 0};
+    // per-call workspaces
+    xp::DevBuf rays, best, active_a, active_b, pairs, counters;
+    xp::DevBuf sort_ka, sort_kb;   // sphere Morton keys (ping-pong)
+    xp::DevBuf io_in, io_out, io_hit, io_tri, io_status, io_iter, io_normal, io_col;
+    // stats
+    xp_stats stats;
+    cudaEvent_t ev[2 * XP_STAGE_COUNT] = {};
+    bool ev_used[XP_STAGE_COUNT] = {};
+    bool ev_created = false;
+};

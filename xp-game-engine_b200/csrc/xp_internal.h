@@ -1,0 +1,44 @@
+// xp_internal.h -- host-side declarations shared by xp_api.cu / xp_build.cu / xp_query.cu.
+#pragma once
+
+#include "xp_device.cuh"
+
+namespace xp {
+
+// RAII stage timer: with XP_OPT_TIMING=1 brackets the stage with CUDA events on the scene's
+// stream and accumulates the elapsed ms into stats.stage_ms (synchronises; diagnostic mode).
+struct StageTimer {
+    xp_scene *s; int stage;
+    StageTimer(xp_scene *scene, int st);
+    ~StageTimer();
+};
+
+inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+// ---- xp_build.cu ----
+// LSD radix sort of (key, value) pairs on `bits` key bits, 8 bits per pass, CUB-free.
+// Ping-pongs between (ka,va) and (kb,vb); *in_a tells where the sorted result ended up.
+cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb,
+                             uint64_t n, int bits, bool *in_a);
+cudaError_t build_lbvh(xp_scene *s);
+// order[k] = index of the k-th sphere in Morton order of its centre (scene bounds).
+cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order);
+
+// ---- xp_query.cu ----
+struct QueryOut {            // device pointers, any may be null
+    xp_collision *col; uint8_t *hit; uint32_t *tri_index; uint32_t *status; xp_contact *contact;
+};
+cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                       const QueryOut &out);
+cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t max_iter,
+                         uint32_t horizon_mode, xp_response *d_out, uint32_t *d_iter,
+                         uint32_t *d_status, xp_vec3 *d_normal);
+cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                      uint64_t cap, uint32_t *d_sphere, uint32_t *d_tri, uint64_t *h_count);
+cudaError_t single_detect_dev(const xp_response *h_resp, const xp_triangle *h_tri,
+                              xp_collision *h_out, int *result);
+cudaError_t single_respond_dev(const xp_response *h_resp, const xp_collision *h_col,
+                               xp_response *h_out, int *result);
+cudaError_t probe_fp32(double *tflops);
+
+}  // namespace xp

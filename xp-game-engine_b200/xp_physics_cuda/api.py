@@ -1,0 +1,325 @@
+"""Host-side mirror of the xp_physics public API on top of the C ABI (ctypes).
+
+Names, argument meaning and error behaviour follow /root/reference/xp_physics/src/lib.rs:9-15:
+    Sphere, Triangle, Response, Collision                       (sphere.rs, triangle.rs, response.rs, collision.rs)
+    collision_response(response, triangles) -> Response         (lib.rs:29)
+    collision_response_non_trianulated(response, vec3s)         (lib.rs:17)
+    sphere_triangle_detect_collision(response, triangle)        (collision_detect.rs:155) -> Collision | None
+    sphere_triangle_calculate_response(response, collision)     (collision_response.rs:6)
+Where the reference panics these raise AssertionError (assert_eq!/assert!) or IndexError
+(the chunks(3) out-of-bounds of lib.rs:19-24).  The batch forms live on `Scene`, which is the
+"upload the triangle soup once, sweep many spheres" object the GPU needs.
+
+All arithmetic happens on the GPU inside libxp_physics_cuda.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+RESPONSE_DTYPE = np.dtype([("c", "<f4", (3,)), ("r", "<f4"), ("movement", "<f4", (3,))])
+COLLISION_DTYPE = np.dtype([("time_to", "<f4"), ("distance_to", "<f4"),
+                            ("position", "<f4", (3,)), ("intersection", "<f4", (3,))])
+CONTACT_DTYPE = np.dtype([("time_to", "<f4"), ("distance_to", "<f4"), ("position", "<f4", (3,)),
+                          ("intersection", "<f4", (3,)), ("tri_index", "<u4"), ("flags", "<u4")])
+assert RESPONSE_DTYPE.itemsize == 28 and COLLISION_DTYPE.itemsize == 32 and CONTACT_DTYPE.itemsize == 40
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ---- value types (reference structs) ------------------------------------------------------
+@dataclass
+class Sphere:                       # sphere.rs:4-13
+    c: Sequence[float]
+    r: float = 1.0
+
+
+@dataclass
+class Triangle:                     # triangle.rs:4-8,41-43
+    v0: Sequence[float]
+    v1: Sequence[float]
+    v2: Sequence[float]
+
+    def as_array(self) -> np.ndarray:
+        return np.asarray([self.v0, self.v1, self.v2], np.float32)
+
+
+@dataclass
+class Response:                     # response.rs:5-8
+    sphere: Sphere
+    movement: Sequence[float]
+
+    def as_record(self) -> np.ndarray:
+        return make_responses([self.sphere.c], [self.movement], self.sphere.r)
+
+    @staticmethod
+    def from_record(rec) -> "Response":
+        return Response(Sphere([float(x) for x in rec["c"]], float(rec["r"])),
+                        [float(x) for x in rec["movement"]])
+
+
+@dataclass
+class Collision:                    # collision.rs:5-10
+    time_to: float
+    distance_to: float
+    position: Sequence[float]
+    intersection: Sequence[float]
+
+    def as_record(self) -> np.ndarray:
+        out = np.zeros(1, COLLISION_DTYPE)
+        out["time_to"], out["distance_to"] = self.time_to, self.distance_to
+        out["position"], out["intersection"] = self.position, self.intersection
+        return out
+
+    @staticmethod
+    def from_record(rec) -> "Collision":
+        return Collision(float(rec["time_to"]), float(rec["distance_to"]),
+                         [float(x) for x in rec["position"]], [float(x) for x in rec["intersection"]])
+
+
+def make_responses(c, movement, r=1.0) -> np.ndarray:
+    c = np.asarray(c, np.float32).reshape(-1, 3)
+    m = np.asarray(movement, np.float32).reshape(-1, 3)
+    out = np.zeros(len(c), RESPONSE_DTYPE)
+    out["c"], out["movement"], out["r"] = c, m, r
+    return out
+
+
+def as_triangles(t) -> np.ndarray:
+    if isinstance(t, (list, tuple)) and len(t) and isinstance(t[0], Triangle):
+        t = np.stack([x.as_array() for x in t])
+    return np.ascontiguousarray(np.asarray(t, np.float32).reshape(-1, 3, 3))
+
+
+# ---- the scene: triangle soup uploaded once + device LBVH ------------------------------------
+class Scene:
+    """Owns an xp_scene (device triangle records + LBVH) on one GPU."""
+
+    def __init__(self, device: int = 0, triangles=None, *, arith: str = "exact", method: str = "bvh_fused",
+                 prune: bool = False, sort_spheres: bool = True, timing: bool = False):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        check(self._L.xp_scene_create(device, C.byref(h)), "xp_scene_create")
+        self._h = h
+        self.device = device
+        self.set_options(arith=arith, method=method, prune=prune, sort_spheres=sort_spheres, timing=timing)
+        if triangles is not None:
+            self.set_triangles(triangles)
+            self.build()
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.xp_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- options
+    def set_options(self, *, arith=None, method=None, prune=None, sort_spheres=None, timing=None, max_pairs=None):
+        L, h = self._L, self._h
+        if arith is not None:
+            check(L.xp_scene_set_option(h, _lib.OPT_ARITH, {"exact": 0, "fast": 1}[arith]))
+        if method is not None:
+            check(L.xp_scene_set_option(h, _lib.OPT_METHOD, {"bvh_fused": 0, "bvh_pairs": 1, "brute": 2}[method]))
+        if prune is not None:
+            check(L.xp_scene_set_option(h, _lib.OPT_PRUNE, int(bool(prune))))
+        if sort_spheres is not None:
+            check(L.xp_scene_set_option(h, _lib.OPT_SORT_SPHERES, int(bool(sort_spheres))))
+        if timing is not None:
+            check(L.xp_scene_set_option(h, _lib.OPT_TIMING, int(bool(timing))))
+        if max_pairs is not None:
+            check(L.xp_scene_set_option(h, _lib.OPT_MAX_PAIRS, int(max_pairs)))
+
+    def set_stream(self, cuda_stream_ptr: int):
+        check(self._L.xp_scene_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    # -- geometry
+    def set_triangles(self, triangles):
+        t = as_triangles(triangles)
+        self._keep = t
+        check(self._L.xp_scene_set_triangles(self._h, _p(t), len(t)), "xp_scene_set_triangles")
+
+    def set_triangles_dev(self, dev_ptr: int, n: int):
+        check(self._L.xp_scene_set_triangles_dev(self._h, C.c_void_p(dev_ptr), n), "xp_scene_set_triangles_dev")
+
+    def set_positions(self, vec3s):
+        v = np.ascontiguousarray(np.asarray(vec3s, np.float32).reshape(-1, 3))
+        rc = self._L.xp_scene_set_positions(self._h, _p(v), len(v))
+        if rc == _lib.XP_EINVAL:
+            raise IndexError("index out of bounds: chunks(3) of a slice whose length is not a multiple of 3 "
+                             "(xp_physics/src/lib.rs:19-24)")
+        check(rc, "xp_scene_set_positions")
+
+    def build(self):
+        check(self._L.xp_scene_build(self._h), "xp_scene_build")
+
+    @property
+    def triangle_count(self) -> int:
+        return int(self._L.xp_scene_triangle_count(self._h))
+
+    def stats(self) -> dict:
+        st = _lib.XpStats()
+        check(self._L.xp_scene_get_stats(self._h, C.byref(st)))
+        return {"narrowphase_tests": int(st.narrowphase_tests), "broadphase_pairs": int(st.broadphase_pairs),
+                "node_visits": int(st.node_visits), "kernel_launches": int(st.kernel_launches),
+                "iterations_run": int(st.iterations_run),
+                "stage_ms": {n: float(st.stage_ms[i]) for i, n in enumerate(_lib.STAGE_NAMES)}}
+
+    # -- sweeps, host buffers
+    def detect_batch(self, responses: np.ndarray, horizon: str = "inf"):
+        """Closest collision per sphere (a11 + the min_by of lib.rs:33-42).
+        Returns (collisions, hit, tri_index, status)."""
+        r = np.ascontiguousarray(responses, RESPONSE_DTYPE)
+        n = len(r)
+        col = np.zeros(n, COLLISION_DTYPE)
+        hit = np.zeros(n, np.uint8)
+        tri = np.full(n, 0xFFFFFFFF, np.uint32)
+        st = np.zeros(n, np.uint32)
+        check(self._L.xp_detect_batch(self._h, _p(r), n, _horizon(horizon), _p(col), _p(hit), _p(tri), _p(st)),
+              "xp_detect_batch")
+        return col, hit, tri, st
+
+    def collision_response_batch(self, responses: np.ndarray, max_iter: int = 0, horizon: str = "inf"):
+        """collision_response (lib.rs:29-62) for every sphere.
+        Returns (responses_out, iterations, status, last_slide_normal)."""
+        r = np.ascontiguousarray(responses, RESPONSE_DTYPE)
+        n = len(r)
+        out = np.zeros(n, RESPONSE_DTYPE)
+        it = np.zeros(n, np.uint32)
+        st = np.zeros(n, np.uint32)
+        ln = np.zeros((n, 3), np.float32)
+        check(self._L.xp_collision_response_batch(self._h, _p(r), n, max_iter, _horizon(horizon), _p(out),
+                                                  _p(it), _p(st), _p(ln)), "xp_collision_response_batch")
+        return out, it, st, ln
+
+    def broadphase_pairs(self, responses: np.ndarray, horizon: str = "inf", cap: Optional[int] = None):
+        r = np.ascontiguousarray(responses, RESPONSE_DTYPE)
+        cap = int(cap if cap is not None else max(1024, min(len(r) * max(self.triangle_count, 1), 1 << 26)))
+        si = np.zeros(cap, np.uint32)
+        ti = np.zeros(cap, np.uint32)
+        cnt = C.c_uint64()
+        rc = self._L.xp_broadphase_pairs(self._h, _p(r), len(r), _horizon(horizon), cap, _p(si), _p(ti), C.byref(cnt))
+        if rc == _lib.XP_ECAP:
+            raise MemoryError(f"broadphase pair capacity {cap} < {cnt.value}")
+        check(rc, "xp_broadphase_pairs")
+        return si[:cnt.value].copy(), ti[:cnt.value].copy()
+
+    def debug_tree(self):
+        n = self.triangle_count
+        ni = max(n - 1, 1)
+        sorted_tri = np.zeros(n, np.uint32)
+        morton = np.zeros(n, np.uint32)
+        child = np.zeros((ni, 2), np.int32)
+        lo = np.zeros((ni, 3), np.float32)
+        hi = np.zeros((ni, 3), np.float32)
+        check(self._L.xp_scene_debug_tree(self._h, _p(sorted_tri), _p(morton), _p(child), _p(lo), _p(hi)))
+        return sorted_tri, morton, child, lo, hi
+
+    # -- sweeps, device pointers (ints, e.g. torch.Tensor.data_ptr())
+    def detect_batch_dev(self, d_in: int, n: int, d_col: int = 0, d_hit: int = 0, d_tri: int = 0,
+                         d_status: int = 0, horizon: str = "inf"):
+        vp = C.c_void_p
+        check(self._L.xp_detect_batch_dev(self._h, vp(d_in), n, _horizon(horizon), vp(d_col or None), vp(d_hit or None),
+                                          vp(d_tri or None), vp(d_status or None)), "xp_detect_batch_dev")
+
+    def detect_contacts_dev(self, d_in: int, n: int, d_contacts: int, horizon: str = "inf"):
+        vp = C.c_void_p
+        check(self._L.xp_detect_contacts_dev(self._h, vp(d_in), n, _horizon(horizon), vp(d_contacts)),
+              "xp_detect_contacts_dev")
+
+    def collision_response_batch_dev(self, d_in: int, n: int, d_out: int, max_iter: int = 0, d_iter: int = 0,
+                                     d_status: int = 0, d_normal: int = 0, horizon: str = "inf"):
+        vp = C.c_void_p
+        check(self._L.xp_collision_response_batch_dev(self._h, vp(d_in), n, max_iter, _horizon(horizon), vp(d_out),
+                                                      vp(d_iter or None), vp(d_status or None), vp(d_normal or None)),
+              "xp_collision_response_batch_dev")
+
+
+def _horizon(h) -> int:
+    return {"inf": _lib.HORIZON_INF, "unit": _lib.HORIZON_UNIT, 0: 0, 1: 1}[h]
+
+
+# ---- the reference's free functions ----------------------------------------------------------
+def sphere_triangle_detect_collision(response: Response, triangle: Triangle, device: int = 0) -> Optional[Collision]:
+    """collision_detect.rs:155-213 (one sphere, one triangle), evaluated on the GPU."""
+    L = _lib.lib()
+    r = response.as_record()
+    t = np.ascontiguousarray(triangle.as_array())
+    out = np.zeros(1, COLLISION_DTYPE)
+    rc = L.xp_sphere_triangle_detect_collision(device, _p(r), _p(t), _p(out))
+    if rc == _lib.XP_EINVAL:
+        raise AssertionError("assertion failed: `(left == right)` sphere.r == 1.0 (collision_detect.rs:161)")
+    check(rc, "xp_sphere_triangle_detect_collision")
+    return Collision.from_record(out[0]) if rc == 1 else None
+
+
+def sphere_triangle_calculate_response(response: Response, collision: Collision, device: int = 0) -> Response:
+    """collision_response.rs:6-35, evaluated on the GPU."""
+    L = _lib.lib()
+    r = response.as_record()
+    c = collision.as_record()
+    out = np.zeros(1, RESPONSE_DTYPE)
+    rc = L.xp_sphere_triangle_calculate_response(device, _p(r), _p(c), _p(out))
+    check(rc, "xp_sphere_triangle_calculate_response")
+    if rc == 1:
+        raise AssertionError("assertion failed: original_destination_to_plane_distance >= 0.0 "
+                             "(collision_response.rs:22)")
+    return Response.from_record(out[0])
+
+
+def collision_response(response: Response, triangles, device: int = 0, *, max_iter: int = 0, **scene_opts) -> Response:
+    """lib.rs:29-62 for one sphere.  Uploads the triangles, builds the LBVH, sweeps."""
+    with Scene(device, triangles, **scene_opts) as s:
+        out, _, st, _ = s.collision_response_batch(response.as_record(), max_iter=max_iter)
+    _raise_status(int(st[0]))
+    return Response.from_record(out[0])
+
+
+def collision_response_non_trianulated(response: Response, vec3s, device: int = 0, *, max_iter: int = 0,
+                                       **scene_opts) -> Response:
+    """lib.rs:17-27: every three Vec3 are one triangle."""
+    with Scene(device, **scene_opts) as s:
+        s.set_positions(vec3s)
+        s.build()
+        out, _, st, _ = s.collision_response_batch(response.as_record(), max_iter=max_iter)
+    _raise_status(int(st[0]))
+    return Response.from_record(out[0])
+
+
+def _raise_status(st: int):
+    if st & _lib.ST_RADIUS_NE_1:
+        raise AssertionError("assertion failed: `(left == right)` sphere.r == 1.0 (collision_detect.rs:161)")
+    if st & _lib.ST_ASSERT_NEG_DISTANCE:
+        raise AssertionError("assertion failed: original_destination_to_plane_distance >= 0.0 "
+                             "(collision_response.rs:22)")
+
+
+def probe_fp32_peak(device: int = 0) -> float:
+    v = C.c_double()
+    check(_lib.lib().xp_probe_fp32_peak(device, C.byref(v)), "xp_probe_fp32_peak")
+    return float(v.value)
+
+
+def device_count() -> int:
+    n = C.c_int()
+    rc = _lib.lib().xp_device_count(C.byref(n))
+    return int(n.value) if rc == 0 else 0
