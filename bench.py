@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- swept-sphere vs triangle narrowphase tests/sec (and spheres resolved/sec).
+
+Workload (BASELINE.json configs[1]): 2^20 swept unit spheres vs a 1 001 112-triangle synthetic
+heightmap terrain, single sweep, per GPU.  A "step" is one closest-collision sweep of the whole
+sphere batch against the resident scene (triangle records + LBVH are uploaded / built once,
+outside the timed region, exactly like the reference's `&[Triangle]` argument exists before
+collision_response is called).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 is launched by torchrun (one rank per GPU): the sphere batch is sharded (weak scaling:
+2^20 spheres per GPU, scene + LBVH replicated), each rank writes 40 B contact records straight
+into its slot of the gather buffer and one NCCL all_gather assembles the global contact list.
+
+Prints ONE JSON line (rank 0).  `value` = narrowphase tests/s with inputs resident in HBM;
+`e2e` = the same metric through the host-pointer C-ABI call (pinned host buffers, H2D + D2H inside
+the timed region); `roofline` = the dominant kernel against the measured fp32 FFMA peak;
+`cpu_baseline` = the CPU oracle (a port of the reference's algorithm: brute force over every
+triangle) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "xp-game-engine_b200")]
+
+NX, NZ = 708, 707                 # 2 * 708 * 707 = 1 001 112 triangles
+N_SPHERES = 1 << 20
+# algorithmic flops per narrowphase test by code path
+PATH_FLOPS = {"cull": 5, "far": 16, "face_hit": 86, "full": 245, "full_pit": 298}
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4
+
+
+def build_workload(seed: int, n_spheres: int = N_SPHERES):
+    from xp_physics_cuda import scenes
+    tris, heights = scenes.sine_terrain(NX, NZ, seed=1)
+    resps = scenes.terrain_spheres(heights, n_spheres, seed=seed)
+    return tris, resps
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "config2: 2^20 swept unit spheres x 1001112-triangle sine+noise heightmap terrain, "
+                        "single sweep per step, horizon=inf (reference-faithful)",
+            "spheres_per_gpu": N_SPHERES, "triangles": 2 * NX * NZ,
+            "parallelism": f"spheres sharded over {n_gpus} GPU(s), scene+LBVH replicated",
+            "l2": "flushed (256 MiB write) between timed steps"}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+
+    def __enter__(self):
+        def run():
+            while not self.stop.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([x.strip() for x in out.strip().split(",")])
+                except Exception:
+                    pass
+                self.stop.wait(0.2)
+        self.t = threading.Thread(target=run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (the only places the oracle is executed by bench.py)
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(tris, resps, n_sample: int, threads: int = 0):
+    """Oracle brute force (the reference's algorithm, lib.rs:33-35) on the first n_sample spheres."""
+    from oracle import xp_oracle as o
+    t0 = time.perf_counter()
+    out = o.detect_batch(resps[:n_sample], tris, threads=threads)
+    dt = time.perf_counter() - t0
+    return out[4] / dt, dt, (threads or o.max_threads())
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (brute force over all triangles per
+    sphere), all host threads, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import xp_oracle as o
+    tris, resps = build_workload(seed=1, n_spheres=1 << 14)
+    cores = o.max_threads()
+    n_sample = 4 * cores                      # 4 spheres x 1M triangles per core per step: ~0.5 s
+    for _ in range(args.warmup):
+        o.detect_batch(resps[:n_sample], tris)
+    t0 = time.perf_counter()
+    tests = 0
+    for k in range(args.steps):
+        lo = (k * n_sample) % (len(resps) - n_sample)
+        tests += o.detect_batch(resps[lo:lo + n_sample], tris)[4]
+    dt = time.perf_counter() - t0
+    v = tests / dt
+    sample = f"{n_sample} spheres x {len(tris)} triangles brute force per step (all {cores} host threads)"
+    line = {"impl": "reference", "metric": "narrowphase_tests_per_sec", "value": v, "unit": "tests/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "spheres_per_sec": n_sample * args.steps / dt,
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": "tests/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "C oracle = op-for-op port of xp_physics (Rust toolchain absent); no per-test "
+                                     "heap allocations or println!, so faster than the Rust original"},
+            "e2e": {"value": v, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import xp_physics_cuda as xp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- xp_physics_cuda has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    tris, resps = build_workload(seed=1 + rank)
+    n = len(resps)
+    scene = xp.Scene(local, arith=args.arith, method=args.method, prune=bool(args.prune), timing=True)
+    stream = torch.cuda.current_stream()
+    scene.set_stream(stream.cuda_stream)
+    scene.set_triangles(tris)
+    scene.build()
+    build_stats = scene.stats()
+
+    # device-resident inputs / outputs
+    d_in = torch.from_numpy(resps.view(np.float32).reshape(n, 7)).to(dev)
+    contacts = torch.empty((world, n, 10), dtype=torch.float32, device=dev)   # 40 B records, gather buffer
+    mine = contacts[rank]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        # writes this rank's contact records straight into its slot of the gather buffer
+        scene.detect_contacts_dev(d_in.data_ptr(), n, mine.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(contacts.view(-1), mine.reshape(-1))
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        stats = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for a, b in ev:
+            flush.fill_(1)                     # L2 flush, outside the event pair
+            a.record(stream)
+            fn()
+            b.record(stream)
+            stats.append(scene.stats())
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, stats
+
+    with ClockSampler(local) as clocks:
+        total_ms, stats = timed(step_device, args.steps, max(args.warmup, 3))
+    tests_local = sum(s["narrowphase_tests"] for s in stats)
+    launches = sum(s["kernel_launches"] for s in stats)
+    tests_all = tests_local
+    if world > 1:
+        t = torch.tensor([tests_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        tests_all = float(t.item())
+    sec = total_ms * 1e-3
+    value = tests_all / sec
+    spheres_per_sec = world * n * args.steps / sec
+
+    # roofline of the dominant kernel (fused traversal + narrowphase), from the stage events the
+    # library records on its stream around that kernel inside the timed steps
+    k_ms = float(np.mean([s["stage_ms"]["traverse"] + s["stage_ms"]["narrowphase"] for s in stats]))
+    paths = {k: float(np.mean([s["path_tests"][k] for s in stats])) for k in PATH_FLOPS}
+    flops = sum(paths[k] * PATH_FLOPS[k] for k in PATH_FLOPS)
+    if sum(paths.values()) == 0:               # path counters unavailable for this method: full path
+        flops = float(np.mean([s["narrowphase_tests"] for s in stats])) * PATH_FLOPS["full"]
+    try:
+        peak = xp.probe_fp32_peak(local)
+        peak_src = "measured FFMA microbenchmark (xp_probe_fp32_peak), this run"
+    except Exception:
+        peak, peak_src = NOMINAL_FP32_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
+    achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    roofline = {"bound": "fp32", "kernel": "k_traverse (LBVH traversal + narrowphase, fused)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
+                "path_mix": paths, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+                "hbm": {"algorithmic_bytes_per_launch": ALGO_BYTES_PER_SPHERE * n,
+                        "achieved_gbs": ALGO_BYTES_PER_SPHERE * n / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
+                        "peak_gbs": measured_hbm_gbs()}}
+
+    # e2e: the host-pointer C-ABI call, pinned host buffers, H2D + D2H inside the timed region
+    h_in = torch.from_numpy(resps.view(np.float32).reshape(n, 7)).pin_memory()
+    h_col = torch.empty((n, 8), dtype=torch.float32).pin_memory()
+    h_hit = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_tri = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_st = torch.empty(n, dtype=torch.int32).pin_memory()
+    L = xp._lib.lib()
+    import ctypes as C
+
+    def step_e2e():
+        rc = L.xp_detect_batch(scene._h, C.c_void_p(h_in.data_ptr()), n, 0, C.c_void_p(h_col.data_ptr()),
+                               C.c_void_p(h_hit.data_ptr()), C.c_void_p(h_tri.data_ptr()), C.c_void_p(h_st.data_ptr()))
+        xp._lib.check(rc, "xp_detect_batch")
+
+    e2e_ms, e2e_stats = timed(step_e2e, args.steps, max(args.warmup, 3))
+    e2e_tests = sum(s["narrowphase_tests"] for s in e2e_stats)
+    if world > 1:
+        t = torch.tensor([e2e_tests], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        e2e_tests = float(t.item())
+    e2e = {"value": e2e_tests / (e2e_ms * 1e-3), "unit": "tests/s", "h2d_bytes_per_step": n * 28,
+           "d2h_bytes_per_step": n * (32 + 1 + 4 + 4), "ms_per_step": e2e_ms / args.steps,
+           "spheres_per_sec": world * n * args.steps / (e2e_ms * 1e-3),
+           "api": "xp_detect_batch (host pointers, pinned)", "hits": int(h_hit.sum().item())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_sample = min(n, 96 * cores)
+        v, dt, used = cpu_sample(tris, resps, n_sample)
+        cpu = {"value": v, "unit": "tests/s", "cores": used, "kind": "port",
+               "sample": f"first {n_sample} spheres of the batch x all {len(tris)} triangles, brute force "
+                         f"(the reference's algorithm, lib.rs:33-35), {dt:.1f} s",
+               "spheres_per_sec": n_sample / dt}
+        v1, dt1, _ = cpu_sample(tris, resps, 8, threads=1)
+        cpu["single_thread"] = {"value": v1, "unit": "tests/s", "cores": 1, "sample": f"8 spheres, {dt1:.1f} s"}
+
+    if rank == 0:
+        line = {"metric": "narrowphase_tests_per_sec", "value": value, "unit": "tests/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(workload_config(world), arith=args.arith, method=args.method,
+                                                    prune=bool(args.prune)),
+                "spheres_per_sec": spheres_per_sec, "tests_per_step": tests_all / args.steps,
+                "hit_fraction": float((mine[:, 9].contiguous().view(torch.int32) & 1).float().mean().item()),
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": cpu,
+                "build": {"ms": sum(build_stats["stage_ms"].values()), "stage_ms": build_stats["stage_ms"],
+                          "launches": build_stats["kernel_launches"]}}
+        print(json.dumps(line), flush=True)
+    scene.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# bytes the dominant kernel must move per sphere (DESIGN.md "Kernels"): 64 B ray record in,
+# 8 B best key out; the 64 MB of nodes + 64 MB of triangle records are L2-resident (126 MB L2).
+ALGO_BYTES_PER_SPHERE = 72
+# dram__bytes_read.sum + dram__bytes_write.sum of k_traverse from the ncu --set full capture
+# under profiles/ (None until captured)
+TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+def measured_hbm_gbs():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--method", default="bvh_fused", choices=["bvh_fused", "bvh_pairs", "brute"])
+    ap.add_argument("--prune", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,7 +59,8 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
 /* ---- scene options (xp_scene_set_option) ---- */
 #define XP_OPT_ARITH      1  /* XP_ARITH_*                                      */
 #define XP_OPT_METHOD     2  /* XP_METHOD_*                                     */
-#define XP_OPT_TIMING     3  /* 1: record CUDA events around every kernel stage */
+#define XP_OPT_TIMING     3  /* 1: record CUDA events around every kernel stage (no extra synchronisation)
+                                and count narrowphase tests per code path */
 #define XP_OPT_SORT_SPHERES 4 /* 1: process spheres in Morton order of their centre (default 1) */
 #define XP_OPT_MAX_PAIRS  5  /* capacity (pairs) of the two-stage candidate buffer per chunk */
 #define XP_OPT_PRUNE      6  /* BVH_FUSED only. 0 (default): evaluate detect on EVERY pair passing P, so
@@ -84,6 +85,8 @@ typedef struct {
     uint32_t kernel_launches;     /* kernels of this library launched by the call                    */
     uint32_t iterations_run;      /* outer response iterations executed (max over spheres)           */
     float    stage_ms[XP_STAGE_COUNT]; /* XP_OPT_TIMING=1: CUDA-event ms per stage, see XP_STAGE_*   */
+    uint64_t path_tests[5];       /* XP_OPT_TIMING=1: tests per code path: back-face cull, parallel-far,
+                                     face hit, full vertex+edge path, full path after a failed face test */
 } xp_stats;
 
 #define XP_STAGE_BUILD_BOUNDS   0

@@ -1,0 +1,87 @@
+"""Structure of the device-built LBVH (new code: the reference has no broadphase)."""
+import numpy as np
+import pytest
+
+import xp_physics_cuda as xp
+from xp_physics_cuda import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _expand(v):
+    v = (v * 0x00010001) & 0xFF0000FF
+    v = (v * 0x00000101) & 0x0F00F00F
+    v = (v * 0x00000011) & 0xC30C30C3
+    v = (v * 0x00000005) & 0x49249249
+    return v
+
+
+def _check_tree(tris, oracle):
+    n = len(tris)
+    with xp.Scene(0, tris) as s:
+        sorted_tri, morton, child, nlo, nhi = s.debug_tree()
+    assert np.array_equal(np.sort(sorted_tri), np.arange(n))                 # a permutation
+    assert (np.diff(morton.astype(np.int64)) >= 0).all()                     # sorted
+    assert (morton < (1 << 30)).all()
+    # stable: equal codes keep upload order
+    same = morton[1:] == morton[:-1]
+    assert (sorted_tri[1:][same] > sorted_tri[:-1][same]).all()
+    # codes are the 30-bit Morton codes of the inflated-box centres
+    lo, hi = oracle.triangle_aabbs(tris)
+    c = 0.5 * (lo + hi)
+    mn, mx = c.min(axis=0), c.max(axis=0)
+    ext = np.where(mx > mn, mx - mn, 1).astype(np.float32)
+    q = np.clip(((c - mn) / ext) * np.float32(1024.0), 0, 1023).astype(np.uint32)
+    code = (_expand(q[:, 0].astype(np.uint64)) << 2) | (_expand(q[:, 1].astype(np.uint64)) << 1) | _expand(q[:, 2].astype(np.uint64))
+    assert (np.abs(code[sorted_tri].astype(np.int64) - morton.astype(np.int64)) == 0).mean() > 0.999
+    if n < 2:
+        return
+    # every leaf and every internal node except the root has exactly one parent; boxes nest
+    seen_leaf = np.zeros(n, np.int32)
+    seen_node = np.zeros(n - 1, np.int32)
+    llo, lhi = lo[sorted_tri], hi[sorted_tri]
+    for i in range(n - 1):
+        for c_ in child[i]:
+            if c_ < 0:
+                seen_leaf[~c_] += 1
+                blo, bhi = llo[~c_], lhi[~c_]
+            else:
+                seen_node[c_] += 1
+                blo, bhi = nlo[c_], nhi[c_]
+            assert (nlo[i] <= blo).all() and (nhi[i] >= bhi).all()
+    assert (seen_leaf == 1).all() and seen_node[0] == 0 and (seen_node[1:] == 1).all()
+    # leaf ranges: an in-order walk visits leaves 0..n-1 in order
+    order = []
+    stack = [0]
+    while stack:
+        x = stack.pop()
+        if x < 0:
+            order.append(~x)
+        else:
+            stack.append(child[x][1]); stack.append(child[x][0])
+    assert order == list(range(n))
+    assert np.array_equal(nlo[0], llo.min(axis=0)) and np.array_equal(nhi[0], lhi.max(axis=0))
+
+
+def test_tree_invariants_terrain(oracle):
+    tris, _ = scenes.sine_terrain(30, 31, seed=4)
+    _check_tree(tris, oracle)
+
+
+def test_tree_invariants_duplicates_and_small(oracle):
+    tris, _ = scenes.sine_terrain(6, 6, seed=4)
+    _check_tree(np.concatenate([tris, tris, tris[:9]]), oracle)              # many identical Morton codes
+    for n in (1, 2, 3, 4, 7):
+        _check_tree(tris[:n], oracle)
+    _check_tree(np.repeat(tris[:1], 37, axis=0), oracle)                      # all codes equal
+
+
+def test_tree_large_sort(oracle):
+    """radix sort across many tiles (T > 4096 * several) incl. a ragged last tile."""
+    tris, lo, hi = scenes.mesh_field(70001, seed=5)
+    with xp.Scene(0, tris) as s:
+        sorted_tri, morton, child, nlo, nhi = s.debug_tree()
+    assert np.array_equal(np.sort(sorted_tri), np.arange(len(tris)))
+    assert (np.diff(morton.astype(np.int64)) >= 0).all()
+    same = morton[1:] == morton[:-1]
+    assert (sorted_tri[1:][same] > sorted_tri[:-1][same]).all()

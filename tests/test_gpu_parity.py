@@ -1,0 +1,373 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs and against the committed golden vectors.
+
+Bars (BASELINE.json north_star / SURVEY.md Appendix F):
+  * broadphase candidate set: bit-exact (sorted pair lists identical to predicate P);
+  * XP_ARITH_EXACT: every output bit-identical to the oracle (t, position, intersection, resolved
+    Response, slide normal), hit / tri_index / iterations / status equal -- zero mismatches;
+  * XP_ARITH_FAST: hit/miss equal except grazing rows (oracle float64 shadow margin < 1e-5),
+    time of impact within 1e-5 * max(1, |t|), positions within 1e-5 * max(1, |c|_inf).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import xp_physics_cuda as xp
+from tests.conftest import assert_bits_equal
+from xp_physics_cuda import scenes
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+METHODS = [("bvh_fused", False), ("bvh_fused", True), ("bvh_pairs", False), ("brute", False)]
+
+
+def col_fields(col):
+    return np.concatenate([col["time_to"][:, None], col["distance_to"][:, None], col["position"],
+                           col["intersection"]], axis=1)
+
+
+def resp_fields(r):
+    return np.concatenate([r["c"], r["r"][:, None], r["movement"]], axis=1)
+
+
+def check_detect_exact(got, want, what, tri_index=True):
+    gcol, ghit, gtri, gst = got
+    wcol, whit, wtri, wst = want[:4]
+    assert np.array_equal(ghit, whit), f"{what}: hit/miss differs on {np.flatnonzero(ghit != whit)[:8]}"
+    h = whit.astype(bool)
+    assert_bits_equal(col_fields(gcol)[h], col_fields(wcol)[h], what)
+    if tri_index:
+        assert np.array_equal(gtri, wtri), f"{what}: tri_index differs"
+    assert np.array_equal(gst, wst), f"{what}: status differs"
+
+
+@pytest.fixture(scope="module")
+def terrain(oracle):
+    tris, h = scenes.sine_terrain(40, 40, seed=31)
+    resps = scenes.terrain_spheres(h, 3000, seed=32)
+    want = oracle.detect_batch(resps, tris)
+    return tris, h, resps, want
+
+
+# ---- known answers of the reference's own tests, on the device -------------------------------
+def test_reference_kats_on_device():
+    T, R, S = xp.Triangle, xp.Response, xp.Sphere
+    c = xp.sphere_triangle_detect_collision(R(S([0, 4, 0], 1.0), [0, -2, 0]), T([-2, 2, -2], [-2, 2, 2], [2, 2, 0]))
+    assert c.time_to == 0.5                                                  # collision_detect.rs:222-232
+    assert c.distance_to == 1.0 and c.position == [0, 3, 0] and c.intersection == [0, 2, 0]
+    c = xp.sphere_triangle_detect_collision(R(S([0, 4, 0], 1.0), [0, -8, 0]), T([0, 0, 0], [-2, -1, 0], [2, -1, 0]))
+    assert c.time_to == 0.375                                                # collision_detect.rs:235-246
+    c = xp.sphere_triangle_detect_collision(R(S([0, 4, 0], 1.0), [0, -8, 0]), T([0, -2, 0], [-2, -1, 0], [2, -1, 0]))
+    assert c.time_to == 0.5                                                  # collision_detect.rs:249-260
+    c = xp.sphere_triangle_detect_collision(R(S([0, 40, 0], 1.0), [0, -8, 0]), T([0, 0, 0], [-2, -1, 0], [2, -1, 0]))
+    assert c.time_to == 4.875                                                # quirk B2
+    assert xp.sphere_triangle_detect_collision(R(S([0, 0, 0], 1.0), [0, 2, 0]), T([-2, 2, -2], [-2, 2, 2], [2, 2, 0])) is None
+    with pytest.raises(AssertionError):                                      # collision_detect.rs:161
+        xp.sphere_triangle_detect_collision(R(S([0, 4, 0], 0.5), [0, -2, 0]), T([-2, 2, -2], [-2, 2, 2], [2, 2, 0]))
+
+
+def test_point_in_triangle_kat_through_the_face_path(oracle):
+    # triangle.rs:62-76: the six points, reached through detect's face path (sphere dropped along -n)
+    tri = np.array([[-1, 0, 0], [0, 1, 1], [1, 0, 0]], np.float32)
+    n = np.cross(tri[1] - tri[0], tri[2] - tri[0])
+    n = n / np.linalg.norm(n)
+    pts = [[0, .5, .5], [0, .6, .6], [0, .99, .99], [0, 1.001, 1.001], [0, 0, 0], [0, 1, 1]]
+    resps = xp.make_responses([np.asarray(p) + 3 * n for p in pts], [-2.5 * n] * len(pts))
+    with xp.Scene(0, tri[None]) as s:
+        got = s.detect_batch(resps)
+    check_detect_exact(got, oracle.detect_batch(resps, tri[None]), "pit kat")
+
+
+def test_single_response_call_matches_oracle(oracle):
+    tri = xp.Triangle([-2, 2, -2], [-2, 2, 2], [2, 2, 0])
+    r = xp.Response(xp.Sphere([0.1, 3.2, 0.05]), [0.3, -0.5, 0.1])
+    col = xp.sphere_triangle_detect_collision(r, tri)
+    out = xp.sphere_triangle_calculate_response(r, col)
+    want, _ = oracle.respond(r.as_record(), col.as_record())
+    assert_bits_equal(np.array(out.sphere.c + [out.sphere.r] + out.movement, np.float32), resp_fields(np.array([want]))[0], "respond")
+    bad = xp.Response(xp.Sphere([0, 4, 0]), [0, -4, 0])
+    with pytest.raises(AssertionError):                                      # collision_response.rs:22
+        xp.sphere_triangle_calculate_response(bad, xp.sphere_triangle_detect_collision(bad, tri))
+
+
+def test_reference_free_functions(oracle):
+    tri = np.array([[[-2, 2, -2], [-2, 2, 2], [2, 2, 0]]], np.float32)
+    r = xp.Response(xp.Sphere([0.1, 3.2, 0.05]), [0.3, -0.5, 0.1])
+    want, it, st, _ = oracle.collision_response(r.as_record(), tri)
+    out = xp.collision_response(r, tri)
+    assert_bits_equal(np.array(out.sphere.c + [out.sphere.r] + out.movement, np.float32), resp_fields(np.array([want]))[0], "collision_response")
+    out2 = xp.collision_response_non_trianulated(r, tri.reshape(-1, 3))
+    assert out2 == out
+    with pytest.raises(IndexError):                                          # lib.rs:19-24
+        xp.collision_response_non_trianulated(r, np.zeros((4, 3), np.float32))
+    with pytest.raises(AssertionError):
+        xp.collision_response(xp.Response(xp.Sphere([0, 4, 0]), [0, -4, 0]), tri)
+
+
+# ---- detect: every method, exact arithmetic, bit-identical -----------------------------------
+@pytest.mark.parametrize("method,prune", METHODS)
+@pytest.mark.parametrize("sort", [True, False])
+def test_detect_exact_bitwise(terrain, method, prune, sort):
+    tris, h, resps, want = terrain
+    with xp.Scene(0, tris, method=method, prune=prune, sort_spheres=sort) as s:
+        got = s.detect_batch(resps)
+        st = s.stats()
+    check_detect_exact(got, want, f"{method} prune={prune} sort={sort}")
+    if method == "brute":
+        assert st["narrowphase_tests"] == len(resps) * len(tris)
+    assert st["kernel_launches"] > 0
+
+
+def test_broadphase_pairs_bit_exact(terrain, oracle):
+    tris, h, resps, _ = terrain
+    for horizon in ("inf", "unit"):
+        wi, wj = oracle.broadphase_pairs(resps, tris, np.inf if horizon == "inf" else 1.0)
+        with xp.Scene(0, tris) as s:
+            gi, gj = s.broadphase_pairs(resps, horizon=horizon)
+            s.set_options(method="bvh_fused", prune=False)
+            s.detect_batch(resps, horizon=horizon)
+            tests = s.stats()["narrowphase_tests"]
+        w = np.sort(wi.astype(np.uint64) << 32 | wj)
+        g = np.sort(gi.astype(np.uint64) << 32 | gj)
+        assert np.array_equal(w, g), f"candidate set differs ({horizon}): {len(w)} vs {len(g)}"
+        assert tests == len(w)            # exhaustive fused mode tests exactly the pairs passing P
+
+
+def test_golden_vectors():
+    g = np.load(os.path.join(GOLDEN, "golden_oracle.npz"))
+    tris, resps = g["triangles"], g["responses"]
+    with xp.Scene(0, tris) as s:
+        got = s.detect_batch(resps)
+        check_detect_exact(got, (g["det_col"], g["det_hit"], g["det_tri"], np.zeros(len(resps), np.uint32)), "golden detect")
+        out, it, st, ln = s.collision_response_batch(resps)
+        gi, gj = s.broadphase_pairs(resps)
+    assert_bits_equal(resp_fields(out), resp_fields(g["resp_out"]), "golden response")
+    assert np.array_equal(it, g["resp_iter"]) and np.array_equal(st, g["resp_status"])
+    assert_bits_equal(ln, g["resp_normal"], "golden slide normal")
+    assert np.array_equal(np.sort(gi.astype(np.uint64) << 32 | gj),
+                          np.sort(g["pair_sphere"].astype(np.uint64) << 32 | g["pair_tri"]))
+
+
+# ---- response loop ---------------------------------------------------------------------------
+@pytest.mark.parametrize("method,prune", METHODS)
+def test_collision_response_exact_bitwise(terrain, oracle, method, prune):
+    tris, h, resps, _ = terrain
+    resps = resps[:1500]
+    for max_iter in (0, 1, 4):
+        want_out, want_it, want_st, want_n, _ = oracle.collision_response_batch(resps, tris, max_iter=max_iter)
+        with xp.Scene(0, tris, method=method, prune=prune) as s:
+            out, it, st, ln = s.collision_response_batch(resps, max_iter=max_iter)
+        what = f"{method} prune={prune} max_iter={max_iter}"
+        assert np.array_equal(it, want_it), what
+        assert np.array_equal(st, want_st), what
+        assert_bits_equal(resp_fields(out), resp_fields(want_out), what)
+        assert_bits_equal(ln, want_n, what + " slide normal")
+    assert want_it.max() >= 3
+
+
+def test_response_status_bits(oracle):
+    tri = np.array([[[-2, 2, -2], [-2, 2, 2], [2, 2, 0]]], np.float32)
+    resps = xp.make_responses([[0, 4, 0], [0, 4, 0], [0.1, 3.2, 0.05], [0, 9, 0]],
+                              [[0, -4, 0], [0, -2, 0], [0.3, -0.5, 0.1], [0, 1, 0]], [1.0, 0.5, 1.0, 1.0])
+    want_out, want_it, want_st, want_n, _ = oracle.collision_response_batch(resps, tri)
+    with xp.Scene(0, tri) as s:
+        out, it, st, ln = s.collision_response_batch(resps)
+    assert list(st) == [xp._lib.ST_ASSERT_NEG_DISTANCE, xp._lib.ST_RADIUS_NE_1, 0, 0] == list(want_st)
+    assert np.array_equal(it, want_it)
+    assert_bits_equal(resp_fields(out), resp_fields(want_out), "status cases")
+    assert_bits_equal(ln, want_n, "status normals")
+    with xp.Scene(0, tri) as s:
+        out1, it1, st1, _ = s.collision_response_batch(resps[2:3], max_iter=1)
+    w = oracle.collision_response_batch(resps[2:3], tri, max_iter=1)
+    assert list(st1) == list(w[2]) and list(it1) == list(w[1])
+
+
+# ---- edge cases ------------------------------------------------------------------------------
+def test_empty_and_tiny_inputs(oracle):
+    tris, h = scenes.sine_terrain(4, 4, seed=2)
+    resps = scenes.terrain_spheres(h, 50, seed=3)
+    with xp.Scene(0, tris) as s:
+        col, hit, tri, st = s.detect_batch(resps[:0])
+        assert len(col) == 0
+        out, it, st, ln = s.collision_response_batch(resps[:0])
+        assert len(out) == 0
+    with xp.Scene(0, tris[:0]) as s:                       # no triangles at all
+        col, hit, tri, st = s.detect_batch(resps)
+        assert not hit.any() and (tri == 0xFFFFFFFF).all()
+        out, it, st, ln = s.collision_response_batch(resps)
+        assert_bits_equal(resp_fields(out), resp_fields(resps), "no triangles: unchanged")
+        assert not it.any()
+    for n in (1, 2, 3, 5):
+        with xp.Scene(0, tris[:n]) as s:
+            got = s.detect_batch(resps)
+            gi, gj = s.broadphase_pairs(resps)
+        check_detect_exact(got, oracle.detect_batch(resps, tris[:n]), f"{n} triangles")
+        wi, wj = oracle.broadphase_pairs(resps, tris[:n])
+        assert np.array_equal(np.sort(gi.astype(np.uint64) << 32 | gj), np.sort(wi.astype(np.uint64) << 32 | wj))
+
+
+def test_quirk_inputs(oracle):
+    """zero / axis-aligned movement, degenerate and duplicated triangles, r != 1, embedded spheres."""
+    rng = np.random.default_rng(5)
+    tris, h = scenes.sine_terrain(12, 12, seed=6)
+    tris = np.concatenate([tris, tris[:40], np.repeat(tris[50:51, :1], 3, axis=1)])      # duplicates + zero-area
+    tris[7, 2] = tris[7, 1]                                                                # degenerate
+    resps = scenes.terrain_spheres(h, 600, seed=7)
+    resps["movement"][::7] = 0.0
+    resps["movement"][1::7, 0] = 0.0
+    resps["movement"][2::7, [0, 2]] = 0.0
+    resps["movement"][3::7, 1] = -0.0
+    resps["c"][4::7, 1] -= 1.5                                                             # start embedded
+    resps["r"][5::50] = 0.5
+    resps["c"][6::7] = np.round(resps["c"][6::7])                                          # on lattice planes
+    want = oracle.detect_batch(resps, tris)
+    for method, prune in METHODS:
+        with xp.Scene(0, tris, method=method, prune=prune) as s:
+            got = s.detect_batch(resps)
+            gi, gj = s.broadphase_pairs(resps)
+        check_detect_exact(got, want, f"quirks {method} {prune}", tri_index=not prune)
+    wi, wj = oracle.broadphase_pairs(resps, tris)
+    valid = resps["r"][gi] == 1.0
+    assert np.array_equal(np.sort(gi[valid].astype(np.uint64) << 32 | gj[valid]),
+                          np.sort(wi[resps["r"][wi] == 1.0].astype(np.uint64) << 32 | wj[resps["r"][wi] == 1.0]))
+    w = oracle.collision_response_batch(resps, tris, max_iter=6)
+    with xp.Scene(0, tris) as s:
+        out, it, st, ln = s.collision_response_batch(resps, max_iter=6)
+    assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
+    assert_bits_equal(resp_fields(out), resp_fields(w[0]), "quirk response")
+
+
+def test_large_coordinates(oracle):
+    tris, h = scenes.sine_terrain(16, 16, seed=8)
+    tris = tris + np.float32([4000, 0, 3000])
+    resps = scenes.terrain_spheres(h, 400, seed=9)
+    resps["c"] += np.float32([4000, 0, 3000])
+    with xp.Scene(0, tris) as s:
+        got = s.detect_batch(resps)
+    check_detect_exact(got, oracle.detect_batch(resps, tris), "large coordinates")
+
+
+# ---- fast (FMA-contracted) arithmetic: tolerance + grazing protocol ----------------------------
+def test_fast_mode_within_tolerance(terrain, oracle):
+    tris, h, resps, want = terrain
+    wcol, whit, wtri, wst = want[:4]
+    with xp.Scene(0, tris, arith="fast") as s:
+        col, hit, tri, st = s.detect_batch(resps)
+        out, it, rst, ln = s.collision_response_batch(resps[:1000], max_iter=1)
+    margins = oracle.grazing_margins(resps, tris)
+    grazing = margins < 1e-5                                   # the stated epsilon
+    differ = hit != whit
+    assert not (differ & ~grazing).any(), "hit/miss differs on non-grazing rows"
+    assert grazing.mean() < 0.01
+    both = (hit & whit).astype(bool) & ~grazing
+    t, wt = col["time_to"][both], wcol["time_to"][both]
+    assert np.all(np.abs(t - wt) <= 1e-5 * np.maximum(1.0, np.abs(wt)))
+    tol = 1e-5 * np.maximum(1.0, np.abs(wcol["position"][both]).max(axis=1, keepdims=True))
+    assert np.all(np.abs(col["position"][both] - wcol["position"][both]) <= tol)
+    w = oracle.collision_response_batch(resps[:1000], tris, max_iter=1)
+    ok = (it == w[1]) & ~grazing[:1000]
+    tol = 1e-5 * np.maximum(1.0, np.abs(w[0]["c"]).max(axis=1, keepdims=True))
+    assert np.all(np.abs(out["c"][ok] - w[0]["c"][ok]) <= tol[ok])
+    assert np.all(np.abs(ln[ok] - w[3][ok]) <= 1e-5)
+    assert (it != w[1])[~grazing[:1000]].sum() == 0
+
+
+# ---- the benchmark configs as parity cases -----------------------------------------------------
+def test_config1_player_vs_heightmap(oracle):
+    """config 1: one swept player sphere vs the res/map heightmap crop (80 000 triangles), one frame."""
+    red = np.load(os.path.join(GOLDEN, "heightmap_crop_red.npy"))
+    tris = scenes.heightmap_from_pixels(red)
+    h00 = red[100, 100] / 10.0
+    resps = xp.make_responses([[0, h00 + 1.5, 0], [0, h00 + 1.02, 0], [10.5, red[110, 95] / 10.0 + 1.2, -5.25]],
+                              [[0.05, -0.05, 0], [0.05, -0.05, 0], [0.03, -0.06, 0.02]])
+    want = oracle.detect_batch(resps, tris)
+    w = oracle.collision_response_batch(resps, tris)
+    for method, prune in METHODS:
+        with xp.Scene(0, tris, method=method, prune=prune) as s:
+            got = s.detect_batch(resps)
+            out, it, st, ln = s.collision_response_batch(resps)
+        check_detect_exact(got, want, f"config1 {method}", tri_index=not prune)
+        assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
+        assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"config1 response {method}")
+
+
+def test_config3_mesh_field_with_rebuild(oracle):
+    """config 3 (scaled down): cubes + icospheres, LBVH rebuilt for every frame's translated meshes."""
+    with xp.Scene(0) as s:
+        for frame in range(3):
+            tris, lo, hi = scenes.mesh_field(4000, seed=2, frame=frame)
+            resps = scenes.field_spheres(lo, hi, 1500, seed=3 + frame)
+            s.set_triangles(tris)
+            s.build()
+            got = s.detect_batch(resps)
+            check_detect_exact(got, oracle.detect_batch(resps, tris), f"config3 frame {frame}")
+            assert got[1].sum() > 20
+
+
+def test_config4_four_iterations(oracle):
+    """config 4 (scaled down): 4-iteration sweep-and-slide; ITER_CAP where the reference would go on."""
+    tris, h = scenes.sine_terrain(48, 48, seed=41)
+    resps = scenes.terrain_spheres(h, 4000, seed=42)
+    w = oracle.collision_response_batch(resps, tris, max_iter=4)
+    with xp.Scene(0, tris, prune=True) as s:
+        out, it, st, ln = s.collision_response_batch(resps, max_iter=4)
+        assert s.stats()["iterations_run"] == 4
+    assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
+    assert (st & xp._lib.ST_ITER_CAP).any()
+    assert_bits_equal(resp_fields(out), resp_fields(w[0]), "config4")
+
+
+# ---- full size (BASELINE config 2: 1M spheres x 1M triangles): size-independent properties ------
+@pytest.fixture(scope="module")
+def full_scene():
+    tris, h = scenes.sine_terrain(708, 707, seed=1)
+    resps = scenes.terrain_spheres(h, 1 << 20, seed=1)
+    return tris, h, resps
+
+
+def test_full_size_properties(full_scene, oracle):
+    tris, h, resps = full_scene
+    with xp.Scene(0, tris) as s:
+        a = s.detect_batch(resps)
+        tests_all = s.stats()["narrowphase_tests"]
+        b = s.detect_batch(resps)                                   # idempotence
+        s.set_options(prune=True)
+        c = s.detect_batch(resps)                                   # pruning must not change any contact
+        tests_pruned = s.stats()["narrowphase_tests"]
+        s.set_options(prune=False, sort_spheres=False)
+        d = s.detect_batch(resps)                                   # processing order must not matter
+        u = s.detect_batch(resps, horizon="unit")
+        s.set_options(sort_spheres=True)
+        perm = np.random.default_rng(0).permutation(len(resps))
+        e = s.detect_batch(resps[perm])                             # permutation equivariance
+    for other, name in ((b, "rerun"), (d, "unsorted")):
+        check_detect_exact(other, a, name)
+    check_detect_exact(c, a, "pruned", tri_index=False)
+    check_detect_exact(e, tuple(x[perm] for x in a), "permuted")
+    col, hit, tri, st = a
+    assert hit.mean() > 0.5
+    assert tests_pruned < tests_all
+    assert 8 * len(resps) < tests_all < 200 * len(resps)
+    hh = hit.astype(bool)
+    assert (col["time_to"][hh] >= 0).all()
+    # a unit-horizon hit is also the infinite-horizon answer whenever t <= 1 ... and never earlier
+    uh = u[1].astype(bool)
+    assert (uh <= hh).all()
+    assert (u[0]["time_to"][uh] >= col["time_to"][uh]).all()
+    # the reported triangle really produces the reported time (single-pair call on the device data)
+    idx = np.flatnonzero(hh)[:: max(1, hh.sum() // 64)][:64]
+    sub = oracle.detect_batch(resps[idx], tris, threads=0)          # brute force: 64 x 1M tests on the CPU
+    check_detect_exact(tuple(x[idx] for x in a), sub, "64-sphere sample vs brute-force oracle")
+
+
+def test_full_size_response_sample(full_scene, oracle):
+    tris, h, resps = full_scene
+    n = 1 << 18
+    with xp.Scene(0, tris, prune=True) as s:
+        out, it, st, ln = s.collision_response_batch(resps[:n], max_iter=4)
+    idx = np.arange(0, n, n // 24)[:24]
+    w = oracle.collision_response_batch(resps[idx], tris, max_iter=4)
+    assert np.array_equal(it[idx], w[1]) and np.array_equal(st[idx], w[2])
+    assert_bits_equal(resp_fields(out[idx]), resp_fields(w[0]), "response sample")
+    assert it.max() == 4

@@ -17,21 +17,31 @@ static int fail_cuda(cudaError_t e) {
     return e == cudaErrorMemoryAllocation ? XP_ENOMEM : XP_ECUDA;
 }
 
-StageTimer::StageTimer(xp_scene *scene, int st) : s(scene), stage(st) {
+StageTimer::StageTimer(xp_scene *scene, int st) : s(scene), slot(-1) {
     if (!s->timing) return;
     if (!s->ev_created) {
-        for (int i = 0; i < 2 * XP_STAGE_COUNT; ++i) cudaEventCreate(&s->ev[i]);
+        for (int i = 0; i < 2 * xp_scene::EV_POOL; ++i) cudaEventCreate(&s->ev[i]);
         s->ev_created = true;
     }
-    cudaEventRecord(s->ev[2 * stage], s->stream);
+    if (s->ev_count >= xp_scene::EV_POOL) {      // pool exhausted (long response loops): drain it
+        cudaStreamSynchronize(s->stream);
+        resolve_stage_timers(s);
+    }
+    slot = s->ev_count++;
+    s->ev_stage[slot] = st;
+    cudaEventRecord(s->ev[2 * slot], s->stream);
 }
 StageTimer::~StageTimer() {
-    if (!s->timing) return;
-    cudaEventRecord(s->ev[2 * stage + 1], s->stream);
-    cudaEventSynchronize(s->ev[2 * stage + 1]);
-    float ms = 0.0f;
-    if (cudaEventElapsedTime(&ms, s->ev[2 * stage], s->ev[2 * stage + 1]) == cudaSuccess)
-        s->stats.stage_ms[stage] += ms;
+    if (slot >= 0) cudaEventRecord(s->ev[2 * slot + 1], s->stream);
+}
+void resolve_stage_timers(xp_scene *s) {
+    for (int i = 0; i < s->ev_count; ++i) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(s->ev[2 * i + 1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]) == cudaSuccess)
+            s->stats.stage_ms[s->ev_stage[i]] += ms;
+    }
+    s->ev_count = 0;
 }
 
 static void reset_stats(xp_scene *s) { memset(&s->stats, 0, sizeof s->stats); }
@@ -81,7 +91,7 @@ void xp_scene_destroy(xp_scene *s) {
                       &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
     for (DevBuf *b : bufs) b->release();
     if (s->ev_created)
-        for (int i = 0; i < 2 * XP_STAGE_COUNT; ++i) cudaEventDestroy(s->ev[i]);
+        for (int i = 0; i < 2 * xp_scene::EV_POOL; ++i) cudaEventDestroy(s->ev[i]);
     delete s;
 }
 
@@ -157,6 +167,7 @@ int xp_scene_build(xp_scene *s) {
     reset_stats(s);
     XP_API_TRY(build_lbvh(s));
     XP_API_TRY(cudaStreamSynchronize(s->stream));
+    resolve_stage_timers(s);
     return XP_OK;
 }
 

@@ -48,9 +48,9 @@ struct DeviceCounters {           // one small block of device memory, zeroed pe
     unsigned long long tests;
     unsigned long long pairs;
     unsigned long long node_visits;
+    unsigned long long path[5];   // tests per code path (XP_PATH_*), only with XP_OPT_TIMING=1
     unsigned int next_active;
     unsigned int stack_overflow;
-    unsigned int pad[2];
 };
 
 }  // namespace xp
@@ -83,7 +83,11 @@ struct xp_scene {
     xp::DevBuf io_in, io_out, io_hit, io_tri, io_status, io_iter, io_normal, io_col;
     // stats
     xp_stats stats;
-    cudaEvent_t ev[2 * XP_STAGE_COUNT] = {};
-    bool ev_used[XP_STAGE_COUNT] = {};
+    // XP_OPT_TIMING: a pool of event pairs recorded without synchronising; resolved into
+    // stats.stage_ms when the call collects its counters
+    static constexpr int EV_POOL = 96;
+    cudaEvent_t ev[2 * EV_POOL] = {};
+    int ev_stage[EV_POOL] = {};
+    int ev_count = 0;
     bool ev_created = false;
 };

@@ -5,13 +5,15 @@
 
 namespace xp {
 
-// RAII stage timer: with XP_OPT_TIMING=1 brackets the stage with CUDA events on the scene's
-// stream and accumulates the elapsed ms into stats.stage_ms (synchronises; diagnostic mode).
+// RAII stage timer: with XP_OPT_TIMING=1 brackets the stage with a pair of CUDA events on the
+// scene's stream (no synchronisation); resolve_stage_timers() turns the recorded pairs into
+// stats.stage_ms once the stream has been synchronised at the end of the call.
 struct StageTimer {
-    xp_scene *s; int stage;
+    xp_scene *s; int slot;
     StageTimer(xp_scene *scene, int st);
     ~StageTimer();
 };
+void resolve_stage_timers(xp_scene *s);
 
 inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 

@@ -76,11 +76,19 @@ __device__ __forceinline__ Ray ray_from(float4 q0, float4 q1, float4 q2) {
 
 template <class O>
 __device__ __forceinline__ bool detect_rec(const Ray &ray, const TriRec *__restrict__ recs, uint32_t leaf,
-                                           unsigned long long &key) {
+                                           unsigned long long &key, unsigned long long *path_ctr = nullptr) {
     const float4 *tp = reinterpret_cast<const float4 *>(recs + leaf);
     const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
     float t;
-    if (!xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t)) return false;
+    bool hit;
+    if (path_ctr) {      // diagnostic launches only (XP_OPT_TIMING): which code path did the test take
+        int path = 0;
+        hit = xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t, &path);
+        atomicAdd(&path_ctr[path], 1ull);
+    } else {
+        hit = xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t);
+    }
+    if (!hit) return false;
     // min_by(time_to) with ties to the later triangle (lib.rs:33-42): smaller t first, then larger index
     key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(~__float_as_uint(t3.w));
     return true;
@@ -127,8 +135,9 @@ __global__ void __launch_bounds__(TRAV_THREADS)
 k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
            const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t na,
            unsigned long long *__restrict__ best, DeviceCounters *__restrict__ ctr,
-           uint2 *__restrict__ pairs_out, uint64_t pair_cap) {
+           uint2 *__restrict__ pairs_out, uint64_t pair_cap, int count_paths) {
     __shared__ WarpShared sh[TRAV_WARPS];
+    unsigned long long *path_ctr = count_paths ? ctr->path : nullptr;
     const int lane = threadIdx.x & 31;
     WarpShared &ws = sh[threadIdx.x >> 5];
     const uint64_t k = ray_base + blockIdx.x * (uint64_t)TRAV_THREADS + threadIdx.x;
@@ -164,7 +173,7 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
         } else {
             const Ray ray = ray_from(ws.ray[0][owner], ws.ray[1][owner], ws.ray[2][owner]);
             unsigned long long key;
-            if (detect_rec<O>(ray, recs, leaf, key)) atomicMin(&ws.best[owner], key);
+            if (detect_rec<O>(ray, recs, leaf, key, path_ctr)) atomicMin(&ws.best[owner], key);
         }
     };
 
@@ -227,7 +236,7 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
             const uint32_t owner = e >> 27;
             const Ray ray = ray_from(ws.ray[0][owner], ws.ray[1][owner], ws.ray[2][owner]);
             unsigned long long key;
-            if (detect_rec<O>(ray, recs, e & LEAF_MASK, key)) atomicMin(&ws.best[owner], key);
+            if (detect_rec<O>(ray, recs, e & LEAF_MASK, key, path_ctr)) atomicMin(&ws.best[owner], key);
         }
     }
     __syncwarp();
@@ -417,7 +426,7 @@ __global__ void k_translate_pairs(const uint2 *__restrict__ pairs, uint64_t n, u
 #define XP_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
 
 // XP_HORIZON_INF is FLT_MAX, not +inf: the branch-free slab test turns "m_k == 0 and outside the
-// slab" into an entry time of +inf, which must reject (predicate P, oracle/xp_oracle.h)
+// slab" into an entry time of +inf, which must reject (predicate P)
 static float horizon_of(uint32_t mode) { return mode == XP_HORIZON_UNIT ? 1.0f : 3.402823466e+38f; }
 
 static cudaError_t zero_counters(xp_scene *s) {
@@ -461,8 +470,8 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
     if (s->method == XP_METHOD_BVH_FUSED) {
         StageTimer t(s, XP_STAGE_TRAVERSE);
         const unsigned blocks = grid_for(na, TRAV_THREADS);
-        if (s->prune) k_traverse<O, true, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, 0, na, best, ctr, nullptr, 0);
-        else k_traverse<O, false, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, 0, na, best, ctr, nullptr, 0);
+        if (s->prune) k_traverse<O, true, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
+        else k_traverse<O, false, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
         ++s->stats.kernel_launches;
         return cudaGetLastError();
     }
@@ -480,7 +489,7 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
         {
             StageTimer t(s, XP_STAGE_TRAVERSE);
             k_traverse<O, false, true><<<grid_for(end - pos, TRAV_THREADS), TRAV_THREADS, 0, st>>>(
-                nodes, recs, rays, pos, end, best, ctr, pairs, cap);
+                nodes, recs, rays, pos, end, best, ctr, pairs, cap, 0);
             ++s->stats.kernel_launches;
         }
         {
@@ -517,6 +526,8 @@ static cudaError_t collect_counters(xp_scene *s) {
     XP_TRY(fetch_counters(s, &h));
     s->stats.narrowphase_tests += h.tests;
     s->stats.node_visits += h.node_visits;
+    for (int i = 0; i < 5; ++i) s->stats.path_tests[i] += h.path[i];
+    resolve_stage_timers(s);
     if (h.stack_overflow) return cudaErrorAssert;
     return cudaSuccess;
 }
@@ -643,7 +654,7 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
         k_traverse<ExactOps, false, true><<<grid_for(end - pos, TRAV_THREADS), TRAV_THREADS, 0, st>>>(
             s->nodes.as<Node>(), s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end,
-            s->best.as<unsigned long long>(), ctr, pairs, buf_cap);
+            s->best.as<unsigned long long>(), ctr, pairs, buf_cap, 0);
         ++s->stats.kernel_launches;
         DeviceCounters h;
         XP_TRY(fetch_counters(s, &h));

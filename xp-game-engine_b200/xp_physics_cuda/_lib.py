@@ -28,7 +28,8 @@ STAGE_NAMES = ["build_bounds", "build_morton", "build_sort", "build_pack", "buil
 class XpStats(C.Structure):
     _fields_ = [("narrowphase_tests", C.c_uint64), ("broadphase_pairs", C.c_uint64),
                 ("node_visits", C.c_uint64), ("kernel_launches", C.c_uint32),
-                ("iterations_run", C.c_uint32), ("stage_ms", C.c_float * 12)]
+                ("iterations_run", C.c_uint32), ("stage_ms", C.c_float * 12),
+                ("path_tests", C.c_uint64 * 5)]
 
 
 class XpError(RuntimeError):

@@ -182,7 +182,9 @@ class Scene:
         return {"narrowphase_tests": int(st.narrowphase_tests), "broadphase_pairs": int(st.broadphase_pairs),
                 "node_visits": int(st.node_visits), "kernel_launches": int(st.kernel_launches),
                 "iterations_run": int(st.iterations_run),
-                "stage_ms": {n: float(st.stage_ms[i]) for i, n in enumerate(_lib.STAGE_NAMES)}}
+                "stage_ms": {n: float(st.stage_ms[i]) for i, n in enumerate(_lib.STAGE_NAMES)},
+                "path_tests": dict(zip(("cull", "far", "face_hit", "full", "full_pit"),
+                                       (int(x) for x in st.path_tests)))}
 
     # -- sweeps, host buffers
     def detect_batch(self, responses: np.ndarray, horizon: str = "inf"):

@@ -48,11 +48,12 @@ def heightmap_from_pixels(red: np.ndarray, height_divisor: float = 10.0) -> np.n
 
 def _hash_noise(ix: np.ndarray, iz: np.ndarray, seed: int) -> np.ndarray:
     """Deterministic per-vertex noise in [0,1) (integer hash; no RNG state, any grid size)."""
-    a = (ix.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) ^ (iz.astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F))
-    a ^= np.uint64(seed) * np.uint64(0x165667B19E3779F9)
-    a ^= a >> np.uint64(29)
-    a *= np.uint64(0xBF58476D1CE4E5B9)
-    a ^= a >> np.uint64(32)
+    with np.errstate(over="ignore"):
+        a = (ix.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) ^ (iz.astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F))
+        a ^= np.uint64((seed * 0x165667B19E3779F9) & 0xFFFFFFFFFFFFFFFF)
+        a ^= a >> np.uint64(29)
+        a *= np.uint64(0xBF58476D1CE4E5B9)
+        a ^= a >> np.uint64(32)
     return ((a >> np.uint64(40)).astype(np.float64) / float(1 << 24)).astype(np.float32)
 
 
