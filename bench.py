@@ -234,7 +234,10 @@ def run_b200(args):
     except Exception:
         peak, peak_src = NOMINAL_FP32_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
     achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    roofline = {"bound": "fp32", "kernel": "k_traverse (LBVH traversal + narrowphase, fused)",
+    kname = {"wide_fused": "k_sweep (32-wide tree traversal + narrowphase, fused)",
+             "wide_pairs": "k_sweep<EMIT> + k_narrow_pairs", "lbvh_fused": "k_traverse (binary LBVH + narrowphase, fused)",
+             "lbvh_pairs": "k_traverse<EMIT> + k_narrow_pairs", "brute": "k_brute"}[args.method]
+    roofline = {"bound": "fp32", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
                 "path_mix": paths, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
@@ -286,6 +289,8 @@ def run_b200(args):
                 "data": "synthetic", "config": dict(workload_config(world), arith=args.arith, method=args.method,
                                                     prune=bool(args.prune)),
                 "spheres_per_sec": spheres_per_sec, "tests_per_step": tests_all / args.steps,
+                "node_visits_per_step": float(np.mean([s["node_visits"] for s in stats])),
+                "stage_ms": {k: float(np.mean([s["stage_ms"][k] for s in stats])) for k in stats[0]["stage_ms"]},
                 "hit_fraction": float((mine[:, 9].contiguous().view(torch.int32) & 1).float().mean().item()),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu,
@@ -319,7 +324,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
-    ap.add_argument("--method", default="bvh_fused", choices=["bvh_fused", "bvh_pairs", "brute"])
+    ap.add_argument("--method", default="wide_fused", choices=["wide_fused", "wide_pairs", "lbvh_fused", "lbvh_pairs", "brute"])
     ap.add_argument("--prune", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -63,7 +63,7 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                 and count narrowphase tests per code path */
 #define XP_OPT_SORT_SPHERES 4 /* 1: process spheres in Morton order of their centre (default 1) */
 #define XP_OPT_MAX_PAIRS  5  /* capacity (pairs) of the two-stage candidate buffer per chunk */
-#define XP_OPT_PRUNE      6  /* BVH_FUSED only. 0 (default): evaluate detect on EVERY pair passing P, so
+#define XP_OPT_PRUNE      6  /* fused methods only. 0 (default): evaluate detect on EVERY pair passing P, so
                                 narrowphase_tests == |P| and the candidate set is the bit-exact one;
                                 1: skip subtrees whose entry time exceeds the best t found so far
                                 (same closest collision, fewer tests) */
@@ -71,10 +71,14 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
 #define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical */
 #define XP_ARITH_FAST     1  /* FMA contraction allowed                          */
 
-#define XP_METHOD_BVH_FUSED  0  /* default. One kernel: per-lane stack traversal feeds a warp-shared candidate queue in
-                                   shared memory; the warp drains it 32 pairs at a time through the narrowphase */
-#define XP_METHOD_BVH_PAIRS  1  /* two kernels: traversal emits every pair passing P to HBM; narrowphase over the pairs */
-#define XP_METHOD_BRUTE      2  /* the reference's literal algorithm: every triangle for every sphere (lib.rs:33-35) */
+#define XP_METHOD_WIDE_FUSED  0  /* default. 32-wide implicit tree over the Morton-sorted triangles; one WARP per
+                                   sphere: the 32 lanes test a node's 32 child boxes (six coalesced 128 B loads),
+                                   leaf hits go to a warp-shared queue in shared memory that is drained 32 pairs at
+                                   a time through the narrowphase */
+#define XP_METHOD_LBVH_FUSED  1  /* binary Karras LBVH, one LANE per sphere with a private stack, same warp queue */
+#define XP_METHOD_LBVH_PAIRS  2  /* binary LBVH traversal emits every pair passing P to HBM; narrowphase over the pairs */
+#define XP_METHOD_BRUTE       3  /* the reference's literal algorithm: every triangle for every sphere (lib.rs:33-35) */
+#define XP_METHOD_WIDE_PAIRS  4  /* 32-wide tree traversal emits the pairs to HBM; narrowphase over the pairs */
 
 /* ---- statistics of the last detect / response call on a scene ---- */
 #define XP_STAGE_COUNT 12

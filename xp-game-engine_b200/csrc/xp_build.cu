@@ -388,6 +388,35 @@ __global__ void __launch_bounds__(256) k_refit(int n, Node *__restrict__ nodes,
     }
 }
 
+// 32-wide implicit tree: one level per launch.  Thread t owns child slot t of the destination
+// level: it copies its source box into the node's SoA planes and the warp (= one node) reduces
+// the union box that becomes the node's own entry one level up.  Missing children get the empty
+// box (+inf, -inf), which the slab test can never hit.
+__global__ void __launch_bounds__(256) k_wide_level(const float4 *__restrict__ src_lo,
+                                                    const float4 *__restrict__ src_hi, uint64_t n_src,
+                                                    float *__restrict__ planes, float4 *__restrict__ dst_lo,
+                                                    float4 *__restrict__ dst_hi, uint64_t n_dst) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_dst * 32) return;                  // whole warps only: n_dst*32 is a multiple of 32
+    const int lane = threadIdx.x & 31;
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+    float4 hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
+    if (t < n_src) { lo = src_lo[t]; hi = src_hi[t]; }
+    float *node = planes + (t >> 5) * WIDE_NODE_FLOATS;
+    node[0 * 32 + lane] = lo.x; node[1 * 32 + lane] = lo.y; node[2 * 32 + lane] = lo.z;
+    node[3 * 32 + lane] = hi.x; node[4 * 32 + lane] = hi.y; node[5 * 32 + lane] = hi.z;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
+        lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+    if (lane == 0) { dst_lo[t >> 5] = lo; dst_hi[t >> 5] = hi; }
+}
+
 // a scene with one triangle: root = (leaf 0, empty); the empty box (+inf,-inf) can never be hit
 __global__ void k_single_root(Node *nodes, const float4 *leaf_lo, const float4 *leaf_hi,
                               float4 *node_lo, float4 *node_hi) {
@@ -474,8 +503,36 @@ cudaError_t build_lbvh(xp_scene *s) {
             ++s->stats.kernel_launches;
         }
     }
+    {   // 32-wide implicit tree over the same Morton order
+        StageTimer t(s, XP_STAGE_BUILD_TREE);
+        uint64_t cnt[WIDE_MAX_LEVELS + 1];
+        int levels = 0;
+        uint64_t total = 0, m = n;
+        do {
+            m = (m + 31) / 32;
+            cnt[levels] = m;
+            s->wide_tree.off[levels] = (unsigned)total;
+            total += m;
+            ++levels;
+        } while (m > 1 && levels < WIDE_MAX_LEVELS);
+        if (m > 1) return cudaErrorInvalidValue;
+        XP_TRY(s->wide.reserve(total * WIDE_NODE_FLOATS * sizeof(float)));
+        XP_TRY(s->wide_lo.reserve(total * 16));
+        XP_TRY(s->wide_hi.reserve(total * 16));
+        const float4 *src_lo = s->leaf_lo.as<float4>(), *src_hi = s->leaf_hi.as<float4>();
+        uint64_t n_src = n;
+        for (int L = 0; L < levels; ++L) {
+            float *planes = s->wide.as<float>() + (uint64_t)s->wide_tree.off[L] * WIDE_NODE_FLOATS;
+            float4 *dlo = s->wide_lo.as<float4>() + s->wide_tree.off[L];
+            float4 *dhi = s->wide_hi.as<float4>() + s->wide_tree.off[L];
+            k_wide_level<<<grid_for(cnt[L] * 32, 256), 256, 0, st>>>(src_lo, src_hi, n_src, planes, dlo, dhi, cnt[L]);
+            ++s->stats.kernel_launches;
+            src_lo = dlo; src_hi = dhi; n_src = cnt[L];
+        }
+        s->wide_tree.planes = s->wide.as<float>();
+        s->wide_tree.top = levels - 1;
+    }
     XP_TRY(cudaGetLastError());
-    // scene bounds on the host too (sphere ordering falls back to identity if degenerate)
     s->built = true;
     return cudaSuccess;
 }

@@ -44,6 +44,18 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// 32-wide implicit tree over the Morton-sorted triangles: level 0 groups 32 consecutive triangles,
+// level L groups 32 consecutive level-(L-1) nodes; node i of level L has children 32i..32i+31.
+// One node = 6 planes of 32 floats (lo.x[32] lo.y[32] lo.z[32] hi.x[32] hi.y[32] hi.z[32]) = 768 B,
+// so a warp reads a node's 32 child boxes with six fully coalesced 128 B loads.
+static constexpr int WIDE_MAX_LEVELS = 6;          // 32^6 > 2^27 triangles
+static constexpr int WIDE_NODE_FLOATS = 192;
+struct WideTree {
+    const float *planes;                           // all levels, level L starts at node off[L]
+    int top;                                       // index of the root level (levels = top + 1)
+    unsigned off[WIDE_MAX_LEVELS];
+};
+
 struct DeviceCounters {           // one small block of device memory, zeroed per call
     unsigned long long tests;
     unsigned long long pairs;
@@ -60,7 +72,7 @@ struct xp_scene {
     cudaStream_t stream = nullptr;
     // options
     int arith = XP_ARITH_EXACT;
-    int method = XP_METHOD_BVH_FUSED;
+    int method = XP_METHOD_WIDE_FUSED;
     int prune = 0;
     int timing = 0;
     int sort_spheres = 1;
@@ -76,6 +88,8 @@ struct xp_scene {
     xp::DevBuf keys_a, keys_b, vals_a, vals_b;       // radix sort ping-pong (triangles / spheres)
     xp::DevBuf hist;          // radix histograms + scan scratch
     xp::DevBuf bounds;        // 6 ordered-int floats: scene AABB of triangle centres
+    xp::DevBuf wide, wide_lo, wide_hi;               // 32-wide implicit tree planes + per-node union boxes
+    xp::WideTree wide_tree = {};
     float h_bounds[6] = {0, 0, 0, 0, 0, 0};
     // per-call workspaces
     xp::DevBuf rays, best, active_a, active_b, pairs, counters;

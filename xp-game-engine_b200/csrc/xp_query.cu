@@ -6,8 +6,10 @@
 //   lib.rs:48-60  exit on no hit / |movement| < DISTANCE_EPSILON        -> active-list compaction
 // for a batch of independent spheres.
 //
-// closest() has three implementations selected by XP_OPT_METHOD:
-//   BVH_FUSED  k_traverse<.., EMIT=false>: one lane per sphere walks the LBVH with a private
+// closest() implementations selected by XP_OPT_METHOD:
+//   WIDE_FUSED k_sweep: one WARP per sphere over the 32-wide implicit tree (default; see k_sweep)
+//   WIDE_PAIRS k_sweep<.., EMIT=true> writes the pairs to HBM, k_narrow_pairs tests them
+//   LBVH_FUSED k_traverse<.., EMIT=false>: one lane per sphere walks the LBVH with a private
 //              stack (one 64 B node = 4 x LDG.128 per step); every leaf whose box passes P is
 //              appended to a warp-shared queue in shared memory; whenever the queue holds >= 32
 //              (sphere, leaf) pairs the whole warp runs the narrowphase on 32 of them, one pair per
@@ -15,7 +17,7 @@
 //              4 x LDG.128, and folds the result with a shared-memory 64-bit atomicMin.  The
 //              narrowphase therefore runs with all 32 lanes on the same (full) code path no matter
 //              how divergent the traversal is.
-//   BVH_PAIRS  k_traverse<.., EMIT=true> writes the pairs to HBM, k_narrow_pairs tests them.
+//   LBVH_PAIRS k_traverse<.., EMIT=true> writes the pairs to HBM, k_narrow_pairs tests them.
 //   BRUTE      k_brute: the reference's literal all-pairs loop, one thread per triangle, rays
 //              staged in shared memory.
 #include <cstdio>
@@ -251,6 +253,158 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// 32-wide implicit tree, one WARP per sphere
+// ------------------------------------------------------------------------------------------
+// Every traversal step is one node: lane i reads child i's box from the node's six SoA planes
+// (six fully coalesced 128 B loads per warp), runs the slab test and the warp ballots.  There is
+// no per-lane divergence and no per-lane stack: the depth-first state is one pending-children mask
+// and one node index per level (<= 6 levels), all warp-uniform.  A warp sweeps 32 consecutive
+// (Morton-sorted) spheres one after the other, so the upper levels stay hot in L1; level-0 hits
+// (triangles whose box passes P) go to the same warp queue as in k_traverse and are drained 32
+// pairs at a time through the narrowphase, with each pair's ray fetched from shared memory.
+static constexpr int SWEEP_THREADS = 256;
+static constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
+static constexpr int SWEEP_QUEUE = 64;        // < 32 left over + at most 32 appended per step
+
+struct SweepShared {
+    float4 ray[4][32];               // the warp's 32 rays: (c,|m|) (m,|m|^2) (m/|m|,horizon) (1/m,flags)
+    unsigned long long best[32];
+    uint32_t queue[SWEEP_QUEUE];     // (ray slot << 27) | triangle slot (Morton order)
+};
+
+template <class O, bool PRUNE, bool EMIT>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__restrict__ rays,
+        uint64_t ray_base, uint64_t na, unsigned long long *__restrict__ best,
+        DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap, int count_paths) {
+    __shared__ SweepShared sh[SWEEP_WARPS];
+    const int lane = threadIdx.x & 31;
+    SweepShared &ws = sh[threadIdx.x >> 5];
+    unsigned long long *path_ctr = count_paths ? ctr->path : nullptr;
+    const uint64_t k0 = ray_base + (blockIdx.x * (uint64_t)SWEEP_WARPS + (threadIdx.x >> 5)) * 32;
+    bool valid = false;
+    if (k0 + lane < na) {
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + k0 + lane);
+        const float4 q0 = __ldg(rp + 0), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+        ws.ray[0][lane] = q0; ws.ray[1][lane] = q1; ws.ray[2][lane] = q2; ws.ray[3][lane] = q3;
+        valid = (__float_as_uint(q3.w) & RAY_VALID) != 0;
+    }
+    ws.best[lane] = BEST_NONE;
+    unsigned todo = __ballot_sync(FULL, valid);
+    __syncwarp();
+
+    unsigned count = 0, n_drains = 0, n_nodes = 0;      // warp-uniform
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    auto drain32 = [&](unsigned from) {
+        const uint32_t e = ws.queue[from + lane];
+        const uint32_t owner = e >> 27, slot = e & LEAF_MASK;
+        if (EMIT) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->pairs, 32ull);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + lane < pair_cap) pairs_out[base + lane] = make_uint2((uint32_t)(k0 + owner), slot);
+        } else {
+            const Ray ray = ray_from(ws.ray[0][owner], ws.ray[1][owner], ws.ray[2][owner]);
+            unsigned long long key;
+            if (detect_rec<O>(ray, recs, slot, key, path_ctr)) atomicMin(&ws.best[owner], key);
+        }
+    };
+
+    while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float4 q0 = ws.ray[0][r], q3 = ws.ray[3][r];          // broadcast reads
+        const V3 c = f4_xyz(q0), inv = f4_xyz(q3);
+        const float horizon = ws.ray[2][r].w;
+
+        // slab test of this lane's child of (level, node); returns the warp's hit mask
+        auto test = [&](int lvl, unsigned node) -> unsigned {
+            const float *nb = tree.planes + ((uint64_t)tree.off[lvl] + node) * WIDE_NODE_FLOATS + lane;
+            const float lox = __ldg(nb), loy = __ldg(nb + 32), loz = __ldg(nb + 64);
+            const float hix = __ldg(nb + 96), hiy = __ldg(nb + 128), hiz = __ldg(nb + 160);
+            float tn;
+            bool hit = slab(c, inv, horizon, lox, loy, loz, hix, hiy, hiz, tn);
+            if (PRUNE) {
+                const float bt = __uint_as_float((unsigned)(ws.best[r] >> 32));   // NaN while there is no hit
+                if (tn > bt) hit = false;
+            }
+            ++n_nodes;
+            return __ballot_sync(FULL, hit);
+        };
+        // level-0 children are triangles: queue every hit as (ray slot, triangle slot)
+        auto enqueue = [&](unsigned m, unsigned group) {
+            if (m & (1u << lane)) ws.queue[count + __popc(m & lt_mask)] = ((uint32_t)r << 27) | (group * 32u + lane);
+            count += __popc(m);
+            __syncwarp();
+            if (count >= 32) {
+                count -= 32;
+                drain32(count);
+                ++n_drains;
+                __syncwarp();
+            }
+        };
+
+        unsigned pend[WIDE_MAX_LEVELS], nidx[WIDE_MAX_LEVELS];
+#pragma unroll
+        for (int l = 0; l < WIDE_MAX_LEVELS; ++l) { pend[l] = 0; nidx[l] = 0; }
+        int lvl = tree.top;
+        unsigned m = test(lvl, 0);
+        if (lvl == 0) {
+            enqueue(m, 0);
+        } else {
+#pragma unroll
+            for (int l = 0; l < WIDE_MAX_LEVELS; ++l) if (l == lvl) pend[l] = m;
+            for (;;) {
+                unsigned p = 0, parent = 0;
+#pragma unroll
+                for (int l = 0; l < WIDE_MAX_LEVELS; ++l) if (l == lvl) { p = pend[l]; parent = nidx[l]; }
+                if (p == 0) {
+                    if (lvl == tree.top) break;
+                    ++lvl;
+                    continue;
+                }
+                const unsigned child = parent * 32u + (unsigned)(__ffs(p) - 1);
+#pragma unroll
+                for (int l = 0; l < WIDE_MAX_LEVELS; ++l) if (l == lvl) pend[l] = p & (p - 1);
+                m = test(lvl - 1, child);
+                if (lvl == 1) {
+                    enqueue(m, child);
+                } else {
+                    --lvl;
+#pragma unroll
+                    for (int l = 0; l < WIDE_MAX_LEVELS; ++l) if (l == lvl) { pend[l] = m; nidx[l] = child; }
+                }
+            }
+        }
+    }
+    // tail: fewer than 32 pairs left
+    if (count > 0) {
+        if (EMIT) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)count);
+            base = __shfl_sync(FULL, base, 0);
+            if (lane < count) {
+                const uint32_t e = ws.queue[lane];
+                if (base + lane < pair_cap) pairs_out[base + lane] = make_uint2((uint32_t)(k0 + (e >> 27)), e & LEAF_MASK);
+            }
+        } else if (lane < count) {
+            const uint32_t e = ws.queue[lane];
+            const uint32_t owner = e >> 27;
+            const Ray ray = ray_from(ws.ray[0][owner], ws.ray[1][owner], ws.ray[2][owner]);
+            unsigned long long key;
+            if (detect_rec<O>(ray, recs, e & LEAF_MASK, key, path_ctr)) atomicMin(&ws.best[owner], key);
+        }
+    }
+    __syncwarp();
+    if (!EMIT && k0 + lane < na) best[k0 + lane] = ws.best[lane];
+    if (lane == 0) {
+        if (!EMIT) atomicAdd(&ctr->tests, (unsigned long long)n_drains * 32ull + count);
+        atomicAdd(&ctr->node_visits, (unsigned long long)n_nodes);
+    }
+}
+
 // stage 2 of BVH_PAIRS: one thread per (ray slot, leaf) pair
 template <class O>
 __global__ void __launch_bounds__(256) k_narrow_pairs(const TriRec *__restrict__ recs,
@@ -467,7 +621,7 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
         s->stats.narrowphase_tests += na * s->n_tris;
         return cudaGetLastError();
     }
-    if (s->method == XP_METHOD_BVH_FUSED) {
+    if (s->method == XP_METHOD_LBVH_FUSED) {
         StageTimer t(s, XP_STAGE_TRAVERSE);
         const unsigned blocks = grid_for(na, TRAV_THREADS);
         if (s->prune) k_traverse<O, true, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
@@ -475,7 +629,16 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
         ++s->stats.kernel_launches;
         return cudaGetLastError();
     }
-    // BVH_PAIRS: chunks of rays sized so the pair buffer holds the candidates
+    if (s->method == XP_METHOD_WIDE_FUSED) {
+        StageTimer t(s, XP_STAGE_TRAVERSE);
+        const unsigned blocks = grid_for(na, SWEEP_THREADS);
+        if (s->prune) k_sweep<O, true, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
+        else k_sweep<O, false, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
+        ++s->stats.kernel_launches;
+        return cudaGetLastError();
+    }
+    // two-stage methods: chunks of rays sized so the pair buffer holds the candidates
+    const bool wide = s->method == XP_METHOD_WIDE_PAIRS;
     const uint64_t cap = s->max_pairs;
     XP_TRY(s->pairs.reserve(cap * sizeof(uint2)));
     uint2 *pairs = s->pairs.as<uint2>();
@@ -488,8 +651,12 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
         {
             StageTimer t(s, XP_STAGE_TRAVERSE);
-            k_traverse<O, false, true><<<grid_for(end - pos, TRAV_THREADS), TRAV_THREADS, 0, st>>>(
-                nodes, recs, rays, pos, end, best, ctr, pairs, cap, 0);
+            if (wide)
+                k_sweep<O, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
+                    s->wide_tree, recs, rays, pos, end, best, ctr, pairs, cap, 0);
+            else
+                k_traverse<O, false, true><<<grid_for(end - pos, TRAV_THREADS), TRAV_THREADS, 0, st>>>(
+                    nodes, recs, rays, pos, end, best, ctr, pairs, cap, 0);
             ++s->stats.kernel_launches;
         }
         {
@@ -652,9 +819,14 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
     while (pos < n) {
         const uint64_t end = (pos + chunk < n) ? pos + chunk : n;
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
-        k_traverse<ExactOps, false, true><<<grid_for(end - pos, TRAV_THREADS), TRAV_THREADS, 0, st>>>(
-            s->nodes.as<Node>(), s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end,
-            s->best.as<unsigned long long>(), ctr, pairs, buf_cap, 0);
+        if (s->method == XP_METHOD_LBVH_FUSED || s->method == XP_METHOD_LBVH_PAIRS)
+            k_traverse<ExactOps, false, true><<<grid_for(end - pos, TRAV_THREADS), TRAV_THREADS, 0, st>>>(
+                s->nodes.as<Node>(), s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end,
+                s->best.as<unsigned long long>(), ctr, pairs, buf_cap, 0);
+        else
+            k_sweep<ExactOps, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
+                s->wide_tree, s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end,
+                s->best.as<unsigned long long>(), ctr, pairs, buf_cap, 0);
         ++s->stats.kernel_launches;
         DeviceCounters h;
         XP_TRY(fetch_counters(s, &h));

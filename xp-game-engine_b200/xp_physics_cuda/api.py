@@ -103,7 +103,7 @@ def as_triangles(t) -> np.ndarray:
 class Scene:
     """Owns an xp_scene (device triangle records + LBVH) on one GPU."""
 
-    def __init__(self, device: int = 0, triangles=None, *, arith: str = "exact", method: str = "bvh_fused",
+    def __init__(self, device: int = 0, triangles=None, *, arith: str = "exact", method: str = "wide_fused",
                  prune: bool = False, sort_spheres: bool = True, timing: bool = False):
         self._L = _lib.lib()
         h = C.c_void_p()
@@ -139,7 +139,7 @@ class Scene:
         if arith is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_ARITH, {"exact": 0, "fast": 1}[arith]))
         if method is not None:
-            check(L.xp_scene_set_option(h, _lib.OPT_METHOD, {"bvh_fused": 0, "bvh_pairs": 1, "brute": 2}[method]))
+            check(L.xp_scene_set_option(h, _lib.OPT_METHOD, _lib.METHODS[method]))
         if prune is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_PRUNE, int(bool(prune))))
         if sort_spheres is not None:
