@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
-    ap.add_argument("--method", default="wide_fused", choices=["wide_fused", "wide_pairs", "lbvh_fused", "lbvh_pairs", "brute"])
+    ap.add_argument("--method", default="lbvh_pairs", choices=["wide_fused", "wide_pairs", "lbvh_fused", "lbvh_pairs", "brute"])
     ap.add_argument("--prune", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

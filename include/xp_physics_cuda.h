@@ -71,12 +71,12 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
 #define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical */
 #define XP_ARITH_FAST     1  /* FMA contraction allowed                          */
 
-#define XP_METHOD_WIDE_FUSED  0  /* default. 32-wide implicit tree over the Morton-sorted triangles; one WARP per
+#define XP_METHOD_WIDE_FUSED  0  /* 32-wide implicit tree over the Morton-sorted triangles; one WARP per
                                    sphere: the 32 lanes test a node's 32 child boxes (six coalesced 128 B loads),
                                    leaf hits go to a warp-shared queue in shared memory that is drained 32 pairs at
                                    a time through the narrowphase */
 #define XP_METHOD_LBVH_FUSED  1  /* binary Karras LBVH, one LANE per sphere with a private stack, same warp queue */
-#define XP_METHOD_LBVH_PAIRS  2  /* binary LBVH traversal emits every pair passing P to HBM; narrowphase over the pairs */
+#define XP_METHOD_LBVH_PAIRS  2  /* default. Persistent-warp binary LBVH traversal (<= 32 registers) emits every pair passing P to HBM; narrowphase over the pairs */
 #define XP_METHOD_BRUTE       3  /* the reference's literal algorithm: every triangle for every sphere (lib.rs:33-35) */
 #define XP_METHOD_WIDE_PAIRS  4  /* 32-wide tree traversal emits the pairs to HBM; narrowphase over the pairs */
 

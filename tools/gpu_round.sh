@@ -10,7 +10,7 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpu
 BRC=$?
 tail -c 6000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "$1" = "variants" ] || [ "$2" = "variants" ]; then
-  for v in "--prune 1" "--arith fast" "--method wide_pairs" "--method lbvh_fused" "--method lbvh_pairs"; do
+  for v in "--arith fast" "--method wide_pairs" "--method wide_fused" "--method lbvh_fused --prune 1"; do
     echo "== bench $v"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu $v > "gpurun_out/bench_$(echo $v | tr -d ' -').json" 2>> gpurun_out/bench.err
     tail -c 1500 "gpurun_out/bench_$(echo $v | tr -d ' -').json"
   done
@@ -23,7 +23,7 @@ if [ $BRC -eq 0 ] && [ "$1" != "noncu" ]; then
   echo "launch list rc=$?"
   echo "== ncu full (k_traverse)"
   timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain2.log 2>&1 &&
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 3 -c 2 -f -o gpurun_out/prof_sweep \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"k_broadphase|k_narrow_pairs" -s 6 -c 4 -f -o gpurun_out/prof_twostage \
       python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
   echo "full rc=$?"
 fi

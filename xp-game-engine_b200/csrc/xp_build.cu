@@ -84,14 +84,21 @@ __device__ __forceinline__ unsigned expand_bits10(unsigned v) {
     return v;
 }
 __device__ __forceinline__ unsigned morton30(V3 c, const unsigned *__restrict__ bounds) {
+    // ISOTROPIC quantisation: every axis is scaled by the LARGEST extent, so a cell is a cube.
+    // (Per-axis scaling would spend 10 bits on the few units of height of a terrain and destroy
+    // the x/z coherence of the curve.)
     float q[3] = {c.x, c.y, c.z};
+    float lo[3], ext = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = dec_f(bounds[k]);
+        ext = fmaxf(ext, dec_f(bounds[3 + k]) - lo[k]);
+    }
+    const float scale = (ext > 0.0f) ? 1024.0f / ext : 0.0f;
     unsigned code = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float lo = dec_f(bounds[k]), hi = dec_f(bounds[3 + k]);
-        float ext = hi - lo;
-        float u = (ext > 0.0f) ? (q[k] - lo) / ext : 0.0f;
-        u = fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f);
+        const float u = fminf(fmaxf((q[k] - lo[k]) * scale, 0.0f), 1023.0f);
         code |= expand_bits10((unsigned)u) << (2 - k);
     }
     return code;

@@ -61,6 +61,7 @@ struct DeviceCounters {           // one small block of device memory, zeroed pe
     unsigned long long pairs;
     unsigned long long node_visits;
     unsigned long long path[5];   // tests per code path (XP_PATH_*), only with XP_OPT_TIMING=1
+    unsigned long long ray_cursor;  // k_broadphase: next unclaimed run of 32 rays
     unsigned int next_active;
     unsigned int stack_overflow;
 };
@@ -72,11 +73,12 @@ struct xp_scene {
     cudaStream_t stream = nullptr;
     // options
     int arith = XP_ARITH_EXACT;
-    int method = XP_METHOD_WIDE_FUSED;
+    int method = XP_METHOD_LBVH_PAIRS;
     int prune = 0;
     int timing = 0;
     int sort_spheres = 1;
     uint64_t max_pairs = 1ull << 26;
+    float cur_horizon = 0.0f;          // horizon of the rays currently in `rays`
     // geometry
     uint64_t n_tris = 0;
     bool built = false;

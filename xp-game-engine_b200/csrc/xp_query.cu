@@ -254,6 +254,113 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
 }
 
 // ------------------------------------------------------------------------------------------
+// stage 1 of the two-stage sweep: broadphase only (binary LBVH, persistent warps)
+// ------------------------------------------------------------------------------------------
+// The traversal is latency-bound pointer chasing, so this kernel is built for memory-level
+// parallelism: <= 32 registers (64 resident warps per SM), a persistent grid, and lanes that pull
+// their next ray as soon as they finish one (warps grab 32 Morton-consecutive rays at a time from
+// a global cursor), so a warp never idles behind its longest ray.  Leaves whose box passes P are
+// staged in a warp-shared queue in shared memory and written to HBM 32 pairs (256 B) at a time.
+static constexpr int BP_THREADS = 256;
+static constexpr int BP_WARPS = BP_THREADS / 32;
+static constexpr int BP_QUEUE = 96;
+
+__global__ void __launch_bounds__(BP_THREADS, 8)
+k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
+             float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap) {
+    __shared__ uint2 queue[BP_WARPS][BP_QUEUE];
+    uint2 *q = queue[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    V3 c = {0, 0, 0}, inv = {0, 0, 0};
+    uint32_t my_ray = 0;
+    int node = -1;                         // internal node to visit next; -1 = lane needs a ray
+    int stack[STACK_DEPTH];
+    int sp = 0;
+    unsigned count = 0;                    // queue fill (warp-uniform)
+    uint64_t pool = 0, pool_end = 0;       // this warp's current run of rays (warp-uniform)
+    bool drained = false;                  // the global cursor has run out (warp-uniform)
+    unsigned n_nodes = 0;
+
+    for (;;) {
+        // ---- hand new rays to idle lanes
+        unsigned idle = __ballot_sync(FULL, node < 0);
+        if (idle) {
+            if (pool >= pool_end && !drained) {
+                unsigned long long start = 0;
+                if (lane == 0) start = atomicAdd(&ctr->ray_cursor, 32ull);
+                start = __shfl_sync(FULL, start, 0);
+                pool = ray_base + start;
+                pool_end = pool + 32 < ray_end ? pool + 32 : ray_end;
+                if (pool >= ray_end) { drained = true; pool = pool_end = ray_end; }
+            }
+            if (pool < pool_end) {
+                const unsigned rank = __popc(idle & lt_mask);
+                if (node < 0 && pool + rank < pool_end) {
+                    my_ray = (uint32_t)(pool + rank);
+                    const float4 *rp = reinterpret_cast<const float4 *>(rays + my_ray);
+                    const float4 q0 = __ldg(rp + 0), q3 = __ldg(rp + 3);
+                    c = f4_xyz(q0); inv = f4_xyz(q3);
+                    sp = 0;
+                    node = (__float_as_uint(q3.w) & RAY_VALID) ? 0 : -1;
+                }
+                const uint64_t taken = __popc(idle);
+                pool = pool + taken < pool_end ? pool + taken : pool_end;
+            } else if (idle == FULL && drained) {
+                break;
+            }
+        }
+        // ---- one traversal step
+        int leaf_a = -1, leaf_b = -1;
+        if (node >= 0) {
+            ++n_nodes;
+            const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+            const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+            const int2 link = __ldg(reinterpret_cast<const int2 *>(np + 3));
+            float ta, tb;
+            bool hit_a = slab(c, inv, horizon, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ta);
+            bool hit_b = slab(c, inv, horizon, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tb);
+            if (hit_a && link.x < 0) { leaf_a = ~link.x; hit_a = false; }
+            if (hit_b && link.y < 0) { leaf_b = ~link.y; hit_b = false; }
+            if (hit_a && hit_b) {
+                node = link.x;
+                if (sp < STACK_DEPTH) stack[sp++] = link.y;
+                else atomicExch(&ctr->stack_overflow, 1u);
+            } else if (hit_a) node = link.x;
+            else if (hit_b) node = link.y;
+            else node = (sp > 0) ? stack[--sp] : -1;
+        }
+        // ---- stage leaf hits; flush 32 pairs at a time
+        const unsigned ma = __ballot_sync(FULL, leaf_a >= 0);
+        const unsigned mb = __ballot_sync(FULL, leaf_b >= 0);
+        if (ma | mb) {
+            if (leaf_a >= 0) q[count + __popc(ma & lt_mask)] = make_uint2(my_ray, (uint32_t)leaf_a);
+            count += __popc(ma);
+            if (leaf_b >= 0) q[count + __popc(mb & lt_mask)] = make_uint2(my_ray, (uint32_t)leaf_b);
+            count += __popc(mb);
+            __syncwarp();
+            while (count >= 32) {
+                count -= 32;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&ctr->pairs, 32ull);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + lane < pair_cap) pairs_out[base + lane] = q[count + lane];
+                __syncwarp();
+            }
+        }
+    }
+    if (count > 0) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)count);
+        base = __shfl_sync(FULL, base, 0);
+        if (lane < count && base + lane < pair_cap) pairs_out[base + lane] = q[lane];
+    }
+    for (int o = 16; o > 0; o >>= 1) n_nodes += __shfl_xor_sync(FULL, n_nodes, o);
+    if (lane == 0) atomicAdd(&ctr->node_visits, (unsigned long long)n_nodes);
+}
+
+// ------------------------------------------------------------------------------------------
 // 32-wide implicit tree, one WARP per sphere
 // ------------------------------------------------------------------------------------------
 // Every traversal step is one node: lane i reads child i's box from the node's six SoA planes
@@ -581,6 +688,12 @@ __global__ void k_translate_pairs(const uint2 *__restrict__ pairs, uint64_t n, u
 
 // XP_HORIZON_INF is FLT_MAX, not +inf: the branch-free slab test turns "m_k == 0 and outside the
 // slab" into an entry time of +inf, which must reject (predicate P)
+// persistent grid: 8 blocks of 256 threads per SM (<= 32 registers), never more blocks than work
+static unsigned bp_grid(uint64_t n_rays) {
+    const uint64_t want = (n_rays + BP_THREADS - 1) / BP_THREADS;
+    return (unsigned)(want < 148ull * 8 ? (want ? want : 1) : 148ull * 8);
+}
+
 static float horizon_of(uint32_t mode) { return mode == XP_HORIZON_UNIT ? 1.0f : 3.402823466e+38f; }
 
 static cudaError_t zero_counters(xp_scene *s) {
@@ -597,6 +710,7 @@ template <class O>
 static cudaError_t ray_setup_t(xp_scene *s, const xp_response *cur, const uint32_t *active, uint64_t na,
                                float horizon, uint32_t *status) {
     StageTimer t(s, XP_STAGE_RAY_SETUP);
+    s->cur_horizon = horizon;
     k_ray_setup<O><<<grid_for(na, 256), 256, 0, s->stream>>>(cur, active, na, horizon, s->rays.as<RayRec>(),
                                                             s->best.as<unsigned long long>(), status);
     ++s->stats.kernel_launches;
@@ -649,14 +763,14 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
     while (pos < na) {
         const uint64_t end = (pos + chunk < na) ? pos + chunk : na;
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
+        XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
         {
             StageTimer t(s, XP_STAGE_TRAVERSE);
             if (wide)
                 k_sweep<O, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
                     s->wide_tree, recs, rays, pos, end, best, ctr, pairs, cap, 0);
             else
-                k_traverse<O, false, true><<<grid_for(end - pos, TRAV_THREADS), TRAV_THREADS, 0, st>>>(
-                    nodes, recs, rays, pos, end, best, ctr, pairs, cap, 0);
+                k_broadphase<<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap);
             ++s->stats.kernel_launches;
         }
         {
@@ -819,10 +933,10 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
     while (pos < n) {
         const uint64_t end = (pos + chunk < n) ? pos + chunk : n;
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
-        if (s->method == XP_METHOD_LBVH_FUSED || s->method == XP_METHOD_LBVH_PAIRS)
-            k_traverse<ExactOps, false, true><<<grid_for(end - pos, TRAV_THREADS), TRAV_THREADS, 0, st>>>(
-                s->nodes.as<Node>(), s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end,
-                s->best.as<unsigned long long>(), ctr, pairs, buf_cap, 0);
+        XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
+        if (s->method != XP_METHOD_WIDE_FUSED && s->method != XP_METHOD_WIDE_PAIRS)
+            k_broadphase<<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
+                                                                  s->cur_horizon, ctr, pairs, buf_cap);
         else
             k_sweep<ExactOps, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
                 s->wide_tree, s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end,

@@ -103,7 +103,7 @@ def as_triangles(t) -> np.ndarray:
 class Scene:
     """Owns an xp_scene (device triangle records + LBVH) on one GPU."""
 
-    def __init__(self, device: int = 0, triangles=None, *, arith: str = "exact", method: str = "wide_fused",
+    def __init__(self, device: int = 0, triangles=None, *, arith: str = "exact", method: str = "lbvh_pairs",
                  prune: bool = False, sort_spheres: bool = True, timing: bool = False):
         self._L = _lib.lib()
         h = C.c_void_p()
