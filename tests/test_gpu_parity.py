@@ -341,10 +341,10 @@ def test_full_size_properties(full_scene, oracle):
         a = s.detect_batch(resps)
         tests_all = s.stats()["narrowphase_tests"]
         b = s.detect_batch(resps)                                   # idempotence
-        s.set_options(prune=True)
+        s.set_options(method="lbvh_fused", prune=True)
         c = s.detect_batch(resps)                                   # pruning must not change any contact
         tests_pruned = s.stats()["narrowphase_tests"]
-        s.set_options(prune=False, sort_spheres=False)
+        s.set_options(method="lbvh_pairs", prune=False, sort_spheres=False)
         d = s.detect_batch(resps)                                   # processing order must not matter
         u = s.detect_batch(resps, horizon="unit")
         s.set_options(sort_spheres=True)

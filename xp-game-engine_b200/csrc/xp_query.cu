@@ -76,6 +76,35 @@ __device__ __forceinline__ Ray ray_from(float4 q0, float4 q1, float4 q2) {
     return r;
 }
 
+// Cooperative gather of one 64 B record per lane.  A lane-private 64 B fetch is four LDG.128 that
+// each touch up to 32 different cache lines (the L1 tag stage, ~2 cycles per line per instruction,
+// was the measured limiter of both sweep kernels).  Here four adjacent lanes fetch the four 16 B
+// quarters of ONE record, so an instruction touches at most 8 lines; the quarters are exchanged
+// through a padded (80 B stride, conflict-free) staging area in shared memory.
+// idx < 0 = this lane wants nothing.  stage: 32 x 5 float4 per warp.
+static constexpr int GATHER_STRIDE = 5;            // float4 per staged record (64 B + 16 B pad)
+__device__ __forceinline__ void warp_gather64(const float4 *__restrict__ base, int idx, float4 *stage,
+                                              float4 &o0, float4 &o1, float4 &o2, float4 &o3) {
+    const int lane = threadIdx.x & 31;
+    const unsigned want = __ballot_sync(0xffffffffu, idx >= 0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int owner = (lane >> 2) + 8 * r;
+        const int src = __shfl_sync(0xffffffffu, idx, owner);
+        if ((want >> (8 * r)) & 0xFFu) {            // warp-uniform: skip octets nobody needs
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src >= 0) v = __ldg(base + (size_t)src * 4 + (lane & 3));
+            stage[owner * GATHER_STRIDE + (lane & 3)] = v;
+        }
+    }
+    __syncwarp();
+    o0 = stage[lane * GATHER_STRIDE + 0];
+    o1 = stage[lane * GATHER_STRIDE + 1];
+    o2 = stage[lane * GATHER_STRIDE + 2];
+    o3 = stage[lane * GATHER_STRIDE + 3];
+    __syncwarp();
+}
+
 template <class O>
 __device__ __forceinline__ bool detect_rec(const Ray &ray, const TriRec *__restrict__ recs, uint32_t leaf,
                                            unsigned long long &key, unsigned long long *path_ctr = nullptr) {
@@ -264,12 +293,15 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
 static constexpr int BP_THREADS = 256;
 static constexpr int BP_WARPS = BP_THREADS / 32;
 static constexpr int BP_QUEUE = 96;
+static constexpr int BP_BLOCKS_PER_SM = 6;     // 48 warps/SM; 6 x 27 KB of staging leaves ~60 KB of L1
 
-__global__ void __launch_bounds__(BP_THREADS, 8)
+__global__ void __launch_bounds__(BP_THREADS, BP_BLOCKS_PER_SM)
 k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
              float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap) {
     __shared__ uint2 queue[BP_WARPS][BP_QUEUE];
+    __shared__ float4 stage_all[BP_WARPS][32 * GATHER_STRIDE];
     uint2 *q = queue[threadIdx.x >> 5];
+    float4 *stage = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -313,11 +345,11 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         }
         // ---- one traversal step
         int leaf_a = -1, leaf_b = -1;
+        float4 n0, n1, n2, n3;
+        warp_gather64(reinterpret_cast<const float4 *>(nodes), node, stage, n0, n1, n2, n3);
         if (node >= 0) {
             ++n_nodes;
-            const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
-            const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-            const int2 link = __ldg(reinterpret_cast<const int2 *>(np + 3));
+            const int2 link = make_int2(__float_as_int(n3.x), __float_as_int(n3.y));
             float ta, tb;
             bool hit_a = slab(c, inv, horizon, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ta);
             bool hit_b = slab(c, inv, horizon, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tb);
@@ -512,7 +544,9 @@ k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__re
     }
 }
 
-// stage 2 of BVH_PAIRS: one thread per (ray slot, leaf) pair
+// stage 2 of the two-stage sweep: one lane per (ray slot, leaf) pair, 32 consecutive pairs per warp
+// step.  The 64 B triangle records are gathered cooperatively (warp_gather64); the rays of
+// consecutive pairs are mostly the same few rays, so they are read directly.
 template <class O>
 __global__ void __launch_bounds__(256) k_narrow_pairs(const TriRec *__restrict__ recs,
                                                       const RayRec *__restrict__ rays,
@@ -520,15 +554,30 @@ __global__ void __launch_bounds__(256) k_narrow_pairs(const TriRec *__restrict__
                                                       const DeviceCounters *__restrict__ ctr,
                                                       uint64_t pair_cap,
                                                       unsigned long long *__restrict__ best) {
+    __shared__ float4 stage_all[8][32 * GATHER_STRIDE];
+    float4 *stage = stage_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
     unsigned long long n = ctr->pairs;
     if (n > pair_cap) n = pair_cap;
-    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n;
-         p += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint2 pr = __ldg(&pairs[p]);
-        const float4 *rp = reinterpret_cast<const float4 *>(rays + pr.x);
-        const Ray ray = ray_from(__ldg(rp + 0), __ldg(rp + 1), __ldg(rp + 2));
-        unsigned long long key;
-        if (detect_rec<O>(ray, recs, pr.y, key)) atomicMin(&best[pr.x], key);
+    const unsigned long long warp_id = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long p0 = warp_id * 32; p0 < n; p0 += n_warps * 32) {
+        const unsigned long long p = p0 + lane;
+        uint2 pr = make_uint2(0u, 0u);
+        const bool on = p < n;
+        if (on) pr = __ldg(&pairs[p]);
+        float4 t0, t1, t2, t3;
+        warp_gather64(reinterpret_cast<const float4 *>(recs), on ? (int)pr.y : -1, stage, t0, t1, t2, t3);
+        if (on) {
+            const float4 *rp = reinterpret_cast<const float4 *>(rays + pr.x);
+            const Ray ray = ray_from(__ldg(rp + 0), __ldg(rp + 1), __ldg(rp + 2));
+            float t;
+            if (xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t)) {
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(~__float_as_uint(t3.w));
+                atomicMin(&best[pr.x], key);
+            }
+        }
     }
 }
 
@@ -688,10 +737,11 @@ __global__ void k_translate_pairs(const uint2 *__restrict__ pairs, uint64_t n, u
 
 // XP_HORIZON_INF is FLT_MAX, not +inf: the branch-free slab test turns "m_k == 0 and outside the
 // slab" into an entry time of +inf, which must reject (predicate P)
-// persistent grid: 8 blocks of 256 threads per SM (<= 32 registers), never more blocks than work
+// persistent grid: BP_BLOCKS_PER_SM blocks of 256 threads per SM, never more blocks than work
 static unsigned bp_grid(uint64_t n_rays) {
     const uint64_t want = (n_rays + BP_THREADS - 1) / BP_THREADS;
-    return (unsigned)(want < 148ull * 8 ? (want ? want : 1) : 148ull * 8);
+    const uint64_t full = 148ull * BP_BLOCKS_PER_SM;
+    return (unsigned)(want < full ? (want ? want : 1) : full);
 }
 
 static float horizon_of(uint32_t mode) { return mode == XP_HORIZON_UNIT ? 1.0f : 3.402823466e+38f; }
