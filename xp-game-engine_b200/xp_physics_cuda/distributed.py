@@ -1,0 +1,87 @@
+"""Multi-GPU sweep: one process per GPU, spheres sharded, scene replicated, one all-gather.
+
+SURVEY.md section 8(e): spheres are independent (collision_response reads only its own Response
+and the read-only triangle set, xp_physics/src/lib.rs:29-62), so the batch is cut into contiguous
+blocks, one per rank; every rank uploads the same triangles and builds the same LBVH; the only
+exchange step is the all-gather of fixed-size 40 B contact records (xp_contact).  Each rank's sweep
+writes its records straight into its slot of the gather buffer (xp_detect_contacts_dev), so there
+is no packing pass between the kernel and the collective.
+
+torch.distributed is plumbing only (process group + NCCL/gloo all_gather).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .api import CONTACT_DTYPE, RESPONSE_DTYPE, Scene
+
+CONTACT_FLOATS = 10      # 40 B
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of rank `rank`; blocks differ by at most one sphere."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_capacity(n: int, world: int) -> int:
+    """Slot size of the gather buffer (the largest block)."""
+    return (n + world - 1) // world
+
+
+def gather_contacts(local, n_total: int, group=None):
+    """All-gather per-rank contact blocks into the global list.
+
+    local: torch tensor [capacity, 10] float32 (this rank's slot content, rows beyond its block are
+    padding).  Returns a [n_total, 10] tensor holding every sphere's record in input order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    cap = shard_capacity(n_total, world)
+    assert local.shape == (cap, CONTACT_FLOATS), (local.shape, cap)
+    buf = torch.empty((world, cap, CONTACT_FLOATS), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf.view(-1), local.reshape(-1).contiguous(), group=group)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        parts.append(buf[r, :hi - lo])
+    return torch.cat(parts, dim=0)
+
+
+def contacts_as_records(t) -> np.ndarray:
+    """[n,10] float32 tensor -> structured CONTACT_DTYPE array (host)."""
+    a = t.detach().cpu().numpy()
+    return np.ascontiguousarray(a).view(CONTACT_DTYPE).reshape(-1)
+
+
+class ShardedSweep:
+    """Rank-local half of the multi-GPU sweep (needs a CUDA device per rank)."""
+
+    def __init__(self, triangles, device: int, **scene_opts):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.scene = Scene(device, **scene_opts)
+        self.scene.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.scene.set_triangles(triangles)          # replicated: every rank builds the same tree
+        self.scene.build()
+
+    def sweep(self, responses: np.ndarray, group=None):
+        """responses: the FULL batch (identical on every rank).  Returns the global contact list
+        [n,10] on this rank's GPU."""
+        import torch.distributed as dist
+        torch = self.torch
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = len(responses)
+        lo, hi = shard_range(n, rank, world)
+        cap = shard_capacity(n, world)
+        mine = np.ascontiguousarray(responses[lo:hi], RESPONSE_DTYPE)
+        d_in = torch.from_numpy(mine.view(np.float32).reshape(-1, 7)).to(self.device)
+        slot = torch.zeros((cap, CONTACT_FLOATS), dtype=torch.float32, device=self.device)
+        if hi > lo:
+            self.scene.detect_contacts_dev(d_in.data_ptr(), hi - lo, slot.data_ptr())
+        return gather_contacts(slot, n, group)
+
+    def close(self):
+        self.scene.close()
