@@ -92,6 +92,11 @@ void xp_scene_destroy(xp_scene *s) {
     for (DevBuf *b : bufs) b->release();
     if (s->ev_created)
         for (int i = 0; i < 2 * xp_scene::EV_POOL; ++i) cudaEventDestroy(s->ev[i]);
+    if (s->io_ready) {
+        cudaStreamDestroy(s->copy_in);
+        cudaStreamDestroy(s->copy_out);
+        for (int i = 0; i < 32; ++i) cudaEventDestroy(s->io_ev[i]);
+    }
     delete s;
 }
 
@@ -203,6 +208,21 @@ int xp_detect_contacts_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uin
     return XP_OK;
 }
 
+// Host-pointer sweep, software-pipelined over chunks of the batch: chunk i+1's H2D copy and chunk
+// i-1's D2H copies run on their own streams (both DMA engines) while chunk i computes.  With
+// pinned caller buffers the copies are truly asynchronous; with pageable memory the runtime stages
+// them and the overlap is partial.
+static constexpr int IO_MAX_CHUNKS = 16;
+
+static int ensure_io_streams(xp_scene *s) {
+    if (s->io_ready) return XP_OK;
+    XP_API_TRY(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
+    XP_API_TRY(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2 * IO_MAX_CHUNKS; ++i) XP_API_TRY(cudaEventCreateWithFlags(&s->io_ev[i], cudaEventDisableTiming));
+    s->io_ready = true;
+    return XP_OK;
+}
+
 int xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
                     xp_collision *out, uint8_t *hit, uint32_t *tri_index, uint32_t *status) {
     int rc = check_query(s, in, n);
@@ -210,21 +230,43 @@ int xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t hor
     XP_BIND(s);
     reset_stats(s);
     if (n == 0) return XP_OK;
+    rc = ensure_io_streams(s);
+    if (rc) return rc;
     cudaStream_t st = s->stream;
     XP_API_TRY(s->io_in.reserve(n * sizeof(xp_response)));
     XP_API_TRY(s->io_col.reserve(n * sizeof(xp_collision)));
     XP_API_TRY(s->io_hit.reserve(n));
     XP_API_TRY(s->io_tri.reserve(n * 4));
     XP_API_TRY(s->io_status.reserve(n * 4));
-    XP_API_TRY(cudaMemcpyAsync(s->io_in.p, in, n * sizeof(xp_response), cudaMemcpyHostToDevice, st));
-    if (out) XP_API_TRY(cudaMemsetAsync(s->io_col.p, 0, n * sizeof(xp_collision), st));
-    QueryOut q = {out ? s->io_col.as<xp_collision>() : nullptr, s->io_hit.as<uint8_t>(),
-                  tri_index ? s->io_tri.as<uint32_t>() : nullptr, s->io_status.as<uint32_t>(), nullptr};
-    XP_API_TRY(detect_dev(s, s->io_in.as<xp_response>(), n, horizon_mode, q));
-    if (out) XP_API_TRY(cudaMemcpyAsync(out, s->io_col.p, n * sizeof(xp_collision), cudaMemcpyDeviceToHost, st));
-    if (hit) XP_API_TRY(cudaMemcpyAsync(hit, s->io_hit.p, n, cudaMemcpyDeviceToHost, st));
-    if (tri_index) XP_API_TRY(cudaMemcpyAsync(tri_index, s->io_tri.p, n * 4, cudaMemcpyDeviceToHost, st));
-    if (status) XP_API_TRY(cudaMemcpyAsync(status, s->io_status.p, n * 4, cudaMemcpyDeviceToHost, st));
+    uint64_t chunk = (n + 3) / 4;
+    if (chunk < (1u << 16)) chunk = 1u << 16;
+    if ((n + chunk - 1) / chunk > IO_MAX_CHUNKS) chunk = (n + IO_MAX_CHUNKS - 1) / IO_MAX_CHUNKS;
+    const int n_chunks = (int)((n + chunk - 1) / chunk);
+    xp_response *d_in = s->io_in.as<xp_response>();
+    // all H2D copies are queued up front on the copy-in stream, one event per chunk
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint64_t off = (uint64_t)c * chunk, m = (n - off < chunk) ? n - off : chunk;
+        XP_API_TRY(cudaMemcpyAsync(d_in + off, in + off, m * sizeof(xp_response), cudaMemcpyHostToDevice, s->copy_in));
+        XP_API_TRY(cudaEventRecord(s->io_ev[c], s->copy_in));
+    }
+    const xp_stats zero_stats = s->stats;
+    (void)zero_stats;
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint64_t off = (uint64_t)c * chunk, m = (n - off < chunk) ? n - off : chunk;
+        XP_API_TRY(cudaStreamWaitEvent(st, s->io_ev[c], 0));
+        if (out) XP_API_TRY(cudaMemsetAsync(s->io_col.as<xp_collision>() + off, 0, m * sizeof(xp_collision), st));
+        QueryOut q = {out ? s->io_col.as<xp_collision>() + off : nullptr, s->io_hit.as<uint8_t>() + off,
+                      tri_index ? s->io_tri.as<uint32_t>() + off : nullptr, s->io_status.as<uint32_t>() + off, nullptr};
+        XP_API_TRY(detect_dev(s, d_in + off, m, horizon_mode, q));
+        XP_API_TRY(cudaEventRecord(s->io_ev[IO_MAX_CHUNKS + c], st));
+        XP_API_TRY(cudaStreamWaitEvent(s->copy_out, s->io_ev[IO_MAX_CHUNKS + c], 0));
+        cudaStream_t so = s->copy_out;
+        if (out) XP_API_TRY(cudaMemcpyAsync(out + off, s->io_col.as<xp_collision>() + off, m * sizeof(xp_collision), cudaMemcpyDeviceToHost, so));
+        if (hit) XP_API_TRY(cudaMemcpyAsync(hit + off, s->io_hit.as<uint8_t>() + off, m, cudaMemcpyDeviceToHost, so));
+        if (tri_index) XP_API_TRY(cudaMemcpyAsync(tri_index + off, s->io_tri.as<uint32_t>() + off, m * 4, cudaMemcpyDeviceToHost, so));
+        if (status) XP_API_TRY(cudaMemcpyAsync(status + off, s->io_status.as<uint32_t>() + off, m * 4, cudaMemcpyDeviceToHost, so));
+    }
+    XP_API_TRY(cudaStreamSynchronize(s->copy_out));
     XP_API_TRY(cudaStreamSynchronize(st));
     return XP_OK;
 }

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) k_morton_spheres(const xp_response *__res
     if (i >= n) return;
     const float *p = reinterpret_cast<const float *>(in) + i * 7;
     V3 c = {__ldg(p + 0), __ldg(p + 1), __ldg(p + 2)};
-    keys[i] = morton30(c, bounds);
+    keys[i] = morton30(c, bounds) >> 6;      // 24 bits (8 per axis) are plenty for processing order: 3 passes
     vals[i] = (uint32_t)i;
 }
 
@@ -553,7 +553,7 @@ cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n
     k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va);
     ++s->stats.kernel_launches;
     bool in_a = true;
-    XP_TRY(radix_sort_pairs(s, ka, kb, va, vb, n, 32, &in_a));
+    XP_TRY(radix_sort_pairs(s, ka, kb, va, vb, n, 24, &in_a));
     if (!in_a) { xp::DevBuf tmp = s->active_a; s->active_a = s->active_b; s->active_b = tmp; }
     *order = s->active_a.as<uint32_t>();
     return cudaGetLastError();

@@ -106,4 +106,8 @@ struct xp_scene {
     int ev_stage[EV_POOL] = {};
     int ev_count = 0;
     bool ev_created = false;
+    // host-pointer calls: copy streams + per-chunk events for the H2D / compute / D2H pipeline
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t io_ev[32] = {};
+    bool io_ready = false;
 };
