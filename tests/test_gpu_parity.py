@@ -150,6 +150,20 @@ def test_golden_vectors():
                           np.sort(g["pair_sphere"].astype(np.uint64) << 32 | g["pair_tri"]))
 
 
+def test_pair_buffer_overflow_is_recovered(terrain):
+    """a tiny candidate buffer forces the optimistic two-stage sweep to overflow; the library must
+    notice, redo the sweep in its synchronous chunk-halving mode and return the same answer."""
+    tris, h, resps, want = terrain
+    for method in ("lbvh_pairs", "wide_pairs"):
+        with xp.Scene(0, tris, method=method) as s:
+            s.set_options(max_pairs=4096)
+            got = s.detect_batch(resps)
+            check_detect_exact(got, want, f"overflow recovery {method}")
+            assert s.stats()["narrowphase_tests"] == want[4] * 0 + s.stats()["broadphase_pairs"]
+            out, it, st, ln = s.collision_response_batch(resps[:300], max_iter=2)
+            assert it.max() == 2
+
+
 # ---- response loop ---------------------------------------------------------------------------
 @pytest.mark.parametrize("method,prune", METHODS)
 def test_collision_response_exact_bitwise(terrain, oracle, method, prune):

@@ -176,6 +176,24 @@ int xp_scene_build(xp_scene *s) {
     return XP_OK;
 }
 
+// One sweep in the optimistic (sync-free) pair mode; if a chunk overflowed the pair buffer the
+// sweep is redone in the synchronous, chunk-halving mode.  Inputs are read-only, so a rerun is safe.
+static cudaError_t detect_retry(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                                const QueryOut &q) {
+    cudaError_t e = detect_dev(s, d_in, n, horizon_mode, q);
+    if (e == cudaSuccess && s->pair_overflowed) {
+        s->pair_overflowed = false;
+        s->safe_pairs = true;
+        const uint32_t launches = s->stats.kernel_launches;
+        memset(&s->stats, 0, sizeof s->stats);
+        s->stats.kernel_launches = launches;
+        e = detect_dev(s, d_in, n, horizon_mode, q);
+        s->safe_pairs = false;
+        s->pair_overflowed = false;
+    }
+    return e;
+}
+
 static int check_query(xp_scene *s, const void *in, uint64_t n) {
     if (!s || (!in && n)) return XP_EINVAL;
     if (!s->built) return XP_ESTATE;
@@ -190,7 +208,7 @@ int xp_detect_batch_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32
     reset_stats(s);
     if (n == 0) return XP_OK;
     QueryOut q = {d_out, d_hit, d_tri_index, d_status, nullptr};
-    XP_API_TRY(detect_dev(s, d_in, n, horizon_mode, q));
+    XP_API_TRY(detect_retry(s, d_in, n, horizon_mode, q));
     return XP_OK;
 }
 
@@ -204,7 +222,7 @@ int xp_detect_contacts_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uin
     if (n == 0) return XP_OK;
     XP_API_TRY(s->io_status.reserve(n * 4));
     QueryOut q = {nullptr, nullptr, nullptr, s->io_status.as<uint32_t>(), d_out};
-    XP_API_TRY(detect_dev(s, d_in, n, horizon_mode, q));
+    XP_API_TRY(detect_retry(s, d_in, n, horizon_mode, q));
     return XP_OK;
 }
 
@@ -257,7 +275,7 @@ int xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t hor
         if (out) XP_API_TRY(cudaMemsetAsync(s->io_col.as<xp_collision>() + off, 0, m * sizeof(xp_collision), st));
         QueryOut q = {out ? s->io_col.as<xp_collision>() + off : nullptr, s->io_hit.as<uint8_t>() + off,
                       tri_index ? s->io_tri.as<uint32_t>() + off : nullptr, s->io_status.as<uint32_t>() + off, nullptr};
-        XP_API_TRY(detect_dev(s, d_in + off, m, horizon_mode, q));
+        XP_API_TRY(detect_dev(s, d_in + off, m, horizon_mode, q, /*collect=*/false));   // no host sync
         XP_API_TRY(cudaEventRecord(s->io_ev[IO_MAX_CHUNKS + c], st));
         XP_API_TRY(cudaStreamWaitEvent(s->copy_out, s->io_ev[IO_MAX_CHUNKS + c], 0));
         cudaStream_t so = s->copy_out;
@@ -267,7 +285,24 @@ int xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t hor
         if (status) XP_API_TRY(cudaMemcpyAsync(status + off, s->io_status.as<uint32_t>() + off, m * 4, cudaMemcpyDeviceToHost, so));
     }
     XP_API_TRY(cudaStreamSynchronize(s->copy_out));
-    XP_API_TRY(cudaStreamSynchronize(st));
+    XP_API_TRY(collect_stats(s));                   // the one synchronisation of the compute stream
+    s->counters_live = false;
+    if (s->pair_overflowed) {                       // rare: redo everything in the synchronous pair mode
+        s->pair_overflowed = false;
+        s->safe_pairs = true;
+        if (out) XP_API_TRY(cudaMemsetAsync(s->io_col.p, 0, n * sizeof(xp_collision), st));
+        QueryOut q = {out ? s->io_col.as<xp_collision>() : nullptr, s->io_hit.as<uint8_t>(),
+                      tri_index ? s->io_tri.as<uint32_t>() : nullptr, s->io_status.as<uint32_t>(), nullptr};
+        cudaError_t e = detect_dev(s, d_in, n, horizon_mode, q);
+        s->safe_pairs = false;
+        s->pair_overflowed = false;
+        if (e != cudaSuccess) return fail_cuda(e);
+        if (out) XP_API_TRY(cudaMemcpyAsync(out, s->io_col.p, n * sizeof(xp_collision), cudaMemcpyDeviceToHost, st));
+        if (hit) XP_API_TRY(cudaMemcpyAsync(hit, s->io_hit.p, n, cudaMemcpyDeviceToHost, st));
+        if (tri_index) XP_API_TRY(cudaMemcpyAsync(tri_index, s->io_tri.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (status) XP_API_TRY(cudaMemcpyAsync(status, s->io_status.p, n * 4, cudaMemcpyDeviceToHost, st));
+        XP_API_TRY(cudaStreamSynchronize(st));
+    }
     return XP_OK;
 }
 

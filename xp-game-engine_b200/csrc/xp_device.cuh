@@ -62,8 +62,11 @@ struct DeviceCounters {           // one small block of device memory, zeroed pe
     unsigned long long node_visits;
     unsigned long long path[5];   // tests per code path (XP_PATH_*), only with XP_OPT_TIMING=1
     unsigned long long ray_cursor;  // k_broadphase: next unclaimed run of 32 rays
+    unsigned long long pairs_total; // candidates over all chunks of the call
     unsigned int next_active;
     unsigned int stack_overflow;
+    unsigned int pair_overflow;     // a chunk produced more candidates than the pair buffer holds
+    unsigned int pad;
 };
 
 }  // namespace xp
@@ -79,6 +82,9 @@ struct xp_scene {
     int sort_spheres = 1;
     uint64_t max_pairs = 1ull << 26;
     float cur_horizon = 0.0f;          // horizon of the rays currently in `rays`
+    bool safe_pairs = false;           // two-stage methods: read the pair count back after every chunk
+    bool pair_overflowed = false;      // optimistic mode dropped candidates: results must be recomputed
+    bool counters_live = false;        // device counters hold uncollected statistics
     // geometry
     uint64_t n_tris = 0;
     bool built = false;

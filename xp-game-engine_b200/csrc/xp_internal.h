@@ -30,8 +30,12 @@ cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n
 struct QueryOut {            // device pointers, any may be null
     xp_collision *col; uint8_t *hit; uint32_t *tri_index; uint32_t *status; xp_contact *contact;
 };
+// collect = false: leave the statistics on the device (no host synchronisation); the caller ends
+// the batch with collect_stats().  After collecting, s->pair_overflowed tells whether the
+// optimistic two-stage mode dropped candidates and the sweep must be redone with s->safe_pairs.
 cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
-                       const QueryOut &out);
+                       const QueryOut &out, bool collect = true);
+cudaError_t collect_stats(xp_scene *s);
 cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t max_iter,
                          uint32_t horizon_mode, xp_response *d_out, uint32_t *d_iter,
                          uint32_t *d_status, xp_vec3 *d_normal);

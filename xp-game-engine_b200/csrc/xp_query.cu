@@ -554,10 +554,15 @@ template <class O>
 __global__ void __launch_bounds__(256) k_narrow_pairs(const TriRec *__restrict__ recs,
                                                       const RayRec *__restrict__ rays,
                                                       const uint2 *__restrict__ pairs,
-                                                      const DeviceCounters *__restrict__ ctr,
+                                                      DeviceCounters *__restrict__ ctr,
                                                       uint64_t pair_cap,
                                                       unsigned long long *__restrict__ best) {
     unsigned long long n = ctr->pairs;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {       // accounting stays on the device: no host round trip per chunk
+        if (n > pair_cap) ctr->pair_overflow = 1u;    // candidates were dropped: the host reruns with smaller chunks
+        atomicAdd(&ctr->tests, n > pair_cap ? (unsigned long long)pair_cap : n);
+        atomicAdd(&ctr->pairs_total, n);
+    }
     if (n > pair_cap) n = pair_cap;
     for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n;
          p += (unsigned long long)gridDim.x * blockDim.x) {
@@ -794,9 +799,8 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
     const uint64_t cap = s->max_pairs;
     XP_TRY(s->pairs.reserve(cap * sizeof(uint2)));
     uint2 *pairs = s->pairs.as<uint2>();
-    uint64_t chunk = cap / 64;
-    if (chunk < TRAV_THREADS) chunk = TRAV_THREADS;
-    chunk = (chunk / TRAV_THREADS) * TRAV_THREADS;
+    uint64_t chunk = (cap / 64 / 32) * 32;      // 64 candidates per sphere on average fit
+    if (chunk < 32) chunk = 32;
     uint64_t pos = 0;
     while (pos < na) {
         const uint64_t end = (pos + chunk < na) ? pos + chunk : na;
@@ -816,16 +820,22 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
             k_narrow_pairs<O><<<148 * 8, 256, 0, st>>>(recs, rays, pairs, ctr, cap, best);
             ++s->stats.kernel_launches;
         }
-        DeviceCounters h;
-        XP_TRY(fetch_counters(s, &h));
-        if (h.pairs > cap) {                 // candidates did not fit: redo this chunk in halves
-            if (chunk <= TRAV_THREADS) return cudaErrorMemoryAllocation;
-            chunk = ((chunk / 2) / TRAV_THREADS) * TRAV_THREADS;
-            if (chunk < TRAV_THREADS) chunk = TRAV_THREADS;
-            continue;                        // atomicMin is idempotent: the partial pass did no harm
+        if (s->safe_pairs) {                 // synchronous mode: check the fill after every chunk
+            DeviceCounters h;
+            XP_TRY(fetch_counters(s, &h));
+            if (h.pairs > cap) {             // candidates did not fit: redo this chunk in halves
+                if (chunk <= 32) return cudaErrorMemoryAllocation;
+                chunk = ((chunk / 2) / 32) * 32;
+                if (chunk < 32) chunk = 32;
+                // atomicMin is idempotent (the partial pass did no harm); undo its accounting
+                XP_TRY(cudaMemsetAsync(&ctr->pair_overflow, 0, sizeof(unsigned), st));
+                s->stats.narrowphase_tests -= cap;
+                s->stats.broadphase_pairs -= h.pairs;
+                continue;
+            }
         }
-        s->stats.broadphase_pairs += h.pairs;
-        s->stats.narrowphase_tests += h.pairs;
+        // optimistic mode (default for sweeps): nothing is read back here; k_narrow_pairs raises
+        // ctr->pair_overflow if a chunk did not fit and the API layer reruns in synchronous mode
         pos = end;
     }
     return cudaGetLastError();
@@ -844,7 +854,9 @@ static cudaError_t collect_counters(xp_scene *s) {
     DeviceCounters h;
     XP_TRY(fetch_counters(s, &h));
     s->stats.narrowphase_tests += h.tests;
+    s->stats.broadphase_pairs += h.pairs_total;
     s->stats.node_visits += h.node_visits;
+    if (h.pair_overflow) s->pair_overflowed = true;
     for (int i = 0; i < 5; ++i) s->stats.path_tests[i] += h.path[i];
     resolve_stage_timers(s);
     if (h.stack_overflow) return cudaErrorAssert;
@@ -853,9 +865,12 @@ static cudaError_t collect_counters(xp_scene *s) {
 
 static constexpr uint64_t SPHERE_CHUNK = 1ull << 24;
 
+cudaError_t collect_stats(xp_scene *s) { return collect_counters(s); }
+
 cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
-                       const QueryOut &out) {
-    XP_TRY(zero_counters(s));
+                       const QueryOut &out, bool collect) {
+    if (collect || !s->counters_live) XP_TRY(zero_counters(s));
+    s->counters_live = !collect;
     for (uint64_t off = 0; off < n; off += SPHERE_CHUNK) {
         const uint64_t m = (n - off < SPHERE_CHUNK) ? n - off : SPHERE_CHUNK;
         const xp_response *in = d_in + off;
@@ -883,6 +898,7 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
         }
     }
     XP_TRY(cudaGetLastError());
+    if (!collect) return cudaSuccess;         // the caller batches several sweeps and collects once
     return collect_counters(s);
 }
 
@@ -891,6 +907,9 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
                          uint32_t *d_status, xp_vec3 *d_normal) {
     cudaStream_t st = s->stream;
     XP_TRY(zero_counters(s));
+    // the loop reads the active count back every iteration anyway: use the synchronous pair mode
+    struct SafeGuard { xp_scene *s; bool old; ~SafeGuard() { s->safe_pairs = old; } } guard{s, s->safe_pairs};
+    s->safe_pairs = true;
     DeviceCounters *ctr = s->counters.as<DeviceCounters>();
     if (d_out != d_in) XP_TRY(cudaMemcpyAsync(d_out, d_in, n * sizeof(xp_response), cudaMemcpyDeviceToDevice, st));
     if (d_iter) XP_TRY(cudaMemsetAsync(d_iter, 0, n * 4, st));
