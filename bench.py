@@ -221,29 +221,46 @@ def run_b200(args):
     value = tests_all / sec
     spheres_per_sec = world * n * args.steps / sec
 
-    # roofline of the dominant kernel (fused traversal + narrowphase), from the stage events the
-    # library records on its stream around that kernel inside the timed steps
-    k_ms = float(np.mean([s["stage_ms"]["traverse"] + s["stage_ms"]["narrowphase"] for s in stats]))
-    paths = {k: float(np.mean([s["path_tests"][k] for s in stats])) for k in PATH_FLOPS}
+    # ---- rooflines, from the CUDA-event stage times the library records on its own stream around
+    # each kernel inside the timed steps (XP_OPT_TIMING; no extra synchronisation)
+    st_ms = {k: float(np.mean([s["stage_ms"][k] for s in stats])) for k in stats[0]["stage_ms"]}
+    two_stage = args.method in ("lbvh_pairs", "wide_pairs")
+    # path mix of the narrowphase tests: one untimed diagnostic sweep with the fused kernel, which
+    # counts the code path of every test (the two-stage kernels carry no counters)
+    scene.set_options(method="lbvh_fused", prune=False)
+    scene.detect_contacts_dev(d_in.data_ptr(), n, mine.data_ptr())
+    paths = {k: float(v) for k, v in scene.stats()["path_tests"].items()}
+    scene.set_options(method=args.method, prune=bool(args.prune))
     flops = sum(paths[k] * PATH_FLOPS[k] for k in PATH_FLOPS)
-    if sum(paths.values()) == 0:               # path counters unavailable for this method: full path
-        flops = float(np.mean([s["narrowphase_tests"] for s in stats])) * PATH_FLOPS["full"]
     try:
         peak = xp.probe_fp32_peak(local)
-        peak_src = "measured FFMA microbenchmark (xp_probe_fp32_peak), this run"
+        peak_src = "measured: FFMA micro-benchmark xp_probe_fp32_peak in this run (nominal 74.4)"
     except Exception:
         peak, peak_src = NOMINAL_FP32_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
-    achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    np_ms = st_ms["narrowphase"] if two_stage else st_ms["traverse"] + st_ms["narrowphase"]
+    achieved = flops / (np_ms * 1e-3) / 1e12 if np_ms > 0 else 0.0
     kname = {"wide_fused": "k_sweep (32-wide tree traversal + narrowphase, fused)",
-             "wide_pairs": "k_sweep<EMIT> + k_narrow_pairs", "lbvh_fused": "k_traverse (binary LBVH + narrowphase, fused)",
-             "lbvh_pairs": "k_traverse<EMIT> + k_narrow_pairs", "brute": "k_brute"}[args.method]
-    roofline = {"bound": "fp32", "kernel": kname,
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
-                "path_mix": paths, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
-                "hbm": {"algorithmic_bytes_per_launch": ALGO_BYTES_PER_SPHERE * n,
-                        "achieved_gbs": ALGO_BYTES_PER_SPHERE * n / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
-                        "peak_gbs": measured_hbm_gbs()}}
+             "wide_pairs": "k_narrow_pairs", "lbvh_fused": "k_traverse (binary LBVH + narrowphase, fused)",
+             "lbvh_pairs": "k_narrow_pairs", "brute": "k_brute"}[args.method]
+    roofline = {"bound": "fp32", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "peak_source": peak_src, "kernel_ms": np_ms,
+                "algorithmic_flops_per_launch": flops, "flops_per_test_by_path": PATH_FLOPS, "path_mix": paths,
+                "traffic": TRAFFIC_NARROW, "traffic_source": TRAFFIC_SOURCE,
+                "note": "245 algorithmic flops are ~630 issued instructions (17 IEEE div, 12 IEEE sqrt); "
+                        "issue slots of this kernel are 74% busy in the ncu capture"}
+    # the broadphase is the longest kernel of the step and is memory-latency / L1-bound, not compute
+    tests_step = float(np.mean([s["narrowphase_tests"] for s in stats]))
+    bp_bytes = 64.0 * n + 8.0 * tests_step                       # ray records in + candidate pairs out
+    bp_ms = st_ms["traverse"]
+    roofline_hbm = {"bound": "hbm", "kernel": "k_broadphase" if args.method == "lbvh_pairs" else "k_sweep<EMIT>",
+                    "achieved": bp_bytes / (bp_ms * 1e-3) / 1e9 if (two_stage and bp_ms > 0) else None,
+                    "peak": measured_hbm_gbs(), "unit": "GB/s", "kernel_ms": bp_ms,
+                    "frac": (bp_bytes / (bp_ms * 1e-3) / 1e9) / measured_hbm_gbs() if (two_stage and bp_ms > 0) else None,
+                    "algorithmic_bytes_per_launch": bp_bytes, "traffic": TRAFFIC_BROADPHASE,
+                    "traffic_source": TRAFFIC_SOURCE,
+                    "note": "64 B ray record per sphere + 8 B per candidate pair; the 64 B nodes it chases "
+                            "(83 M visits) are L1/L2 hits (scene is L2-resident), so the kernel is bound by L1 "
+                            "tag throughput and latency (ncu: L1 77% busy, DRAM 4%), not by HBM"}
 
     # e2e: the host-pointer C-ABI call, pinned host buffers, H2D + D2H inside the timed region
     h_in = torch.from_numpy(resps.view(np.float32).reshape(n, 7)).pin_memory()
@@ -268,7 +285,9 @@ def run_b200(args):
     e2e = {"value": e2e_tests / (e2e_ms * 1e-3), "unit": "tests/s", "h2d_bytes_per_step": n * 28,
            "d2h_bytes_per_step": n * (32 + 1 + 4 + 4), "ms_per_step": e2e_ms / args.steps,
            "spheres_per_sec": world * n * args.steps / (e2e_ms * 1e-3),
-           "api": "xp_detect_batch (host pointers, pinned)", "hits": int(h_hit.sum().item())}
+           "api": "xp_detect_batch (host pointers, pinned)", "hits": int(h_hit.sum().item()),
+           "stage_ms": {k: float(np.mean([s["stage_ms"][k] for s in e2e_stats])) for k in e2e_stats[0]["stage_ms"]
+                        if e2e_stats[0]["stage_ms"][k] > 0}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -293,6 +312,7 @@ def run_b200(args):
                 "stage_ms": {k: float(np.mean([s["stage_ms"][k] for s in stats])) for k in stats[0]["stage_ms"]},
                 "hit_fraction": float((mine[:, 9].contiguous().view(torch.int32) & 1).float().mean().item()),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "roofline_hbm": roofline_hbm,
                 "cpu_baseline": cpu,
                 "build": {"ms": sum(build_stats["stage_ms"].values()), "stage_ms": build_stats["stage_ms"],
                           "launches": build_stats["kernel_launches"]}}
@@ -302,12 +322,11 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-# bytes the dominant kernel must move per sphere (DESIGN.md "Kernels"): 64 B ray record in,
-# 8 B best key out; the 64 MB of nodes + 64 MB of triangle records are L2-resident (126 MB L2).
-ALGO_BYTES_PER_SPHERE = 72
-# dram__bytes_read.sum + dram__bytes_write.sum of k_traverse from the ncu --set full capture
-# under profiles/ (None until captured)
-TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
+# same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r01a_ncu_full.txt
+TRAFFIC_NARROW = 1025.0e6        # k_narrow_pairs: 994.8 MB read + 30.2 MB written
+TRAFFIC_BROADPHASE = 536.2e6     # k_broadphase: 239.8 MB read + 296.4 MB written
+TRAFFIC_SOURCE = "profiles/r01a_ncu_full.txt"
 
 
 def measured_hbm_gbs():
