@@ -13,6 +13,7 @@
 //   K4 tree     Karras 2012 hierarchy emission (one thread per internal node)
 //   K5 refit    bottom-up AABB refit with per-node arrival counters; writes the 64 B nodes
 #include <cstdio>
+#include <cstdlib>
 
 #include "xp_internal.h"
 #include "xp_narrowphase.cuh"
@@ -120,12 +121,21 @@ __global__ void __launch_bounds__(256) k_morton_tris(const float *__restrict__ a
 __global__ void __launch_bounds__(256) k_morton_spheres(const xp_response *__restrict__ in, uint64_t n,
                                                         const unsigned *__restrict__ bounds,
                                                         uint32_t *__restrict__ keys,
-                                                        uint32_t *__restrict__ vals) {
+                                                        uint32_t *__restrict__ vals, int mode) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float *p = reinterpret_cast<const float *>(in) + i * 7;
     V3 c = {__ldg(p + 0), __ldg(p + 1), __ldg(p + 2)};
-    keys[i] = morton30(c, bounds) >> 6;      // 24 bits (8 per axis) are plenty for processing order: 3 passes
+    const unsigned code = morton30(c, bounds);
+    // 24-bit processing-order key (3 radix passes).  mode 0: Morton code of the centre, 8 bits per axis.
+    // mode 1: direction octant (signs of the movement) on top of a 7-bit-per-axis Morton code, so the
+    // lanes of a warp walk the tree in the same order.
+    unsigned key = code >> 6;
+    if (mode == 1) {
+        const unsigned oct = (__ldg(p + 4) < 0.0f ? 4u : 0u) | (__ldg(p + 5) < 0.0f ? 2u : 0u) | (__ldg(p + 6) < 0.0f ? 1u : 0u);
+        key = (oct << 21) | (code >> 9);
+    }
+    keys[i] = key;
     vals[i] = (uint32_t)i;
 }
 
@@ -550,7 +560,8 @@ cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n
     XP_TRY(s->sort_ka.reserve(n * 4)); XP_TRY(s->sort_kb.reserve(n * 4));
     uint32_t *ka = s->sort_ka.as<uint32_t>(), *kb = s->sort_kb.as<uint32_t>();
     uint32_t *va = s->active_a.as<uint32_t>(), *vb = s->active_b.as<uint32_t>();
-    k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va);
+    static const int key_mode = getenv("XP_RAY_KEY") ? atoi(getenv("XP_RAY_KEY")) : 0;
+    k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va, key_mode);
     ++s->stats.kernel_launches;
     bool in_a = true;
     XP_TRY(radix_sort_pairs(s, ka, kb, va, vb, n, 24, &in_a));
