@@ -341,6 +341,25 @@ def test_config4_four_iterations(oracle):
     assert_bits_equal(resp_fields(out), resp_fields(w[0]), "config4")
 
 
+def test_config4_clipmap_and_voxels(oracle):
+    """config 4 geometry (scaled-down batch): the game's clipmap terrain soup + greedy-meshed voxel chunks,
+    4 sweep-and-slide iterations."""
+    tris = scenes.config4_scene()
+    resps = scenes.scene_spheres(tris, 160, seed=3)
+    want = oracle.detect_batch(resps, tris)
+    w = oracle.collision_response_batch(resps, tris, max_iter=4)
+    with xp.Scene(0, tris) as s:
+        got = s.detect_batch(resps)
+        out, it, st, ln = s.collision_response_batch(resps, max_iter=4)
+        gi, gj = s.broadphase_pairs(resps)
+    check_detect_exact(got, want, "config4 scene")
+    assert want[1].sum() > 100
+    assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
+    assert_bits_equal(resp_fields(out), resp_fields(w[0]), "config4 scene response")
+    wi, wj = oracle.broadphase_pairs(resps, tris)
+    assert np.array_equal(np.sort(gi.astype(np.uint64) << 32 | gj), np.sort(wi.astype(np.uint64) << 32 | wj))
+
+
 # ---- full size (BASELINE config 2: 1M spheres x 1M triangles): size-independent properties ------
 @pytest.fixture(scope="module")
 def full_scene():

@@ -58,3 +58,34 @@ def test_mesh_field():
     assert not np.array_equal(t, t2) and t.shape == t2.shape
     s = scenes.field_spheres(lo, hi, 100)
     assert np.linalg.norm(s["movement"], axis=1).max() < 1.0
+
+
+def test_clipmap_soup():
+    c = scenes.clipmap_triangles((37.0, -21.0), scenes.sine_height)
+    # level 0: 126^2 quads; each ring level: 12 m x m (31^2) + 2 p x m + 2 m x p (2*31) + trims 2 * 64 quads
+    per_ring = 12 * 31 * 31 + 4 * 2 * 31 + 2 * 64
+    assert len(c) == 2 * (126 * 126 + 4 * per_ring)
+    n = _normals(c)
+    assert (n[:, 1] > 0).all()                              # no zero-area stitch triangles, all facing up
+    # level l vertices sit on the 2 * 2^l lattice and rings nest around the centre
+    assert np.all(np.mod(c[: 2 * 126 * 126, :, [0, 2]], 2.0) == 0)
+    ext = np.abs(c[:, :, [0, 2]] - np.float32([37.0, -21.0])).max()
+    assert 126 * 16 - 64 < ext <= 128 * 16 + 64
+
+
+def test_greedy_voxel_mesh_is_closed_and_outward():
+    solid = scenes.procedural_chunk((0, 0, 0))
+    g = scenes.greedy_voxel_mesh(solid)
+    vol = np.einsum("ij,ij->i", g[:, 0], np.cross(g[:, 1], g[:, 2])).sum() / 6.0
+    assert abs(vol - solid.sum() * 1e-3) < 1e-3             # divergence theorem: closed + outward wound
+    one = np.zeros((4, 4, 4), bool)
+    one[1:3, 1:3, 1:3] = True
+    assert len(scenes.greedy_voxel_mesh(one)) == 12         # a 2x2x2 block merges into 6 quads
+    assert len(scenes.greedy_voxel_mesh(np.zeros((3, 3, 3), bool))) == 0
+
+
+def test_config4_scene():
+    t = scenes.config4_scene()
+    assert t.shape[1:] == (3, 3) and len(t) > 127000
+    s = scenes.scene_spheres(t, 100)
+    assert (s["r"] == 1).all()

@@ -164,3 +164,163 @@ def field_spheres(lo, hi, n: int, seed: int = 2) -> np.ndarray:
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     m = d * (rng.uniform(0.0, 1.0, (n, 1)) ** (1.0 / 3.0)) * 0.999
     return make_responses(c, m.astype(np.float32))
+
+
+# ---------------------------------------------------------------------------------------------
+# clipmap terrain (config 4): the triangles the game's clipmap vertex shader places
+# ---------------------------------------------------------------------------------------------
+CM_N, CM_M, CM_P = 127, 32, 3                    # game/src/graphics/clipmap.rs:14-21
+CM_UNIT = 2.0                                    # CM_UNIT_SIZE_SMALLEST
+CM_BASE_OFFSET = (CM_N - 3) // 2                 # clipmap.rs:70
+
+
+def _cm_unit(level: int) -> float:
+    return float(2 ** level) * CM_UNIT           # clipmap.rs:793-795
+
+
+def _cm_snap_down(val: float, level: int) -> float:
+    s = _cm_unit(level + 1)
+    return float(np.floor(val / s) * s)          # clipmap.rs:801-804
+
+
+def _cm_grid_quads(size_x: int, size_z: int):
+    """create_grid (clipmap.rs:752-786): per quad vertices i0=(x,z) i1=(x+1,z) i2=(x,z+1) i3=(x+1,z+1),
+    triangles [i0,i2,i1] and [i3,i1,i2]."""
+    x, z = np.meshgrid(np.arange(size_x - 1), np.arange(size_z - 1), indexing="xy")
+    x, z = x.reshape(-1), z.reshape(-1)
+    i0, i1 = np.stack([x, z], 1), np.stack([x + 1, z], 1)
+    i2, i3 = np.stack([x, z + 1], 1), np.stack([x + 1, z + 1], 1)
+    return np.concatenate([np.stack([i0, i2, i1], 1), np.stack([i3, i1, i2], 1)])       # (2q, 3, 2) integer offsets
+
+
+def clipmap_triangles(center_xz, height_fn, levels: int = 5) -> np.ndarray:
+    """Collision soup of the clipmap around `center_xz`: level 0 as the full N x N grid, levels 1..levels-1 as
+    rings of 12 m x m blocks, 2 p x m, 2 m x p fix-ups and the two interior trims chosen like
+    clipmap.rs:566-625; vertex = (ix * unit, h, iz * unit) as in shader_clipmap.vert:43-65.  The zero-area
+    stitching strips (create_degenerates_*, clipmap.rs:664-750) are render-only and left out."""
+    m1 = CM_M - 1
+    off_mxm = [[0, 0], [m1, 0], [2 * m1 + 2, 0], [3 * m1 + 2, 0], [0, m1], [3 * m1 + 2, m1], [0, 2 * m1 + 2],
+               [3 * m1 + 2, 2 * m1 + 2], [0, 3 * m1 + 2], [m1, 3 * m1 + 2], [2 * m1 + 2, 3 * m1 + 2], [3 * m1 + 2, 3 * m1 + 2]]
+    off_pxm = [[2 * m1, 0], [2 * m1, 3 * m1 + 2]]
+    off_mxp = [[0, 2 * m1], [3 * m1 + 2, 2 * m1]]
+    g_mxm, g_pxm, g_mxp = _cm_grid_quads(CM_M, CM_M), _cm_grid_quads(CM_P, CM_M), _cm_grid_quads(CM_M, CM_P)
+    g_nxn = _cm_grid_quads(CM_N, CM_N)
+    g_ih, g_iv = _cm_grid_quads(2 * CM_M + 1, 2), _cm_grid_quads(2, 2 * CM_M + 1)
+    cx, cz = float(center_xz[0]), float(center_xz[1])
+    out = []
+    for level in range(levels):
+        unit = _cm_unit(level)
+        snap = unit * 2.0
+        centre = np.array([int(np.floor(cx / snap) * 2.0), int(np.floor(cz / snap) * 2.0)]) - CM_BASE_OFFSET
+        parts = []
+        if level == 0:
+            parts.append(g_nxn)
+        else:
+            parts += [g_mxm + np.array(o) for o in off_mxm]
+            parts += [g_pxm + np.array(o) for o in off_pxm]
+            parts += [g_mxp + np.array(o) for o in off_mxp]
+            dz = _cm_snap_down(cz, level - 1) - _cm_snap_down(cz, level)
+            dx = _cm_snap_down(cx, level - 1) - _cm_snap_down(cx, level)
+            parts.append(g_ih + np.array([m1, m1] if dz > 1e-7 else [m1, 3 * m1 + 1]))        # h_top / h_bottom
+            parts.append(g_iv + np.array([m1, m1] if dx > 1e-7 else [3 * m1 + 1, m1]))        # v_left / v_right
+        idx = np.concatenate(parts) + centre                                                   # (t, 3, 2)
+        x = idx[..., 0].astype(np.float32) * np.float32(unit)
+        z = idx[..., 1].astype(np.float32) * np.float32(unit)
+        y = height_fn(x, z).astype(np.float32)
+        out.append(np.stack([x, y, z], axis=-1))
+    return np.ascontiguousarray(np.concatenate(out), dtype=np.float32)
+
+
+def sine_height(x, z):
+    """game/src/terrain/sine.rs:6-8."""
+    return np.sin(x / 4.0) + np.sin(z / 4.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# voxel chunks (config 4): greedy-meshed 32^3 chunks, voxel 0.1 (low_poly_nice_graphics world.rs)
+# ---------------------------------------------------------------------------------------------
+def procedural_chunk(chunk, size: int = 32, voxel: float = 0.1) -> np.ndarray:
+    """bool[size,size,size] fill of world.rs:146-157: y_w > -5 and sin(x_w) * sin(z_w) > y_w."""
+    i = np.arange(size, dtype=np.float32)
+    xw = np.float32(chunk[0] * size * voxel) + i * np.float32(voxel)
+    yw = np.float32(chunk[1] * size * voxel) + i * np.float32(voxel)
+    zw = np.float32(chunk[2] * size * voxel) + i * np.float32(voxel)
+    X, Y, Z = np.meshgrid(xw, yw, zw, indexing="ij")
+    return (Y > -5.0) & (np.sin(X) * np.sin(Z) > Y)
+
+
+def greedy_voxel_mesh(solid: np.ndarray, origin=(0.0, 0.0, 0.0), voxel: float = 0.1) -> np.ndarray:
+    """Greedy quads over the boundary faces of a boolean voxel block, 2 outward-wound triangles per quad
+    (an equivalent of world.rs:234-365: same surface, same merge rule -- widest run first, then extend rows)."""
+    solid = np.asarray(solid, bool)
+    tris = []
+    org = np.asarray(origin, np.float32)
+    for u in range(3):                               # axis normal to the face
+        v, w = (u + 1) % 3, (u + 2) % 3
+        for sign in (1, -1):
+            shifted = np.zeros_like(solid)
+            src = [slice(None)] * 3
+            dst = [slice(None)] * 3
+            if sign == 1:
+                src[u], dst[u] = slice(1, None), slice(0, -1)
+            else:
+                src[u], dst[u] = slice(0, -1), slice(1, None)
+            shifted[tuple(dst)] = solid[tuple(src)]
+            exposed = solid & ~shifted               # faces looking along +u (sign=1) or -u
+            for s in range(solid.shape[u]):
+                sl = [slice(None)] * 3
+                sl[u] = s
+                mask = exposed[tuple(sl)]
+                if u == 1:                           # keep (v, w) = (z, x) orientation consistent
+                    mask = mask.T
+                mask = mask.copy()
+                nv, nw = mask.shape
+                for b in range(nw):
+                    a = 0
+                    while a < nv:
+                        if not mask[a, b]:
+                            a += 1
+                            continue
+                        wdt = 1
+                        while a + wdt < nv and mask[a + wdt, b]:
+                            wdt += 1
+                        hgt = 1
+                        while b + hgt < nw and mask[a:a + wdt, b + hgt].all():
+                            hgt += 1
+                        mask[a:a + wdt, b:b + hgt] = False
+                        p = np.zeros((4, 3), np.float32)
+                        plane = s + (1 if sign == 1 else 0)
+                        for k, (da, db) in enumerate(((0, 0), (wdt, 0), (wdt, hgt), (0, hgt))):
+                            p[k, u] = plane
+                            p[k, v] = a + da
+                            p[k, w] = b + db
+                        p = org + p * np.float32(voxel)
+                        quad = (p[0], p[1], p[2], p[3]) if sign == 1 else (p[0], p[3], p[2], p[1])
+                        tris.append([quad[0], quad[1], quad[2]])
+                        tris.append([quad[0], quad[2], quad[3]])
+                        a += wdt
+    if not tris:
+        return np.zeros((0, 3, 3), np.float32)
+    return np.ascontiguousarray(np.asarray(tris, np.float32))
+
+
+def config4_scene(center_xz=(37.0, -21.0), chunks=((0, -1, 0), (1, -1, 0), (0, -1, 1), (0, 0, 0)), radius: float = 0.5):
+    """Clipmap terrain + greedy-meshed procedural voxel chunks, scaled by 1/radius into unit-sphere space
+    (the player sphere has r = 0.5 in low_poly_nice_graphics/src/main.rs:122)."""
+    parts = [clipmap_triangles(center_xz, sine_height)]
+    for c in chunks:
+        origin = (c[0] * 3.2 + center_xz[0], c[1] * 3.2 + 4.0, c[2] * 3.2 + center_xz[1])
+        parts.append(greedy_voxel_mesh(procedural_chunk(c), origin=origin))
+    tris = np.concatenate(parts) / np.float32(radius)
+    return np.ascontiguousarray(tris, dtype=np.float32)
+
+
+def scene_spheres(tris: np.ndarray, n: int, seed: int = 3, extent: float = 60.0) -> np.ndarray:
+    """Spheres dropped from above the central part of a scene (config 4 batch)."""
+    rng = np.random.default_rng(seed)
+    mid = 0.5 * (tris.reshape(-1, 3).min(axis=0) + tris.reshape(-1, 3).max(axis=0))
+    top = tris.reshape(-1, 3)[:, 1].max()
+    c = np.stack([mid[0] + rng.uniform(-extent, extent, n), top + rng.uniform(1.05, 4.0, n),
+                  mid[2] + rng.uniform(-extent, extent, n)], axis=1).astype(np.float32)
+    m = np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.6, -0.05, n), rng.uniform(-0.3, 0.3, n)], axis=1)
+    return make_responses(c, m.astype(np.float32))
