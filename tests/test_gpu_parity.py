@@ -164,6 +164,18 @@ def test_pair_buffer_overflow_is_recovered(terrain):
             assert it.max() == 2
 
 
+def test_host_pipeline_chunks(terrain, monkeypatch):
+    """the host-pointer sweep cut into H2D / compute / D2H pipeline chunks gives the same answer as one piece"""
+    tris, h, resps, want = terrain
+    with xp.Scene(0, tris) as s:
+        for k in ("1", "3", "7"):
+            monkeypatch.setenv("XP_IO_CHUNKS", k)
+            got = s.detect_batch(resps)
+            check_detect_exact(got, want, f"{k} pipeline chunks")
+            assert s.stats()["narrowphase_tests"] == s.stats()["broadphase_pairs"] > 0
+    monkeypatch.delenv("XP_IO_CHUNKS")
+
+
 # ---- response loop ---------------------------------------------------------------------------
 @pytest.mark.parametrize("method,prune", METHODS)
 def test_collision_response_exact_bitwise(terrain, oracle, method, prune):
@@ -401,6 +413,19 @@ def test_full_size_properties(full_scene, oracle):
     idx = np.flatnonzero(hh)[:: max(1, hh.sum() // 64)][:64]
     sub = oracle.detect_batch(resps[idx], tris, threads=0)          # brute force: 64 x 1M tests on the CPU
     check_detect_exact(tuple(x[idx] for x in a), sub, "64-sphere sample vs brute-force oracle")
+
+
+def test_full_size_host_batch_above_pipeline_threshold(full_scene):
+    """3 x 2^20 spheres through the host ABI: above 2^21 the call is pipelined in chunks by default"""
+    tris, h, resps = full_scene
+    big = np.concatenate([resps, resps[::-1], resps])
+    with xp.Scene(0, tris) as s:
+        a = s.detect_batch(resps)
+        b = s.detect_batch(big)
+    n = len(resps)
+    check_detect_exact(tuple(x[:n] for x in b), a, "first third")
+    check_detect_exact(tuple(x[n:2 * n][::-1] for x in b), a, "second third (reversed)")
+    check_detect_exact(tuple(x[2 * n:] for x in b), a, "last third")
 
 
 def test_full_size_response_sample(full_scene, oracle):

@@ -142,20 +142,20 @@ __device__ __forceinline__ bool slab(const V3 &c, const V3 &inv, float horizon, 
     {
         const float a = __fmul_rn(__fsub_rn(lox, c.x), inv.x), b = __fmul_rn(__fsub_rn(hix, c.x), inv.x);
         const float nr = (inv.x > 0.0f) ? a : b, fr = (inv.x > 0.0f) ? b : a;
-        if (nr > tmin) tmin = nr;
-        if (fr < tmax) tmax = fr;
+        tmin = fmaxf(tmin, nr);      // == "if (nr > tmin) tmin = nr": fmaxf ignores a NaN operand and tmin is never NaN
+        tmax = fminf(tmax, fr);
     }
     {
         const float a = __fmul_rn(__fsub_rn(loy, c.y), inv.y), b = __fmul_rn(__fsub_rn(hiy, c.y), inv.y);
         const float nr = (inv.y > 0.0f) ? a : b, fr = (inv.y > 0.0f) ? b : a;
-        if (nr > tmin) tmin = nr;
-        if (fr < tmax) tmax = fr;
+        tmin = fmaxf(tmin, nr);      // == "if (nr > tmin) tmin = nr": fmaxf ignores a NaN operand and tmin is never NaN
+        tmax = fminf(tmax, fr);
     }
     {
         const float a = __fmul_rn(__fsub_rn(loz, c.z), inv.z), b = __fmul_rn(__fsub_rn(hiz, c.z), inv.z);
         const float nr = (inv.z > 0.0f) ? a : b, fr = (inv.z > 0.0f) ? b : a;
-        if (nr > tmin) tmin = nr;
-        if (fr < tmax) tmax = fr;
+        tmin = fmaxf(tmin, nr);      // == "if (nr > tmin) tmin = nr": fmaxf ignores a NaN operand and tmin is never NaN
+        tmax = fminf(tmax, fr);
     }
     tnear = tmin;
     return tmin <= tmax;
