@@ -224,7 +224,7 @@ def run_b200(args):
     # ---- rooflines, from the CUDA-event stage times the library records on its own stream around
     # each kernel inside the timed steps (XP_OPT_TIMING; no extra synchronisation)
     st_ms = {k: float(np.mean([s["stage_ms"][k] for s in stats])) for k in stats[0]["stage_ms"]}
-    two_stage = args.method in ("lbvh_pairs", "wide_pairs")
+    two_stage = args.method in ("lbvh_pairs", "wide_pairs", "q4_pairs")
     # path mix of the narrowphase tests: one untimed diagnostic sweep with the fused kernel, which
     # counts the code path of every test (the two-stage kernels carry no counters)
     scene.set_options(method="lbvh_fused", prune=False)
@@ -241,7 +241,7 @@ def run_b200(args):
     achieved = flops / (np_ms * 1e-3) / 1e12 if np_ms > 0 else 0.0
     kname = {"wide_fused": "k_sweep (32-wide tree traversal + narrowphase, fused)",
              "wide_pairs": "k_narrow_pairs", "lbvh_fused": "k_traverse (binary LBVH + narrowphase, fused)",
-             "lbvh_pairs": "k_narrow_pairs", "brute": "k_brute"}[args.method]
+             "lbvh_pairs": "k_narrow_pairs", "q4_pairs": "k_narrow_pairs<FILTER>", "brute": "k_brute"}[args.method]
     roofline = {"bound": "fp32", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "peak_source": peak_src, "kernel_ms": np_ms,
                 "algorithmic_flops_per_launch": flops, "flops_per_test_by_path": PATH_FLOPS, "path_mix": paths,
@@ -252,7 +252,7 @@ def run_b200(args):
     tests_step = float(np.mean([s["narrowphase_tests"] for s in stats]))
     bp_bytes = 64.0 * n + 8.0 * tests_step                       # ray records in + candidate pairs out
     bp_ms = st_ms["traverse"]
-    roofline_hbm = {"bound": "hbm", "kernel": "k_broadphase" if args.method == "lbvh_pairs" else "k_sweep<EMIT>",
+    roofline_hbm = {"bound": "hbm", "kernel": {"lbvh_pairs": "k_broadphase", "q4_pairs": "k_broadphase4"}.get(args.method, "k_sweep<EMIT>"),
                     "achieved": bp_bytes / (bp_ms * 1e-3) / 1e9 if (two_stage and bp_ms > 0) else None,
                     "peak": measured_hbm_gbs(), "unit": "GB/s", "kernel_ms": bp_ms,
                     "frac": (bp_bytes / (bp_ms * 1e-3) / 1e9) / measured_hbm_gbs() if (two_stage and bp_ms > 0) else None,
@@ -365,7 +365,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
-    ap.add_argument("--method", default="lbvh_pairs", choices=["wide_fused", "wide_pairs", "lbvh_fused", "lbvh_pairs", "brute"])
+    ap.add_argument("--method", default="lbvh_pairs", choices=["wide_fused", "wide_pairs", "lbvh_fused", "lbvh_pairs", "brute", "q4_pairs"])
     ap.add_argument("--prune", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -79,6 +79,8 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
 #define XP_METHOD_LBVH_PAIRS  2  /* default. Persistent-warp binary LBVH traversal (<= 32 registers) emits every pair passing P to HBM; narrowphase over the pairs */
 #define XP_METHOD_BRUTE       3  /* the reference's literal algorithm: every triangle for every sphere (lib.rs:33-35) */
 #define XP_METHOD_WIDE_PAIRS  4  /* 32-wide tree traversal emits the pairs to HBM; narrowphase over the pairs */
+#define XP_METHOD_Q4_PAIRS    5  /* quantised 4-wide collapse of the LBVH (64 B nodes, 8-bit boxes rounded outward):
+                                   stage 1 emits a superset, stage 2 re-checks the exact P before the narrowphase */
 
 /* ---- statistics of the last detect / response call on a scene ---- */
 #define XP_STAGE_COUNT 12

@@ -87,7 +87,7 @@ void xp_scene_destroy(xp_scene *s) {
     cudaStreamSynchronize(s->stream);
     DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_lo, &s->node_hi, &s->leaf_lo, &s->leaf_hi,
                       &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
-                      &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->rays, &s->best, &s->active_a,
+                      &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->rays, &s->best, &s->active_a,
                       &s->active_b, &s->pairs, &s->counters, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
                       &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
     for (DevBuf *b : bufs) b->release();
@@ -114,7 +114,7 @@ int xp_scene_set_option(xp_scene *s, int option, int64_t value) {
         if (value != XP_ARITH_EXACT && value != XP_ARITH_FAST) return XP_EINVAL;
         s->arith = (int)value; return XP_OK;
     case XP_OPT_METHOD:
-        if (value < XP_METHOD_WIDE_FUSED || value > XP_METHOD_WIDE_PAIRS) return XP_EINVAL;
+        if (value < XP_METHOD_WIDE_FUSED || value > XP_METHOD_Q4_PAIRS) return XP_EINVAL;
         s->method = (int)value; return XP_OK;
     case XP_OPT_TIMING: s->timing = value ? 1 : 0; return XP_OK;
     case XP_OPT_SORT_SPHERES: s->sort_spheres = value ? 1 : 0; return XP_OK;

@@ -434,6 +434,76 @@ __global__ void __launch_bounds__(256) k_wide_level(const float4 *__restrict__ s
     if (lane == 0) { dst_lo[t >> 5] = lo; dst_hi[t >> 5] = hi; }
 }
 
+// Quantised 4-wide collapse: Node4[X] holds the (up to four) grandchildren of binary node X -- the
+// children of X's internal children, or X's leaf children themselves.  Only the nodes reachable from
+// the root in hops of two levels are ever visited; the others are written and never read.
+__device__ __forceinline__ void q4_add(float (&lo)[4][3], float (&hi)[4][3], int (&link)[4], int &cnt,
+                                       int l, float lx, float ly, float lz, float hx, float hy, float hz) {
+    lo[cnt][0] = lx; lo[cnt][1] = ly; lo[cnt][2] = lz;
+    hi[cnt][0] = hx; hi[cnt][1] = hy; hi[cnt][2] = hz;
+    link[cnt] = l;
+    ++cnt;
+}
+
+__global__ void __launch_bounds__(256) k_collapse4(const Node *__restrict__ nodes, int n_internal,
+                                                   Node4 *__restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_internal) return;
+    float lo[4][3], hi[4][3];
+    int link[4] = {Q4_EMPTY, Q4_EMPTY, Q4_EMPTY, Q4_EMPTY};
+    int cnt = 0;
+    const Node nx = nodes[x];
+    const int kid[2] = {nx.link.x, nx.link.y};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (kid[k] < 0) {                                  // leaf child of X (the empty child of a 1-triangle root has an inverted box)
+            if (k == 0) q4_add(lo, hi, link, cnt, kid[k], nx.q0.x, nx.q0.y, nx.q0.z, nx.q0.w, nx.q1.x, nx.q1.y);
+            else if (nx.q1.z <= nx.q2.y) q4_add(lo, hi, link, cnt, kid[k], nx.q1.z, nx.q1.w, nx.q2.x, nx.q2.y, nx.q2.z, nx.q2.w);
+        } else {
+            const Node ny = nodes[kid[k]];
+            q4_add(lo, hi, link, cnt, ny.link.x, ny.q0.x, ny.q0.y, ny.q0.z, ny.q0.w, ny.q1.x, ny.q1.y);
+            q4_add(lo, hi, link, cnt, ny.link.y, ny.q1.z, ny.q1.w, ny.q2.x, ny.q2.y, ny.q2.z, ny.q2.w);
+        }
+    }
+    float org[3], ext[3];
+    unsigned ebits = 0;
+    float inv_cell[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float mn = lo[0][a], mx = hi[0][a];
+        for (int c = 1; c < cnt; ++c) { mn = fminf(mn, lo[c][a]); mx = fmaxf(mx, hi[c][a]); }
+        org[a] = mn; ext[a] = mx - mn;
+        // smallest power-of-two cell with ext <= 252 cells (leaves room for the one-cell outward margins)
+        int e;
+        frexpf(fmaxf(ext[a], 1e-30f) / 252.0f, &e);        // ext/252 = f * 2^e, f in [0.5,1)  ->  cell = 2^e >= ext/252
+        e = max(-126, min(126, e));
+        ebits |= (unsigned)(e + 127) << (8 * a);
+        inv_cell[a] = __uint_as_float((unsigned)(127 - e) << 23);      // 2^-e, exact
+    }
+    unsigned qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0};
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            unsigned l = 255u, h = 0u;                      // empty slot: inverted box, never hit
+            if (c < cnt) {
+                const float fl = floorf((lo[c][a] - org[a]) * inv_cell[a]) - 1.0f;    // one cell outward
+                const float fh = ceilf((hi[c][a] - org[a]) * inv_cell[a]) + 1.0f;
+                l = (unsigned)fminf(fmaxf(fl, 0.0f), 255.0f);
+                h = (unsigned)fminf(fmaxf(fh, 0.0f), 255.0f);
+            }
+            qlo[a] |= l << (8 * c);
+            qhi[a] |= h << (8 * c);
+        }
+    }
+    // qlo is clamped at 0 = the origin itself, which is <= every child's lo, so clamping stays conservative
+    Node4 o;
+    o.w0 = make_uint4(__float_as_uint(org[0]), __float_as_uint(org[1]), __float_as_uint(org[2]), ebits);
+    o.w1 = make_uint4(qlo[0], qlo[1], qlo[2], qhi[0]);
+    o.w2 = make_uint4(qhi[1], qhi[2], (unsigned)link[0], (unsigned)link[1]);
+    o.w3 = make_uint4((unsigned)link[2], (unsigned)link[3], 0u, 0u);
+    out[x] = o;
+}
+
 // a scene with one triangle: root = (leaf 0, empty); the empty box (+inf,-inf) can never be hit
 __global__ void k_single_root(Node *nodes, const float4 *leaf_lo, const float4 *leaf_hi,
                               float4 *node_lo, float4 *node_hi) {
@@ -519,6 +589,13 @@ cudaError_t build_lbvh(xp_scene *s) {
                                                      s->refit_flags.as<unsigned>());
             ++s->stats.kernel_launches;
         }
+    }
+    {   // quantised 4-wide collapse of the binary tree (XP_METHOD_Q4_PAIRS)
+        StageTimer t(s, XP_STAGE_BUILD_TREE);
+        const uint64_t ni = n > 1 ? n - 1 : 1;
+        XP_TRY(s->nodes4.reserve(ni * sizeof(Node4)));
+        k_collapse4<<<grid_for(ni, 256), 256, 0, st>>>(s->nodes.as<Node>(), (int)ni, s->nodes4.as<Node4>());
+        ++s->stats.kernel_launches;
     }
     {   // 32-wide implicit tree over the same Morton order
         StageTimer t(s, XP_STAGE_BUILD_TREE);

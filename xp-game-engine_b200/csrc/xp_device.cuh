@@ -21,6 +21,16 @@ namespace xp {
 struct __align__(16) TriRec { float4 q0, q1, q2, q3; };
 struct __align__(16) Node { float4 q0, q1, q2; int4 link; };
 struct __align__(16) RayRec { float4 q0, q1, q2, q3; };
+// Quantised 4-wide node (64 B), built by collapsing two levels of the binary LBVH.  Child boxes are
+// 8-bit offsets from the node's own origin in power-of-two cells, rounded OUTWARD by one extra cell,
+// so a stage-1 traversal over these nodes emits a superset of P; stage 2 re-checks the exact
+// predicate on the triangle's own fp32 box before the narrowphase.
+//   w0.xyz = origin (fp32), w0.w = cell exponents (ex | ey << 8 | ez << 16, biased by 127)
+//   w1 = (qlo.x[4], qlo.y[4], qlo.z[4], qhi.x[4])   one byte per child
+//   w2 = (qhi.y[4], qhi.z[4], link0, link1)         links: >= 0 node, < 0 leaf ~c, Q4_EMPTY = no child
+//   w3 = (link2, link3, 0, 0)
+struct __align__(16) Node4 { uint4 w0, w1, w2, w3; };
+static constexpr int Q4_EMPTY = (int)0x80000000;
 
 static constexpr unsigned long long BEST_NONE = 0xFFFFFFFFFFFFFFFFull;
 static constexpr uint32_t RAY_VALID = 1u;
@@ -97,6 +107,7 @@ struct xp_scene {
     xp::DevBuf hist;          // radix histograms + scan scratch
     xp::DevBuf bounds;        // 6 ordered-int floats: scene AABB of triangle centres
     xp::DevBuf wide, wide_lo, wide_hi;               // 32-wide implicit tree planes + per-node union boxes
+    xp::DevBuf nodes4;                               // Node4[max(T-1,1)], indexed like the binary nodes
     xp::WideTree wide_tree = {};
     float h_bounds[6] = {0, 0, 0, 0, 0, 0};
     // per-call workspaces

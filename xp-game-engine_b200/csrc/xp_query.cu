@@ -393,6 +393,127 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
 }
 
 // ------------------------------------------------------------------------------------------
+// stage 1 over the quantised 4-wide tree (XP_METHOD_Q4_PAIRS)
+// ------------------------------------------------------------------------------------------
+// Same persistent-warp scheme as k_broadphase, but one step reads a 64 B Node4 = four child boxes:
+// half the dependent steps and half the node bytes per sphere.  The 8-bit boxes are rounded outward,
+// so the emitted pairs are a SUPERSET of P; k_narrow_pairs<.., FILTER=true> re-checks the exact
+// predicate on the triangle's own box, which keeps the tested set equal to P bit for bit.
+static constexpr int BP4_QUEUE = 160;          // < 32 left over + at most 4 x 32 appended per step
+static constexpr int BP4_STACK = 96;
+
+__device__ __forceinline__ float byte_to_float(unsigned word, int j) {
+    // (float)((word >> 8j) & 255) without an I2F: 0x4B000000 | b is 2^23 + b exactly
+    return __uint_as_float(0x4B000000u | ((word >> (8 * j)) & 0xFFu)) - 8388608.0f;
+}
+
+__global__ void __launch_bounds__(BP_THREADS, BP_BLOCKS_PER_SM)
+k_broadphase4(const Node4 *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
+              float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap) {
+    __shared__ uint2 queue[BP_WARPS][BP4_QUEUE];
+    __shared__ float4 stage_all[BP_WARPS][32 * GATHER_STRIDE];
+    uint2 *q = queue[threadIdx.x >> 5];
+    float4 *stage = stage_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    V3 c = {0, 0, 0}, inv = {0, 0, 0};
+    uint32_t my_ray = 0;
+    int node = -1;
+    int stack[BP4_STACK];
+    int sp = 0;
+    unsigned count = 0;
+    uint64_t pool = 0, pool_end = 0;
+    bool drained = false;
+    unsigned n_nodes = 0;
+
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, node < 0);
+        if (idle) {
+            if (pool >= pool_end && !drained) {
+                unsigned long long start = 0;
+                if (lane == 0) start = atomicAdd(&ctr->ray_cursor, 32ull);
+                start = __shfl_sync(FULL, start, 0);
+                pool = ray_base + start;
+                pool_end = pool + 32 < ray_end ? pool + 32 : ray_end;
+                if (pool >= ray_end) { drained = true; pool = pool_end = ray_end; }
+            }
+            if (pool < pool_end) {
+                const unsigned rank = __popc(idle & lt_mask);
+                if (node < 0 && pool + rank < pool_end) {
+                    my_ray = (uint32_t)(pool + rank);
+                    const float4 *rp = reinterpret_cast<const float4 *>(rays + my_ray);
+                    const float4 q0 = __ldg(rp + 0), q3 = __ldg(rp + 3);
+                    c = f4_xyz(q0); inv = f4_xyz(q3);
+                    sp = 0;
+                    node = (__float_as_uint(q3.w) & RAY_VALID) ? 0 : -1;
+                }
+                const uint64_t taken = __popc(idle);
+                pool = pool + taken < pool_end ? pool + taken : pool_end;
+            } else if (idle == FULL && drained) {
+                break;
+            }
+        }
+        float4 f0, f1, f2, f3;
+        warp_gather64(reinterpret_cast<const float4 *>(nodes), node, stage, f0, f1, f2, f3);
+        int leaf[4] = {-1, -1, -1, -1};
+        if (node >= 0) {
+            ++n_nodes;
+            const unsigned ebits = __float_as_uint(f0.w);
+            const float sx = __uint_as_float((ebits & 0xFFu) << 23);
+            const float sy = __uint_as_float(((ebits >> 8) & 0xFFu) << 23);
+            const float sz = __uint_as_float(((ebits >> 16) & 0xFFu) << 23);
+            const V3 cr = {c.x - f0.x, c.y - f0.y, c.z - f0.z};          // ray origin in the node's frame
+            const unsigned lx = __float_as_uint(f1.x), ly = __float_as_uint(f1.y), lz = __float_as_uint(f1.z);
+            const unsigned hx = __float_as_uint(f1.w), hy = __float_as_uint(f2.x), hz = __float_as_uint(f2.y);
+            const int link[4] = {__float_as_int(f2.z), __float_as_int(f2.w), __float_as_int(f3.x), __float_as_int(f3.y)};
+            int next = -1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float tn;
+                const bool hit = link[j] != Q4_EMPTY &&
+                                 slab(cr, inv, horizon, byte_to_float(lx, j) * sx, byte_to_float(ly, j) * sy,
+                                      byte_to_float(lz, j) * sz, byte_to_float(hx, j) * sx, byte_to_float(hy, j) * sy,
+                                      byte_to_float(hz, j) * sz, tn);
+                if (hit) {
+                    if (link[j] < 0) leaf[j] = ~link[j];
+                    else if (next < 0) next = link[j];
+                    else if (sp < BP4_STACK) stack[sp++] = link[j];
+                    else atomicExch(&ctr->stack_overflow, 1u);
+                }
+            }
+            node = (next >= 0) ? next : ((sp > 0) ? stack[--sp] : -1);
+        }
+        const unsigned any_leaf = __ballot_sync(FULL, (leaf[0] & leaf[1] & leaf[2] & leaf[3]) >= 0);   // any sign bit clear
+        if (any_leaf) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned m = __ballot_sync(FULL, leaf[j] >= 0);
+                if (leaf[j] >= 0) q[count + __popc(m & lt_mask)] = make_uint2(my_ray, (uint32_t)leaf[j]);
+                count += __popc(m);
+            }
+            __syncwarp();
+            while (count >= 32) {
+                count -= 32;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&ctr->pairs, 32ull);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + lane < pair_cap) pairs_out[base + lane] = q[count + lane];
+                __syncwarp();
+            }
+        }
+    }
+    if (count > 0) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)count);
+        base = __shfl_sync(FULL, base, 0);
+        if (lane < count && base + lane < pair_cap) pairs_out[base + lane] = q[lane];
+    }
+    for (int o = 16; o > 0; o >>= 1) n_nodes += __shfl_xor_sync(FULL, n_nodes, o);
+    if (lane == 0) atomicAdd(&ctr->node_visits, (unsigned long long)n_nodes);
+}
+
+// ------------------------------------------------------------------------------------------
 // 32-wide implicit tree, one WARP per sphere
 // ------------------------------------------------------------------------------------------
 // Every traversal step is one node: lane i reads child i's box from the node's six SoA planes
@@ -550,27 +671,49 @@ k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__re
 // pairs come from the same few rays) with 3 x LDG.128, and folds hits with a 64-bit atomicMin.
 // (A cooperative shared-memory gather of the triangle records was measured and was slower here:
 // 1.12 ms vs 0.93 ms; this kernel is bound by instruction issue, not by the L1 tag stage.)
-template <class O>
+template <class O, bool FILTER>
 __global__ void __launch_bounds__(256) k_narrow_pairs(const TriRec *__restrict__ recs,
                                                       const RayRec *__restrict__ rays,
                                                       const uint2 *__restrict__ pairs,
                                                       DeviceCounters *__restrict__ ctr,
-                                                      uint64_t pair_cap,
+                                                      uint64_t pair_cap, float horizon,
                                                       unsigned long long *__restrict__ best) {
     unsigned long long n = ctr->pairs;
     if (blockIdx.x == 0 && threadIdx.x == 0) {       // accounting stays on the device: no host round trip per chunk
         if (n > pair_cap) ctr->pair_overflow = 1u;    // candidates were dropped: the host reruns with smaller chunks
-        atomicAdd(&ctr->tests, n > pair_cap ? (unsigned long long)pair_cap : n);
+        if (!FILTER) atomicAdd(&ctr->tests, n > pair_cap ? (unsigned long long)pair_cap : n);
         atomicAdd(&ctr->pairs_total, n);
     }
     if (n > pair_cap) n = pair_cap;
+    unsigned kept = 0;
     for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n;
          p += (unsigned long long)gridDim.x * blockDim.x) {
         const uint2 pr = __ldg(&pairs[p]);
         const float4 *rp = reinterpret_cast<const float4 *>(rays + pr.x);
-        const Ray ray = ray_from(__ldg(rp + 0), __ldg(rp + 1), __ldg(rp + 2));
-        unsigned long long key;
-        if (detect_rec<O>(ray, recs, pr.y, key)) atomicMin(&best[pr.x], key);
+        const float4 *tp = reinterpret_cast<const float4 *>(recs + pr.y);
+        const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
+        const float4 r0 = __ldg(rp + 0);
+        if (FILTER) {
+            // stage 1 walked conservatively quantised boxes: apply the exact predicate P to the
+            // triangle's own inflated fp32 box, so that exactly the pairs of P are tested
+            const float4 r3 = __ldg(rp + 3);
+            V3 lo, hi;
+            xp_tri_aabb(f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), lo, hi);
+            float tn;
+            if (!slab(f4_xyz(r0), f4_xyz(r3), horizon, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tn)) continue;
+            ++kept;
+        }
+        const Ray ray = ray_from(r0, __ldg(rp + 1), __ldg(rp + 2));
+        float t;
+        if (xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t)) {
+            const unsigned long long key =
+                ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(~__float_as_uint(t3.w));
+            atomicMin(&best[pr.x], key);
+        }
+    }
+    if (FILTER) {
+        for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(FULL, kept, o);
+        if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&ctr->tests, (unsigned long long)kept);
     }
 }
 
@@ -796,12 +939,20 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
     }
     // two-stage methods: chunks of rays sized so the pair buffer holds the candidates
     const bool wide = s->method == XP_METHOD_WIDE_PAIRS;
+    const bool q4 = s->method == XP_METHOD_Q4_PAIRS;
     const uint64_t cap = s->max_pairs;
     XP_TRY(s->pairs.reserve(cap * sizeof(uint2)));
     uint2 *pairs = s->pairs.as<uint2>();
     uint64_t chunk = (cap / 64 / 32) * 32;      // 64 candidates per sphere on average fit
     if (chunk < 32) chunk = 32;
     uint64_t pos = 0;
+    unsigned long long snap_tests = 0, snap_pairs = 0;   // synchronous mode: accounting before the current chunk
+    if (s->safe_pairs) {
+        DeviceCounters h0;
+        XP_TRY(fetch_counters(s, &h0));
+        snap_tests = h0.tests;
+        snap_pairs = h0.pairs_total;
+    }
     while (pos < na) {
         const uint64_t end = (pos + chunk < na) ? pos + chunk : na;
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
@@ -811,13 +962,16 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
             if (wide)
                 k_sweep<O, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
                     s->wide_tree, recs, rays, pos, end, best, ctr, pairs, cap, 0);
+            else if (q4)
+                k_broadphase4<<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes4.as<Node4>(), rays, pos, end, s->cur_horizon, ctr, pairs, cap);
             else
                 k_broadphase<<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap);
             ++s->stats.kernel_launches;
         }
         {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
-            k_narrow_pairs<O><<<148 * 8, 256, 0, st>>>(recs, rays, pairs, ctr, cap, best);
+            if (q4) k_narrow_pairs<O, true><<<148 * 8, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
+            else k_narrow_pairs<O, false><<<148 * 8, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
             ++s->stats.kernel_launches;
         }
         if (s->safe_pairs) {                 // synchronous mode: check the fill after every chunk
@@ -827,12 +981,15 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
                 if (chunk <= 32) return cudaErrorMemoryAllocation;
                 chunk = ((chunk / 2) / 32) * 32;
                 if (chunk < 32) chunk = 32;
-                // atomicMin is idempotent (the partial pass did no harm); undo its accounting
+                // atomicMin is idempotent (the partial pass did no harm); roll its accounting back
                 XP_TRY(cudaMemsetAsync(&ctr->pair_overflow, 0, sizeof(unsigned), st));
-                s->stats.narrowphase_tests -= cap;
-                s->stats.broadphase_pairs -= h.pairs;
+                XP_TRY(cudaMemcpyAsync(&ctr->tests, &snap_tests, 8, cudaMemcpyHostToDevice, st));
+                XP_TRY(cudaMemcpyAsync(&ctr->pairs_total, &snap_pairs, 8, cudaMemcpyHostToDevice, st));
+                XP_TRY(cudaStreamSynchronize(st));
                 continue;
             }
+            snap_tests = h.tests;
+            snap_pairs = h.pairs_total;
         }
         // optimistic mode (default for sweeps): nothing is read back here; k_narrow_pairs raises
         // ctr->pair_overflow if a chunk did not fit and the API layer reruns in synchronous mode
