@@ -86,22 +86,17 @@ static constexpr int GATHER_STRIDE = 5;            // float4 per staged record (
 __device__ __forceinline__ void warp_gather64(const float4 *__restrict__ base, int idx, float4 *stage,
                                               float4 &o0, float4 &o1, float4 &o2, float4 &o3) {
     const int lane = threadIdx.x & 31;
-    const unsigned want = __ballot_sync(0xffffffffu, idx >= 0);
+    const int want = idx < 0 ? 0 : idx;             // idle lanes fetch record 0 (hot in L1): no predication needed
+    const float4 *src = base + (lane & 3);
+    float4 *dst = stage + (lane >> 2) * GATHER_STRIDE + (lane & 3);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const int owner = (lane >> 2) + 8 * r;
-        const int src = __shfl_sync(0xffffffffu, idx, owner);
-        if ((want >> (8 * r)) & 0xFFu) {            // warp-uniform: skip octets nobody needs
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (src >= 0) v = __ldg(base + (size_t)src * 4 + (lane & 3));
-            stage[owner * GATHER_STRIDE + (lane & 3)] = v;
-        }
+        const int rec = __shfl_sync(0xffffffffu, want, (lane >> 2) + 8 * r);
+        dst[8 * r * GATHER_STRIDE] = __ldg(src + (size_t)(unsigned)rec * 4);
     }
     __syncwarp();
-    o0 = stage[lane * GATHER_STRIDE + 0];
-    o1 = stage[lane * GATHER_STRIDE + 1];
-    o2 = stage[lane * GATHER_STRIDE + 2];
-    o3 = stage[lane * GATHER_STRIDE + 3];
+    const float4 *mine = stage + lane * GATHER_STRIDE;
+    o0 = mine[0]; o1 = mine[1]; o2 = mine[2]; o3 = mine[3];
     __syncwarp();
 }
 
@@ -304,51 +299,53 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     float4 *stage = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+    rays += ray_base;                                   // 32-bit ray indices relative to the chunk
+    const unsigned n_rays = (unsigned)(ray_end - ray_base);
+    const unsigned ray0 = (unsigned)ray_base;
 
     V3 c = {0, 0, 0}, inv = {0, 0, 0};
-    uint32_t my_ray = 0;
+    unsigned my_ray = 0;
     int node = -1;                         // internal node to visit next; -1 = lane needs a ray
     int stack[STACK_DEPTH];
     int sp = 0;
     unsigned count = 0;                    // queue fill (warp-uniform)
-    uint64_t pool = 0, pool_end = 0;       // this warp's current run of rays (warp-uniform)
+    unsigned pool = 0, pool_end = 0;       // this warp's current run of rays (warp-uniform)
     bool drained = false;                  // the global cursor has run out (warp-uniform)
-    unsigned n_nodes = 0;
+    unsigned n_nodes = 0;                  // warp-uniform: lane-steps, counted with one POPC per step
 
     for (;;) {
         // ---- hand new rays to idle lanes
-        unsigned idle = __ballot_sync(FULL, node < 0);
+        const unsigned idle = __ballot_sync(FULL, node < 0);
         if (idle) {
             if (pool >= pool_end && !drained) {
-                unsigned long long start = 0;
-                if (lane == 0) start = atomicAdd(&ctr->ray_cursor, 32ull);
+                unsigned start = 0;
+                if (lane == 0) start = (unsigned)atomicAdd(&ctr->ray_cursor, 32ull);
                 start = __shfl_sync(FULL, start, 0);
-                pool = ray_base + start;
-                pool_end = pool + 32 < ray_end ? pool + 32 : ray_end;
-                if (pool >= ray_end) { drained = true; pool = pool_end = ray_end; }
+                pool = start < n_rays ? start : n_rays;
+                pool_end = pool + 32 < n_rays ? pool + 32 : n_rays;
+                drained = pool >= n_rays;
             }
             if (pool < pool_end) {
-                const unsigned rank = __popc(idle & lt_mask);
-                if (node < 0 && pool + rank < pool_end) {
-                    my_ray = (uint32_t)(pool + rank);
-                    const float4 *rp = reinterpret_cast<const float4 *>(rays + my_ray);
+                const unsigned mine = pool + __popc(idle & lt_mask);
+                if (node < 0 && mine < pool_end) {
+                    my_ray = mine;
+                    const float4 *rp = reinterpret_cast<const float4 *>(rays + mine);
                     const float4 q0 = __ldg(rp + 0), q3 = __ldg(rp + 3);
                     c = f4_xyz(q0); inv = f4_xyz(q3);
                     sp = 0;
                     node = (__float_as_uint(q3.w) & RAY_VALID) ? 0 : -1;
                 }
-                const uint64_t taken = __popc(idle);
-                pool = pool + taken < pool_end ? pool + taken : pool_end;
-            } else if (idle == FULL && drained) {
-                break;
+                pool = min(pool + __popc(idle), pool_end);
+            } else if (idle == FULL) {
+                break;                      // nothing in flight, nothing left to claim
             }
         }
         // ---- one traversal step
-        int leaf_a = -1, leaf_b = -1;
         float4 n0, n1, n2, n3;
         warp_gather64(reinterpret_cast<const float4 *>(nodes), node, stage, n0, n1, n2, n3);
+        n_nodes += __popc(__ballot_sync(FULL, node >= 0));
+        int leaf_a = -1, leaf_b = -1;
         if (node >= 0) {
-            ++n_nodes;
             const int2 link = make_int2(__float_as_int(n3.x), __float_as_int(n3.y));
             float ta, tb;
             bool hit_a = slab(c, inv, horizon, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ta);
@@ -367,10 +364,10 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         const unsigned ma = __ballot_sync(FULL, leaf_a >= 0);
         const unsigned mb = __ballot_sync(FULL, leaf_b >= 0);
         if (ma | mb) {
-            if (leaf_a >= 0) q[count + __popc(ma & lt_mask)] = make_uint2(my_ray, (uint32_t)leaf_a);
-            count += __popc(ma);
-            if (leaf_b >= 0) q[count + __popc(mb & lt_mask)] = make_uint2(my_ray, (uint32_t)leaf_b);
-            count += __popc(mb);
+            const unsigned na = __popc(ma);
+            if (leaf_a >= 0) q[count + __popc(ma & lt_mask)] = make_uint2(ray0 + my_ray, (uint32_t)leaf_a);
+            if (leaf_b >= 0) q[count + na + __popc(mb & lt_mask)] = make_uint2(ray0 + my_ray, (uint32_t)leaf_b);
+            count += na + __popc(mb);
             __syncwarp();
             while (count >= 32) {
                 count -= 32;
@@ -388,7 +385,6 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         base = __shfl_sync(FULL, base, 0);
         if (lane < count && base + lane < pair_cap) pairs_out[base + lane] = q[lane];
     }
-    for (int o = 16; o > 0; o >>= 1) n_nodes += __shfl_xor_sync(FULL, n_nodes, o);
     if (lane == 0) atomicAdd(&ctr->node_visits, (unsigned long long)n_nodes);
 }
 
