@@ -193,7 +193,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
         for a, b in ev:
-            flush.fill_(1)                     # L2 flush, outside the event pair
+            if not os.environ.get("XP_BENCH_NO_FLUSH"):       # experiment knob; reported numbers always flush
+                flush.fill_(1)                 # L2 flush, outside the event pair
             a.record(stream)
             fn()
             b.record(stream)

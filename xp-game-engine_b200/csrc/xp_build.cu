@@ -590,14 +590,30 @@ cudaError_t build_lbvh(xp_scene *s) {
             ++s->stats.kernel_launches;
         }
     }
-    {   // quantised 4-wide collapse of the binary tree (XP_METHOD_Q4_PAIRS)
+    s->q4_built = s->wide_built = false;      // optional structures are (re)built on first use by build_aux()
+    XP_TRY(cudaGetLastError());
+    s->built = true;
+    return cudaSuccess;
+}
+
+// Structures only some methods walk (Node4 for Q4_PAIRS, the 32-wide planes for WIDE_*), built from the
+// binary tree on first use after a (re)build so that the per-frame rebuild of config 3 pays only for
+// what the active method needs.
+cudaError_t build_aux(xp_scene *s) {
+    if (s->n_tris == 0) return cudaSuccess;
+    const uint64_t n = s->n_tris;
+    cudaStream_t st = s->stream;
+    const bool need_q4 = s->method == XP_METHOD_Q4_PAIRS;
+    const bool need_wide = s->method == XP_METHOD_WIDE_FUSED || s->method == XP_METHOD_WIDE_PAIRS;
+    if (need_q4 && !s->q4_built) {
         StageTimer t(s, XP_STAGE_BUILD_TREE);
         const uint64_t ni = n > 1 ? n - 1 : 1;
         XP_TRY(s->nodes4.reserve(ni * sizeof(Node4)));
         k_collapse4<<<grid_for(ni, 256), 256, 0, st>>>(s->nodes.as<Node>(), (int)ni, s->nodes4.as<Node4>());
         ++s->stats.kernel_launches;
+        s->q4_built = true;
     }
-    {   // 32-wide implicit tree over the same Morton order
+    if (need_wide && !s->wide_built) {
         StageTimer t(s, XP_STAGE_BUILD_TREE);
         uint64_t cnt[WIDE_MAX_LEVELS + 1];
         int levels = 0;
@@ -625,10 +641,9 @@ cudaError_t build_lbvh(xp_scene *s) {
         }
         s->wide_tree.planes = s->wide.as<float>();
         s->wide_tree.top = levels - 1;
+        s->wide_built = true;
     }
-    XP_TRY(cudaGetLastError());
-    s->built = true;
-    return cudaSuccess;
+    return cudaGetLastError();
 }
 
 cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order) {

@@ -98,6 +98,7 @@ struct xp_scene {
     // geometry
     uint64_t n_tris = 0;
     bool built = false;
+    bool q4_built = false, wide_built = false;   // optional structures, see build_aux()
     xp::DevBuf tris_aos;      // xp_triangle[T], upload order
     xp::DevBuf recs;          // TriRec[T], Morton order
     xp::DevBuf nodes;         // Node[max(T-1,1)]

@@ -374,7 +374,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&ctr->pairs, 32ull);
                 base = __shfl_sync(FULL, base, 0);
-                if (base + lane < pair_cap) pairs_out[base + lane] = q[count + lane];
+                if (base + lane < pair_cap) __stcs(&pairs_out[base + lane], q[count + lane]);   // streaming: keep the tree in L2
                 __syncwarp();
             }
         }
@@ -383,7 +383,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)count);
         base = __shfl_sync(FULL, base, 0);
-        if (lane < count && base + lane < pair_cap) pairs_out[base + lane] = q[lane];
+        if (lane < count && base + lane < pair_cap) __stcs(&pairs_out[base + lane], q[lane]);
     }
     if (lane == 0) atomicAdd(&ctr->node_visits, (unsigned long long)n_nodes);
 }
@@ -494,7 +494,7 @@ k_broadphase4(const Node4 *__restrict__ nodes, const RayRec *__restrict__ rays, 
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&ctr->pairs, 32ull);
                 base = __shfl_sync(FULL, base, 0);
-                if (base + lane < pair_cap) pairs_out[base + lane] = q[count + lane];
+                if (base + lane < pair_cap) __stcs(&pairs_out[base + lane], q[count + lane]);   // streaming: keep the tree in L2
                 __syncwarp();
             }
         }
@@ -503,7 +503,7 @@ k_broadphase4(const Node4 *__restrict__ nodes, const RayRec *__restrict__ rays, 
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)count);
         base = __shfl_sync(FULL, base, 0);
-        if (lane < count && base + lane < pair_cap) pairs_out[base + lane] = q[lane];
+        if (lane < count && base + lane < pair_cap) __stcs(&pairs_out[base + lane], q[lane]);
     }
     for (int o = 16; o > 0; o >>= 1) n_nodes += __shfl_xor_sync(FULL, n_nodes, o);
     if (lane == 0) atomicAdd(&ctr->node_visits, (unsigned long long)n_nodes);
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(256) k_narrow_pairs(const TriRec *__restrict__
     unsigned kept = 0;
     for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n;
          p += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint2 pr = __ldg(&pairs[p]);
+        const uint2 pr = __ldcs(&pairs[p]);              // read once: streaming
         const float4 *rp = reinterpret_cast<const float4 *>(rays + pr.x);
         const float4 *tp = reinterpret_cast<const float4 *>(recs + pr.y);
         const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
@@ -903,6 +903,7 @@ static cudaError_t ray_setup_t(xp_scene *s, const xp_response *cur, const uint32
 template <class O>
 static cudaError_t closest_t(xp_scene *s, uint64_t na) {
     if (na == 0 || s->n_tris == 0) return cudaSuccess;
+    XP_TRY(build_aux(s));
     cudaStream_t st = s->stream;
     const Node *nodes = s->nodes.as<Node>();
     const TriRec *recs = s->recs.as<TriRec>();
@@ -1134,6 +1135,7 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
     XP_TRY(s->rays.reserve(n * sizeof(RayRec)));
     XP_TRY(s->best.reserve(n * 8));
     XP_TRY(ray_setup(s, d_in, nullptr, n, horizon_of(horizon_mode), nullptr));
+    XP_TRY(build_aux(s));
     const uint64_t buf_cap = s->max_pairs;
     XP_TRY(s->pairs.reserve(buf_cap * sizeof(uint2)));
     uint2 *pairs = s->pairs.as<uint2>();
