@@ -270,6 +270,31 @@ def test_quirk_inputs(oracle):
     assert_bits_equal(resp_fields(out), resp_fields(w[0]), "quirk response")
 
 
+def test_non_finite_and_extreme_spheres(oracle):
+    """NaN / infinite / astronomically large / vanishing sphere inputs: same answers as the oracle's brute
+    force (the triangle soup itself must be finite -- that is the upload contract)."""
+    rng = np.random.default_rng(11)
+    tris, h = scenes.sine_terrain(14, 14, seed=12)
+    resps = scenes.terrain_spheres(h, 900, seed=13)
+    c, m = resps["c"], resps["movement"]
+    for k, bad in enumerate([np.nan, np.inf, -np.inf]):
+        c[k::30, rng.integers(0, 3)] = bad
+        m[k + 3::30, rng.integers(0, 3)] = bad
+    m[7::30] *= np.float32(1e-25)                         # |m|^2 underflows
+    m[8::30] *= np.float32(1e25)                          # b, det overflow
+    c[9::30] *= np.float32(1e20)
+    m[10::30] = 0.0
+    want = oracle.detect_batch(resps, tris)
+    w = oracle.collision_response_batch(resps, tris, max_iter=3)
+    for method, prune in METHODS:
+        with xp.Scene(0, tris, method=method, prune=prune) as s:
+            got = s.detect_batch(resps)
+            out, it, st, ln = s.collision_response_batch(resps, max_iter=3)
+        check_detect_exact(got, want, f"non-finite {method} {prune}", tri_index=not prune)
+        assert np.array_equal(it, w[1]) and np.array_equal(st, w[2]), method
+        assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"non-finite response {method}")
+
+
 def test_large_coordinates(oracle):
     tris, h = scenes.sine_terrain(16, 16, seed=8)
     tris = tris + np.float32([4000, 0, 3000])

@@ -24,7 +24,7 @@ def _emul_detect(E, resp, tri):
 def _cases(seed, n):
     rng = np.random.default_rng(seed)
     for _ in range(n):
-        kind = rng.integers(0, 6)
+        kind = rng.integers(0, 11)
         tri = rng.uniform(-3, 3, (3, 3)).astype(np.float32)
         c = rng.uniform(-4, 4, 3).astype(np.float32)
         m = rng.uniform(-1, 1, 3).astype(np.float32)
@@ -42,6 +42,30 @@ def _cases(seed, n):
             tri[2] = tri[1]
         elif kind == 5:    # already touching / embedded (|sd| < 1)
             c = (tri.mean(axis=0) + rng.uniform(-0.8, 0.8, 3)).astype(np.float32)
+        elif kind == 6:    # zero movement: a == 0, roots are +-inf / NaN (quirk B11)
+            m[:] = 0.0
+            c = (tri.mean(axis=0) + rng.uniform(-1.5, 1.5, 3)).astype(np.float32)
+        elif kind == 7:    # astronomically large values: b, det overflow to inf
+            scale = np.float32(10.0 ** rng.integers(15, 25))
+            tri = (tri * scale).astype(np.float32)
+            c = (c * scale).astype(np.float32)
+            m = (m * np.float32(10.0 ** rng.integers(0, 20))).astype(np.float32)
+        elif kind == 8:    # NaN / inf in the inputs
+            which = rng.integers(0, 3)
+            bad = np.float32([np.nan, np.inf, -np.inf][rng.integers(0, 3)])
+            if which == 0:
+                tri[rng.integers(0, 3), rng.integers(0, 3)] = bad
+            elif which == 1:
+                c[rng.integers(0, 3)] = bad
+            else:
+                m[rng.integers(0, 3)] = bad
+        elif kind == 9:    # vanishing movement: |m|^2 underflows (denormal / zero denominators)
+            m = (m * np.float32(10.0 ** -rng.integers(18, 30))).astype(np.float32)
+            c = (tri.mean(axis=0) + rng.uniform(-1.5, 1.5, 3)).astype(np.float32)
+        elif kind == 10:   # movement along an edge: a of the edge quadratic rounds to ~0 of either sign
+            k = rng.integers(0, 3)
+            m = ((tri[(k + 1) % 3] - tri[k]) * np.float32(rng.uniform(0.05, 0.5))).astype(np.float32)
+            c = (tri[k] + rng.uniform(-1.2, 1.2, 3)).astype(np.float32)
         yield c, m, np.ascontiguousarray(tri)
 
 

@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256) k_morton_spheres(const xp_response *__res
         const unsigned oct = (__ldg(p + 4) < 0.0f ? 4u : 0u) | (__ldg(p + 5) < 0.0f ? 2u : 0u) | (__ldg(p + 6) < 0.0f ? 1u : 0u);
         key = (oct << 21) | (code >> 9);
     }
+    if (mode == 2) key = code >> 14;        // 16 bits (two radix passes): 5-6 bits per axis
     keys[i] = key;
     vals[i] = (uint32_t)i;
 }
@@ -656,7 +657,7 @@ cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n
     k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va, key_mode);
     ++s->stats.kernel_launches;
     bool in_a = true;
-    XP_TRY(radix_sort_pairs(s, ka, kb, va, vb, n, 24, &in_a));
+    XP_TRY(radix_sort_pairs(s, ka, kb, va, vb, n, key_mode == 2 ? 16 : 24, &in_a));
     if (!in_a) { xp::DevBuf tmp = s->active_a; s->active_a = s->active_b; s->active_b = tmp; }
     *order = s->active_a.as<uint32_t>();
     return cudaGetLastError();
