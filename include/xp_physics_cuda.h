@@ -14,7 +14,11 @@
  *     return after the results are back in the caller's buffers;
  *   - one xp_scene per device; calls on one scene are serialised by the caller (the reference
  *     is single-threaded); different scenes are independent;
- *   - there is no CPU fallback: without a usable CUDA device every call fails with XP_ECUDA.
+ *   - there is no CPU fallback: without a usable CUDA device every call fails with XP_ECUDA;
+ *   - inputs: triangle vertices must be finite; sphere centres / movements may be anything except
+ *     +-infinity, and a non-zero movement must be long enough that |m|^2 does not underflow to zero
+ *     (|m| > ~1e-19); NaN, exactly zero and huge finite values behave exactly like the reference.
+ *     (For the two excluded inputs the reference reports "hits" at t = +inf; this library reports none.)
  *
  * All arithmetic is IEEE binary32.  XP_ARITH_EXACT (default) evaluates the reference's
  * operations in the reference's order without fused multiply-add and is bit-identical to
