@@ -19,7 +19,7 @@ from xp_physics_cuda import scenes
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-METHODS = [("q4_pairs", False), ("wide_fused", False), ("wide_fused", True), ("wide_pairs", False), ("lbvh_fused", False),
+METHODS = [("lbvh_pairs", True), ("q4_pairs", False), ("wide_fused", False), ("wide_fused", True), ("wide_pairs", False), ("lbvh_fused", False),
            ("lbvh_fused", True), ("lbvh_pairs", False), ("brute", False)]
 
 
@@ -420,6 +420,9 @@ def test_full_size_properties(full_scene, oracle):
         s.set_options(method="lbvh_fused", prune=True)
         c = s.detect_batch(resps)                                   # pruning must not change any contact
         tests_pruned = s.stats()["narrowphase_tests"]
+        s.set_options(method="lbvh_pairs", prune=True)             # distance-window passes of the two-stage sweep
+        c2 = s.detect_batch(resps)
+        tests_windowed = s.stats()["narrowphase_tests"]
         s.set_options(method="lbvh_pairs", prune=False, sort_spheres=False)
         d = s.detect_batch(resps)                                   # processing order must not matter
         u = s.detect_batch(resps, horizon="unit")
@@ -429,6 +432,8 @@ def test_full_size_properties(full_scene, oracle):
     for other, name in ((b, "rerun"), (d, "unsorted")):
         check_detect_exact(other, a, name)
     check_detect_exact(c, a, "pruned", tri_index=False)
+    check_detect_exact(c2, a, "windowed", tri_index=False)
+    assert tests_windowed < tests_all
     check_detect_exact(e, tuple(x[perm] for x in a), "permuted")
     col, hit, tri, st = a
     assert hit.mean() > 0.5

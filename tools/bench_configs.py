@@ -34,6 +34,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,3,4,5")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink sphere / triangle counts (smoke runs)")
+    ap.add_argument("--method", default="lbvh_pairs")
+    ap.add_argument("--prune", type=int, default=0)
     args = ap.parse_args()
     import torch
 
@@ -71,7 +73,7 @@ def main():
         d_tris = torch.from_numpy(tris.reshape(-1, 9)).to(dev)
         d_in = dev_resps(resps)
         contacts = torch.empty((S, 10), dtype=torch.float32, device=dev)
-        s = xp.Scene(0, timing=True)
+        s = xp.Scene(0, timing=True, method=args.method, prune=bool(args.prune))
         s.set_stream(stream.cuda_stream)
         shift = torch.tensor([0.01, 0.0, 0.01] * 3, device=dev)
         build_ms, sweep_ms, tests = [], [], []
@@ -85,7 +87,8 @@ def main():
             st = s.stats()
             sweep_ms.append(sum(st["stage_ms"].values())); tests.append(st["narrowphase_tests"])
         ms = ev_time(torch, frame, 5)
-        print(json.dumps({"config": 3, "what": f"{S} spheres x {len(tris)}-triangle cube+icosphere field, LBVH rebuild per frame",
+        print(json.dumps({"config": 3, "method": args.method, "prune": args.prune,
+                          "what": f"{S} spheres x {len(tris)}-triangle cube+icosphere field, LBVH rebuild per frame",
                           "ms_per_frame": ms, "build_ms": float(np.mean(build_ms[2:])), "sweep_ms": float(np.mean(sweep_ms[2:])),
                           "tests_per_frame": float(np.mean(tests[2:])), "tests_per_sec": float(np.mean(tests[2:])) / (ms * 1e-3),
                           "spheres_per_sec": S / (ms * 1e-3), "build_triangles_per_sec": len(tris) / (np.mean(build_ms[2:]) * 1e-3),
