@@ -301,13 +301,9 @@ def run_b200(args):
                                            d_iter=d_it.data_ptr(), d_status=d_st.data_ptr())
 
     r_steps = max(3, args.steps // 4)
-    # the loop only needs each sphere's CLOSEST collision, so it runs the pruned (distance-window) sweep:
-    # identical contacts (tests/test_gpu_parity.py), fewer narrowphase tests
-    scene.set_options(method="lbvh_pairs", prune=True)
     r_ms, r_stats = timed(step_response, r_steps, 3)
-    scene.set_options(method=args.method, prune=bool(args.prune))
     resolved = {"metric": "spheres_resolved_per_sec", "value": world * n * r_steps / (r_ms * 1e-3), "unit": "spheres/s",
-                "max_iter": 4, "ms_per_step": r_ms / r_steps, "steps": r_steps, "method": "lbvh_pairs, prune=1",
+                "max_iter": 4, "ms_per_step": r_ms / r_steps, "steps": r_steps,
                 "mean_iterations": float(d_it.float().mean().item()),
                 "iter_cap_fraction": float(((d_st & 4) != 0).float().mean().item()),
                 "tests_per_step": float(np.mean([s["narrowphase_tests"] for s in r_stats])),

@@ -104,7 +104,7 @@ def main():
         d_out = torch.empty_like(d_in)
         d_it = torch.empty(S, dtype=torch.int32, device=dev)
         d_st = torch.empty(S, dtype=torch.int32, device=dev)
-        s = xp.Scene(0, tris, timing=True)
+        s = xp.Scene(0, tris, timing=True, method=args.method, prune=bool(args.prune))
         s.set_stream(stream.cuda_stream)
         tests = []
 

@@ -121,7 +121,9 @@ int xp_scene_set_option(xp_scene *s, int option, int64_t value) {
     case XP_OPT_MAX_PAIRS:
         if (value < 4096) return XP_EINVAL;
         s->max_pairs = (uint64_t)value; return XP_OK;
-    case XP_OPT_PRUNE: s->prune = value ? 1 : 0; return XP_OK;
+    case XP_OPT_PRUNE:
+        if (value < 0 || value > 2) return XP_EINVAL;
+        s->prune = (int)value; s->cand_per_ray = 0.0; return XP_OK;
     default: return XP_EINVAL;
     }
 }

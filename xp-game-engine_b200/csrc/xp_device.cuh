@@ -95,6 +95,8 @@ struct xp_scene {
     bool safe_pairs = false;           // two-stage methods: read the pair count back after every chunk
     bool pair_overflowed = false;      // optimistic mode dropped candidates: results must be recomputed
     bool counters_live = false;        // device counters hold uncollected statistics
+    uint64_t swept_rays = 0;           // rays swept since the counters were zeroed
+    double cand_per_ray = 0.0;         // candidates per sphere of the last exhaustive sweep (XP_OPT_PRUNE = 2)
     // geometry
     uint64_t n_tris = 0;
     bool built = false;

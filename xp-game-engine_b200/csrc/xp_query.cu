@@ -924,6 +924,7 @@ static unsigned bp_grid(uint64_t n_rays) {
 static float horizon_of(uint32_t mode) { return mode == XP_HORIZON_UNIT ? 1.0f : 3.402823466e+38f; }
 
 static cudaError_t zero_counters(xp_scene *s) {
+    s->swept_rays = 0;
     XP_TRY(s->counters.reserve(sizeof(DeviceCounters)));
     return cudaMemsetAsync(s->counters.p, 0, sizeof(DeviceCounters), s->stream);
 }
@@ -994,7 +995,7 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
     // on the volumetric config-3 scene).  No read-back between passes: a pass over finished spheres only
     // costs their ray fetch.
     static const float kWin[] = {0.0f, 4.0f, 16.0f, 64.0f, 256.0f, 1024.0f, INFINITY};
-    const bool windows = s->prune && s->method == XP_METHOD_LBVH_PAIRS;
+    const bool windows = s->method == XP_METHOD_LBVH_PAIRS && (s->prune == 1 || (s->prune == 2 && s->cand_per_ray > 96.0));
     const int n_pass = windows ? 6 : 1;
     uint64_t pos = 0;
     unsigned long long snap_tests = 0, snap_pairs = 0;   // synchronous mode: accounting before the current chunk
@@ -1070,6 +1071,9 @@ static cudaError_t collect_counters(xp_scene *s) {
     s->stats.broadphase_pairs += h.pairs_total;
     s->stats.node_visits += h.node_visits;
     if (h.pair_overflow) s->pair_overflowed = true;
+    // XP_OPT_PRUNE = 2 (auto): remember how many candidates a sphere had in the exhaustive sweep
+    if (s->swept_rays && h.pairs_total && !(s->prune == 2 && s->cand_per_ray > 96.0))
+        s->cand_per_ray = (double)h.pairs_total / (double)s->swept_rays;
     for (int i = 0; i < 5; ++i) s->stats.path_tests[i] += h.path[i];
     resolve_stage_timers(s);
     if (h.stack_overflow) return cudaErrorAssert;
@@ -1095,6 +1099,7 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
         if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, in, m, &order));
         XP_TRY(ray_setup(s, in, order, m, horizon_of(horizon_mode), status));
         XP_TRY(closest(s, m));
+        s->swept_rays += m;
         {
             StageTimer t(s, XP_STAGE_FINALIZE);
             const RayRec *rays = s->rays.as<RayRec>();
@@ -1155,6 +1160,7 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
             }
             XP_TRY(ray_setup(s, cur, active, na, horizon, status));
             XP_TRY(closest(s, na));
+            s->swept_rays += na;
             XP_TRY(cudaMemsetAsync(&ctr->next_active, 0, sizeof(unsigned), st));
             {
                 StageTimer t(s, XP_STAGE_RESPONSE);

@@ -141,7 +141,7 @@ class Scene:
         if method is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_METHOD, _lib.METHODS[method]))
         if prune is not None:
-            check(L.xp_scene_set_option(h, _lib.OPT_PRUNE, int(bool(prune))))
+            check(L.xp_scene_set_option(h, _lib.OPT_PRUNE, {False: 0, True: 1, "auto": 2}.get(prune, prune)))
         if sort_spheres is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_SORT_SPHERES, int(bool(sort_spheres))))
         if timing is not None:
