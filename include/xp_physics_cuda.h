@@ -131,6 +131,13 @@ int  xp_scene_set_triangles_dev(xp_scene *s, const xp_triangle *d_aos, uint64_t 
 /* The `&[Vec3]` argument of collision_response_non_trianulated (lib.rs:17-25): every three
  * consecutive Vec3 form one triangle; n_vec3 % 3 != 0 -> XP_EINVAL (the reference panics). */
 int  xp_scene_set_positions(xp_scene *s, const xp_vec3 *soup, uint64_t n_vec3);
+/* Row f2: heightmap terrain emitted as triangles ON THE DEVICE.  heights is a host
+ * array of (nx+1) x (nz+1) floats, x-major (heights[ix*(nz+1)+iz]); quad (ix,iz) yields the triangles
+ * (p00,p01,p11), (p00,p11,p10) with p_ab = (x0+spacing*(ix+a), h, z0+spacing*(iz+b)), x outer / z inner --
+ * the order of low_poly_nice_graphics/src/world/heightmap_loader.rs:19-63.  Equivalent to
+ * xp_scene_set_triangles on that soup, with 4 B per vertex uploaded instead of 36 B per triangle. */
+int  xp_scene_set_heightmap(xp_scene *s, const float *heights, uint32_t nx, uint32_t nz, float x0, float z0,
+                            float spacing);
 /* (Re)build the device LBVH: per-triangle normal / plane constant / inflated AABB, 30-bit
  * Morton codes, radix sort, Karras hierarchy, bottom-up refit.  New: the reference has no
  * broadphase (lib.rs:33-35 walks every triangle). */

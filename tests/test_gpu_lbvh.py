@@ -86,3 +86,24 @@ def test_tree_large_sort(oracle):
     assert (np.diff(morton.astype(np.int64)) >= 0).all()
     same = morton[1:] == morton[:-1]
     assert (sorted_tri[1:][same] > sorted_tri[:-1][same]).all()
+
+
+def test_device_heightmap_emission_equals_host_soup(oracle):
+    """xp_scene_set_heightmap (row f2) builds exactly the scene xp_scene_set_triangles builds from the
+    host-generated soup: same Morton order, same tree, same contacts."""
+    h = scenes.sine_terrain_heights(37, 23, seed=9)
+    tris = scenes.heightmap_from_heights(h, x0=-5.5, z0=2.25, spacing=0.75)
+    resps = scenes.terrain_spheres(h, 500, seed=4)
+    resps["c"][:, 0] = resps["c"][:, 0] * 0.75 - 5.5
+    resps["c"][:, 2] = resps["c"][:, 2] * 0.75 + 2.25
+    with xp.Scene(0, tris) as a, xp.Scene(0) as b:
+        b.set_heightmap(h, x0=-5.5, z0=2.25, spacing=0.75)
+        b.build()
+        assert b.triangle_count == len(tris)
+        ta, tb = a.debug_tree(), b.debug_tree()
+        for x, y in zip(ta, tb):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+        ra, rb = a.detect_batch(resps), b.detect_batch(resps)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+        assert ra[1].sum() > 100

@@ -163,6 +163,23 @@ int xp_scene_set_triangles_dev(xp_scene *s, const xp_triangle *d_aos, uint64_t n
     return XP_OK;
 }
 
+int xp_scene_set_heightmap(xp_scene *s, const float *heights, uint32_t nx, uint32_t nz, float x0, float z0,
+                           float spacing) {
+    if (!s || !heights || nx == 0 || nz == 0) return XP_EINVAL;
+    const uint64_t n = 2ull * nx * nz;
+    if (n >= (1ull << 27)) return XP_EINVAL;
+    XP_BIND(s);
+    s->built = false;
+    s->n_tris = 0;
+    const uint64_t hbytes = ((uint64_t)nx + 1) * ((uint64_t)nz + 1) * sizeof(float);
+    XP_API_TRY(s->io_in.reserve(hbytes));
+    XP_API_TRY(cudaMemcpyAsync(s->io_in.p, heights, hbytes, cudaMemcpyHostToDevice, s->stream));
+    XP_API_TRY(emit_heightmap(s, s->io_in.as<float>(), nx, nz, x0, z0, spacing));
+    XP_API_TRY(cudaStreamSynchronize(s->stream));
+    s->n_tris = n;
+    return XP_OK;
+}
+
 int xp_scene_set_positions(xp_scene *s, const xp_vec3 *soup, uint64_t n_vec3) {
     if (n_vec3 % 3 != 0) return XP_EINVAL;     // lib.rs:19-24: chunks(3) then vs[2] panics
     // Vec3 triples are exactly the Triangle layout (lib.rs:20-24), so this is one upload

@@ -517,7 +517,37 @@ __global__ void k_single_root(Node *nodes, const float4 *leaf_lo, const float4 *
     node_lo[0] = lo; node_hi[0] = hi;
 }
 
+// Row f2 of SURVEY.md section 8: heightmap terrain -> triangle soup ON THE DEVICE.  Emits, for every quad
+// (ix, iz) of an (nx+1) x (nz+1) height grid, the two triangles (p00,p01,p11) and (p00,p11,p10) with
+// p_ab = (x0 + spacing*(ix+a), h[ix+a][iz+b], z0 + spacing*(iz+b)) -- x outer, z inner: the vertex order of
+// low_poly_nice_graphics/src/world/heightmap_loader.rs:19-63 and of the clipmap vertex shader
+// (game/src/shaders/shader_clipmap.vert:43-65).  4 B per vertex cross PCIe instead of 36 B per triangle.
+__global__ void __launch_bounds__(256) k_emit_heightmap(const float *__restrict__ h, unsigned nx, unsigned nz,
+                                                        float x0, float z0, float spacing, float *__restrict__ tris) {
+    const uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (q >= (uint64_t)nx * nz) return;
+    const unsigned ix = (unsigned)(q / nz), iz = (unsigned)(q % nz);
+    const float xa = __fadd_rn(x0, __fmul_rn(spacing, (float)ix)), xb = __fadd_rn(x0, __fmul_rn(spacing, (float)(ix + 1)));
+    const float za = __fadd_rn(z0, __fmul_rn(spacing, (float)iz)), zb = __fadd_rn(z0, __fmul_rn(spacing, (float)(iz + 1)));
+    const uint64_t row = (uint64_t)nz + 1;
+    const float h00 = __ldg(h + ix * row + iz), h01 = __ldg(h + ix * row + iz + 1);
+    const float h10 = __ldg(h + (ix + 1) * row + iz), h11 = __ldg(h + (ix + 1) * row + iz + 1);
+    float *o = tris + q * 18;
+    o[0] = xa; o[1] = h00; o[2] = za;   o[3] = xa; o[4] = h01; o[5] = zb;   o[6] = xb; o[7] = h11; o[8] = zb;
+    o[9] = xa; o[10] = h00; o[11] = za; o[12] = xb; o[13] = h11; o[14] = zb; o[15] = xb; o[16] = h10; o[17] = za;
+}
+
 #define XP_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
+
+cudaError_t emit_heightmap(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz, float x0, float z0,
+                           float spacing) {
+    const uint64_t quads = (uint64_t)nx * nz;
+    XP_TRY(s->tris_aos.reserve(quads * 2 * sizeof(xp_triangle)));
+    k_emit_heightmap<<<grid_for(quads, 256), 256, 0, s->stream>>>(d_heights, nx, nz, x0, z0, spacing,
+                                                                  s->tris_aos.as<float>());
+    ++s->stats.kernel_launches;
+    return cudaGetLastError();
+}
 
 cudaError_t build_lbvh(xp_scene *s) {
     const uint64_t n = s->n_tris;

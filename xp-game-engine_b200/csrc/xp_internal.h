@@ -23,6 +23,7 @@ inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + bl
 cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb,
                              uint64_t n, int bits, bool *in_a);
 cudaError_t build_lbvh(xp_scene *s);
+cudaError_t emit_heightmap(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz, float x0, float z0, float spacing);
 cudaError_t build_aux(xp_scene *s);      // Node4 / 32-wide planes, on first use by the method that needs them
 // order[k] = index of the k-th sphere in Morton order of its centre (scene bounds).
 cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order);

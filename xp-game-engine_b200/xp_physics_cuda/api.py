@@ -169,6 +169,13 @@ class Scene:
                              "(xp_physics/src/lib.rs:19-24)")
         check(rc, "xp_scene_set_positions")
 
+    def set_heightmap(self, heights, x0: float = 0.0, z0: float = 0.0, spacing: float = 1.0):
+        """heights[(nx+1),(nz+1)] -> 2*nx*nz triangles emitted on the device (same soup and order as
+        scenes.heightmap_from_heights)."""
+        h = np.ascontiguousarray(heights, np.float32)
+        check(self._L.xp_scene_set_heightmap(self._h, _p(h), h.shape[0] - 1, h.shape[1] - 1, x0, z0, spacing),
+              "xp_scene_set_heightmap")
+
     def build(self):
         check(self._L.xp_scene_build(self._h), "xp_scene_build")
 
