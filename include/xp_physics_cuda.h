@@ -201,6 +201,20 @@ typedef struct { xp_collision col; uint32_t tri_index; uint32_t flags; } xp_cont
 int  xp_detect_contacts_dev(xp_scene *s, const xp_response *d_in, uint64_t n,
                             uint32_t horizon_mode, xp_contact *d_out);
 
+/* ---- fused contact build + all-gather over NVLink peer memory (one process per GPU) ----
+ * Each rank allocates its gather buffer with xp_exchange_alloc, the 64-byte IPC handles are exchanged by
+ * the host (any transport), every rank maps its peers' buffers with xp_exchange_open, and
+ * xp_detect_contacts_exchange_dev then writes each sphere's 40 B contact record into ALL buffers (its own
+ * included, bufs[] holds n_bufs device pointers) at record index slot_first + i -- the kernel that builds
+ * the records performs the all-gather with P2P stores.  slot_first must be even (8-byte aligned spans).
+ * The caller synchronises the ranks (a barrier) before reading the buffers. */
+int  xp_exchange_alloc(xp_scene *s, uint64_t bytes, void **dev_ptr, uint8_t ipc_handle[64]);
+int  xp_exchange_free(xp_scene *s, void *dev_ptr);
+int  xp_exchange_open(xp_scene *s, const uint8_t ipc_handle[64], void **peer_ptr);
+int  xp_exchange_close(xp_scene *s, void *peer_ptr);
+int  xp_detect_contacts_exchange_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                                     void *const *bufs, int n_bufs, uint64_t slot_first);
+
 /* ---- measurement helpers ---- */
 /* Dependent-free FFMA loop on every SM: the fp32 CUDA-core peak used as roofline denominator. */
 int  xp_probe_fp32_peak(int device, double *tflops);

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, out_dir):
+def _worker(rank, world, port, n, out_dir, exchange="auto"):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "xp-game-engine_b200")]
     import torch
     import torch.distributed as dist
@@ -31,21 +31,27 @@ def _worker(rank, world, port, n, out_dir):
                             device_id=torch.device("cuda", rank))
     tris, h = scenes.sine_terrain(40, 40, seed=15)
     resps = scenes.terrain_spheres(h, n, seed=16)
-    sw = ShardedSweep(tris, rank)
+    sw = ShardedSweep(tris, rank, exchange=exchange)
     full = sw.sweep(resps)
+    full2 = sw.sweep(resps)                      # buffers are reused across sweeps
     torch.cuda.synchronize()
+    assert torch.equal(full.view(torch.int32), full2.view(torch.int32))
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), full.cpu().numpy())
+    with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+        f.write(sw.last_exchange)
     sw.close()
     dist.destroy_process_group()
 
 
-def test_sharded_sweep_nccl(tmp_path, oracle):
+@pytest.mark.parametrize("exchange", ["nccl", "auto"])
+def test_sharded_sweep(tmp_path, oracle, exchange):
     import torch
     import torch.multiprocessing as mp
     from xp_physics_cuda import CONTACT_DTYPE, scenes
     world = min(torch.cuda.device_count(), 2)
     n = 5001
-    mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path), exchange), nprocs=world, join=True)
+    print("exchange used:", open(tmp_path / "rank0.txt").read())
     tris, h = scenes.sine_terrain(40, 40, seed=15)
     resps = scenes.terrain_spheres(h, n, seed=16)
     col, hit, tri, st, _ = oracle.detect_batch(resps, tris)

@@ -227,7 +227,7 @@ int xp_detect_batch_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32
     XP_BIND(s);
     reset_stats(s);
     if (n == 0) return XP_OK;
-    QueryOut q = {d_out, d_hit, d_tri_index, d_status, nullptr};
+    QueryOut q = {d_out, d_hit, d_tri_index, d_status, nullptr, {}, 0};
     XP_API_TRY(detect_retry(s, d_in, n, horizon_mode, q));
     return XP_OK;
 }
@@ -241,7 +241,7 @@ int xp_detect_contacts_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uin
     reset_stats(s);
     if (n == 0) return XP_OK;
     XP_API_TRY(s->io_status.reserve(n * 4));
-    QueryOut q = {nullptr, nullptr, nullptr, s->io_status.as<uint32_t>(), d_out};
+    QueryOut q = {nullptr, nullptr, nullptr, s->io_status.as<uint32_t>(), d_out, {}, 0};
     XP_API_TRY(detect_retry(s, d_in, n, horizon_mode, q));
     return XP_OK;
 }
@@ -258,6 +258,63 @@ static int ensure_io_streams(xp_scene *s) {
     XP_API_TRY(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
     for (int i = 0; i < 2 * IO_MAX_CHUNKS; ++i) XP_API_TRY(cudaEventCreateWithFlags(&s->io_ev[i], cudaEventDisableTiming));
     s->io_ready = true;
+    return XP_OK;
+}
+
+// ---- multi-GPU contact exchange over peer memory -------------------------------------------------
+int xp_exchange_alloc(xp_scene *s, uint64_t bytes, void **dev_ptr, uint8_t ipc_handle[64]) {
+    if (!s || !dev_ptr || !ipc_handle || bytes == 0) return XP_EINVAL;
+    XP_BIND(s);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    XP_API_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail_cuda(e); }
+    memcpy(ipc_handle, &h, 64);
+    *dev_ptr = p;
+    return XP_OK;
+}
+
+int xp_exchange_free(xp_scene *s, void *dev_ptr) {
+    if (!s) return XP_EINVAL;
+    XP_BIND(s);
+    if (dev_ptr) XP_API_TRY(cudaFree(dev_ptr));
+    return XP_OK;
+}
+
+int xp_exchange_open(xp_scene *s, const uint8_t ipc_handle[64], void **peer_ptr) {
+    if (!s || !ipc_handle || !peer_ptr) return XP_EINVAL;
+    XP_BIND(s);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    XP_API_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return XP_OK;
+}
+
+int xp_exchange_close(xp_scene *s, void *peer_ptr) {
+    if (!s) return XP_EINVAL;
+    XP_BIND(s);
+    if (peer_ptr) XP_API_TRY(cudaIpcCloseMemHandle(peer_ptr));
+    return XP_OK;
+}
+
+int xp_detect_contacts_exchange_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                                    void *const *bufs, int n_bufs, uint64_t slot_first) {
+    int rc = check_query(s, d_in, n);
+    if (rc) return rc;
+    if (!bufs || n_bufs <= 0 || n_bufs > XP_MAX_PEERS || (slot_first & 1)) return XP_EINVAL;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    XP_API_TRY(s->io_status.reserve(n * 4));
+    QueryOut q = {nullptr, nullptr, nullptr, s->io_status.as<uint32_t>(), nullptr, {}, slot_first};
+    q.peers.n = n_bufs;
+    for (int i = 0; i < n_bufs; ++i) {
+        if (!bufs[i]) return XP_EINVAL;
+        q.peers.p[i] = static_cast<xp_contact *>(bufs[i]);
+    }
+    XP_API_TRY(detect_retry(s, d_in, n, horizon_mode, q));
     return XP_OK;
 }
 
@@ -301,7 +358,7 @@ int xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t hor
         XP_API_TRY(cudaStreamWaitEvent(st, s->io_ev[c], 0));
         if (out) XP_API_TRY(cudaMemsetAsync(s->io_col.as<xp_collision>() + off, 0, m * sizeof(xp_collision), st));
         QueryOut q = {out ? s->io_col.as<xp_collision>() + off : nullptr, s->io_hit.as<uint8_t>() + off,
-                      tri_index ? s->io_tri.as<uint32_t>() + off : nullptr, s->io_status.as<uint32_t>() + off, nullptr};
+                      tri_index ? s->io_tri.as<uint32_t>() + off : nullptr, s->io_status.as<uint32_t>() + off, nullptr, {}, 0};
         XP_API_TRY(detect_dev(s, d_in + off, m, horizon_mode, q, /*collect=*/false));   // no host sync
         XP_API_TRY(cudaEventRecord(s->io_ev[IO_MAX_CHUNKS + c], st));
         XP_API_TRY(cudaStreamWaitEvent(s->copy_out, s->io_ev[IO_MAX_CHUNKS + c], 0));
@@ -319,7 +376,7 @@ int xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t hor
         s->safe_pairs = true;
         if (out) XP_API_TRY(cudaMemsetAsync(s->io_col.p, 0, n * sizeof(xp_collision), st));
         QueryOut q = {out ? s->io_col.as<xp_collision>() : nullptr, s->io_hit.as<uint8_t>(),
-                      tri_index ? s->io_tri.as<uint32_t>() : nullptr, s->io_status.as<uint32_t>(), nullptr};
+                      tri_index ? s->io_tri.as<uint32_t>() : nullptr, s->io_status.as<uint32_t>(), nullptr, {}, 0};
         cudaError_t e = detect_dev(s, d_in, n, horizon_mode, q);
         s->safe_pairs = false;
         s->pair_overflowed = false;

@@ -29,8 +29,13 @@ cudaError_t build_aux(xp_scene *s);      // Node4 / 32-wide planes, on first use
 cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order);
 
 // ---- xp_query.cu ----
+static constexpr int XP_MAX_PEERS = 16;
+struct PeerBufs { xp_contact *p[XP_MAX_PEERS]; int n; };
 struct QueryOut {            // device pointers, any may be null
     xp_collision *col; uint8_t *hit; uint32_t *tri_index; uint32_t *status; xp_contact *contact;
+    // fused contact exchange: when peers.n > 0 every contact record is written into each peer buffer at
+    // record index slot_first + i (the buffers are mapped peer memory, NVLink P2P stores)
+    PeerBufs peers; uint64_t slot_first;
 };
 // collect = false: leave the statistics on the device (no host synchronisation); the caller ends
 // the batch with collect_stats().  After collecting, s->pair_overflowed tells whether the

@@ -846,6 +846,55 @@ __global__ void __launch_bounds__(256) k_finalize_detect(const RayRec *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// fused contact build + all-gather over peer memory (multi-GPU)
+// ------------------------------------------------------------------------------------------
+// Instead of writing the contact records locally and handing them to an NCCL all-gather, the kernel
+// that BUILDS the records stores them straight into every rank's gather buffer (mapped peer memory:
+// NVLink P2P stores through NVSwitch).  A block builds 256 records in shared memory (thread i = sphere
+// i in input order, so the block's records are one contiguous 10 KB span) and then streams that span
+// to each peer with fully coalesced 8 B stores, so the transfer overlaps the record construction of
+// the other blocks.  The ranks only need a barrier afterwards.
+__global__ void k_invert_order(const uint32_t *__restrict__ order, uint64_t n, uint32_t *__restrict__ inv) {
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (k < n) inv[order[k]] = (uint32_t)k;
+}
+
+template <class O>
+__global__ void __launch_bounds__(256) k_finalize_exchange(const RayRec *__restrict__ rays,
+                                                           const unsigned long long *__restrict__ best,
+                                                           const uint32_t *__restrict__ inv_order, uint64_t n,
+                                                           const uint32_t *__restrict__ status, PeerBufs peers,
+                                                           uint64_t slot_first) {
+    __shared__ __align__(16) float rec[256 * 10];
+    const uint64_t i0 = blockIdx.x * 256ull;
+    const uint64_t i = i0 + threadIdx.x;
+    if (i < n) {
+        const uint64_t k = inv_order ? inv_order[i] : i;
+        const unsigned long long b = best[k];
+        const bool h = b != BEST_NONE;
+        Contact ct = {0.0f, 0.0f, {0, 0, 0}, {0, 0, 0}};
+        if (h) {
+            const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
+            ct = xp_make_collision<O>(ray_from(rp[0], rp[1], rp[2]), __uint_as_float((unsigned)(b >> 32)));
+        }
+        float *o = rec + threadIdx.x * 10;
+        o[0] = ct.time_to; o[1] = ct.distance_to;
+        o[2] = ct.position.x; o[3] = ct.position.y; o[4] = ct.position.z;
+        o[5] = ct.intersection.x; o[6] = ct.intersection.y; o[7] = ct.intersection.z;
+        o[8] = __uint_as_float(h ? ~(uint32_t)(b & 0xFFFFFFFFull) : 0xFFFFFFFFu);
+        o[9] = __uint_as_float((h ? 1u : 0u) | (((status ? status[i] : 0u) & 0xFFu) << 8));
+    }
+    __syncthreads();
+    const unsigned cnt = (unsigned)((n - i0 < 256) ? (n - i0) : 256);       // records of this block
+    const unsigned n8 = cnt * 5;                                            // 8-byte words
+    const float2 *src = reinterpret_cast<const float2 *>(rec);
+    for (int p = 0; p < peers.n; ++p) {
+        float2 *dst = reinterpret_cast<float2 *>(peers.p[p]) + (slot_first + i0) * 5;
+        for (unsigned w = threadIdx.x; w < n8; w += 256) dst[w] = src[w];
+    }
+}
+
 // lib.rs:43-60 for every active sphere: respond to the closest collision, then decide whether the
 // sphere iterates again.  cur[] holds the current Response of every sphere (in/out).
 template <class O>
@@ -1108,7 +1157,20 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
             uint8_t *hit = out.hit ? out.hit + off : nullptr;
             uint32_t *tri = out.tri_index ? out.tri_index + off : nullptr;
             xp_contact *ct = out.contact ? out.contact + off : nullptr;
-            if (s->arith == XP_ARITH_FAST)
+            if (out.peers.n > 0) {
+                const uint32_t *inv = nullptr;
+                if (order) {
+                    XP_TRY(s->sort_ka.reserve(m * 4));
+                    k_invert_order<<<grid_for(m, 256), 256, 0, s->stream>>>(order, m, s->sort_ka.as<uint32_t>());
+                    ++s->stats.kernel_launches;
+                    inv = s->sort_ka.as<uint32_t>();
+                }
+                if (s->arith == XP_ARITH_FAST)
+                    k_finalize_exchange<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, out.peers, out.slot_first + off);
+                else
+                    k_finalize_exchange<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, out.peers, out.slot_first + off);
+                ++s->stats.kernel_launches;
+            } else if (s->arith == XP_ARITH_FAST)
                 k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, order, m, col, hit, tri, status, ct);
             else
                 k_finalize_detect<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, order, m, col, hit, tri, status, ct);

@@ -255,6 +255,34 @@ class Scene:
         check(self._L.xp_detect_contacts_dev(self._h, vp(d_in), n, _horizon(horizon), vp(d_contacts)),
               "xp_detect_contacts_dev")
 
+    # -- fused contact exchange over peer memory (multi-GPU)
+    def exchange_alloc(self, nbytes: int):
+        """Allocate a gather buffer on this scene's GPU.  Returns (device pointer, 64-byte IPC handle)."""
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        check(self._L.xp_exchange_alloc(self._h, nbytes, C.byref(ptr), handle), "xp_exchange_alloc")
+        return int(ptr.value), bytes(handle)
+
+    def exchange_free(self, ptr: int):
+        check(self._L.xp_exchange_free(self._h, C.c_void_p(ptr)), "xp_exchange_free")
+
+    def exchange_open(self, handle: bytes) -> int:
+        """Map a peer rank's gather buffer (IPC handle from its exchange_alloc) into this process."""
+        ptr = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        check(self._L.xp_exchange_open(self._h, buf, C.byref(ptr)), "xp_exchange_open")
+        return int(ptr.value)
+
+    def exchange_close(self, ptr: int):
+        check(self._L.xp_exchange_close(self._h, C.c_void_p(ptr)), "xp_exchange_close")
+
+    def detect_contacts_exchange_dev(self, d_in: int, n: int, bufs, slot_first: int, horizon: str = "inf"):
+        """Sweep and write every contact record into each buffer of `bufs` (own + mapped peers) at record
+        index slot_first + i: the record-building kernel performs the all-gather with P2P stores."""
+        arr = (C.c_void_p * len(bufs))(*[C.c_void_p(b) for b in bufs])
+        check(self._L.xp_detect_contacts_exchange_dev(self._h, C.c_void_p(d_in), n, _horizon(horizon), arr, len(bufs),
+                                                      slot_first), "xp_detect_contacts_exchange_dev")
+
     def collision_response_batch_dev(self, d_in: int, n: int, d_out: int, max_iter: int = 0, d_iter: int = 0,
                                      d_status: int = 0, d_normal: int = 0, horizon: str = "inf"):
         vp = C.c_void_p

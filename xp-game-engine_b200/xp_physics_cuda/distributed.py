@@ -55,10 +55,24 @@ def contacts_as_records(t) -> np.ndarray:
     return np.ascontiguousarray(a).view(CONTACT_DTYPE).reshape(-1)
 
 
-class ShardedSweep:
-    """Rank-local half of the multi-GPU sweep (needs a CUDA device per rank)."""
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ wrapper so torch can view library-allocated device memory."""
 
-    def __init__(self, triangles, device: int, **scene_opts):
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class ShardedSweep:
+    """Rank-local half of the multi-GPU sweep (needs a CUDA device per rank).
+
+    exchange = "p2p":  every rank maps every other rank's gather buffer (CUDA IPC over NVLink) and the
+                       kernel that builds the contact records stores them into all buffers -- compute and
+                       all-gather are one kernel; the ranks only meet at a barrier.
+    exchange = "nccl": records are written to the local slot and all_gather_into_tensor moves them.
+    exchange = "auto": p2p when the peer mapping succeeds on all ranks, else nccl.
+    """
+
+    def __init__(self, triangles, device: int, exchange: str = "auto", **scene_opts):
         import torch
         self.torch = torch
         self.device = torch.device("cuda", device)
@@ -66,6 +80,55 @@ class ShardedSweep:
         self.scene.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.scene.set_triangles(triangles)          # replicated: every rank builds the same tree
         self.scene.build()
+        self.exchange = exchange
+        self._own = None           # (ptr, nbytes) of this rank's gather buffer
+        self._bufs = None          # device pointers of all ranks' buffers, in rank order
+        self._cap = 0
+
+    # -- peer-memory setup: one gather buffer per rank, mapped by everyone
+    def _setup_p2p(self, n_total: int, group=None) -> bool:
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        cap = shard_capacity(n_total, world)
+        cap += cap & 1                               # even slots: 8-byte aligned spans
+        if self._bufs is not None and self._cap == cap:
+            return True
+        self._teardown_p2p()
+        ok, handle, ptr = True, b"", 0
+        try:
+            ptr, handle = self.scene.exchange_alloc(world * cap * 4 * CONTACT_FLOATS)
+        except Exception:
+            ok = False
+        handles = [None] * world
+        dist.all_gather_object(handles, (ok, handle), group=group)
+        bufs = []
+        if all(h[0] for h in handles):
+            try:
+                for r, (_, h) in enumerate(handles):
+                    bufs.append(ptr if r == rank else self.scene.exchange_open(h))
+            except Exception:
+                ok = False
+        else:
+            ok = False
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            for r, b in enumerate(bufs):
+                if r != rank:
+                    self.scene.exchange_close(b)
+            if ptr:
+                self.scene.exchange_free(ptr)
+            return False
+        self._own, self._bufs, self._cap = (ptr, world * cap * 4 * CONTACT_FLOATS), bufs, cap
+        return True
+
+    def _teardown_p2p(self):
+        if self._bufs is not None:
+            for b in self._bufs:
+                if b != self._own[0]:
+                    self.scene.exchange_close(b)
+            self.scene.exchange_free(self._own[0])
+        self._own = self._bufs = None
 
     def sweep(self, responses: np.ndarray, group=None):
         """responses: the FULL batch (identical on every rank).  Returns the global contact list
@@ -75,13 +138,29 @@ class ShardedSweep:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         n = len(responses)
         lo, hi = shard_range(n, rank, world)
-        cap = shard_capacity(n, world)
         mine = np.ascontiguousarray(responses[lo:hi], RESPONSE_DTYPE)
         d_in = torch.from_numpy(mine.view(np.float32).reshape(-1, 7)).to(self.device)
+        use_p2p = self.exchange in ("auto", "p2p") and self._setup_p2p(n, group)
+        if self.exchange == "p2p" and not use_p2p:
+            raise RuntimeError("peer-memory exchange requested but CUDA IPC mapping failed")
+        self.last_exchange = "p2p" if use_p2p else "nccl"
+        if use_p2p:
+            cap = self._cap
+            if hi > lo:
+                self.scene.detect_contacts_exchange_dev(d_in.data_ptr(), hi - lo, self._bufs, rank * cap)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)                       # every rank's stores have landed
+            buf = torch.as_tensor(_DeviceArray(self._own[0], (world, cap, CONTACT_FLOATS)), device=self.device)
+            parts = [buf[r, :shard_range(n, r, world)[1] - shard_range(n, r, world)[0]] for r in range(world)]
+            out = torch.cat(parts, dim=0)
+            dist.barrier(group)                       # nobody overwrites a buffer that is still being read
+            return out
+        cap = shard_capacity(n, world)
         slot = torch.zeros((cap, CONTACT_FLOATS), dtype=torch.float32, device=self.device)
         if hi > lo:
             self.scene.detect_contacts_dev(d_in.data_ptr(), hi - lo, slot.data_ptr())
         return gather_contacts(slot, n, group)
 
     def close(self):
+        self._teardown_p2p()
         self.scene.close()
