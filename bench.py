@@ -178,7 +178,22 @@ def run_b200(args):
     mine = contacts[rank]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    # N > 1: the kernel that builds the contact records stores them into every rank's gather buffer over
+    # NVLink peer memory (CUDA IPC); if the mapping is unavailable, fall back to an NCCL all-gather
+    exchange = None
+    if world > 1 and not os.environ.get("XP_BENCH_NCCL_EXCHANGE"):
+        from xp_physics_cuda.distributed import ContactExchange
+        exchange = ContactExchange(scene, n, dev)
+        if not exchange.ok:
+            exchange = None
+        else:
+            mine = exchange.view[rank][:n]
+
     def step_device():
+        if exchange is not None:
+            exchange.sweep(d_in.data_ptr(), n)       # compute + all-gather in one kernel (P2P stores)
+            dist.barrier()                           # every rank's records have landed everywhere
+            return
         # writes this rank's contact records straight into its slot of the gather buffer
         scene.detect_contacts_dev(d_in.data_ptr(), n, mine.data_ptr())
         if world > 1:
@@ -327,7 +342,10 @@ def run_b200(args):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(workload_config(world), arith=args.arith, method=args.method,
-                                                    prune=bool(args.prune)),
+                                                    prune=bool(args.prune),
+                                                    exchange=("none" if world == 1 else
+                                                              "p2p stores into mapped peer buffers (fused with the record build)"
+                                                              if exchange is not None else "nccl all_gather")),
                 "spheres_per_sec": spheres_per_sec, "tests_per_step": tests_all / args.steps,
                 "node_visits_per_step": float(np.mean([s["node_visits"] for s in stats])),
                 "stage_ms": {k: float(np.mean([s["stage_ms"][k] for s in stats])) for k in stats[0]["stage_ms"]},

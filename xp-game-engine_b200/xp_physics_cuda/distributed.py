@@ -62,6 +62,56 @@ class _DeviceArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+class ContactExchange:
+    """One gather buffer per rank ([world, cap, 10] float32), each mapped by every other rank through CUDA
+    IPC, so a kernel on any rank can store into all of them (NVLink P2P).  `ok` is False when the mapping
+    failed on some rank (the callers then fall back to the NCCL all-gather)."""
+
+    def __init__(self, scene: Scene, cap: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.scene, self.group = scene, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.cap = cap + (cap & 1)                   # even slots: 8-byte aligned spans
+        self.nbytes = self.world * self.cap * 4 * CONTACT_FLOATS
+        self.ptr, self.bufs, self.ok = 0, [], True
+        handle = b""
+        try:
+            self.ptr, handle = scene.exchange_alloc(self.nbytes)
+        except Exception:
+            self.ok = False
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.ok, handle), group=group)
+        if all(h[0] for h in handles):
+            try:
+                for r, (_, h) in enumerate(handles):
+                    self.bufs.append(self.ptr if r == self.rank else scene.exchange_open(h))
+            except Exception:
+                self.ok = False
+        else:
+            self.ok = False
+        flags = [None] * self.world
+        dist.all_gather_object(flags, self.ok, group=group)
+        if not all(flags):
+            self.ok = False
+            self.close()
+        else:
+            self.view = torch.as_tensor(_DeviceArray(self.ptr, (self.world, self.cap, CONTACT_FLOATS)), device=device)
+
+    def sweep(self, d_in_ptr: int, n_local: int, horizon: str = "inf"):
+        """Sweep this rank's spheres; their contact records land in slot `rank` of EVERY rank's buffer."""
+        self.scene.detect_contacts_exchange_dev(d_in_ptr, n_local, self.bufs, self.rank * self.cap, horizon)
+
+    def close(self):
+        for r, b in enumerate(self.bufs):
+            if r != self.rank and b:
+                self.scene.exchange_close(b)
+        self.bufs = []
+        if self.ptr:
+            self.scene.exchange_free(self.ptr)
+            self.ptr = 0
+
+
 class ShardedSweep:
     """Rank-local half of the multi-GPU sweep (needs a CUDA device per rank).
 
@@ -81,54 +131,17 @@ class ShardedSweep:
         self.scene.set_triangles(triangles)          # replicated: every rank builds the same tree
         self.scene.build()
         self.exchange = exchange
-        self._own = None           # (ptr, nbytes) of this rank's gather buffer
-        self._bufs = None          # device pointers of all ranks' buffers, in rank order
-        self._cap = 0
+        self._ex = None
 
-    # -- peer-memory setup: one gather buffer per rank, mapped by everyone
     def _setup_p2p(self, n_total: int, group=None) -> bool:
         import torch.distributed as dist
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        cap = shard_capacity(n_total, world)
-        cap += cap & 1                               # even slots: 8-byte aligned spans
-        if self._bufs is not None and self._cap == cap:
+        cap = shard_capacity(n_total, dist.get_world_size(group))
+        if self._ex is not None and self._ex.ok and self._ex.cap >= cap:
             return True
-        self._teardown_p2p()
-        ok, handle, ptr = True, b"", 0
-        try:
-            ptr, handle = self.scene.exchange_alloc(world * cap * 4 * CONTACT_FLOATS)
-        except Exception:
-            ok = False
-        handles = [None] * world
-        dist.all_gather_object(handles, (ok, handle), group=group)
-        bufs = []
-        if all(h[0] for h in handles):
-            try:
-                for r, (_, h) in enumerate(handles):
-                    bufs.append(ptr if r == rank else self.scene.exchange_open(h))
-            except Exception:
-                ok = False
-        else:
-            ok = False
-        flags = [None] * world
-        dist.all_gather_object(flags, ok, group=group)
-        if not all(flags):
-            for r, b in enumerate(bufs):
-                if r != rank:
-                    self.scene.exchange_close(b)
-            if ptr:
-                self.scene.exchange_free(ptr)
-            return False
-        self._own, self._bufs, self._cap = (ptr, world * cap * 4 * CONTACT_FLOATS), bufs, cap
-        return True
-
-    def _teardown_p2p(self):
-        if self._bufs is not None:
-            for b in self._bufs:
-                if b != self._own[0]:
-                    self.scene.exchange_close(b)
-            self.scene.exchange_free(self._own[0])
-        self._own = self._bufs = None
+        if self._ex is not None:
+            self._ex.close()
+        self._ex = ContactExchange(self.scene, cap, self.device, group)
+        return self._ex.ok
 
     def sweep(self, responses: np.ndarray, group=None):
         """responses: the FULL batch (identical on every rank).  Returns the global contact list
@@ -145,12 +158,11 @@ class ShardedSweep:
             raise RuntimeError("peer-memory exchange requested but CUDA IPC mapping failed")
         self.last_exchange = "p2p" if use_p2p else "nccl"
         if use_p2p:
-            cap = self._cap
             if hi > lo:
-                self.scene.detect_contacts_exchange_dev(d_in.data_ptr(), hi - lo, self._bufs, rank * cap)
+                self._ex.sweep(d_in.data_ptr(), hi - lo)
             torch.cuda.synchronize(self.device)
             dist.barrier(group)                       # every rank's stores have landed
-            buf = torch.as_tensor(_DeviceArray(self._own[0], (world, cap, CONTACT_FLOATS)), device=self.device)
+            buf = self._ex.view
             parts = [buf[r, :shard_range(n, r, world)[1] - shard_range(n, r, world)[0]] for r in range(world)]
             out = torch.cat(parts, dim=0)
             dist.barrier(group)                       # nobody overwrites a buffer that is still being read
@@ -162,5 +174,6 @@ class ShardedSweep:
         return gather_contacts(slot, n, group)
 
     def close(self):
-        self._teardown_p2p()
+        if self._ex is not None:
+            self._ex.close()
         self.scene.close()
