@@ -310,6 +310,7 @@ int xp_detect_contacts_exchange_dev(xp_scene *s, const xp_response *d_in, uint64
     XP_API_TRY(s->io_status.reserve(n * 4));
     QueryOut q = {nullptr, nullptr, nullptr, s->io_status.as<uint32_t>(), nullptr, {}, slot_first};
     q.peers.n = n_bufs;
+    q.peers.rot = (int)((slot_first / (n ? n : 1)) % (uint64_t)n_bufs) + 1;     // ~ this rank's position + 1
     for (int i = 0; i < n_bufs; ++i) {
         if (!bufs[i]) return XP_EINVAL;
         q.peers.p[i] = static_cast<xp_contact *>(bufs[i]);

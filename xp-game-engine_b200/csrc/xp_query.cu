@@ -889,7 +889,10 @@ __global__ void __launch_bounds__(256) k_finalize_exchange(const RayRec *__restr
     const unsigned cnt = (unsigned)((n - i0 < 256) ? (n - i0) : 256);       // records of this block
     const unsigned n8 = cnt * 5;                                            // 8-byte words
     const float2 *src = reinterpret_cast<const float2 *>(rec);
-    for (int p = 0; p < peers.n; ++p) {
+    // every rank starts with a different peer and consecutive blocks rotate, so at any instant the
+    // stores of the whole machine are spread over all receivers instead of converging on one
+    for (int j = 0; j < peers.n; ++j) {
+        const int p = (int)((j + peers.rot + blockIdx.x) % (unsigned)peers.n);
         float2 *dst = reinterpret_cast<float2 *>(peers.p[p]) + (slot_first + i0) * 5;
         for (unsigned w = threadIdx.x; w < n8; w += 256) dst[w] = src[w];
     }
