@@ -112,7 +112,6 @@ struct xp_scene {
     xp::DevBuf wide, wide_lo, wide_hi;               // 32-wide implicit tree planes + per-node union boxes
     xp::DevBuf nodes4;                               // Node4[max(T-1,1)], indexed like the binary nodes
     xp::WideTree wide_tree = {};
-    float h_bounds[6] = {0, 0, 0, 0, 0, 0};
     // per-call workspaces
     xp::DevBuf rays, best, active_a, active_b, pairs, counters;
     xp::DevBuf sort_ka, sort_kb;   // sphere Morton keys (ping-pong)

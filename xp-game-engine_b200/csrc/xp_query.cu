@@ -8,8 +8,11 @@
 //
 // closest() implementations selected by XP_OPT_METHOD:
 //   WIDE_FUSED k_sweep: one WARP per sphere over the 32-wide implicit tree (default; see k_sweep)
+//   LBVH_PAIRS k_broadphase (persistent warps over the binary LBVH) writes the pairs of P to HBM,
+//              k_narrow_pairs tests them (default; see k_broadphase)
+//   Q4_PAIRS   k_broadphase4 over the quantised 4-wide collapse, k_narrow_pairs<FILTER> re-checks P
 //   WIDE_PAIRS k_sweep<.., EMIT=true> writes the pairs to HBM, k_narrow_pairs tests them
-//   LBVH_FUSED k_traverse<.., EMIT=false>: one lane per sphere walks the LBVH with a private
+//   LBVH_FUSED k_traverse: one lane per sphere walks the LBVH with a private
 //              stack (one 64 B node = 4 x LDG.128 per step); every leaf whose box passes P is
 //              appended to a warp-shared queue in shared memory; whenever the queue holds >= 32
 //              (sphere, leaf) pairs the whole warp runs the narrowphase on 32 of them, one pair per
@@ -17,7 +20,6 @@
 //              4 x LDG.128, and folds the result with a shared-memory 64-bit atomicMin.  The
 //              narrowphase therefore runs with all 32 lanes on the same (full) code path no matter
 //              how divergent the traversal is.
-//   LBVH_PAIRS k_traverse<.., EMIT=true> writes the pairs to HBM, k_narrow_pairs tests them.
 //   BRUTE      k_brute: the reference's literal all-pairs loop, one thread per triangle, rays
 //              staged in shared memory.
 #include <cstdio>
@@ -180,18 +182,16 @@ __device__ __forceinline__ bool slab2(const V3 &c, const V3 &inv, float horizon,
     return tmin <= tmax;
 }
 
-template <class O, bool PRUNE, bool EMIT>
+template <class O, bool PRUNE>
 __global__ void __launch_bounds__(TRAV_THREADS)
 k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
-           const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t na,
-           unsigned long long *__restrict__ best, DeviceCounters *__restrict__ ctr,
-           uint2 *__restrict__ pairs_out, uint64_t pair_cap, int count_paths) {
+           const RayRec *__restrict__ rays, uint64_t na,
+           unsigned long long *__restrict__ best, DeviceCounters *__restrict__ ctr, int count_paths) {
     __shared__ WarpShared sh[TRAV_WARPS];
     unsigned long long *path_ctr = count_paths ? ctr->path : nullptr;
     const int lane = threadIdx.x & 31;
     WarpShared &ws = sh[threadIdx.x >> 5];
-    const uint64_t k = ray_base + blockIdx.x * (uint64_t)TRAV_THREADS + threadIdx.x;
-    const uint64_t warp_k0 = k - lane;
+    const uint64_t k = blockIdx.x * (uint64_t)TRAV_THREADS + threadIdx.x;
 
     V3 c = {0, 0, 0}, inv = {0, 0, 0};
     float horizon = 0.0f;
@@ -212,19 +212,11 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
     unsigned n_tests = 0, n_nodes = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    auto drain32 = [&](unsigned from) {  // every lane takes queue[from + lane]
-        const uint32_t e = ws.queue[from + lane];
-        const uint32_t owner = e >> 27, leaf = e & LEAF_MASK;
-        if (EMIT) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->pairs, 32ull);
-            base = __shfl_sync(FULL, base, 0);
-            if (base + lane < pair_cap) pairs_out[base + lane] = make_uint2((uint32_t)(warp_k0 + owner), leaf);
-        } else {
-            const Ray ray = ray_from(ws.ray[0][owner], ws.ray[1][owner], ws.ray[2][owner]);
-            unsigned long long key;
-            if (detect_rec<O>(ray, recs, leaf, key, path_ctr)) atomicMin(&ws.best[owner], key);
-        }
+    auto test_entry = [&](uint32_t e) {  // narrowphase of one queued (owner lane, leaf) pair
+        const uint32_t owner = e >> 27;
+        const Ray ray = ray_from(ws.ray[0][owner], ws.ray[1][owner], ws.ray[2][owner]);
+        unsigned long long key;
+        if (detect_rec<O>(ray, recs, e & LEAF_MASK, key, path_ctr)) atomicMin(&ws.best[owner], key);
     };
 
     while (__any_sync(FULL, node >= 0)) {
@@ -263,40 +255,21 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
         if (leaf_b >= 0) ws.queue[count + __popc(mb & lt_mask)] = ((uint32_t)lane << 27) | (uint32_t)leaf_b;
         count += __popc(mb);
         __syncwarp();
-        while (count >= 32) {
+        while (count >= 32) {            // the whole warp tests 32 queued pairs, one per lane
             count -= 32;
-            drain32(count);
+            test_entry(ws.queue[count + lane]);
             n_tests += 1;
             __syncwarp();
         }
     }
-    // tail: fewer than 32 pairs left
-    if (count > 0) {
-        if (EMIT) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)count);
-            base = __shfl_sync(FULL, base, 0);
-            if (lane < count) {
-                const uint32_t e = ws.queue[lane];
-                if (base + lane < pair_cap)
-                    pairs_out[base + lane] = make_uint2((uint32_t)(warp_k0 + (e >> 27)), e & LEAF_MASK);
-            }
-        } else if (lane < count) {
-            const uint32_t e = ws.queue[lane];
-            const uint32_t owner = e >> 27;
-            const Ray ray = ray_from(ws.ray[0][owner], ws.ray[1][owner], ws.ray[2][owner]);
-            unsigned long long key;
-            if (detect_rec<O>(ray, recs, e & LEAF_MASK, key, path_ctr)) atomicMin(&ws.best[owner], key);
-        }
-    }
+    if (lane < count) test_entry(ws.queue[lane]);      // tail: fewer than 32 pairs left
     __syncwarp();
-    if (!EMIT && k < na) best[k] = ws.best[lane];
+    if (k < na) best[k] = ws.best[lane];
     // statistics: one atomic per warp
-    unsigned long long tests = (unsigned long long)n_tests * 32ull + count;   // warp-uniform
     unsigned nn = n_nodes;
     for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(FULL, nn, o);
     if (lane == 0) {
-        if (!EMIT) atomicAdd(&ctr->tests, tests);
+        atomicAdd(&ctr->tests, (unsigned long long)n_tests * 32ull + count);
         atomicAdd(&ctr->node_visits, (unsigned long long)nn);
     }
 }
@@ -1019,8 +992,8 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
     if (s->method == XP_METHOD_LBVH_FUSED) {
         StageTimer t(s, XP_STAGE_TRAVERSE);
         const unsigned blocks = grid_for(na, TRAV_THREADS);
-        if (s->prune) k_traverse<O, true, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
-        else k_traverse<O, false, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
+        if (s->prune) k_traverse<O, true><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, best, ctr, s->timing);
+        else k_traverse<O, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, best, ctr, s->timing);
         ++s->stats.kernel_launches;
         return cudaGetLastError();
     }
