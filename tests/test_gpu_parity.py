@@ -296,6 +296,45 @@ def test_non_finite_and_extreme_spheres(oracle):
         assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"non-finite response {method}")
 
 
+def test_random_soups_fuzz(oracle):
+    """many small random triangle soups (arbitrary orientation, slivers, duplicates, zero-area triangles, 1..400
+    triangles) x random spheres: detect, broadphase pairs and a 3-iteration response against the oracle."""
+    rng = np.random.default_rng(2024)
+    total_hits = 0
+    with xp.Scene(0) as s:
+        for case in range(48):
+            nt = int(rng.choice([1, 2, 3, 7, 33, 64, 65, 200, 400]))
+            ext = float(rng.choice([2.0, 8.0, 40.0]))
+            base = rng.uniform(-ext, ext, (nt, 1, 3))
+            tris = (base + rng.normal(0, rng.choice([0.05, 1.0, 4.0]), (nt, 3, 3))).astype(np.float32)
+            if nt > 3:
+                tris[1] = tris[0]                              # duplicate
+                tris[2, 2] = tris[2, 1]                        # zero area
+                tris[3, 1] = (tris[3, 0] + tris[3, 2]) / 2     # collinear sliver
+            ns = 150
+            c = rng.uniform(-ext - 3, ext + 3, (ns, 3)).astype(np.float32)
+            m = rng.normal(0, 1, (ns, 3))
+            m = (m / np.linalg.norm(m, axis=1, keepdims=True) * rng.uniform(0.01, 0.95, (ns, 1))).astype(np.float32)
+            m[::17, rng.integers(0, 3)] = 0.0
+            resps = xp.make_responses(c, m)
+            s.set_options(method=str(rng.choice(["lbvh_pairs", "q4_pairs", "wide_pairs", "lbvh_fused", "wide_fused"])),
+                          prune=bool(rng.integers(0, 2)))
+            s.set_triangles(tris)
+            s.build()
+            got = s.detect_batch(resps)
+            want = oracle.detect_batch(resps, tris)
+            check_detect_exact(got, want, f"fuzz case {case}", tri_index=False)
+            total_hits += int(want[1].sum())
+            gi, gj = s.broadphase_pairs(resps)
+            wi, wj = oracle.broadphase_pairs(resps, tris)
+            assert np.array_equal(np.sort(gi.astype(np.uint64) << 32 | gj), np.sort(wi.astype(np.uint64) << 32 | wj)), case
+            out, it, st, ln = s.collision_response_batch(resps, max_iter=3)
+            w = oracle.collision_response_batch(resps, tris, max_iter=3)
+            assert np.array_equal(it, w[1]) and np.array_equal(st, w[2]), case
+            assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"fuzz response {case}")
+    assert total_hits > 500
+
+
 def test_large_coordinates(oracle):
     tris, h = scenes.sine_terrain(16, 16, seed=8)
     tris = tris + np.float32([4000, 0, 3000])
