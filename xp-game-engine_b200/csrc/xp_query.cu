@@ -285,7 +285,16 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
 static constexpr int BP_THREADS = 256;
 static constexpr int BP_WARPS = BP_THREADS / 32;
 static constexpr int BP_QUEUE = 96;
-static constexpr int BP_BLOCKS_PER_SM = 6;     // 48 warps/SM; 6 x 27 KB of staging leaves ~60 KB of L1
+#ifndef XP_BP_BLOCKS
+#define XP_BP_BLOCKS 3
+#endif
+#ifndef XP_BP_GATHER
+#define XP_BP_GATHER 1
+#endif
+// Measured on config 2 (stage-1 ms): 2 blocks/SM 1.34, 3: 1.22, 4: 1.26, 5: 1.32, 6: 1.38, 7 (spills): 1.59.
+// Fewer resident warps leave more of the 228 KB to L1 (3 x 27 KB of staging -> ~148 KB of L1), and the node
+// walk gains more from cache hits than from extra warps.
+static constexpr int BP_BLOCKS_PER_SM = XP_BP_BLOCKS;
 
 __global__ void __launch_bounds__(BP_THREADS, BP_BLOCKS_PER_SM)
 k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
@@ -295,9 +304,11 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     // ray ENTERS inside the window are emitted, and spheres whose best hit so far lies before the window
     // are skipped.  The exhaustive sweep is the single window [0, +inf) with best == nullptr.
     __shared__ uint2 queue[BP_WARPS][BP_QUEUE];
+#if XP_BP_GATHER
     __shared__ float4 stage_all[BP_WARPS][32 * GATHER_STRIDE];
-    uint2 *q = queue[threadIdx.x >> 5];
     float4 *stage = stage_all[threadIdx.x >> 5];
+#endif
+    uint2 *q = queue[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     rays += ray_base;                                   // 32-bit ray indices relative to the chunk
@@ -332,7 +343,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                 if (node < 0 && mine < pool_end) {
                     my_ray = mine;
                     const float4 *rp = reinterpret_cast<const float4 *>(rays + mine);
-                    const float4 q0 = __ldg(rp + 0), q3 = __ldg(rp + 3);
+                    const float4 q0 = __ldcs(rp + 0), q3 = __ldcs(rp + 3);     // read once: do not displace nodes
                     c = f4_xyz(q0); inv = f4_xyz(q3);
                     sp = 0;
                     bool go = (__float_as_uint(q3.w) & RAY_VALID) != 0;
@@ -356,7 +367,14 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         }
         // ---- one traversal step
         float4 n0, n1, n2, n3;
+#if XP_BP_GATHER
         warp_gather64(reinterpret_cast<const float4 *>(nodes), node, stage, n0, n1, n2, n3);
+#else
+        {
+            const float4 *np = reinterpret_cast<const float4 *>(nodes + (node < 0 ? 0 : node));
+            n0 = __ldg(np + 0); n1 = __ldg(np + 1); n2 = __ldg(np + 2); n3 = __ldg(np + 3);
+        }
+#endif
         n_nodes += __popc(__ballot_sync(FULL, node >= 0));
         int leaf_a = -1, leaf_b = -1;
         if (node >= 0) {
@@ -685,8 +703,11 @@ k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__re
 // pairs come from the same few rays) with 3 x LDG.128, and folds hits with a 64-bit atomicMin.
 // (A cooperative shared-memory gather of the triangle records was measured and was slower here:
 // 1.12 ms vs 0.93 ms; this kernel is bound by instruction issue, not by the L1 tag stage.)
+#ifndef XP_NP_BLOCKS
+#define XP_NP_BLOCKS 4
+#endif
 template <class O, bool FILTER>
-__global__ void __launch_bounds__(256) k_narrow_pairs(const TriRec *__restrict__ recs,
+__global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec *__restrict__ recs,
                                                       const RayRec *__restrict__ rays,
                                                       const uint2 *__restrict__ pairs,
                                                       DeviceCounters *__restrict__ ctr,

@@ -11,7 +11,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_PKG, "..", "csrc"))
-SO_PATH = os.path.join(CSRC, "libxp_physics_cuda.so")
+SO_PATH = os.environ.get("XP_PHYSICS_CUDA_SO") or os.path.join(CSRC, "libxp_physics_cuda.so")   # override: A/B builds
 HEADER = os.path.normpath(os.path.join(_PKG, "..", "..", "include", "xp_physics_cuda.h"))
 
 # constants of include/xp_physics_cuda.h
