@@ -284,7 +284,11 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
 // staged in a warp-shared queue in shared memory and written to HBM 32 pairs (256 B) at a time.
 static constexpr int BP_THREADS = 256;
 static constexpr int BP_WARPS = BP_THREADS / 32;
-static constexpr int BP_QUEUE = 96;
+#ifndef XP_BP_SPAN
+#define XP_BP_SPAN 256
+#endif
+static constexpr int BP_SPAN = XP_BP_SPAN;          // pairs written per flush: long coherent runs help the narrowphase's L1
+static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at most 64 appended per step
 #ifndef XP_BP_BLOCKS
 #define XP_BP_BLOCKS 3
 #endif
@@ -405,12 +409,14 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
             if (leaf_b >= 0) q[count + na + __popc(mb & lt_mask)] = make_uint2(ray0 + my_ray, (uint32_t)leaf_b);
             count += na + __popc(mb);
             __syncwarp();
-            while (count >= 32) {
-                count -= 32;
+            if (count >= BP_SPAN) {          // flush a whole span: these pairs share rays and triangles
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&ctr->pairs, 32ull);
+                if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)BP_SPAN);
                 base = __shfl_sync(FULL, base, 0);
-                if (base + lane < pair_cap) __stcs(&pairs_out[base + lane], q[count + lane]);   // streaming: keep the tree in L2
+                count -= BP_SPAN;
+#pragma unroll 4
+                for (int w = lane; w < BP_SPAN; w += 32)
+                    if (base + w < pair_cap) __stcs(&pairs_out[base + w], q[count + w]);   // streaming: keep the tree in L2
                 __syncwarp();
             }
         }
@@ -419,7 +425,8 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)count);
         base = __shfl_sync(FULL, base, 0);
-        if (lane < count && base + lane < pair_cap) __stcs(&pairs_out[base + lane], q[lane]);
+        for (unsigned w = lane; w < count; w += 32)
+            if (base + w < pair_cap) __stcs(&pairs_out[base + w], q[w]);
     }
     if (lane == 0) atomicAdd(&ctr->node_visits, (unsigned long long)n_nodes);
 }
@@ -721,8 +728,11 @@ __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec
     }
     if (n > pair_cap) n = pair_cap;
     unsigned kept = 0;
-    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n;
-         p += (unsigned long long)gridDim.x * blockDim.x) {
+    // a block works through contiguous spans of the pair list (the broadphase writes it in runs that
+    // share rays and triangles), so the gathers below find most of their lines already in L1
+    constexpr unsigned long long NP_SPAN = 2048;
+    for (unsigned long long s0 = blockIdx.x * NP_SPAN; s0 < n; s0 += (unsigned long long)gridDim.x * NP_SPAN)
+    for (unsigned long long p = s0 + threadIdx.x; p < n && p < s0 + NP_SPAN; p += blockDim.x) {
         const uint2 pr = __ldcs(&pairs[p]);              // read once: streaming
         const float4 *rp = reinterpret_cast<const float4 *>(rays + pr.x);
         const float4 *tp = reinterpret_cast<const float4 *>(recs + pr.y);
