@@ -285,7 +285,7 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
 static constexpr int BP_THREADS = 256;
 static constexpr int BP_WARPS = BP_THREADS / 32;
 #ifndef XP_BP_SPAN
-#define XP_BP_SPAN 256
+#define XP_BP_SPAN 128
 #endif
 static constexpr int BP_SPAN = XP_BP_SPAN;          // pairs written per flush: long coherent runs help the narrowphase's L1
 static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at most 64 appended per step
@@ -312,7 +312,11 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     __shared__ float4 stage_all[BP_WARPS][32 * GATHER_STRIDE];
     float4 *stage = stage_all[threadIdx.x >> 5];
 #endif
+    __shared__ float4 rpool_all[BP_WARPS][64];          // the warp's current run of rays: (c,|m|)[32], (1/m,flags)[32]
+    __shared__ float rbest_all[BP_WARPS][32];
     uint2 *q = queue[threadIdx.x >> 5];
+    float4 *rpool = rpool_all[threadIdx.x >> 5];
+    float *rbest = rbest_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     rays += ray_base;                                   // 32-bit ray indices relative to the chunk
@@ -326,7 +330,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     int stack[STACK_DEPTH];
     int sp = 0;
     unsigned count = 0;                    // queue fill (warp-uniform)
-    unsigned pool = 0, pool_end = 0;       // this warp's current run of rays (warp-uniform)
+    unsigned pool = 0, pool_end = 0, pool_base = 0;   // this warp's current run of rays (warp-uniform)
     bool drained = false;                  // the global cursor has run out (warp-uniform)
     unsigned n_nodes = 0;                  // warp-uniform: lane-steps, counted with one POPC per step
 
@@ -335,19 +339,30 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         const unsigned idle = __ballot_sync(FULL, node < 0);
         if (idle) {
             if (pool >= pool_end && !drained) {
+                // claim the next run of 32 rays and stage what the walk needs of them in shared memory
+                // with one coalesced load per lane, so that handing a ray to a lane later costs no
+                // global-memory round trip in the middle of the walk
                 unsigned start = 0;
                 if (lane == 0) start = (unsigned)atomicAdd(&ctr->ray_cursor, 32ull);
                 start = __shfl_sync(FULL, start, 0);
                 pool = start < n_rays ? start : n_rays;
                 pool_end = pool + 32 < n_rays ? pool + 32 : n_rays;
                 drained = pool >= n_rays;
+                pool_base = pool;
+                __syncwarp();
+                if (pool + lane < pool_end) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(rays + pool + lane);
+                    rpool[lane] = __ldcs(rp + 0);           // (c, |m|)      read once: do not displace nodes
+                    rpool[32 + lane] = __ldcs(rp + 3);      // (1/m, flags)
+                    if (best) rbest[lane] = __uint_as_float((unsigned)(__ldg(&best[ray0 + pool + lane]) >> 32));
+                }
+                __syncwarp();
             }
             if (pool < pool_end) {
                 const unsigned mine = pool + __popc(idle & lt_mask);
                 if (node < 0 && mine < pool_end) {
                     my_ray = mine;
-                    const float4 *rp = reinterpret_cast<const float4 *>(rays + mine);
-                    const float4 q0 = __ldcs(rp + 0), q3 = __ldcs(rp + 3);     // read once: do not displace nodes
+                    const float4 q0 = rpool[mine - pool_base], q3 = rpool[32 + mine - pool_base];
                     c = f4_xyz(q0); inv = f4_xyz(q3);
                     sp = 0;
                     bool go = (__float_as_uint(q3.w) & RAY_VALID) != 0;
@@ -357,7 +372,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                         t_lo = sane ? __fdiv_rn(d_lo, ml) : 0.0f;
                         t_hi = sane ? __fdiv_rn(d_hi, ml) : INFINITY;     // |m| == 0 / NaN: everything in the first pass
                         if (!sane && d_lo > 0.0f) go = false;
-                        const float bt = __uint_as_float((unsigned)(__ldg(&best[ray0 + mine]) >> 32));   // NaN = no hit yet
+                        const float bt = rbest[mine - pool_base];        // best t so far, NaN = no hit yet
                         if (bt <= t_lo) go = false;         // nothing entered at or after t_lo can beat it
                     } else {
                         t_lo = 0.0f; t_hi = INFINITY;
