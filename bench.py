@@ -263,7 +263,7 @@ def run_b200(args):
                 "algorithmic_flops_per_launch": flops, "flops_per_test_by_path": PATH_FLOPS, "path_mix": paths,
                 "traffic": TRAFFIC_NARROW, "traffic_source": TRAFFIC_SOURCE,
                 "note": "245 algorithmic flops are ~630 issued instructions (17 IEEE div, 12 IEEE sqrt); "
-                        "ncu (profiles/r01d_ncu_full.txt): issue slots 75% busy, L1/LSU 92% busy, FMA pipe 40% busy, 30.3/32 lanes active"}
+                        "ncu (profiles/r01e_ncu_full.txt): issue slots 75% busy, L1/LSU 92% busy, FMA pipe 40% busy, 30.3/32 lanes active"}
     # the broadphase is the longest kernel of the step and is memory-latency / L1-bound, not compute
     tests_step = float(np.mean([s["narrowphase_tests"] for s in stats]))
     bp_bytes = 64.0 * n + 8.0 * tests_step                       # ray records in + candidate pairs out
@@ -364,10 +364,10 @@ def run_b200(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
-# same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r01d_ncu_full.txt
-TRAFFIC_NARROW = 627.3e6         # k_narrow_pairs: ~607 MB read + ~20 MB written (315 MB of the reads is the pair list)
-TRAFFIC_BROADPHASE = 407.5e6     # k_broadphase: ~130 MB read + ~278 MB written (the pair list)
-TRAFFIC_SOURCE = "profiles/r01d_ncu_full.txt"
+# same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r01e_ncu_full.txt
+TRAFFIC_NARROW = 615.2e6         # k_narrow_pairs: ~595 MB read + ~20 MB written (315 MB of the reads is the pair list)
+TRAFFIC_BROADPHASE = 404.8e6     # k_broadphase: ~128 MB read + ~277 MB written (the pair list)
+TRAFFIC_SOURCE = "profiles/r01e_ncu_full.txt"
 
 
 def measured_hbm_gbs():
