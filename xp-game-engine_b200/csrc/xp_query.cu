@@ -78,27 +78,40 @@ __device__ __forceinline__ Ray ray_from(float4 q0, float4 q1, float4 q2) {
     return r;
 }
 
+// 256-bit read-only load (LDG.E.256, sm_100+): the two aligned halves of a 64 B record cost one L1
+// wavefront per distinct line each, where four LDG.128 cost four.  p must be 32 B aligned.
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+
 // Cooperative gather of one 64 B record per lane.  A lane-private 64 B fetch is four LDG.128 that
-// each touch up to 32 different cache lines (the L1 tag stage, ~2 cycles per line per instruction,
-// was the measured limiter of both sweep kernels).  Here four adjacent lanes fetch the four 16 B
+// each touch up to 32 different cache lines (one L1 wavefront per line per instruction; the L1 data
+// pipe is the measured limiter of both sweep kernels).  Here four adjacent lanes fetch the four 16 B
 // quarters of ONE record, so an instruction touches at most 8 lines; the quarters are exchanged
-// through a padded (80 B stride, conflict-free) staging area in shared memory.
-// idx < 0 = this lane wants nothing.  stage: 32 x 5 float4 per warp.
-static constexpr int GATHER_STRIDE = 5;            // float4 per staged record (64 B + 16 B pad)
+// through a staging area in shared memory.  Quarter q of record R sits at 16 B unit
+// 4R + (q ^ ((R >> 1) & 3)): a 128-bit shared access is served 8 lanes at a time, and with this
+// swizzle both the stores (2 records x 4 quarters per group of 8 lanes) and the loads (8 records,
+// same quarter) hit 8 different 16 B bank groups -- no padding, no conflicts (the earlier 80 B
+// stride was conflict-free for the loads only: ncu counted 2 wavefronts per 8 stored lanes).
+// idx < 0 = this lane wants nothing.  stage: 32 x 4 float4 per warp.
+static constexpr int GATHER_STRIDE = 4;            // float4 per staged record
 __device__ __forceinline__ void warp_gather64(const float4 *__restrict__ base, int idx, float4 *stage,
                                               float4 &o0, float4 &o1, float4 &o2, float4 &o3) {
     const int lane = threadIdx.x & 31;
     const int want = idx < 0 ? 0 : idx;             // idle lanes fetch record 0 (hot in L1): no predication needed
     const float4 *src = base + (lane & 3);
-    float4 *dst = stage + (lane >> 2) * GATHER_STRIDE + (lane & 3);
+    float4 *dst = stage + (lane & ~3) + ((lane & 3) ^ ((lane >> 3) & 3));      // record lane>>2 (+ 8 per round)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int rec = __shfl_sync(0xffffffffu, want, (lane >> 2) + 8 * r);
-        dst[8 * r * GATHER_STRIDE] = __ldg(src + (size_t)(unsigned)rec * 4);
+        dst[32 * r] = __ldg(src + (size_t)(unsigned)rec * 4);
     }
     __syncwarp();
-    const float4 *mine = stage + lane * GATHER_STRIDE;
-    o0 = mine[0]; o1 = mine[1]; o2 = mine[2]; o3 = mine[3];
+    const float4 *mine = stage + lane * 4;
+    const int sw = (lane >> 1) & 3;
+    o0 = mine[sw]; o1 = mine[1 ^ sw]; o2 = mine[2 ^ sw]; o3 = mine[3 ^ sw];
     __syncwarp();
 }
 
@@ -308,7 +321,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     // ray ENTERS inside the window are emitted, and spheres whose best hit so far lies before the window
     // are skipped.  The exhaustive sweep is the single window [0, +inf) with best == nullptr.
     __shared__ uint2 queue[BP_WARPS][BP_QUEUE];
-#if XP_BP_GATHER
+#if XP_BP_GATHER == 1
     __shared__ float4 stage_all[BP_WARPS][32 * GATHER_STRIDE];
     float4 *stage = stage_all[threadIdx.x >> 5];
 #endif
@@ -386,8 +399,13 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         }
         // ---- one traversal step
         float4 n0, n1, n2, n3;
-#if XP_BP_GATHER
+#if XP_BP_GATHER == 1
         warp_gather64(reinterpret_cast<const float4 *>(nodes), node, stage, n0, n1, n2, n3);
+#elif XP_BP_GATHER == 2
+        {
+            const float4 *np = reinterpret_cast<const float4 *>(nodes + (node < 0 ? 0 : node));
+            ldg256(np, n0, n1); ldg256(np + 2, n2, n3);
+        }
 #else
         {
             const float4 *np = reinterpret_cast<const float4 *>(nodes + (node < 0 ? 0 : node));
@@ -723,10 +741,13 @@ k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__re
 // list.  Every lane runs the same straight-line narrowphase (xp_detect is select-based), reads
 // its 64 B triangle record with 4 x LDG.128 and its ray (shared with its neighbours: consecutive
 // pairs come from the same few rays) with 3 x LDG.128, and folds hits with a 64-bit atomicMin.
-// (A cooperative shared-memory gather of the triangle records was measured and was slower here:
-// 1.12 ms vs 0.93 ms; this kernel is bound by instruction issue, not by the L1 tag stage.)
+// (A cooperative shared-memory gather of the triangle records was measured twice and was slower here:
+// 1.12 vs 0.93 ms with the padded staging, 0.94 vs 0.90 ms with the conflict-free swizzled one.)
 #ifndef XP_NP_BLOCKS
 #define XP_NP_BLOCKS 4
+#endif
+#ifndef XP_NP_LDG256
+#define XP_NP_LDG256 1
 #endif
 template <class O, bool FILTER>
 __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec *__restrict__ recs,
@@ -751,8 +772,13 @@ __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec
         const uint2 pr = __ldcs(&pairs[p]);              // read once: streaming
         const float4 *rp = reinterpret_cast<const float4 *>(rays + pr.x);
         const float4 *tp = reinterpret_cast<const float4 *>(recs + pr.y);
+#if XP_NP_LDG256
+        float4 t0, t1, t2, t3, r0, r1;
+        ldg256(tp, t0, t1); ldg256(tp + 2, t2, t3); ldg256(rp, r0, r1);
+#else
         const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
-        const float4 r0 = __ldg(rp + 0);
+        const float4 r0 = __ldg(rp + 0), r1 = __ldg(rp + 1);
+#endif
         if (FILTER) {
             // stage 1 walked conservatively quantised boxes: apply the exact predicate P to the
             // triangle's own inflated fp32 box, so that exactly the pairs of P are tested
@@ -763,7 +789,7 @@ __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec
             if (!slab(f4_xyz(r0), f4_xyz(r3), horizon, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tn)) continue;
             ++kept;
         }
-        const Ray ray = ray_from(r0, __ldg(rp + 1), __ldg(rp + 2));
+        const Ray ray = ray_from(r0, r1, __ldg(rp + 2));
         float t;
         if (xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t)) {
             const unsigned long long key =
