@@ -88,7 +88,7 @@ void xp_scene_destroy(xp_scene *s) {
     DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_lo, &s->node_hi, &s->leaf_lo, &s->leaf_hi,
                       &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
                       &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->rays, &s->best, &s->active_a,
-                      &s->active_b, &s->pairs, &s->counters, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
+                      &s->active_b, &s->inv_order, &s->pairs, &s->counters, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
                       &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
     for (DevBuf *b : bufs) b->release();
     if (s->ev_created)

@@ -113,7 +113,7 @@ struct xp_scene {
     xp::DevBuf nodes4;                               // Node4[max(T-1,1)], indexed like the binary nodes
     xp::WideTree wide_tree = {};
     // per-call workspaces
-    xp::DevBuf rays, best, active_a, active_b, pairs, counters;
+    xp::DevBuf rays, best, active_a, active_b, inv_order, pairs, counters;
     xp::DevBuf sort_ka, sort_kb;   // sphere Morton keys (ping-pong)
     xp::DevBuf io_in, io_out, io_hit, io_tri, io_status, io_iter, io_normal, io_col;
     // stats

@@ -20,13 +20,14 @@ inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + bl
 // ---- xp_build.cu ----
 // LSD radix sort of (key, value) pairs on `bits` key bits, 8 bits per pass, CUB-free.
 // Ping-pongs between (ka,va) and (kb,vb); *in_a tells where the sorted result ended up.
+// inv_out (optional): the last pass also writes the inverse permutation, inv_out[value] = position.
 cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb,
-                             uint64_t n, int bits, bool *in_a);
+                             uint64_t n, int bits, bool *in_a, uint32_t *inv_out = nullptr);
 cudaError_t build_lbvh(xp_scene *s);
 cudaError_t emit_heightmap(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz, float x0, float z0, float spacing);
 cudaError_t build_aux(xp_scene *s);      // Node4 / 32-wide planes, on first use by the method that needs them
 // order[k] = index of the k-th sphere in Morton order of its centre (scene bounds).
-cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order);
+cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order, uint32_t **inv_order);
 
 // ---- xp_query.cu ----
 static constexpr int XP_MAX_PEERS = 16;

@@ -852,33 +852,42 @@ __global__ void __launch_bounds__(BRUTE_THREADS) k_brute(const TriRec *__restric
 // ------------------------------------------------------------------------------------------
 // results
 // ------------------------------------------------------------------------------------------
+// One thread per sphere in INPUT order (inv_order maps it to its slot in processing order), so every
+// output array is written coalesced -- 16 B stores for the 32 B collision records when the caller's
+// buffer allows -- and only the 8 B best key and the ray record are gathered.
 template <class O>
 __global__ void __launch_bounds__(256) k_finalize_detect(const RayRec *__restrict__ rays,
                                                          const unsigned long long *__restrict__ best,
-                                                         const uint32_t *__restrict__ active, uint64_t na,
+                                                         const uint32_t *__restrict__ inv_order, uint64_t na,
                                                          xp_collision *__restrict__ col, uint8_t *__restrict__ hit,
                                                          uint32_t *__restrict__ tri_index,
                                                          const uint32_t *__restrict__ status,
-                                                         xp_contact *__restrict__ contact) {
-    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (k >= na) return;
-    const uint64_t i = active ? active[k] : k;
+                                                         xp_contact *__restrict__ contact, int col_vec) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= na) return;
+    const uint64_t k = inv_order ? inv_order[i] : i;
     const unsigned long long b = best[k];
     const bool h = b != BEST_NONE;
     const uint32_t tri = h ? ~(uint32_t)(b & 0xFFFFFFFFull) : 0xFFFFFFFFu;
     Contact ct = {0.0f, 0.0f, {0, 0, 0}, {0, 0, 0}};
     if (h) {
         const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
-        const Ray ray = ray_from(rp[0], rp[1], rp[2]);
+        const Ray ray = ray_from(__ldg(rp + 0), __ldg(rp + 1), __ldg(rp + 2));
         ct = xp_make_collision<O>(ray, __uint_as_float((unsigned)(b >> 32)));
     }
     if (hit) hit[i] = h ? 1 : 0;
     if (tri_index) tri_index[i] = tri;
     if (col && h) {
-        float *o = reinterpret_cast<float *>(col) + i * 8;
-        o[0] = ct.time_to; o[1] = ct.distance_to;
-        o[2] = ct.position.x; o[3] = ct.position.y; o[4] = ct.position.z;
-        o[5] = ct.intersection.x; o[6] = ct.intersection.y; o[7] = ct.intersection.z;
+        if (col_vec) {
+            float4 *o = reinterpret_cast<float4 *>(col) + i * 2;
+            o[0] = make_float4(ct.time_to, ct.distance_to, ct.position.x, ct.position.y);
+            o[1] = make_float4(ct.position.z, ct.intersection.x, ct.intersection.y, ct.intersection.z);
+        } else {
+            float *o = reinterpret_cast<float *>(col) + i * 8;
+            o[0] = ct.time_to; o[1] = ct.distance_to;
+            o[2] = ct.position.x; o[3] = ct.position.y; o[4] = ct.position.z;
+            o[5] = ct.intersection.x; o[6] = ct.intersection.y; o[7] = ct.intersection.z;
+        }
     }
     if (contact) {
         float *o = reinterpret_cast<float *>(contact) + i * 10;
@@ -900,11 +909,6 @@ __global__ void __launch_bounds__(256) k_finalize_detect(const RayRec *__restric
 // i in input order, so the block's records are one contiguous 10 KB span) and then streams that span
 // to each peer with fully coalesced 8 B stores, so the transfer overlaps the record construction of
 // the other blocks.  The ranks only need a barrier afterwards.
-__global__ void k_invert_order(const uint32_t *__restrict__ order, uint64_t n, uint32_t *__restrict__ inv) {
-    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (k < n) inv[order[k]] = (uint32_t)k;
-}
-
 template <class O>
 __global__ void __launch_bounds__(256) k_finalize_exchange(const RayRec *__restrict__ rays,
                                                            const unsigned long long *__restrict__ best,
@@ -1192,8 +1196,8 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
         XP_TRY(s->best.reserve(m * 8));
         uint32_t *status = out.status ? out.status + off : nullptr;
         if (status) XP_TRY(cudaMemsetAsync(status, 0, m * 4, s->stream));
-        uint32_t *order = nullptr;
-        if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, in, m, &order));
+        uint32_t *order = nullptr, *inv = nullptr;       // processing order and its inverse (null = identity)
+        if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, in, m, &order, &inv));
         XP_TRY(ray_setup(s, in, order, m, horizon_of(horizon_mode), status));
         XP_TRY(closest(s, m));
         s->swept_rays += m;
@@ -1205,23 +1209,16 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
             uint8_t *hit = out.hit ? out.hit + off : nullptr;
             uint32_t *tri = out.tri_index ? out.tri_index + off : nullptr;
             xp_contact *ct = out.contact ? out.contact + off : nullptr;
+            const int col_vec = (reinterpret_cast<uintptr_t>(col) & 15u) == 0;
             if (out.peers.n > 0) {
-                const uint32_t *inv = nullptr;
-                if (order) {
-                    XP_TRY(s->sort_ka.reserve(m * 4));
-                    k_invert_order<<<grid_for(m, 256), 256, 0, s->stream>>>(order, m, s->sort_ka.as<uint32_t>());
-                    ++s->stats.kernel_launches;
-                    inv = s->sort_ka.as<uint32_t>();
-                }
                 if (s->arith == XP_ARITH_FAST)
                     k_finalize_exchange<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, out.peers, out.slot_first + off);
                 else
                     k_finalize_exchange<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, out.peers, out.slot_first + off);
-                ++s->stats.kernel_launches;
             } else if (s->arith == XP_ARITH_FAST)
-                k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, order, m, col, hit, tri, status, ct);
+                k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
             else
-                k_finalize_detect<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, order, m, col, hit, tri, status, ct);
+                k_finalize_detect<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
             ++s->stats.kernel_launches;
         }
     }
@@ -1256,7 +1253,7 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
         XP_TRY(s->active_a.reserve(m * 4));
         XP_TRY(s->active_b.reserve(m * 4));
         uint32_t *order = nullptr;
-        if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, cur, m, &order));
+        if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, cur, m, &order, nullptr));
         const uint32_t *active = order;            // null = identity
         uint32_t *next = (order == s->active_a.as<uint32_t>()) ? s->active_b.as<uint32_t>()
                                                                 : s->active_a.as<uint32_t>();
