@@ -121,23 +121,78 @@ __global__ void __launch_bounds__(256) k_morton_tris(const float *__restrict__ a
 __global__ void __launch_bounds__(256) k_morton_spheres(const xp_response *__restrict__ in, uint64_t n,
                                                         const unsigned *__restrict__ bounds,
                                                         uint32_t *__restrict__ keys,
-                                                        uint32_t *__restrict__ vals, int mode) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float *p = reinterpret_cast<const float *>(in) + i * 7;
-    V3 c = {__ldg(p + 0), __ldg(p + 1), __ldg(p + 2)};
-    const unsigned code = morton30(c, bounds);
-    // 24-bit processing-order key (3 radix passes).  mode 0: Morton code of the centre, 8 bits per axis.
-    // mode 1: direction octant (signs of the movement) on top of a 7-bit-per-axis Morton code, so the
-    // lanes of a warp walk the tree in the same order.
-    unsigned key = code >> 6;
-    if (mode == 1) {
-        const unsigned oct = (__ldg(p + 4) < 0.0f ? 4u : 0u) | (__ldg(p + 5) < 0.0f ? 2u : 0u) | (__ldg(p + 6) < 0.0f ? 1u : 0u);
-        key = (oct << 21) | (code >> 9);
+                                                        uint32_t *__restrict__ vals, int mode,
+                                                        uint32_t *__restrict__ bins) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    unsigned key = 0xFFFFFFFFu;              // lanes past the end: a key no sphere has
+    if (i < n) {
+        const float *p = reinterpret_cast<const float *>(in) + i * 7;
+        V3 c = {__ldg(p + 0), __ldg(p + 1), __ldg(p + 2)};
+        const unsigned code = morton30(c, bounds);
+        // mode 0: 24-bit Morton code of the centre, 8 bits per axis.  mode 1: direction octant (signs of
+        // the movement) on top of a 7-bit-per-axis Morton code, so the lanes of a warp walk the tree in
+        // the same order.  mode 2 (default): 16 bits, 5-6 bits per axis.
+        key = code >> 6;
+        if (mode == 1) {
+            const unsigned oct = (__ldg(p + 4) < 0.0f ? 4u : 0u) | (__ldg(p + 5) < 0.0f ? 2u : 0u) | (__ldg(p + 6) < 0.0f ? 1u : 0u);
+            key = (oct << 21) | (code >> 9);
+        }
+        if (mode == 2) key = code >> 14;
+        keys[i] = key;
+        if (!bins) vals[i] = (uint32_t)i;
     }
-    if (mode == 2) key = code >> 14;        // 16 bits (two radix passes): 5-6 bits per axis
-    keys[i] = key;
-    vals[i] = (uint32_t)i;
+    if (bins) {                              // counting sort: one atomic per distinct key per warp
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (i < n && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&bins[key], (unsigned)__popc(peers));
+    }
+}
+
+// Counting sort on 16-bit keys (the default processing order of the spheres): bin sizes come from
+// k_morton_spheres, one block turns them into bin offsets, and every sphere takes the next free slot of
+// its bin.  The order INSIDE a bin depends on the atomics' timing; that is harmless -- the order only
+// decides which lanes walk the tree together, every result is written back through the inverse
+// permutation and the closest hit is an order-independent atomicMin.
+static constexpr int CS_BINS = 1 << 16;
+__global__ void __launch_bounds__(1024) k_bin_offsets(uint32_t *__restrict__ bins) {
+    __shared__ unsigned warp_tot[32];
+    uint4 *b4 = reinterpret_cast<uint4 *>(bins);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned running = 0;                                    // bins before this sweep of 4096
+    for (int it = 0; it < CS_BINS / 4096; ++it) {            // coalesced: thread t owns bins 4t..4t+3 of the sweep
+        const uint4 v = b4[it * 1024 + threadIdx.x];
+        const unsigned tot = v.x + v.y + v.z + v.w;
+        unsigned inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        const unsigned t = warp_tot[lane];                   // every warp scans the 32 warp totals itself
+        unsigned ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += y; }
+        const unsigned a = running + __shfl_sync(0xffffffffu, ti - t, w) + (inc - tot);
+        const unsigned b = a + v.x, c = b + v.y, d = c + v.z;
+        b4[it * 1024 + threadIdx.x] = make_uint4(a, b, c, d);
+        running += __shfl_sync(0xffffffffu, ti, 31);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict__ keys, uint64_t n,
+                                                     uint32_t *__restrict__ offs, uint32_t *__restrict__ order,
+                                                     uint32_t *__restrict__ inv) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned key = i < n ? keys[i] : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (i < n && lane == leader) base = atomicAdd(&offs[key], (unsigned)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i >= n) return;
+    const unsigned pos = base + __popc(peers & ((1u << lane) - 1u));
+    order[pos] = (uint32_t)i;
+    if (inv) inv[i] = pos;
 }
 
 // K3: radix sort -------------------------------------------------------------------------------
@@ -686,14 +741,25 @@ cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n
     XP_TRY(s->sort_ka.reserve(n * 4)); XP_TRY(s->sort_kb.reserve(n * 4));
     uint32_t *ka = s->sort_ka.as<uint32_t>(), *kb = s->sort_kb.as<uint32_t>();
     uint32_t *va = s->active_a.as<uint32_t>(), *vb = s->active_b.as<uint32_t>();
-    // default: 16-bit keys, two radix passes (measured on config 2: the walk is as fast as with 24-bit
-    // keys -- 0.955 vs 0.950 ms -- and the sort drops from 0.141 to 0.097 ms); XP_RAY_KEY=0/1 select the 24-bit modes
+    // default: 16-bit keys (measured on config 2: the walk is as fast as with 24-bit keys, 0.955 vs 0.950 ms)
+    // sorted by counting; XP_RAY_KEY=0/1 select the 24-bit modes (three stable radix passes)
     static const int key_mode = getenv("XP_RAY_KEY") ? atoi(getenv("XP_RAY_KEY")) : 2;
-    k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va, key_mode);
-    ++s->stats.kernel_launches;
-    bool in_a = true;
     uint32_t *inv = nullptr;
     if (inv_order) { XP_TRY(s->inv_order.reserve(n * 4)); inv = s->inv_order.as<uint32_t>(); *inv_order = inv; }
+    if (key_mode == 2) {                    // counting sort: three launches
+        XP_TRY(s->hist.reserve(CS_BINS * sizeof(uint32_t)));
+        uint32_t *bins = s->hist.as<uint32_t>();
+        XP_TRY(cudaMemsetAsync(bins, 0, CS_BINS * sizeof(uint32_t), s->stream));
+        k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va, key_mode, bins);
+        k_bin_offsets<<<1, 1024, 0, s->stream>>>(bins);
+        k_bin_scatter<<<grid_for(n, 256), 256, 0, s->stream>>>(ka, n, bins, va, inv);
+        s->stats.kernel_launches += 3;
+        *order = va;
+        return cudaGetLastError();
+    }
+    k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va, key_mode, nullptr);
+    ++s->stats.kernel_launches;
+    bool in_a = true;
     XP_TRY(radix_sort_pairs(s, ka, kb, va, vb, n, key_mode == 2 ? 16 : 24, &in_a, inv));
     if (!in_a) { xp::DevBuf tmp = s->active_a; s->active_a = s->active_b; s->active_b = tmp; }
     *order = s->active_a.as<uint32_t>();
