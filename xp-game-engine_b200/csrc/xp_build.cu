@@ -148,46 +148,50 @@ __global__ void __launch_bounds__(256) k_morton_spheres(const xp_response *__res
 }
 
 // Counting sort on 16-bit keys (the default processing order of the spheres): bin sizes come from
-// k_morton_spheres, one block turns them into bin offsets, and every sphere takes the next free slot of
+// k_morton_spheres, k_bin_offsets turns them into offsets (per group of 1024 bins; the scatter adds the
+// prefix of the 64 group totals), and every sphere takes the next free slot of
 // its bin.  The order INSIDE a bin depends on the atomics' timing; that is harmless -- the order only
 // decides which lanes walk the tree together, every result is written back through the inverse
 // permutation and the closest hit is an order-independent atomicMin.
 static constexpr int CS_BINS = 1 << 16;
-__global__ void __launch_bounds__(1024) k_bin_offsets(uint32_t *__restrict__ bins) {
+static constexpr int CS_GROUPS = CS_BINS / 1024;             // one block of k_bin_offsets per 1024 bins
+__global__ void __launch_bounds__(1024) k_bin_offsets(uint32_t *__restrict__ bins, uint32_t *__restrict__ group_tot) {
     __shared__ unsigned warp_tot[32];
-    uint4 *b4 = reinterpret_cast<uint4 *>(bins);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned running = 0;                                    // bins before this sweep of 4096
-    for (int it = 0; it < CS_BINS / 4096; ++it) {            // coalesced: thread t owns bins 4t..4t+3 of the sweep
-        const uint4 v = b4[it * 1024 + threadIdx.x];
-        const unsigned tot = v.x + v.y + v.z + v.w;
-        unsigned inc = tot;
+    const unsigned v = bins[blockIdx.x * 1024 + threadIdx.x];
+    unsigned inc = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-        if (lane == 31) warp_tot[w] = inc;
-        __syncthreads();
-        const unsigned t = warp_tot[lane];                   // every warp scans the 32 warp totals itself
-        unsigned ti = t;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    const unsigned t = warp_tot[lane];                       // every warp scans the 32 warp totals itself
+    unsigned ti = t;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += y; }
-        const unsigned a = running + __shfl_sync(0xffffffffu, ti - t, w) + (inc - tot);
-        const unsigned b = a + v.x, c = b + v.y, d = c + v.z;
-        b4[it * 1024 + threadIdx.x] = make_uint4(a, b, c, d);
-        running += __shfl_sync(0xffffffffu, ti, 31);
-        __syncthreads();
-    }
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += y; }
+    bins[blockIdx.x * 1024 + threadIdx.x] = __shfl_sync(0xffffffffu, ti - t, w) + (inc - v);   // offset inside the group
+    if (threadIdx.x == 1023) group_tot[blockIdx.x] = ti;
 }
 
 __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict__ keys, uint64_t n,
-                                                     uint32_t *__restrict__ offs, uint32_t *__restrict__ order,
-                                                     uint32_t *__restrict__ inv) {
+                                                     uint32_t *__restrict__ offs, const uint32_t *__restrict__ group_tot,
+                                                     uint32_t *__restrict__ order, uint32_t *__restrict__ inv) {
+    __shared__ unsigned group_base[CS_GROUPS];
+    if (threadIdx.x < 32) {                                  // exclusive prefix of the 64 group totals
+        const unsigned a = group_tot[2 * threadIdx.x], b = group_tot[2 * threadIdx.x + 1];
+        unsigned inc = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += y; }
+        group_base[2 * threadIdx.x] = inc - a - b;
+        group_base[2 * threadIdx.x + 1] = inc - b;
+    }
+    __syncthreads();
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const unsigned key = i < n ? keys[i] : 0xFFFFFFFFu;
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     const int leader = __ffs(peers) - 1;
     unsigned base = 0;
-    if (i < n && lane == leader) base = atomicAdd(&offs[key], (unsigned)__popc(peers));
+    if (i < n && lane == leader) base = group_base[key >> 10] + atomicAdd(&offs[key], (unsigned)__popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (i >= n) return;
     const unsigned pos = base + __popc(peers & ((1u << lane) - 1u));
@@ -747,12 +751,13 @@ cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n
     uint32_t *inv = nullptr;
     if (inv_order) { XP_TRY(s->inv_order.reserve(n * 4)); inv = s->inv_order.as<uint32_t>(); *inv_order = inv; }
     if (key_mode == 2) {                    // counting sort: three launches
-        XP_TRY(s->hist.reserve(CS_BINS * sizeof(uint32_t)));
+        static_assert(CS_GROUPS == 64, "k_bin_scatter scans 64 group totals with one warp");
+        XP_TRY(s->hist.reserve((CS_BINS + CS_GROUPS) * sizeof(uint32_t)));
         uint32_t *bins = s->hist.as<uint32_t>();
         XP_TRY(cudaMemsetAsync(bins, 0, CS_BINS * sizeof(uint32_t), s->stream));
         k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va, key_mode, bins);
-        k_bin_offsets<<<1, 1024, 0, s->stream>>>(bins);
-        k_bin_scatter<<<grid_for(n, 256), 256, 0, s->stream>>>(ka, n, bins, va, inv);
+        k_bin_offsets<<<CS_GROUPS, 1024, 0, s->stream>>>(bins, bins + CS_BINS);
+        k_bin_scatter<<<grid_for(n, 256), 256, 0, s->stream>>>(ka, n, bins, bins + CS_BINS, va, inv);
         s->stats.kernel_launches += 3;
         *order = va;
         return cudaGetLastError();

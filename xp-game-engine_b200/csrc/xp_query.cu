@@ -1210,11 +1210,18 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
             uint32_t *tri = out.tri_index ? out.tri_index + off : nullptr;
             xp_contact *ct = out.contact ? out.contact + off : nullptr;
             const int col_vec = (reinterpret_cast<uintptr_t>(col) & 15u) == 0;
-            if (out.peers.n > 0) {
+            PeerBufs peers = out.peers;
+            uint64_t slot = out.slot_first + off;
+            if (peers.n == 0 && ct && !col && !hit && !tri && (reinterpret_cast<uintptr_t>(ct) & 7u) == 0) {
+                // contact records only: the exchange kernel with this buffer as its single "peer" builds a
+                // block's records in shared memory and writes them as one coalesced span
+                peers.n = 1; peers.rot = 0; peers.p[0] = out.contact; slot = off;
+            }
+            if (peers.n > 0) {
                 if (s->arith == XP_ARITH_FAST)
-                    k_finalize_exchange<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, out.peers, out.slot_first + off);
+                    k_finalize_exchange<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, peers, slot);
                 else
-                    k_finalize_exchange<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, out.peers, out.slot_first + off);
+                    k_finalize_exchange<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, peers, slot);
             } else if (s->arith == XP_ARITH_FAST)
                 k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
             else
