@@ -513,3 +513,40 @@ def test_full_size_response_sample(full_scene, oracle):
     assert np.array_equal(it[idx], w[1]) and np.array_equal(st[idx], w[2])
     assert_bits_equal(resp_fields(out[idx]), resp_fields(w[0]), "response sample")
     assert it.max() == 4
+
+
+# ---- row f3: soups ingested from the reference's OBJ / glTF / .vox assets ----------------------
+def ingested_scene():
+    """The committed golden soups (tests/golden/make_ingest_golden.py) assembled into one scene in
+    unit-sphere space: two greedy-meshed treehouse chunks, the ground plane, and the small props."""
+    g = np.load(os.path.join(GOLDEN, "ingest_scenes.npz"))
+    radius = np.float32(0.5)                                         # player sphere, main.rs:122
+    parts = [g["vox_chunk_1_1_1"], g["vox_chunk_2_0_1"],
+             g["obj_ground_plane_20x20"] + np.array([5, 0, 5], np.float32),
+             g["obj_axis"] + np.array([4, 4, 4], np.float32), g["obj_arrow"] + np.array([6, 5, 3], np.float32),
+             g["gltf_Cube_0"] + np.array([8, 1, 2], np.float32), g["gltf_Cube_1"] + np.array([2, 7, 6], np.float32)]
+    return np.ascontiguousarray(np.concatenate(parts) / radius, dtype=np.float32)
+
+
+@pytest.mark.parametrize("method", ["lbvh_pairs", "wide_fused", "q4_pairs"])
+def test_ingested_assets_scene(oracle, method):
+    tris = ingested_scene()
+    assert len(tris) == 3016 + 1788 + 128 + 52 + 12 + 12 + 12
+    rng = np.random.default_rng(77)
+    lo, hi = tris.reshape(-1, 3).min(axis=0), tris.reshape(-1, 3).max(axis=0)
+    n = 2500
+    c = rng.uniform(lo - 1.5, hi + 1.5, (n, 3)).astype(np.float32)
+    m = rng.normal(0, 1.2, (n, 3)).astype(np.float32)
+    resps = xp.make_responses(c, m)
+    want = oracle.detect_batch(resps, tris)
+    w = oracle.collision_response_batch(resps, tris, max_iter=3)
+    with xp.Scene(0, tris, method=method) as s:
+        got = s.detect_batch(resps)
+        out, it, st, ln = s.collision_response_batch(resps, max_iter=3)
+        gi, gj = s.broadphase_pairs(resps)
+    check_detect_exact(got, want, f"ingested scene {method}")
+    assert want[1].sum() > 500
+    assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
+    assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"ingested scene response {method}")
+    wi, wj = oracle.broadphase_pairs(resps, tris)
+    assert np.array_equal(np.sort(gi.astype(np.uint64) << 32 | gj), np.sort(wi.astype(np.uint64) << 32 | wj))
