@@ -153,6 +153,18 @@ int  xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t ho
 int  xp_detect_batch_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
                          xp_collision *d_out, uint8_t *d_hit, uint32_t *d_tri_index,
                          uint32_t *d_status);
+/* The same sweep for a STREAM of batches (new; the reference's call is synchronous, lib.rs:29):
+ * submit queues the H2D copy, the sweep and the D2H copies of one batch and returns a ticket;
+ * wait blocks until that batch's results are in the caller's buffers and fills xp_scene_get_stats
+ * for it.  Up to XP_ASYNC_SLOTS batches may be in flight, so one batch's copies run under another
+ * batch's kernels.  The caller's buffers must stay valid and untouched until wait returns, and
+ * should be page-locked (pageable memory makes the copies synchronous).  submit returns XP_ESTATE
+ * when every slot is in flight, wait returns XP_ESTATE for a ticket that is not in flight. */
+#define XP_ASYNC_SLOTS 2
+int  xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                            xp_collision *out, uint8_t *hit, uint32_t *tri_index, uint32_t *status,
+                            int *ticket);
+int  xp_detect_batch_wait(xp_scene *s, int ticket);
 
 /* ---- a16: collision_response (lib.rs:29-62) for a batch of independent spheres.
  * max_iter == 0: unbounded like the reference (an internal guard of 65536 iterations sets

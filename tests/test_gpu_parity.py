@@ -550,3 +550,64 @@ def test_ingested_assets_scene(oracle, method):
     assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"ingested scene response {method}")
     wi, wj = oracle.broadphase_pairs(resps, tris)
     assert np.array_equal(np.sort(gi.astype(np.uint64) << 32 | gj), np.sort(wi.astype(np.uint64) << 32 | wj))
+
+
+# ---- asynchronous stream of batches: xp_detect_batch_submit / _wait ----------------------------
+def test_async_stream_of_batches(terrain, oracle):
+    import torch
+    tris, h, resps, want = terrain
+    n = len(resps)
+    batches = [resps, scenes.terrain_spheres(h, n, seed=91), scenes.terrain_spheres(h, n, seed=92)]
+    wants = [want, oracle.detect_batch(batches[1], tris), oracle.detect_batch(batches[2], tris)]
+
+    def pinned(dtype):
+        return torch.from_numpy(np.zeros(n, dtype).view(np.uint8)).pin_memory()
+    bufs = [{"in": pinned(xp.RESPONSE_DTYPE), "col": pinned(xp.COLLISION_DTYPE), "hit": pinned(np.uint8),
+             "tri": pinned(np.uint32), "st": pinned(np.uint32)} for _ in range(2)]
+    with xp.Scene(0, tris) as s:
+        tickets = {}
+        results = {}
+
+        def collect(k):
+            s.detect_batch_wait(tickets.pop(k))
+            b = bufs[k % 2]
+            assert s.stats()["narrowphase_tests"] > 0
+            results[k] = (b["col"].numpy().view(xp.COLLISION_DTYPE).copy(), b["hit"].numpy().copy(),
+                          b["tri"].numpy().view(np.uint32).copy(), b["st"].numpy().view(np.uint32).copy())
+        for rep in range(2):
+            for k, r in enumerate(batches):
+                k += 3 * rep
+                if k >= 2:
+                    collect(k - 2)                                   # frees the slot and the buffers of batch k - 2
+                b = bufs[k % 2]
+                b["in"].numpy()[:] = np.ascontiguousarray(r).view(np.uint8)
+                tickets[k] = s.detect_batch_submit(b["in"].data_ptr(), n, b["col"].data_ptr(), b["hit"].data_ptr(),
+                                                   b["tri"].data_ptr(), b["st"].data_ptr())
+                if k == 1:                                           # both slots in flight: a third submit is refused
+                    with pytest.raises(xp.XpError):
+                        s.detect_batch_submit(b["in"].data_ptr(), n)
+        collect(4)
+        collect(5)
+        with pytest.raises(xp.XpError):
+            s.detect_batch_wait(0)                                   # not in flight
+        # a synchronous call still works after the stream
+        check_detect_exact(s.detect_batch(resps), want, "sync after async")
+    for k in range(6):
+        check_detect_exact(results[k], wants[k % 3], f"async batch {k}")
+
+
+def test_async_batch_overflow_is_redone(terrain):
+    import torch
+    tris, h, resps, want = terrain
+    n = len(resps)
+    h_in = torch.from_numpy(np.ascontiguousarray(resps).view(np.uint8).copy()).pin_memory()
+    h_col = torch.zeros(n * 32, dtype=torch.uint8).pin_memory()
+    h_hit = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    h_tri = torch.zeros(n * 4, dtype=torch.uint8).pin_memory()
+    h_st = torch.zeros(n * 4, dtype=torch.uint8).pin_memory()
+    with xp.Scene(0, tris) as s:
+        s.set_options(max_pairs=4096)                                # far too small: candidates are dropped
+        t = s.detect_batch_submit(h_in.data_ptr(), n, h_col.data_ptr(), h_hit.data_ptr(), h_tri.data_ptr(), h_st.data_ptr())
+        s.detect_batch_wait(t)
+    got = (h_col.numpy().view(xp.COLLISION_DTYPE), h_hit.numpy(), h_tri.numpy().view(np.uint32), h_st.numpy().view(np.uint32))
+    check_detect_exact(got, want, "async overflow redo")

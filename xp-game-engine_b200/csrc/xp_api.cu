@@ -85,12 +85,21 @@ void xp_scene_destroy(xp_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
+    if (s->io_ready) { cudaStreamSynchronize(s->copy_in); cudaStreamSynchronize(s->copy_out); }   // batches still in flight
     DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_lo, &s->node_hi, &s->leaf_lo, &s->leaf_hi,
                       &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
                       &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->rays, &s->best, &s->active_a,
                       &s->active_b, &s->inv_order, &s->pairs, &s->counters, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
                       &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
     for (DevBuf *b : bufs) b->release();
+    for (auto &a : s->async_slot) {
+        DevBuf *ab[] = {&a.in, &a.col, &a.hit, &a.tri, &a.status};
+        for (DevBuf *b : ab) b->release();
+        if (a.h2d) cudaEventDestroy(a.h2d);
+        if (a.done) cudaEventDestroy(a.done);
+        if (a.d2h) cudaEventDestroy(a.d2h);
+        if (a.h_ctr) cudaFreeHost(a.h_ctr);
+    }
     if (s->ev_created)
         for (int i = 0; i < 2 * xp_scene::EV_POOL; ++i) cudaEventDestroy(s->ev[i]);
     if (s->io_ready) {
@@ -388,6 +397,101 @@ int xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t hor
         if (status) XP_API_TRY(cudaMemcpyAsync(status, s->io_status.p, n * 4, cudaMemcpyDeviceToHost, st));
         XP_API_TRY(cudaStreamSynchronize(st));
     }
+    return XP_OK;
+}
+
+
+// ---- asynchronous host-pointer sweep ----------------------------------------------------------
+// submit() queues H2D copy -> sweep -> D2H copies of one batch on three streams and returns; wait()
+// blocks until that batch's results are in the caller's buffers.  With XP_ASYNC_SLOTS batches in
+// flight the copies of one batch run under the kernels of another, so a stream of batches moves at
+// the pace of the slower of compute and PCIe instead of their sum.  The optimistic pair buffer is
+// checked from a counter snapshot copied back with the results; a batch that dropped candidates is
+// redone synchronously inside wait() (inputs are read-only, so that is safe).
+static int ensure_async(xp_scene *s) {
+    int rc = ensure_io_streams(s);
+    if (rc) return rc;
+    if (s->async_ready) return XP_OK;
+    for (auto &a : s->async_slot) {
+        XP_API_TRY(cudaEventCreateWithFlags(&a.h2d, cudaEventDisableTiming));
+        XP_API_TRY(cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming));
+        XP_API_TRY(cudaEventCreateWithFlags(&a.d2h, cudaEventDisableTiming));
+        XP_API_TRY(cudaHostAlloc(reinterpret_cast<void **>(&a.h_ctr), sizeof(DeviceCounters), cudaHostAllocDefault));
+    }
+    s->async_ready = true;
+    return XP_OK;
+}
+
+int xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                           xp_collision *out, uint8_t *hit, uint32_t *tri_index, uint32_t *status, int *ticket) {
+    int rc = check_query(s, in, n);
+    if (rc) return rc;
+    if (!ticket) return XP_EINVAL;
+    XP_BIND(s);
+    rc = ensure_async(s);
+    if (rc) return rc;
+    int slot = -1;
+    for (int i = 0; i < xp_scene::ASYNC_SLOTS; ++i)
+        if (!s->async_slot[i].busy) { slot = i; break; }
+    if (slot < 0) return XP_ESTATE;                  // every slot is in flight: wait for a ticket first
+    xp_scene::AsyncSlot &a = s->async_slot[slot];
+    a.h_in = in; a.n = n; a.horizon_mode = horizon_mode;
+    a.out = out; a.hit_out = hit; a.tri_out = tri_index; a.status_out = status;
+    a.launches = 0;
+    *ticket = slot;
+    a.busy = true;
+    if (n == 0) { memset(a.h_ctr, 0, sizeof(DeviceCounters)); return XP_OK; }
+    cudaStream_t st = s->stream;
+    XP_API_TRY(a.in.reserve(n * sizeof(xp_response)));
+    XP_API_TRY(a.col.reserve(n * sizeof(xp_collision)));
+    XP_API_TRY(a.hit.reserve(n));
+    XP_API_TRY(a.tri.reserve(n * 4));
+    XP_API_TRY(a.status.reserve(n * 4));
+    XP_API_TRY(cudaMemcpyAsync(a.in.p, in, n * sizeof(xp_response), cudaMemcpyHostToDevice, s->copy_in));
+    XP_API_TRY(cudaEventRecord(a.h2d, s->copy_in));
+    XP_API_TRY(cudaStreamWaitEvent(st, a.h2d, 0));
+    if (out) XP_API_TRY(cudaMemsetAsync(a.col.p, 0, n * sizeof(xp_collision), st));
+    QueryOut q = {out ? a.col.as<xp_collision>() : nullptr, a.hit.as<uint8_t>(), tri_index ? a.tri.as<uint32_t>() : nullptr,
+                  a.status.as<uint32_t>(), nullptr, {}, 0};
+    const int timing = s->timing;
+    s->timing = 0;                                   // stage events are resolved by synchronous calls only
+    s->counters_live = false;                        // this batch gets freshly zeroed counters
+    const uint32_t before = s->stats.kernel_launches;
+    cudaError_t e = detect_dev(s, a.in.as<xp_response>(), n, horizon_mode, q, /*collect=*/false);
+    s->timing = timing;
+    s->counters_live = false;
+    a.launches = s->stats.kernel_launches - before;
+    if (e != cudaSuccess) { a.busy = false; return fail_cuda(e); }
+    XP_API_TRY(cudaMemcpyAsync(a.h_ctr, s->counters.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
+    XP_API_TRY(cudaEventRecord(a.done, st));
+    cudaStream_t so = s->copy_out;
+    XP_API_TRY(cudaStreamWaitEvent(so, a.done, 0));
+    if (out) XP_API_TRY(cudaMemcpyAsync(out, a.col.p, n * sizeof(xp_collision), cudaMemcpyDeviceToHost, so));
+    if (hit) XP_API_TRY(cudaMemcpyAsync(hit, a.hit.p, n, cudaMemcpyDeviceToHost, so));
+    if (tri_index) XP_API_TRY(cudaMemcpyAsync(tri_index, a.tri.p, n * 4, cudaMemcpyDeviceToHost, so));
+    if (status) XP_API_TRY(cudaMemcpyAsync(status, a.status.p, n * 4, cudaMemcpyDeviceToHost, so));
+    XP_API_TRY(cudaEventRecord(a.d2h, so));
+    return XP_OK;
+}
+
+int xp_detect_batch_wait(xp_scene *s, int ticket) {
+    if (!s || ticket < 0 || ticket >= xp_scene::ASYNC_SLOTS) return XP_EINVAL;
+    xp_scene::AsyncSlot &a = s->async_slot[ticket];
+    if (!a.busy) return XP_ESTATE;
+    XP_BIND(s);
+    a.busy = false;
+    reset_stats(s);
+    if (a.n == 0) return XP_OK;
+    XP_API_TRY(cudaEventSynchronize(a.d2h));
+    const DeviceCounters &h = *a.h_ctr;
+    if (h.stack_overflow) return fail_cuda(cudaErrorAssert);
+    if (h.pair_overflow) {                           // rare: candidates were dropped -- redo this batch synchronously
+        return xp_detect_batch(s, a.h_in, a.n, a.horizon_mode, a.out, a.hit_out, a.tri_out, a.status_out);
+    }
+    s->stats.narrowphase_tests = h.tests;
+    s->stats.broadphase_pairs = h.pairs_total;
+    s->stats.node_visits = h.node_visits;
+    s->stats.kernel_launches = a.launches;
     return XP_OK;
 }
 

@@ -129,4 +129,21 @@ struct xp_scene {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t io_ev[32] = {};
     bool io_ready = false;
+    // xp_detect_batch_submit / _wait: batches in flight, each with its own device buffers, so that
+    // one batch's copies overlap another batch's kernels
+    static constexpr int ASYNC_SLOTS = 2;
+    struct AsyncSlot {
+        xp::DevBuf in, col, hit, tri, status;
+        cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
+        xp::DeviceCounters *h_ctr = nullptr;     // pinned snapshot of the device counters of this batch
+        bool busy = false;
+        const xp_response *h_in = nullptr;       // the call's arguments (a dropped-candidate batch is redone)
+        uint64_t n = 0;
+        uint32_t horizon_mode = 0, launches = 0;
+        xp_collision *out = nullptr;
+        uint8_t *hit_out = nullptr;
+        uint32_t *tri_out = nullptr, *status_out = nullptr;
+    };
+    AsyncSlot async_slot[ASYNC_SLOTS];
+    bool async_ready = false;
 };

@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
         "xp_scene_triangle_count": ([vp], u64),
         "xp_detect_batch": ([vp, vp, u64, u32, vp, vp, vp, vp], i32),
         "xp_detect_batch_dev": ([vp, vp, u64, u32, vp, vp, vp, vp], i32),
+        "xp_detect_batch_submit": ([vp, vp, u64, u32, vp, vp, vp, vp, vp], i32),
+        "xp_detect_batch_wait": ([vp, i32], i32),
         "xp_collision_response_batch": ([vp, vp, u64, u32, u32, vp, vp, vp, vp], i32),
         "xp_collision_response_batch_dev": ([vp, vp, u64, u32, u32, vp, vp, vp, vp], i32),
         "xp_sphere_triangle_detect_collision": ([i32, vp, vp, vp], i32),
@@ -105,6 +107,7 @@ EXPORTED_SYMBOLS = [
     "xp_device_count", "xp_scene_create", "xp_scene_destroy", "xp_scene_set_stream", "xp_scene_set_option",
     "xp_scene_get_stats", "xp_scene_set_triangles", "xp_scene_set_triangles_dev", "xp_scene_set_positions", "xp_scene_set_heightmap",
     "xp_scene_build", "xp_scene_triangle_count", "xp_detect_batch", "xp_detect_batch_dev",
+    "xp_detect_batch_submit", "xp_detect_batch_wait",
     "xp_collision_response_batch", "xp_collision_response_batch_dev", "xp_sphere_triangle_detect_collision",
     "xp_sphere_triangle_calculate_response", "xp_broadphase_pairs", "xp_scene_debug_tree",
     "xp_detect_contacts_dev", "xp_exchange_alloc", "xp_exchange_free", "xp_exchange_open", "xp_exchange_close",

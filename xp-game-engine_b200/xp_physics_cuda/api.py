@@ -207,6 +207,22 @@ class Scene:
               "xp_detect_batch")
         return col, hit, tri, st
 
+    def detect_batch_submit(self, h_in: int, n: int, h_col: int = 0, h_hit: int = 0, h_tri: int = 0,
+                            h_status: int = 0, horizon: str = "inf") -> int:
+        """Queue one batch of a stream of batches (xp_detect_batch_submit): host addresses (ints) of
+        page-locked buffers that stay untouched until `detect_batch_wait(ticket)`.  Up to
+        XP_ASYNC_SLOTS = 2 batches may be in flight; one batch's copies overlap another's kernels."""
+        vp = C.c_void_p
+        ticket = C.c_int(-1)
+        check(self._L.xp_detect_batch_submit(self._h, vp(h_in), n, _horizon(horizon), vp(h_col or None),
+                                             vp(h_hit or None), vp(h_tri or None), vp(h_status or None),
+                                             C.byref(ticket)), "xp_detect_batch_submit")
+        return ticket.value
+
+    def detect_batch_wait(self, ticket: int) -> None:
+        """Block until the batch behind `ticket` is in the caller's buffers; `stats()` then describes it."""
+        check(self._L.xp_detect_batch_wait(self._h, ticket), "xp_detect_batch_wait")
+
     def collision_response_batch(self, responses: np.ndarray, max_iter: int = 0, horizon: str = "inf"):
         """collision_response (lib.rs:29-62) for every sphere.
         Returns (responses_out, iterations, status, last_slide_normal)."""
