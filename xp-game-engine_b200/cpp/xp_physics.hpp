@@ -59,6 +59,18 @@ class Scene {
                               o.status.data()), "xp_detect_batch");
         return o;
     }
+    // stream of batches: submit() returns a ticket, wait() blocks until that batch is in `out`; up to
+    // XP_ASYNC_SLOTS in flight.  `in` and `out` must outlive wait() and should be page-locked.
+    int detect_batch_submit(const Response *in, size_t n, Closest &out, uint32_t horizon = XP_HORIZON_INF) {
+        out.collision.resize(n); out.hit.resize(n); out.tri_index.resize(n); out.status.resize(n);
+        int ticket = -1;
+        check(xp_detect_batch_submit(s_, reinterpret_cast<const xp_response *>(in), n, horizon,
+                                     reinterpret_cast<xp_collision *>(out.collision.data()), out.hit.data(),
+                                     out.tri_index.data(), out.status.data(), &ticket), "xp_detect_batch_submit");
+        return ticket;
+    }
+    void detect_batch_wait(int ticket) { check(xp_detect_batch_wait(s_, ticket), "xp_detect_batch_wait"); }
+
     struct Resolved { std::vector<Response> response; std::vector<uint32_t> iterations, status; std::vector<Vec3> slide_normal; };
     Resolved collision_response_batch(const std::vector<Response> &in, uint32_t max_iter = 0,
                                       uint32_t horizon = XP_HORIZON_INF) {
