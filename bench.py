@@ -387,9 +387,11 @@ def run_b200(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(workload_config(world), arith=args.arith, method=args.method,
                                                     prune=bool(args.prune),
-                                                    exchange=("none" if world == 1 else
-                                                              "p2p stores into mapped peer buffers (fused with the record build)"
-                                                              if exchange is not None else "nccl all_gather")),
+                                                    exchange=("none" if world == 1 else "nccl all_gather" if exchange is None else
+                                                              "one multimem.st per record span into an NVSwitch multicast address bound to "
+                                                              "every rank's gather buffer (fused with the record build)"
+                                                              if exchange.mode == "multicast" else
+                                                              "p2p stores into mapped peer buffers (fused with the record build)")),
                 "spheres_per_sec": spheres_per_sec, "tests_per_step": tests_all / args.steps,
                 "node_visits_per_step": float(np.mean([s["node_visits"] for s in stats])),
                 "stage_ms": {k: float(np.mean([s["stage_ms"][k] for s in stats])) for k in stats[0]["stage_ms"]},

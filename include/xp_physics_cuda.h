@@ -226,6 +226,12 @@ int  xp_exchange_open(xp_scene *s, const uint8_t ipc_handle[64], void **peer_ptr
 int  xp_exchange_close(xp_scene *s, void *peer_ptr);
 int  xp_detect_contacts_exchange_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
                                      void *const *bufs, int n_bufs, uint64_t slot_first);
+/* The same with ONE store per record: multicast_buf is a multicast address of the NVSwitch fabric bound to
+ * every rank's gather buffer (cuMulticast* / torch symmetric memory set it up; 16-byte aligned), so a span
+ * leaves this GPU once and the switch replicates it into all buffers, this rank's included
+ * (multimem.st).  slot_first must be even.  The caller synchronises the ranks before reading. */
+int  xp_detect_contacts_multicast_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                                      void *multicast_buf, uint64_t slot_first);
 
 /* ---- measurement helpers ---- */
 /* Dependent-free FFMA loop on every SM: the fp32 CUDA-core peak used as roofline denominator. */

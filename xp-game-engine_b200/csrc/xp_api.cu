@@ -328,6 +328,23 @@ int xp_detect_contacts_exchange_dev(xp_scene *s, const xp_response *d_in, uint64
     return XP_OK;
 }
 
+int xp_detect_contacts_multicast_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                                     void *multicast_buf, uint64_t slot_first) {
+    int rc = check_query(s, d_in, n);
+    if (rc) return rc;
+    if (!multicast_buf || (slot_first & 1) || (reinterpret_cast<uintptr_t>(multicast_buf) & 15u)) return XP_EINVAL;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    XP_API_TRY(s->io_status.reserve(n * 4));
+    QueryOut q = {nullptr, nullptr, nullptr, s->io_status.as<uint32_t>(), nullptr, {}, slot_first};
+    q.peers.n = 1;
+    q.peers.multicast = 1;
+    q.peers.p[0] = static_cast<xp_contact *>(multicast_buf);
+    XP_API_TRY(detect_retry(s, d_in, n, horizon_mode, q));
+    return XP_OK;
+}
+
 int xp_detect_batch(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
                     xp_collision *out, uint8_t *hit, uint32_t *tri_index, uint32_t *status) {
     int rc = check_query(s, in, n);

@@ -31,7 +31,7 @@ cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n
 
 // ---- xp_query.cu ----
 static constexpr int XP_MAX_PEERS = 16;
-struct PeerBufs { xp_contact *p[XP_MAX_PEERS]; int n; int rot; };
+struct PeerBufs { xp_contact *p[XP_MAX_PEERS]; int n; int rot; int multicast; };   // multicast: p[0] is an NVSwitch multicast address
 struct QueryOut {            // device pointers, any may be null
     xp_collision *col; uint8_t *hit; uint32_t *tri_index; uint32_t *status; xp_contact *contact;
     // fused contact exchange: when peers.n > 0 every contact record is written into each peer buffer at

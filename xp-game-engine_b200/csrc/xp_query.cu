@@ -938,6 +938,22 @@ __global__ void __launch_bounds__(256) k_finalize_exchange(const RayRec *__restr
     const unsigned cnt = (unsigned)((n - i0 < 256) ? (n - i0) : 256);       // records of this block
     const unsigned n8 = cnt * 5;                                            // 8-byte words
     const float2 *src = reinterpret_cast<const float2 *>(rec);
+    if (peers.multicast) {
+        // p[0] is a multicast address of the NVSwitch fabric: one store, every rank's buffer (this rank's
+        // included) receives it -- the span leaves this GPU once instead of once per peer
+        float2 *dst = reinterpret_cast<float2 *>(peers.p[0]) + (slot_first + i0) * 5;   // 16 B aligned: both terms are even
+        const unsigned n16 = n8 >> 1;
+        for (unsigned w = threadIdx.x; w < n16; w += 256) {
+            const float4 v = reinterpret_cast<const float4 *>(rec)[w];
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                         :: "l"(dst + 2 * w), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+        if ((n8 & 1) && threadIdx.x == 0) {
+            const float2 v = src[n8 - 1];
+            asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" :: "l"(dst + (n8 - 1)), "f"(v.x), "f"(v.y) : "memory");
+        }
+        return;
+    }
     // every rank starts with a different peer and consecutive blocks rotate, so at any instant the
     // stores of the whole machine are spread over all receivers instead of converging on one
     for (int j = 0; j < peers.n; ++j) {
@@ -1215,7 +1231,7 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
             if (peers.n == 0 && ct && !col && !hit && !tri && (reinterpret_cast<uintptr_t>(ct) & 7u) == 0) {
                 // contact records only: the exchange kernel with this buffer as its single "peer" builds a
                 // block's records in shared memory and writes them as one coalesced span
-                peers.n = 1; peers.rot = 0; peers.p[0] = out.contact; slot = off;
+                peers.n = 1; peers.rot = 0; peers.multicast = 0; peers.p[0] = out.contact; slot = off;
             }
             if (peers.n > 0) {
                 if (s->arith == XP_ARITH_FAST)

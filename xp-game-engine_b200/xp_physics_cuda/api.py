@@ -299,6 +299,13 @@ class Scene:
         check(self._L.xp_detect_contacts_exchange_dev(self._h, C.c_void_p(d_in), n, _horizon(horizon), arr, len(bufs),
                                                       slot_first), "xp_detect_contacts_exchange_dev")
 
+    def detect_contacts_multicast_dev(self, d_in: int, n: int, multicast_buf: int, slot_first: int, horizon: str = "inf"):
+        """Sweep and write every contact record ONCE, to an NVSwitch multicast address bound to all ranks'
+        gather buffers (record index slot_first + i): the switch performs the replication."""
+        check(self._L.xp_detect_contacts_multicast_dev(self._h, C.c_void_p(d_in), n, _horizon(horizon),
+                                                       C.c_void_p(multicast_buf), slot_first),
+              "xp_detect_contacts_multicast_dev")
+
     def collision_response_batch_dev(self, d_in: int, n: int, d_out: int, max_iter: int = 0, d_iter: int = 0,
                                      d_status: int = 0, d_normal: int = 0, horizon: str = "inf"):
         vp = C.c_void_p

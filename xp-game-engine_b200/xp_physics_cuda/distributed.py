@@ -11,6 +11,8 @@ torch.distributed is plumbing only (process group + NCCL/gloo all_gather).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .api import CONTACT_DTYPE, RESPONSE_DTYPE, Scene
@@ -63,18 +65,30 @@ class _DeviceArray:
 
 
 class ContactExchange:
-    """One gather buffer per rank ([world, cap, 10] float32), each mapped by every other rank through CUDA
-    IPC, so a kernel on any rank can store into all of them (NVLink P2P).  `ok` is False when the mapping
-    failed on some rank (the callers then fall back to the NCCL all-gather)."""
+    """One gather buffer per rank ([world, cap, 10] float32) that a kernel on any rank can store into.
+
+    Two transports, tried in this order (`mode` says which one is live):
+      "multicast": the buffers are torch symmetric memory bound to one NVSwitch multicast address; the
+                   record-building kernel stores every span ONCE (multimem.st) and the switch replicates
+                   it into all ranks' buffers -- 1/world of the NVLink egress of the unicast path;
+      "p2p":       every rank maps every other rank's buffer through CUDA IPC and the kernel stores each
+                   span into all of them (NVLink P2P).
+    `ok` is False when neither could be set up on every rank (callers fall back to the NCCL all-gather).
+    XP_EXCHANGE_MULTICAST=0 skips the multicast attempt."""
 
     def __init__(self, scene: Scene, cap: int, device, group=None):
         import torch
         import torch.distributed as dist
         self.scene, self.group = scene, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.cap = cap + (cap & 1)                   # even slots: 8-byte aligned spans
+        self.cap = cap + (cap & 1)                   # even slots: 16-byte aligned spans
         self.nbytes = self.world * self.cap * 4 * CONTACT_FLOATS
-        self.ptr, self.bufs, self.ok = 0, [], True
+        self.ptr, self.bufs, self.ok, self.mode = 0, [], True, "p2p"
+        self.mc_ptr, self._symm = 0, None
+        shape = (self.world, self.cap, CONTACT_FLOATS)
+        if os.environ.get("XP_EXCHANGE_MULTICAST", "1") != "0" and self._try_multicast(torch, dist, device, shape):
+            self.mode = "multicast"
+            return
         handle = b""
         try:
             self.ptr, handle = scene.exchange_alloc(self.nbytes)
@@ -96,11 +110,38 @@ class ContactExchange:
             self.ok = False
             self.close()
         else:
-            self.view = torch.as_tensor(_DeviceArray(self.ptr, (self.world, self.cap, CONTACT_FLOATS)), device=device)
+            self.view = torch.as_tensor(_DeviceArray(self.ptr, shape), device=device)
+
+    def _try_multicast(self, torch, dist, device, shape) -> bool:
+        """Symmetric memory + multicast address through torch (plumbing only: allocation and rendezvous)."""
+        mc, t, why = 0, None, ""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            g = self.group if self.group is not None else dist.group.WORLD
+            t = symm_mem.empty(shape, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(t, g)
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if mc & 15:
+                mc = 0
+        except Exception as e:                       # noqa: BLE001 -- any failure means "not available here"
+            mc, why = 0, repr(e)[:200]
+        flags = [None] * self.world
+        dist.all_gather_object(flags, mc != 0, group=self.group)
+        self.multicast_note = why
+        if not all(flags):
+            return False
+        t.zero_()
+        self._symm, self.view, self.mc_ptr = t, t, mc
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+        return True
 
     def sweep(self, d_in_ptr: int, n_local: int, horizon: str = "inf"):
         """Sweep this rank's spheres; their contact records land in slot `rank` of EVERY rank's buffer."""
-        self.scene.detect_contacts_exchange_dev(d_in_ptr, n_local, self.bufs, self.rank * self.cap, horizon)
+        if self.mode == "multicast":
+            self.scene.detect_contacts_multicast_dev(d_in_ptr, n_local, self.mc_ptr, self.rank * self.cap, horizon)
+        else:
+            self.scene.detect_contacts_exchange_dev(d_in_ptr, n_local, self.bufs, self.rank * self.cap, horizon)
 
     def close(self):
         for r, b in enumerate(self.bufs):
@@ -110,6 +151,7 @@ class ContactExchange:
         if self.ptr:
             self.scene.exchange_free(self.ptr)
             self.ptr = 0
+        self._symm = None
 
 
 class ShardedSweep:
@@ -156,7 +198,7 @@ class ShardedSweep:
         use_p2p = self.exchange in ("auto", "p2p") and self._setup_p2p(n, group)
         if self.exchange == "p2p" and not use_p2p:
             raise RuntimeError("peer-memory exchange requested but CUDA IPC mapping failed")
-        self.last_exchange = "p2p" if use_p2p else "nccl"
+        self.last_exchange = self._ex.mode if use_p2p else "nccl"
         if use_p2p:
             if hi > lo:
                 self._ex.sweep(d_in.data_ptr(), hi - lo)
