@@ -232,6 +232,17 @@ int  xp_detect_contacts_exchange_dev(xp_scene *s, const xp_response *d_in, uint6
  * (multimem.st).  slot_first must be even.  The caller synchronises the ranks before reading. */
 int  xp_detect_contacts_multicast_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
                                       void *multicast_buf, uint64_t slot_first);
+/* A LOOP of steps: submit queues one step and returns; the sweep runs on the scene's stream, the record
+ * build + exchange behind it on the stream given to xp_scene_set_exchange_stream, so the NEXT step's sweep
+ * overlaps this step's exchange (two steps may be in flight; each owns the buffers its exchange reads).
+ * The caller orders its cross-rank barrier after the exchange on that second stream.  wait blocks until
+ * the step's records have left this GPU, fills xp_scene_get_stats for it, and returns XP_ECAP in the rare
+ * case that the optimistic candidate buffer overflowed: redo that step with the synchronous call.
+ * n <= 2^24 per step; d_in must stay untouched until wait returns. */
+int  xp_scene_set_exchange_stream(xp_scene *s, void *cuda_stream);
+int  xp_detect_contacts_exchange_submit(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                                        void *const *bufs, int n_bufs, uint64_t slot_first, int *ticket);
+int  xp_detect_contacts_exchange_wait(xp_scene *s, int ticket);
 
 /* ---- measurement helpers ---- */
 /* Dependent-free FFMA loop on every SM: the fp32 CUDA-core peak used as roofline denominator. */

@@ -7,6 +7,7 @@
 #include <new>
 
 #include "xp_internal.h"
+#include <utility>
 
 namespace xp {
 
@@ -24,11 +25,11 @@ StageTimer::StageTimer(xp_scene *scene, int st) : s(scene), slot(-1) {
         for (int i = 0; i < 2 * xp_scene::EV_POOL; ++i) cudaEventCreate(&s->ev[i]);
         s->ev_created = true;
     }
-    if (s->ev_count >= xp_scene::EV_POOL) {      // pool exhausted (long response loops): drain it
+    if (s->ev_base + s->ev_count >= xp_scene::EV_POOL) {      // pool exhausted (long response loops): drain it
         cudaStreamSynchronize(s->stream);
         resolve_stage_timers(s);
     }
-    slot = s->ev_count++;
+    slot = s->ev_base + s->ev_count++;
     s->ev_stage[slot] = st;
     cudaEventRecord(s->ev[2 * slot], s->stream);
 }
@@ -36,7 +37,7 @@ StageTimer::~StageTimer() {
     if (slot >= 0) cudaEventRecord(s->ev[2 * slot + 1], s->stream);
 }
 void resolve_stage_timers(xp_scene *s) {
-    for (int i = 0; i < s->ev_count; ++i) {
+    for (int i = s->ev_base; i < s->ev_base + s->ev_count; ++i) {
         float ms = 0.0f;
         if (cudaEventSynchronize(s->ev[2 * i + 1]) == cudaSuccess &&
             cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]) == cudaSuccess)
@@ -86,6 +87,7 @@ void xp_scene_destroy(xp_scene *s) {
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     if (s->io_ready) { cudaStreamSynchronize(s->copy_in); cudaStreamSynchronize(s->copy_out); }   // batches still in flight
+    for (auto &x : s->ex_slot) if (x.busy) cudaEventSynchronize(x.fin);
     DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_lo, &s->node_hi, &s->leaf_lo, &s->leaf_hi,
                       &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
                       &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->rays, &s->best, &s->active_a,
@@ -99,6 +101,13 @@ void xp_scene_destroy(xp_scene *s) {
         if (a.done) cudaEventDestroy(a.done);
         if (a.d2h) cudaEventDestroy(a.d2h);
         if (a.h_ctr) cudaFreeHost(a.h_ctr);
+    }
+    for (auto &x : s->ex_slot) {
+        DevBuf *xb[] = {&x.rays, &x.best, &x.inv_order, &x.status};
+        for (DevBuf *b : xb) b->release();
+        if (x.np) cudaEventDestroy(x.np);
+        if (x.fin) cudaEventDestroy(x.fin);
+        if (x.h_ctr) cudaFreeHost(x.h_ctr);
     }
     if (s->ev_created)
         for (int i = 0; i < 2 * xp_scene::EV_POOL; ++i) cudaEventDestroy(s->ev[i]);
@@ -509,6 +518,94 @@ int xp_detect_batch_wait(xp_scene *s, int ticket) {
     s->stats.broadphase_pairs = h.pairs_total;
     s->stats.node_visits = h.node_visits;
     s->stats.kernel_launches = a.launches;
+    return XP_OK;
+}
+
+// ---- asynchronous fused exchange: step i's record build + all-gather under step i+1's sweep ----------
+int xp_scene_set_exchange_stream(xp_scene *s, void *cuda_stream) {
+    if (!s) return XP_EINVAL;
+    s->exchange_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return XP_OK;
+}
+
+static int ensure_exchange_slots(xp_scene *s) {
+    if (s->ex_ready) return XP_OK;
+    for (auto &x : s->ex_slot) {
+        XP_API_TRY(cudaEventCreateWithFlags(&x.np, cudaEventDisableTiming));
+        XP_API_TRY(cudaEventCreateWithFlags(&x.fin, cudaEventDisableTiming));
+        XP_API_TRY(cudaHostAlloc(reinterpret_cast<void **>(&x.h_ctr), sizeof(DeviceCounters), cudaHostAllocDefault));
+    }
+    s->ex_ready = true;
+    return XP_OK;
+}
+
+int xp_detect_contacts_exchange_submit(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                                       void *const *bufs, int n_bufs, uint64_t slot_first, int *ticket) {
+    int rc = check_query(s, d_in, n);
+    if (rc) return rc;
+    if (!bufs || !ticket || n_bufs <= 0 || n_bufs > XP_MAX_PEERS || (slot_first & 1)) return XP_EINVAL;
+    if (n == 0 || n > (1ull << 24)) return XP_EINVAL;            // one chunk per step: its buffers stay untouched until the exchange has read them
+    if (!s->exchange_stream || s->exchange_stream == s->stream) return XP_ESTATE;
+    XP_BIND(s);
+    rc = ensure_exchange_slots(s);
+    if (rc) return rc;
+    const int t = s->ex_next;
+    xp_scene::ExSlot &x = s->ex_slot[t];
+    if (x.busy) return XP_ESTATE;                                // wait for this ticket first
+    QueryOut q = {nullptr, nullptr, nullptr, nullptr, nullptr, {}, slot_first, s->exchange_stream, x.np, x.fin, x.h_ctr};
+    q.peers.n = n_bufs;
+    q.peers.rot = (int)((slot_first / (n ? n : 1)) % (uint64_t)n_bufs) + 1;
+    for (int i = 0; i < n_bufs; ++i) {
+        if (!bufs[i]) return XP_EINVAL;
+        q.peers.p[i] = static_cast<xp_contact *>(bufs[i]);
+    }
+    // this step works in its slot's buffers: the previous user of the slot (two steps ago) must have been read
+    if (x.used) XP_API_TRY(cudaStreamWaitEvent(s->stream, x.fin, 0));
+    struct Swap {
+        xp_scene *s; xp_scene::ExSlot &x;
+        void flip() { std::swap(s->rays, x.rays); std::swap(s->best, x.best); std::swap(s->inv_order, x.inv_order); std::swap(s->io_status, x.status); }
+        Swap(xp_scene *s_, xp_scene::ExSlot &x_) : s(s_), x(x_) { flip(); }
+        ~Swap() { flip(); }
+    } swap(s, x);
+    cudaError_t e = s->io_status.reserve(n * 4);
+    if (e != cudaSuccess) return fail_cuda(e);
+    q.status = s->io_status.as<uint32_t>();
+    reset_stats(s);
+    s->ev_base = t * (xp_scene::EV_POOL / 2);
+    s->ev_count = 0;
+    s->counters_live = false;                                    // freshly zeroed counters for this step
+    e = detect_dev(s, d_in, n, horizon_mode, q, /*collect=*/false);
+    s->counters_live = false;
+    x.ev_count = s->ev_count;
+    x.launches = s->stats.kernel_launches;
+    s->ev_base = 0;
+    s->ev_count = 0;
+    if (e != cudaSuccess) return fail_cuda(e);
+    x.busy = x.used = true;
+    s->ex_next = t ^ 1;
+    *ticket = t;
+    return XP_OK;
+}
+
+int xp_detect_contacts_exchange_wait(xp_scene *s, int ticket) {
+    if (!s || ticket < 0 || ticket > 1) return XP_EINVAL;
+    xp_scene::ExSlot &x = s->ex_slot[ticket];
+    if (!x.busy) return XP_ESTATE;
+    XP_BIND(s);
+    x.busy = false;
+    XP_API_TRY(cudaEventSynchronize(x.fin));
+    reset_stats(s);
+    const DeviceCounters &h = *x.h_ctr;
+    s->stats.narrowphase_tests = h.tests;
+    s->stats.broadphase_pairs = h.pairs_total;
+    s->stats.node_visits = h.node_visits;
+    s->stats.kernel_launches = x.launches;
+    s->ev_base = ticket * (xp_scene::EV_POOL / 2);
+    s->ev_count = x.ev_count;
+    resolve_stage_timers(s);
+    s->ev_base = 0;
+    if (h.stack_overflow) return fail_cuda(cudaErrorAssert);
+    if (h.pair_overflow) return XP_ECAP;                         // candidates were dropped: redo the step with the synchronous call
     return XP_OK;
 }
 

@@ -124,6 +124,7 @@ struct xp_scene {
     cudaEvent_t ev[2 * EV_POOL] = {};
     int ev_stage[EV_POOL] = {};
     int ev_count = 0;
+    int ev_base = 0;               // first pool entry of the call being recorded (asynchronous steps use half a pool each)
     bool ev_created = false;
     // host-pointer calls: copy streams + per-chunk events for the H2D / compute / D2H pipeline
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -146,4 +147,19 @@ struct xp_scene {
     };
     AsyncSlot async_slot[ASYNC_SLOTS];
     bool async_ready = false;
+    // xp_detect_contacts_exchange_submit / _wait: the record build + exchange of step i runs on
+    // exchange_stream (caller-provided) under the sweep of step i+1; each step in flight owns the
+    // buffers its finalize kernel reads
+    cudaStream_t exchange_stream = nullptr;
+    struct ExSlot {
+        xp::DevBuf rays, best, inv_order, status;
+        cudaEvent_t np = nullptr, fin = nullptr;
+        xp::DeviceCounters *h_ctr = nullptr;     // pinned snapshot of the counters after the narrowphase
+        bool busy = false, used = false;
+        int ev_count = 0;
+        uint32_t launches = 0;
+    };
+    ExSlot ex_slot[2];
+    int ex_next = 0;
+    bool ex_ready = false;
 };

@@ -37,6 +37,9 @@ struct QueryOut {            // device pointers, any may be null
     // fused contact exchange: when peers.n > 0 every contact record is written into each peer buffer at
     // record index slot_first + i (the buffers are mapped peer memory, NVLink P2P stores)
     PeerBufs peers; uint64_t slot_first;
+    // asynchronous steps: the result kernel is launched on finalize_stream once ev_np (recorded after the
+    // narrowphase and the counter snapshot) has passed, and ev_fin is recorded behind it
+    cudaStream_t finalize_stream; cudaEvent_t ev_np, ev_fin; xp::DeviceCounters *ctr_snapshot;
 };
 // collect = false: leave the statistics on the device (no host synchronisation); the caller ends
 // the batch with collect_stats().  After collecting, s->pair_overflowed tells whether the

@@ -1217,6 +1217,15 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
         XP_TRY(ray_setup(s, in, order, m, horizon_of(horizon_mode), status));
         XP_TRY(closest(s, m));
         s->swept_rays += m;
+        // asynchronous steps: snapshot the counters, then hand the result kernel to the second stream
+        struct StreamGuard { xp_scene *s; cudaStream_t main; ~StreamGuard() { s->stream = main; } } sg{s, s->stream};
+        if (out.ctr_snapshot)
+            XP_TRY(cudaMemcpyAsync(out.ctr_snapshot, s->counters.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, s->stream));
+        if (out.finalize_stream) {
+            XP_TRY(cudaEventRecord(out.ev_np, s->stream));
+            XP_TRY(cudaStreamWaitEvent(out.finalize_stream, out.ev_np, 0));
+            s->stream = out.finalize_stream;
+        }
         {
             StageTimer t(s, XP_STAGE_FINALIZE);
             const RayRec *rays = s->rays.as<RayRec>();
@@ -1244,6 +1253,7 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
                 k_finalize_detect<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
             ++s->stats.kernel_launches;
         }
+        if (out.finalize_stream) XP_TRY(cudaEventRecord(out.ev_fin, s->stream));
     }
     XP_TRY(cudaGetLastError());
     if (!collect) return cudaSuccess;         // the caller batches several sweeps and collects once

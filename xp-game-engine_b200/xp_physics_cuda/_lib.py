@@ -91,6 +91,9 @@ def lib() -> C.CDLL:
         "xp_exchange_close": ([vp, vp], i32),
         "xp_detect_contacts_exchange_dev": ([vp, vp, u64, u32, vp, i32, u64], i32),
         "xp_detect_contacts_multicast_dev": ([vp, vp, u64, u32, vp, u64], i32),
+        "xp_scene_set_exchange_stream": ([vp, vp], i32),
+        "xp_detect_contacts_exchange_submit": ([vp, vp, u64, u32, vp, i32, u64, vp], i32),
+        "xp_detect_contacts_exchange_wait": ([vp, i32], i32),
         "xp_probe_fp32_peak": ([i32, vp], i32),
         "xp_strerror": ([i32], C.c_char_p),
         "xp_last_cuda_error": ([], C.c_char_p),
@@ -112,7 +115,8 @@ EXPORTED_SYMBOLS = [
     "xp_collision_response_batch", "xp_collision_response_batch_dev", "xp_sphere_triangle_detect_collision",
     "xp_sphere_triangle_calculate_response", "xp_broadphase_pairs", "xp_scene_debug_tree",
     "xp_detect_contacts_dev", "xp_exchange_alloc", "xp_exchange_free", "xp_exchange_open", "xp_exchange_close",
-    "xp_detect_contacts_exchange_dev", "xp_detect_contacts_multicast_dev", "xp_probe_fp32_peak", "xp_strerror", "xp_last_cuda_error", "xp_version",
+    "xp_detect_contacts_exchange_dev", "xp_detect_contacts_multicast_dev", "xp_scene_set_exchange_stream",
+    "xp_detect_contacts_exchange_submit", "xp_detect_contacts_exchange_wait", "xp_probe_fp32_peak", "xp_strerror", "xp_last_cuda_error", "xp_version",
 ]
 
 

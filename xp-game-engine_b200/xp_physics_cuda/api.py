@@ -299,6 +299,28 @@ class Scene:
         check(self._L.xp_detect_contacts_exchange_dev(self._h, C.c_void_p(d_in), n, _horizon(horizon), arr, len(bufs),
                                                       slot_first), "xp_detect_contacts_exchange_dev")
 
+    def set_exchange_stream(self, cuda_stream: int):
+        """Second stream for `detect_contacts_exchange_submit` (record build + exchange of a step)."""
+        check(self._L.xp_scene_set_exchange_stream(self._h, C.c_void_p(cuda_stream)), "xp_scene_set_exchange_stream")
+
+    def detect_contacts_exchange_submit(self, d_in: int, n: int, bufs, slot_first: int, horizon: str = "inf") -> int:
+        """Queue one step of a loop (sweep on the scene's stream, exchange on the exchange stream) and
+        return its ticket; `detect_contacts_exchange_wait(ticket)` completes it.  Two steps may be in flight."""
+        arr = (C.c_void_p * len(bufs))(*[C.c_void_p(b) for b in bufs])
+        ticket = C.c_int(-1)
+        check(self._L.xp_detect_contacts_exchange_submit(self._h, C.c_void_p(d_in), n, _horizon(horizon), arr, len(bufs),
+                                                         slot_first, C.byref(ticket)), "xp_detect_contacts_exchange_submit")
+        return ticket.value
+
+    def detect_contacts_exchange_wait(self, ticket: int) -> bool:
+        """Block until the step's records have left this GPU.  False = the candidate buffer overflowed and
+        the step must be redone with the synchronous call (rare)."""
+        rc = self._L.xp_detect_contacts_exchange_wait(self._h, ticket)
+        if rc == _lib.XP_ECAP:
+            return False
+        check(rc, "xp_detect_contacts_exchange_wait")
+        return True
+
     def detect_contacts_multicast_dev(self, d_in: int, n: int, multicast_buf: int, slot_first: int, horizon: str = "inf"):
         """Sweep and write every contact record ONCE, to an NVSwitch multicast address bound to all ranks'
         gather buffers (record index slot_first + i): the switch performs the replication."""

@@ -80,14 +80,19 @@ class ContactExchange:
     def __init__(self, scene: Scene, cap: int, device, group=None):
         import torch
         import torch.distributed as dist
-        self.scene, self.group = scene, group
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.scene, self.group, self.device = scene, group, device
+        self.solo = not (dist.is_available() and dist.is_initialized())        # one process, no peers
+        self.world = 1 if self.solo else dist.get_world_size(group)
+        self.rank = 0 if self.solo else dist.get_rank(group)
         self.cap = cap + (cap & 1)                   # even slots: 16-byte aligned spans
-        self.nbytes = self.world * self.cap * 4 * CONTACT_FLOATS
+        self.half = self.world * self.cap            # records per gather buffer; there are two (steps alternate)
+        self.nbytes = 2 * self.half * 4 * CONTACT_FLOATS
         self.ptr, self.bufs, self.ok, self.mode = 0, [], True, "p2p"
         self.mc_ptr, self._symm = 0, None
-        shape = (self.world, self.cap, CONTACT_FLOATS)
-        if os.environ.get("XP_EXCHANGE_MULTICAST", "0") == "1" and self._try_multicast(torch, dist, device, shape):
+        self._side, self._done, self._flag = None, {}, None
+        shape = (2, self.world, self.cap, CONTACT_FLOATS)
+        if (not self.solo and os.environ.get("XP_EXCHANGE_MULTICAST", "0") == "1"
+                and self._try_multicast(torch, dist, device, shape)):
             self.mode = "multicast"
             return
         handle = b""
@@ -95,6 +100,12 @@ class ContactExchange:
             self.ptr, handle = scene.exchange_alloc(self.nbytes)
         except Exception:
             self.ok = False
+        if self.solo:
+            if self.ok:
+                self.bufs = [self.ptr]
+                self.views = torch.as_tensor(_DeviceArray(self.ptr, shape), device=device)
+                self.view = self.views[0]
+            return
         handles = [None] * self.world
         dist.all_gather_object(handles, (self.ok, handle), group=group)
         if all(h[0] for h in handles):
@@ -111,7 +122,8 @@ class ContactExchange:
             self.ok = False
             self.close()
         else:
-            self.view = torch.as_tensor(_DeviceArray(self.ptr, shape), device=device)
+            self.views = torch.as_tensor(_DeviceArray(self.ptr, shape), device=device)
+            self.view = self.views[0]
 
     def _try_multicast(self, torch, dist, device, shape) -> bool:
         """Symmetric memory + multicast address through torch (plumbing only: allocation and rendezvous)."""
@@ -132,17 +144,52 @@ class ContactExchange:
         if not all(flags):
             return False
         t.zero_()
-        self._symm, self.view, self.mc_ptr = t, t, mc
+        self._symm, self.views, self.view, self.mc_ptr = t, t, t[0], mc
         torch.cuda.synchronize(device)
         dist.barrier(self.group)
         return True
 
     def sweep(self, d_in_ptr: int, n_local: int, horizon: str = "inf"):
-        """Sweep this rank's spheres; their contact records land in slot `rank` of EVERY rank's buffer."""
+        """Sweep this rank's spheres; their contact records land in slot `rank` of EVERY rank's buffer
+        (`view`, the first of the two gather buffers).  Synchronous; the caller adds the barrier."""
         if self.mode == "multicast":
             self.scene.detect_contacts_multicast_dev(d_in_ptr, n_local, self.mc_ptr, self.rank * self.cap, horizon)
         else:
             self.scene.detect_contacts_exchange_dev(d_in_ptr, n_local, self.bufs, self.rank * self.cap, horizon)
+
+    # -- a loop of steps: step i's exchange runs under step i+1's sweep -----------------------------
+    def sweep_async(self, d_in_ptr: int, n_local: int, horizon: str = "inf") -> int:
+        """Queue one step: the sweep on the scene's stream, the record build + exchange on a second stream,
+        the cross-rank barrier (a one-element NCCL all-reduce) behind it on that stream.  Steps alternate
+        between the two gather buffers; `wait(ticket)` returns the buffer of that step."""
+        import torch
+        import torch.distributed as dist
+        if self.mode != "p2p":
+            raise RuntimeError("sweep_async uses the P2P transport")
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self.scene.set_exchange_stream(self._side.cuda_stream)
+            self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        half = self._half_i = (getattr(self, "_half_i", 1) + 1) % 2
+        ticket = self.scene.detect_contacts_exchange_submit(d_in_ptr, n_local, self.bufs,
+                                                            half * self.half + self.rank * self.cap, horizon)
+        if not self.solo:
+            with torch.cuda.stream(self._side):
+                dist.all_reduce(self._flag, group=self.group)        # every rank's exchange kernel has finished
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        self._done[ticket] = (ev, half)
+        return ticket
+
+    def wait(self, ticket: int):
+        """Complete a queued step; returns its gather buffer [world, cap, 10] (valid until the step after the
+        next one is queued)."""
+        ev, half = self._done.pop(ticket)
+        ok = self.scene.detect_contacts_exchange_wait(ticket)
+        ev.synchronize()
+        if not ok:
+            raise RuntimeError("candidate buffer overflow in an asynchronous step: raise max_pairs or use sweep()")
+        return self.views[half]
 
     def close(self):
         for r, b in enumerate(self.bufs):
