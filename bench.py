@@ -178,21 +178,24 @@ def run_b200(args):
     mine = contacts[rank]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    # N > 1: the kernel that builds the contact records stores them into every rank's gather buffer over
-    # NVLink peer memory (CUDA IPC); if the mapping is unavailable, fall back to an NCCL all-gather
+    # The kernel that builds the contact records stores them into every rank's gather buffer over NVLink peer
+    # memory (CUDA IPC); with one GPU the only "peer" is the local buffer.  If the mapping is unavailable the
+    # steps fall back to the synchronous path + an NCCL all-gather.
     exchange = None
-    if world > 1 and not os.environ.get("XP_BENCH_NCCL_EXCHANGE"):
+    if not os.environ.get("XP_BENCH_NCCL_EXCHANGE"):
         from xp_physics_cuda.distributed import ContactExchange
         exchange = ContactExchange(scene, n, dev)
         if not exchange.ok:
             exchange = None
         else:
             mine = exchange.view[rank][:n]
+    pipelined = exchange is not None and exchange.mode == "p2p" and not os.environ.get("XP_BENCH_SYNC_STEPS")
 
     def step_device():
         if exchange is not None:
             exchange.sweep(d_in.data_ptr(), n)       # compute + all-gather in one kernel (P2P stores)
-            dist.barrier()                           # every rank's records have landed everywhere
+            if world > 1:
+                dist.barrier()                       # every rank's records have landed everywhere
             return
         # writes this rank's contact records straight into its slot of the gather buffer
         scene.detect_contacts_dev(d_in.data_ptr(), n, mine.data_ptr())
@@ -224,8 +227,42 @@ def run_b200(args):
             total_ms = float(t.item())
         return total_ms, stats
 
+    def loop_device(k):
+        """k steps as a loop: submit step i, then complete step i-1 -- step i's sweep runs while step i-1's
+        records cross NVLink (second stream) and its barrier completes.  Returns the per-step stats."""
+        pending, out = [], []
+        for _ in range(k):
+            if len(pending) == 2:
+                exchange.wait(pending.pop(0))
+                out.append(scene.stats())
+            pending.append(exchange.sweep_async(d_in.data_ptr(), n))
+        while pending:
+            exchange.wait(pending.pop(0))
+            out.append(scene.stats())
+        return out
+
+    sync_ms, sync_stats = timed(step_device, args.steps, max(args.warmup, 3))     # one synchronous call per step, L2 flushed
     with ClockSampler(local) as clocks:
-        total_ms, stats = timed(step_device, args.steps, max(args.warmup, 3))
+        if pipelined:
+            loop_device(max(args.warmup, 3))
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            stats = loop_device(args.steps)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            total_ms = ev0.elapsed_time(ev1)
+            if world > 1:
+                t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                total_ms = float(t.item())
+        else:
+            total_ms, stats = sync_ms, sync_stats
+    last_records = (exchange.views[exchange._half_i][rank][:n] if pipelined else mine).clone()
     tests_local = sum(s["narrowphase_tests"] for s in stats)
     launches = sum(s["kernel_launches"] for s in stats)
     tests_all = tests_local
@@ -387,6 +424,13 @@ def run_b200(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(workload_config(world), arith=args.arith, method=args.method,
                                                     prune=bool(args.prune),
+                                                    l2=("not flushed inside the loop (steps overlap): one step's inputs -- 128 MB of "
+                                                        "scene records + 29 MB of spheres -- exceed the 126 MB L2 and a step streams "
+                                                        "~0.5 GB through it; single_step is the same step with an explicit L2 flush"
+                                                        if pipelined else "flushed (256 MiB write) between timed steps"),
+                                                    step=("loop of steps, two in flight: step i's record build + exchange runs on a "
+                                                          "second stream under step i+1's sweep" if pipelined else
+                                                          "one synchronous call per step"),
                                                     exchange=("none" if world == 1 else "nccl all_gather" if exchange is None else
                                                               "one multimem.st per record span into an NVSwitch multicast address bound to "
                                                               "every rank's gather buffer (fused with the record build)"
@@ -395,7 +439,11 @@ def run_b200(args):
                 "spheres_per_sec": spheres_per_sec, "tests_per_step": tests_all / args.steps,
                 "node_visits_per_step": float(np.mean([s["node_visits"] for s in stats])),
                 "stage_ms": {k: float(np.mean([s["stage_ms"][k] for s in stats])) for k in stats[0]["stage_ms"]},
-                "hit_fraction": float((mine[:, 9].contiguous().view(torch.int32) & 1).float().mean().item()),
+                "hit_fraction": float((last_records[:, 9].contiguous().view(torch.int32) & 1).float().mean().item()),
+                "single_step": {"ms_per_step": sync_ms / args.steps,
+                                "value": sum(s_["narrowphase_tests"] for s_ in sync_stats) * world / (sync_ms * 1e-3),
+                                "note": "one synchronous call per step (host waits for the result), L2 flushed between steps"
+                                        + ("" if world == 1 else "; value assumes every rank ran the same number of tests")},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "roofline_hbm": roofline_hbm, "resolved": resolved,
                 "cpu_baseline": cpu,

@@ -916,50 +916,56 @@ __global__ void __launch_bounds__(256) k_finalize_exchange(const RayRec *__restr
                                                            const uint32_t *__restrict__ status, PeerBufs peers,
                                                            uint64_t slot_first) {
     __shared__ __align__(16) float rec[256 * 10];
-    const uint64_t i0 = blockIdx.x * 256ull;
-    const uint64_t i = i0 + threadIdx.x;
-    if (i < n) {
-        const uint64_t k = inv_order ? inv_order[i] : i;
-        const unsigned long long b = best[k];
-        const bool h = b != BEST_NONE;
-        Contact ct = {0.0f, 0.0f, {0, 0, 0}, {0, 0, 0}};
-        if (h) {
-            const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
-            ct = xp_make_collision<O>(ray_from(rp[0], rp[1], rp[2]), __uint_as_float((unsigned)(b >> 32)));
+    // grid-stride over spans of 256 records: the asynchronous steps launch one block per SM, so that the
+    // next step's sweep (launched right behind on the other stream) finds room on every SM while these
+    // blocks wait on NVLink
+    for (uint64_t i0 = blockIdx.x * 256ull; i0 < n; i0 += gridDim.x * 256ull) {
+        const uint64_t i = i0 + threadIdx.x;
+        if (i < n) {
+            const uint64_t k = inv_order ? inv_order[i] : i;
+            const unsigned long long b = best[k];
+            const bool h = b != BEST_NONE;
+            Contact ct = {0.0f, 0.0f, {0, 0, 0}, {0, 0, 0}};
+            if (h) {
+                const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
+                ct = xp_make_collision<O>(ray_from(rp[0], rp[1], rp[2]), __uint_as_float((unsigned)(b >> 32)));
+            }
+            float *o = rec + threadIdx.x * 10;
+            o[0] = ct.time_to; o[1] = ct.distance_to;
+            o[2] = ct.position.x; o[3] = ct.position.y; o[4] = ct.position.z;
+            o[5] = ct.intersection.x; o[6] = ct.intersection.y; o[7] = ct.intersection.z;
+            o[8] = __uint_as_float(h ? ~(uint32_t)(b & 0xFFFFFFFFull) : 0xFFFFFFFFu);
+            o[9] = __uint_as_float((h ? 1u : 0u) | (((status ? status[i] : 0u) & 0xFFu) << 8));
         }
-        float *o = rec + threadIdx.x * 10;
-        o[0] = ct.time_to; o[1] = ct.distance_to;
-        o[2] = ct.position.x; o[3] = ct.position.y; o[4] = ct.position.z;
-        o[5] = ct.intersection.x; o[6] = ct.intersection.y; o[7] = ct.intersection.z;
-        o[8] = __uint_as_float(h ? ~(uint32_t)(b & 0xFFFFFFFFull) : 0xFFFFFFFFu);
-        o[9] = __uint_as_float((h ? 1u : 0u) | (((status ? status[i] : 0u) & 0xFFu) << 8));
-    }
-    __syncthreads();
-    const unsigned cnt = (unsigned)((n - i0 < 256) ? (n - i0) : 256);       // records of this block
-    const unsigned n8 = cnt * 5;                                            // 8-byte words
-    const float2 *src = reinterpret_cast<const float2 *>(rec);
-    if (peers.multicast) {
-        // p[0] is a multicast address of the NVSwitch fabric: one store, every rank's buffer (this rank's
-        // included) receives it -- the span leaves this GPU once instead of once per peer
-        float2 *dst = reinterpret_cast<float2 *>(peers.p[0]) + (slot_first + i0) * 5;   // 16 B aligned: both terms are even
-        const unsigned n16 = n8 >> 1;
-        for (unsigned w = threadIdx.x; w < n16; w += 256) {
-            const float4 v = reinterpret_cast<const float4 *>(rec)[w];
-            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
-                         :: "l"(dst + 2 * w), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        __syncthreads();
+        const unsigned cnt = (unsigned)((n - i0 < 256) ? (n - i0) : 256);       // records of this span
+        const unsigned n8 = cnt * 5;                                            // 8-byte words
+        const float2 *src = reinterpret_cast<const float2 *>(rec);
+        if (peers.multicast) {
+            // p[0] is a multicast address of the NVSwitch fabric: one store, every rank's buffer (this rank's
+            // included) receives it -- the span leaves this GPU once instead of once per peer
+            float2 *dst = reinterpret_cast<float2 *>(peers.p[0]) + (slot_first + i0) * 5;   // 16 B aligned: both terms are even
+            const unsigned n16 = n8 >> 1;
+            for (unsigned w = threadIdx.x; w < n16; w += 256) {
+                const float4 v = reinterpret_cast<const float4 *>(rec)[w];
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                             :: "l"(dst + 2 * w), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+            if ((n8 & 1) && threadIdx.x == 0) {
+                const float2 v = src[n8 - 1];
+                asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" :: "l"(dst + (n8 - 1)), "f"(v.x), "f"(v.y) : "memory");
+            }
+        } else {
+            // every rank starts with a different peer and consecutive spans rotate, so at any instant the
+            // stores of the whole machine are spread over all receivers instead of converging on one
+            const unsigned span = (unsigned)(i0 >> 8);
+            for (int j = 0; j < peers.n; ++j) {
+                const int p = (int)((j + peers.rot + span) % (unsigned)peers.n);
+                float2 *dst = reinterpret_cast<float2 *>(peers.p[p]) + (slot_first + i0) * 5;
+                for (unsigned w = threadIdx.x; w < n8; w += 256) dst[w] = src[w];
+            }
         }
-        if ((n8 & 1) && threadIdx.x == 0) {
-            const float2 v = src[n8 - 1];
-            asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" :: "l"(dst + (n8 - 1)), "f"(v.x), "f"(v.y) : "memory");
-        }
-        return;
-    }
-    // every rank starts with a different peer and consecutive blocks rotate, so at any instant the
-    // stores of the whole machine are spread over all receivers instead of converging on one
-    for (int j = 0; j < peers.n; ++j) {
-        const int p = (int)((j + peers.rot + blockIdx.x) % (unsigned)peers.n);
-        float2 *dst = reinterpret_cast<float2 *>(peers.p[p]) + (slot_first + i0) * 5;
-        for (unsigned w = threadIdx.x; w < n8; w += 256) dst[w] = src[w];
+        __syncthreads();                                                        // rec is rewritten by the next span
     }
 }
 
@@ -1198,6 +1204,9 @@ static cudaError_t collect_counters(xp_scene *s) {
 }
 
 static constexpr uint64_t SPHERE_CHUNK = 1ull << 24;
+#ifndef XP_EX_BLOCKS
+#define XP_EX_BLOCKS 1          // blocks per SM of the exchange kernel in asynchronous steps
+#endif
 
 cudaError_t collect_stats(xp_scene *s) { return collect_counters(s); }
 
@@ -1243,10 +1252,12 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
                 peers.n = 1; peers.rot = 0; peers.multicast = 0; peers.p[0] = out.contact; slot = off;
             }
             if (peers.n > 0) {
+                unsigned fgrid = grid_for(m, 256);
+                if (out.finalize_stream && fgrid > 148u * XP_EX_BLOCKS) fgrid = 148u * XP_EX_BLOCKS;   // leave the SMs to the next sweep
                 if (s->arith == XP_ARITH_FAST)
-                    k_finalize_exchange<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, peers, slot);
+                    k_finalize_exchange<FastOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, peers, slot);
                 else
-                    k_finalize_exchange<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, status, peers, slot);
+                    k_finalize_exchange<ExactOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, peers, slot);
             } else if (s->arith == XP_ARITH_FAST)
                 k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
             else
