@@ -238,10 +238,14 @@ int  xp_detect_contacts_multicast_dev(xp_scene *s, const xp_response *d_in, uint
  * The caller orders its cross-rank barrier after the exchange on that second stream.  wait blocks until
  * the step's records have left this GPU, fills xp_scene_get_stats for it, and returns XP_ECAP in the rare
  * case that the optimistic candidate buffer overflowed: redo that step with the synchronous call.
+ * self_index >= 0 names this rank's own buffer in bufs[]: the kernel then fills only that buffer and the
+ * copy engines carry the span to the others (peer stores issued by SMs stall a concurrent sweep while
+ * NVLink is saturated; DMA copies do not); self_index = -1 keeps the kernel's P2P stores.
  * n <= 2^24 per step; d_in must stay untouched until wait returns. */
 int  xp_scene_set_exchange_stream(xp_scene *s, void *cuda_stream);
 int  xp_detect_contacts_exchange_submit(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
-                                        void *const *bufs, int n_bufs, uint64_t slot_first, int *ticket);
+                                        void *const *bufs, int n_bufs, int self_index, uint64_t slot_first,
+                                        int *ticket);
 int  xp_detect_contacts_exchange_wait(xp_scene *s, int ticket);
 
 /* ---- measurement helpers ---- */

@@ -540,10 +540,11 @@ static int ensure_exchange_slots(xp_scene *s) {
 }
 
 int xp_detect_contacts_exchange_submit(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
-                                       void *const *bufs, int n_bufs, uint64_t slot_first, int *ticket) {
+                                       void *const *bufs, int n_bufs, int self_index, uint64_t slot_first, int *ticket) {
     int rc = check_query(s, d_in, n);
     if (rc) return rc;
     if (!bufs || !ticket || n_bufs <= 0 || n_bufs > XP_MAX_PEERS || (slot_first & 1)) return XP_EINVAL;
+    if (self_index < -1 || self_index >= n_bufs) return XP_EINVAL;
     if (n == 0 || n > (1ull << 24)) return XP_EINVAL;            // one chunk per step: its buffers stay untouched until the exchange has read them
     if (!s->exchange_stream || s->exchange_stream == s->stream) return XP_ESTATE;
     XP_BIND(s);
@@ -552,7 +553,7 @@ int xp_detect_contacts_exchange_submit(xp_scene *s, const xp_response *d_in, uin
     const int t = s->ex_next;
     xp_scene::ExSlot &x = s->ex_slot[t];
     if (x.busy) return XP_ESTATE;                                // wait for this ticket first
-    QueryOut q = {nullptr, nullptr, nullptr, nullptr, nullptr, {}, slot_first, s->exchange_stream, x.np, x.fin, x.h_ctr};
+    QueryOut q = {nullptr, nullptr, nullptr, nullptr, nullptr, {}, slot_first, s->exchange_stream, x.np, x.fin, x.h_ctr, self_index + 1};
     q.peers.n = n_bufs;
     q.peers.rot = (int)((slot_first / (n ? n : 1)) % (uint64_t)n_bufs) + 1;
     for (int i = 0; i < n_bufs; ++i) {

@@ -40,6 +40,9 @@ struct QueryOut {            // device pointers, any may be null
     // asynchronous steps: the result kernel is launched on finalize_stream once ev_np (recorded after the
     // narrowphase and the counter snapshot) has passed, and ev_fin is recorded behind it
     cudaStream_t finalize_stream; cudaEvent_t ev_np, ev_fin; xp::DeviceCounters *ctr_snapshot;
+    // asynchronous steps with copy_self >= 0: the kernel writes only peers.p[copy_self] (this rank's buffer)
+    // and the copy engines push that span to the other buffers, so no SM waits on NVLink
+    int copy_self_plus1;
 };
 // collect = false: leave the statistics on the device (no host synchronisation); the caller ends
 // the batch with collect_stats().  After collecting, s->pair_overflowed tells whether the

@@ -916,9 +916,7 @@ __global__ void __launch_bounds__(256) k_finalize_exchange(const RayRec *__restr
                                                            const uint32_t *__restrict__ status, PeerBufs peers,
                                                            uint64_t slot_first) {
     __shared__ __align__(16) float rec[256 * 10];
-    // grid-stride over spans of 256 records: the asynchronous steps launch one block per SM, so that the
-    // next step's sweep (launched right behind on the other stream) finds room on every SM while these
-    // blocks wait on NVLink
+    // grid-stride over spans of 256 records
     for (uint64_t i0 = blockIdx.x * 256ull; i0 < n; i0 += gridDim.x * 256ull) {
         const uint64_t i = i0 + threadIdx.x;
         if (i < n) {
@@ -1204,9 +1202,6 @@ static cudaError_t collect_counters(xp_scene *s) {
 }
 
 static constexpr uint64_t SPHERE_CHUNK = 1ull << 24;
-#ifndef XP_EX_BLOCKS
-#define XP_EX_BLOCKS 1          // blocks per SM of the exchange kernel in asynchronous steps
-#endif
 
 cudaError_t collect_stats(xp_scene *s) { return collect_counters(s); }
 
@@ -1253,11 +1248,23 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
             }
             if (peers.n > 0) {
                 unsigned fgrid = grid_for(m, 256);
-                if (out.finalize_stream && fgrid > 148u * XP_EX_BLOCKS) fgrid = 148u * XP_EX_BLOCKS;   // leave the SMs to the next sweep
+                const int self = out.copy_self_plus1 - 1;
+                PeerBufs kp = peers;
+                if (self >= 0) { kp.n = 1; kp.rot = 0; kp.p[0] = peers.p[self]; }       // the kernel fills this rank's buffer only
                 if (s->arith == XP_ARITH_FAST)
-                    k_finalize_exchange<FastOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, peers, slot);
+                    k_finalize_exchange<FastOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
                 else
-                    k_finalize_exchange<ExactOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, peers, slot);
+                    k_finalize_exchange<ExactOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
+                if (self >= 0) {
+                    // ... and the copy engines carry the span to the peers.  Measured on 8 B200s: peer stores issued
+                    // by SMs back-pressure the memory system while NVLink is saturated and stall the next step's
+                    // sweep for as long as the exchange lasts (no gain from overlapping); DMA copies do not.
+                    const xp_contact *src = peers.p[self] + slot;
+                    for (int j = 1; j < peers.n; ++j) {
+                        const int p = (self + j) % peers.n;
+                        XP_TRY(cudaMemcpyAsync(peers.p[p] + slot, src, m * sizeof(xp_contact), cudaMemcpyDeviceToDevice, s->stream));
+                    }
+                }
             } else if (s->arith == XP_ARITH_FAST)
                 k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
             else

@@ -92,7 +92,7 @@ def lib() -> C.CDLL:
         "xp_detect_contacts_exchange_dev": ([vp, vp, u64, u32, vp, i32, u64], i32),
         "xp_detect_contacts_multicast_dev": ([vp, vp, u64, u32, vp, u64], i32),
         "xp_scene_set_exchange_stream": ([vp, vp], i32),
-        "xp_detect_contacts_exchange_submit": ([vp, vp, u64, u32, vp, i32, u64, vp], i32),
+        "xp_detect_contacts_exchange_submit": ([vp, vp, u64, u32, vp, i32, i32, u64, vp], i32),
         "xp_detect_contacts_exchange_wait": ([vp, i32], i32),
         "xp_probe_fp32_peak": ([i32, vp], i32),
         "xp_strerror": ([i32], C.c_char_p),

@@ -303,13 +303,15 @@ class Scene:
         """Second stream for `detect_contacts_exchange_submit` (record build + exchange of a step)."""
         check(self._L.xp_scene_set_exchange_stream(self._h, C.c_void_p(cuda_stream)), "xp_scene_set_exchange_stream")
 
-    def detect_contacts_exchange_submit(self, d_in: int, n: int, bufs, slot_first: int, horizon: str = "inf") -> int:
+    def detect_contacts_exchange_submit(self, d_in: int, n: int, bufs, slot_first: int, horizon: str = "inf",
+                                        self_index: int = -1) -> int:
         """Queue one step of a loop (sweep on the scene's stream, exchange on the exchange stream) and
         return its ticket; `detect_contacts_exchange_wait(ticket)` completes it.  Two steps may be in flight."""
         arr = (C.c_void_p * len(bufs))(*[C.c_void_p(b) for b in bufs])
         ticket = C.c_int(-1)
         check(self._L.xp_detect_contacts_exchange_submit(self._h, C.c_void_p(d_in), n, _horizon(horizon), arr, len(bufs),
-                                                         slot_first, C.byref(ticket)), "xp_detect_contacts_exchange_submit")
+                                                         self_index, slot_first, C.byref(ticket)),
+              "xp_detect_contacts_exchange_submit")
         return ticket.value
 
     def detect_contacts_exchange_wait(self, ticket: int) -> bool:

@@ -171,8 +171,9 @@ class ContactExchange:
             self.scene.set_exchange_stream(self._side.cuda_stream)
             self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         half = self._half_i = (getattr(self, "_half_i", 1) + 1) % 2
-        ticket = self.scene.detect_contacts_exchange_submit(d_in_ptr, n_local, self.bufs,
-                                                            half * self.half + self.rank * self.cap, horizon)
+        ticket = self.scene.detect_contacts_exchange_submit(
+            d_in_ptr, n_local, self.bufs, half * self.half + self.rank * self.cap, horizon,
+            self_index=self.rank if os.environ.get("XP_EXCHANGE_COPY", "1") != "0" else -1)
         if not self.solo:
             with torch.cuda.stream(self._side):
                 dist.all_reduce(self._flag, group=self.group)        # every rank's exchange kernel has finished
