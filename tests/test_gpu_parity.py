@@ -611,3 +611,42 @@ def test_async_batch_overflow_is_redone(terrain):
         s.detect_batch_wait(t)
     got = (h_col.numpy().view(xp.COLLISION_DTYPE), h_hit.numpy(), h_tri.numpy().view(np.uint32), h_st.numpy().view(np.uint32))
     check_detect_exact(got, want, "async overflow redo")
+
+
+# ---- a loop of steps through the asynchronous fused exchange (one process: the only peer is the local buffer)
+def test_async_exchange_loop_single_process(terrain, oracle):
+    import torch
+    from xp_physics_cuda.distributed import ContactExchange, contacts_as_records
+    tris, h, resps, want = terrain
+    n = len(resps)
+    batches = [resps, scenes.terrain_spheres(h, n, seed=93), scenes.terrain_spheres(h, n - 7, seed=94)]
+    wants = [want, oracle.detect_batch(batches[1], tris), oracle.detect_batch(batches[2], tris)]
+    dev = torch.device("cuda", 0)
+    with xp.Scene(0, tris) as s:
+        s.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        ex = ContactExchange(s, n, dev)
+        assert ex.ok and ex.solo and ex.mode == "p2p"
+        d_in = [torch.from_numpy(np.ascontiguousarray(b).view(np.float32).reshape(-1, 7)).to(dev) for b in batches]
+        pending, got = [], {}
+
+        def finish():
+            k, t = pending.pop(0)
+            buf = ex.wait(t)
+            assert s.stats()["narrowphase_tests"] > 0
+            got[k] = contacts_as_records(buf[0, :len(batches[k % 3])])
+        for k in range(7):
+            if len(pending) == 2:
+                finish()
+            pending.append((k, ex.sweep_async(d_in[k % 3].data_ptr(), len(batches[k % 3]))))
+        while pending:
+            finish()
+        ex.close()
+    for k in range(7):
+        rec, w = got[k], wants[k % 3]
+        hit = (rec["flags"] & 1).astype(np.uint8)
+        assert np.array_equal(hit, w[1]), f"step {k}"
+        hm = hit.astype(bool)
+        assert np.array_equal(rec["tri_index"][hm], w[2][hm])
+        assert_bits_equal(rec["time_to"][hm], w[0]["time_to"][hm], f"async exchange step {k}")
+        assert_bits_equal(rec["position"][hm], w[0]["position"][hm], f"async exchange step {k}")
+        assert_bits_equal(rec["intersection"][hm], w[0]["intersection"][hm], f"async exchange step {k}")
