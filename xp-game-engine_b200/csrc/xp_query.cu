@@ -308,6 +308,9 @@ static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at 
 #ifndef XP_BP_GATHER
 #define XP_BP_GATHER 1
 #endif
+#ifndef XP_BP_STEAL
+#define XP_BP_STEAL 1
+#endif
 // Measured on config 2 (stage-1 ms): 2 blocks/SM 1.34, 3: 1.22, 4: 1.26, 5: 1.32, 6: 1.38, 7 (spills): 1.59.
 // Fewer resident warps leave more of the 228 KB to L1 (3 x 27 KB of staging -> ~148 KB of L1), and the node
 // walk gains more from cache hits than from extra warps.
@@ -341,7 +344,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     unsigned my_ray = 0;
     int node = -1;                         // internal node to visit next; -1 = lane needs a ray
     int stack[STACK_DEPTH];
-    int sp = 0;
+    int sp = 0, sbase = 0;                 // live entries: stack[sbase .. sp)
     unsigned count = 0;                    // queue fill (warp-uniform)
     unsigned pool = 0, pool_end = 0, pool_base = 0;   // this warp's current run of rays (warp-uniform)
     bool drained = false;                  // the global cursor has run out (warp-uniform)
@@ -377,7 +380,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                     my_ray = mine;
                     const float4 q0 = rpool[mine - pool_base], q3 = rpool[32 + mine - pool_base];
                     c = f4_xyz(q0); inv = f4_xyz(q3);
-                    sp = 0;
+                    sp = 0; sbase = 0;
                     bool go = (__float_as_uint(q3.w) & RAY_VALID) != 0;
                     if (best) {                              // windowed pass: t = distance / |m|
                         const float ml = q0.w;
@@ -396,6 +399,32 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
             } else if (idle == FULL) {
                 break;                      // nothing in flight, nothing left to claim
             }
+#if XP_BP_STEAL
+            else {
+                // The cursor has run dry and this warp still walks a few long rays: idle lanes take over
+                // pending subtrees of the busy ones (the OLDEST stack entry = the largest subtree), ray
+                // state and all, so the tail of the kernel is walked by 32 lanes instead of a handful.
+                // Every (ray, leaf) pair still comes out exactly once: a subtree moves, it is not copied.
+                const unsigned rich = __ballot_sync(FULL, node >= 0 && sp > sbase);
+                if (rich) {
+                    const int pairs_n = min(__popc(idle), __popc(rich));
+                    const bool donor = ((rich >> lane) & 1u) && __popc(rich & lt_mask) < pairs_n;
+                    const bool thief = ((idle >> lane) & 1u) && __popc(idle & lt_mask) < pairs_n;
+                    int give = -1;
+                    if (donor) give = stack[sbase++];
+                    const int from = thief ? (int)__fns(rich, 0, __popc(idle & lt_mask) + 1) : lane;
+                    const int got = __shfl_sync(FULL, give, from);
+                    const float cx = __shfl_sync(FULL, c.x, from), cy = __shfl_sync(FULL, c.y, from), cz = __shfl_sync(FULL, c.z, from);
+                    const float ix = __shfl_sync(FULL, inv.x, from), iy = __shfl_sync(FULL, inv.y, from), iz = __shfl_sync(FULL, inv.z, from);
+                    const float lo_ = __shfl_sync(FULL, t_lo, from), hi_ = __shfl_sync(FULL, t_hi, from);
+                    const unsigned ray_ = __shfl_sync(FULL, my_ray, from);
+                    if (thief) {
+                        node = got; c = {cx, cy, cz}; inv = {ix, iy, iz}; t_lo = lo_; t_hi = hi_; my_ray = ray_;
+                        sp = 0; sbase = 0;
+                    }
+                }
+            }
+#endif
         }
         // ---- one traversal step
         float4 n0, n1, n2, n3;
@@ -431,7 +460,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                 else atomicExch(&ctr->stack_overflow, 1u);
             } else if (hit_a) node = link.x;
             else if (hit_b) node = link.y;
-            else node = (sp > 0) ? stack[--sp] : -1;
+            else node = (sp > sbase) ? stack[--sp] : -1;
         }
         // ---- stage leaf hits; flush 32 pairs at a time
         const unsigned ma = __ballot_sync(FULL, leaf_a >= 0);
