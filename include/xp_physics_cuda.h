@@ -138,6 +138,15 @@ int  xp_scene_set_positions(xp_scene *s, const xp_vec3 *soup, uint64_t n_vec3);
  * xp_scene_set_triangles on that soup, with 4 B per vertex uploaded instead of 36 B per triangle. */
 int  xp_scene_set_heightmap(xp_scene *s, const float *heights, uint32_t nx, uint32_t nz, float x0, float z0,
                             float spacing);
+/* Row f2, clipmap half: the triangles of the geometry clipmap (game/src/graphics/clipmap.rs:566-625 parts,
+ * vertices placed like game/src/shaders/shader_clipmap.vert:43-65) emitted on the device from the per-level
+ * toroidal height textures: heights[levels][size][size] (host), vertex (ix, iz) of level L =
+ * (ix * unit0 * 2^L, heights[L][iz mod size][ix mod size], iz * unit0 * 2^L).  parts holds n_parts rows of 8
+ * int32 {level, first vertex x, first vertex z, vertices per side x, z, first triangle, triangles, 0}; a part
+ * emits its quads x fastest, all [i0,i2,i1] triangles first, then all [i3,i1,i2] (create_grid,
+ * clipmap.rs:752-786).  xp_physics_cuda/clipmap.py builds both arrays (the host mirror of `Clipmap`). */
+int  xp_scene_set_clipmap(xp_scene *s, const float *heights, uint32_t levels, uint32_t size,
+                          const int32_t *parts, uint32_t n_parts, float unit0);
 /* (Re)build the device LBVH: per-triangle normal / plane constant / inflated AABB, 30-bit
  * Morton codes, radix sort, Karras hierarchy, bottom-up refit.  New: the reference has no
  * broadphase (lib.rs:33-35 walks every triangle). */

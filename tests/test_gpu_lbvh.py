@@ -107,3 +107,28 @@ def test_device_heightmap_emission_equals_host_soup(oracle):
         for x, y in zip(ra, rb):
             assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
         assert ra[1].sum() > 100
+
+
+def test_device_clipmap_emission_equals_host_soup(oracle):
+    """xp_scene_set_clipmap (row f2, clipmap half): the device emits, from the toroidal height store, exactly the
+    soup the host mirror emits -- also after an incremental update around a moved centre."""
+    from xp_physics_cuda import clipmap as cm
+    c = cm.Clipmap(5)
+    for centre in ((37.0, -21.0), (44.5, -3.0), (-300.0, 910.0)):
+        c.update_heightmap(centre, scenes.sine_height)
+        tris = c.triangles()
+        assert np.array_equal(tris.view(np.uint32),
+                              scenes.clipmap_triangles(centre, scenes.sine_height).view(np.uint32))
+        resps = scenes.scene_spheres(tris, 600, seed=3, extent=40.0)
+        with xp.Scene(0, tris) as a, xp.Scene(0) as b:
+            b.set_clipmap(c)
+            b.build()
+            assert b.triangle_count == len(tris) == 127016
+            for x, y in zip(a.debug_tree(), b.debug_tree()):
+                assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+            ra, rb = a.detect_batch(resps), b.detect_batch(resps)
+            for x, y in zip(ra, rb):
+                assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+            assert ra[1].sum() > 100
+    want = oracle.detect_batch(resps[:150], tris)
+    assert np.array_equal(rb[1][:150], want[1])

@@ -198,6 +198,31 @@ int xp_scene_set_heightmap(xp_scene *s, const float *heights, uint32_t nx, uint3
     return XP_OK;
 }
 
+int xp_scene_set_clipmap(xp_scene *s, const float *heights, uint32_t levels, uint32_t size, const int32_t *parts,
+                         uint32_t n_parts, float unit0) {
+    if (!s || !heights || !parts || levels == 0 || levels > 24 || size == 0 || n_parts == 0 || n_parts > 4096) return XP_EINVAL;
+    uint64_t n = 0;
+    for (uint32_t i = 0; i < n_parts; ++i) {             // rows: level, x0, z0, size_x, size_z, first, count, 0
+        const int32_t *r = parts + 8 * (size_t)i;
+        if (r[0] < 0 || (uint32_t)r[0] >= levels || r[3] < 2 || r[4] < 2) return XP_EINVAL;
+        if ((uint64_t)r[5] != n || (int64_t)r[6] != 2ll * (r[3] - 1) * (r[4] - 1)) return XP_EINVAL;
+        n += (uint64_t)r[6];
+    }
+    if (n == 0 || n >= (1ull << 27)) return XP_EINVAL;
+    XP_BIND(s);
+    s->built = false;
+    s->n_tris = 0;
+    const uint64_t hbytes = (uint64_t)levels * size * size * sizeof(float), pbytes = (uint64_t)n_parts * 8 * sizeof(int32_t);
+    XP_API_TRY(s->io_in.reserve(hbytes + pbytes));
+    char *d = static_cast<char *>(s->io_in.p);
+    XP_API_TRY(cudaMemcpyAsync(d, heights, hbytes, cudaMemcpyHostToDevice, s->stream));
+    XP_API_TRY(cudaMemcpyAsync(d + hbytes, parts, pbytes, cudaMemcpyHostToDevice, s->stream));
+    XP_API_TRY(emit_clipmap(s, reinterpret_cast<const float *>(d), size, reinterpret_cast<const int *>(d + hbytes), n_parts, unit0, n));
+    XP_API_TRY(cudaStreamSynchronize(s->stream));
+    s->n_tris = n;
+    return XP_OK;
+}
+
 int xp_scene_set_positions(xp_scene *s, const xp_vec3 *soup, uint64_t n_vec3) {
     if (n_vec3 % 3 != 0) return XP_EINVAL;     // lib.rs:19-24: chunks(3) then vs[2] panics
     // Vec3 triples are exactly the Triangle layout (lib.rs:20-24), so this is one upload

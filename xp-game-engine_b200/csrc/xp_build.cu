@@ -611,6 +611,53 @@ cudaError_t emit_heightmap(xp_scene *s, const float *d_heights, unsigned nx, uns
     return cudaGetLastError();
 }
 
+// Row f2, clipmap half: the triangles the geometry-clipmap renderer draws, emitted from the per-level
+// TOROIDAL height textures exactly like game/src/shaders/shader_clipmap.vert:43-65 places its vertices:
+// vertex (ix, iz) of level L = (ix * unit_L, heights[L][iz mod S][ix mod S], iz * unit_L).  A part is one
+// create_grid (clipmap.rs:752-786): its quads with x fastest, first every [i0, i2, i1] triangle, then
+// every [i3, i1, i2]; parts[] rows are {level, x0, z0, size_x, size_z, first_triangle, triangles, 0}.
+__global__ void __launch_bounds__(256) k_emit_clipmap(const float *__restrict__ heights, unsigned size,
+                                                      const int4 *__restrict__ parts, unsigned n_parts,
+                                                      float unit0, uint64_t n_tris, float *__restrict__ tris) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    unsigned lo = 0, hi = n_parts - 1;                   // last part whose first triangle is <= t
+    while (lo < hi) {
+        const unsigned mid = (lo + hi + 1) >> 1;
+        if ((uint64_t)(unsigned)__ldg(&parts[2 * mid + 1].y) <= t) lo = mid; else hi = mid - 1;
+    }
+    const int4 a = __ldg(&parts[2 * lo]), b = __ldg(&parts[2 * lo + 1]);    // a = level, x0, z0, size_x;  b = size_z, first, count, 0
+    const int level = a.x, x0 = a.y, z0 = a.z, sx = a.w;
+    const unsigned quads = (unsigned)b.z >> 1;
+    unsigned q = (unsigned)(t - (unsigned)b.y);
+    const bool second = q >= quads;
+    if (second) q -= quads;
+    const int qx = x0 + (int)(q % (unsigned)(sx - 1)), qz = z0 + (int)(q / (unsigned)(sx - 1));
+    // [i0, i2, i1] = (x,z) (x,z+1) (x+1,z);   [i3, i1, i2] = (x+1,z+1) (x+1,z) (x,z+1)
+    const int vx[3] = {second ? qx + 1 : qx, second ? qx + 1 : qx, second ? qx : qx + 1};
+    const int vz[3] = {second ? qz + 1 : qz, second ? qz : qz + 1, second ? qz + 1 : qz};
+    const float unit = __fmul_rn((float)(1u << level), unit0);
+    const float *tex = heights + (size_t)level * size * size;
+    float *o = tris + t * 9;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o[3 * k + 0] = __fmul_rn((float)vx[k], unit);
+        o[3 * k + 1] = __ldg(tex + (size_t)((unsigned)vz[k] % size) * size + ((unsigned)vx[k] % size));
+        o[3 * k + 2] = __fmul_rn((float)vz[k], unit);
+    }
+}
+
+#define XP_TRY_(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
+cudaError_t emit_clipmap(xp_scene *s, const float *d_heights, unsigned size, const int *d_parts, unsigned n_parts,
+                         float unit0, uint64_t n_tris) {
+    XP_TRY_(s->tris_aos.reserve(n_tris * sizeof(xp_triangle)));
+    k_emit_clipmap<<<grid_for(n_tris, 256), 256, 0, s->stream>>>(d_heights, size, reinterpret_cast<const int4 *>(d_parts),
+                                                                n_parts, unit0, n_tris, s->tris_aos.as<float>());
+    ++s->stats.kernel_launches;
+    return cudaGetLastError();
+}
+#undef XP_TRY_
+
 cudaError_t build_lbvh(xp_scene *s) {
     const uint64_t n = s->n_tris;
     s->built = false;

@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         "xp_scene_set_triangles_dev": ([vp, vp, u64], i32),
         "xp_scene_set_positions": ([vp, vp, u64], i32),
         "xp_scene_set_heightmap": ([vp, vp, u32, u32, C.c_float, C.c_float, C.c_float], i32),
+        "xp_scene_set_clipmap": ([vp, vp, u32, u32, vp, u32, C.c_float], i32),
         "xp_scene_build": ([vp], i32),
         "xp_scene_triangle_count": ([vp], u64),
         "xp_detect_batch": ([vp, vp, u64, u32, vp, vp, vp, vp], i32),
@@ -109,7 +110,7 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "xp_device_count", "xp_scene_create", "xp_scene_destroy", "xp_scene_set_stream", "xp_scene_set_option",
-    "xp_scene_get_stats", "xp_scene_set_triangles", "xp_scene_set_triangles_dev", "xp_scene_set_positions", "xp_scene_set_heightmap",
+    "xp_scene_get_stats", "xp_scene_set_triangles", "xp_scene_set_triangles_dev", "xp_scene_set_positions", "xp_scene_set_heightmap", "xp_scene_set_clipmap",
     "xp_scene_build", "xp_scene_triangle_count", "xp_detect_batch", "xp_detect_batch_dev",
     "xp_detect_batch_submit", "xp_detect_batch_wait",
     "xp_collision_response_batch", "xp_collision_response_batch_dev", "xp_sphere_triangle_detect_collision",

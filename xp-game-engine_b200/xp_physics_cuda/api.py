@@ -176,6 +176,15 @@ class Scene:
         check(self._L.xp_scene_set_heightmap(self._h, _p(h), h.shape[0] - 1, h.shape[1] - 1, x0, z0, spacing),
               "xp_scene_set_heightmap")
 
+    def set_clipmap(self, clipmap):
+        """The collision soup of a `clipmap.Clipmap` (toroidal height store + part layout), emitted on the
+        device; same triangles, same order as `clipmap.triangles()`."""
+        from .clipmap import CM_UNIT_SIZE_SMALLEST
+        h = np.ascontiguousarray(clipmap.data, np.float32)
+        parts = np.ascontiguousarray(clipmap.part_table(), np.int32)
+        check(self._L.xp_scene_set_clipmap(self._h, _p(h), clipmap.levels, clipmap.size, _p(parts), len(parts),
+                                           float(CM_UNIT_SIZE_SMALLEST)), "xp_scene_set_clipmap")
+
     def build(self):
         check(self._L.xp_scene_build(self._h), "xp_scene_build")
 
