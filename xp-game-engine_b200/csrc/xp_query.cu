@@ -290,11 +290,12 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
 // ------------------------------------------------------------------------------------------
 // stage 1 of the two-stage sweep: broadphase only (binary LBVH, persistent warps)
 // ------------------------------------------------------------------------------------------
-// The traversal is latency-bound pointer chasing, so this kernel is built for memory-level
-// parallelism: <= 32 registers (64 resident warps per SM), a persistent grid, and lanes that pull
-// their next ray as soon as they finish one (warps grab 32 Morton-consecutive rays at a time from
-// a global cursor), so a warp never idles behind its longest ray.  Leaves whose box passes P are
-// staged in a warp-shared queue in shared memory and written to HBM 32 pairs (256 B) at a time.
+// The traversal is pointer chasing, so this kernel is built around the memory system: a persistent
+// grid of 3 blocks per SM (L1 capacity beats occupancy here), lanes that pull their next ray as soon as
+// they finish one (warps grab 32 Morton-consecutive rays at a time from a global cursor), a cooperative
+// conflict-free gather of the 64 B nodes (warp_gather64), and, once the cursor has run dry, idle lanes
+// that take over pending subtrees of their warp's busy lanes.  Leaves whose box passes P are staged in a
+// warp-shared queue in shared memory and written to HBM in spans of BP_SPAN pairs (1 KB).
 static constexpr int BP_THREADS = 256;
 static constexpr int BP_WARPS = BP_THREADS / 32;
 #ifndef XP_BP_SPAN
@@ -311,7 +312,8 @@ static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at 
 #ifndef XP_BP_STEAL
 #define XP_BP_STEAL 1
 #endif
-// Measured on config 2 (stage-1 ms): 2 blocks/SM 1.34, 3: 1.22, 4: 1.26, 5: 1.32, 6: 1.38, 7 (spills): 1.59.
+// Measured on config 2 (stage-1 ms, before the swizzled gather): 2 blocks/SM 1.34, 3: 1.22, 4: 1.26, 5: 1.32,
+// 6: 1.38, 7 (spills): 1.59; with it 3: 0.95, 4: 0.98, 5: 1.06.
 // Fewer resident warps leave more of the 228 KB to L1 (3 x 27 KB of staging -> ~148 KB of L1), and the node
 // walk gains more from cache hits than from extra warps.
 static constexpr int BP_BLOCKS_PER_SM = XP_BP_BLOCKS;
@@ -462,7 +464,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
             else if (hit_b) node = link.y;
             else node = (sp > sbase) ? stack[--sp] : -1;
         }
-        // ---- stage leaf hits; flush 32 pairs at a time
+        // ---- stage leaf hits; flush a span of BP_SPAN pairs at a time
         const unsigned ma = __ballot_sync(FULL, leaf_a >= 0);
         const unsigned mb = __ballot_sync(FULL, leaf_b >= 0);
         if (ma | mb) {
