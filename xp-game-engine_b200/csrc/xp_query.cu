@@ -318,6 +318,7 @@ static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at 
 // walk gains more from cache hits than from extra warps.
 static constexpr int BP_BLOCKS_PER_SM = XP_BP_BLOCKS;
 
+template <bool WINDOWED>
 __global__ void __launch_bounds__(BP_THREADS, BP_BLOCKS_PER_SM)
 k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
              float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap,
@@ -372,7 +373,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                     const float4 *rp = reinterpret_cast<const float4 *>(rays + pool + lane);
                     rpool[lane] = __ldcs(rp + 0);           // (c, |m|)      read once: do not displace nodes
                     rpool[32 + lane] = __ldcs(rp + 3);      // (1/m, flags)
-                    if (best) rbest[lane] = __uint_as_float((unsigned)(__ldg(&best[ray0 + pool + lane]) >> 32));
+                    if (WINDOWED) rbest[lane] = __uint_as_float((unsigned)(__ldg(&best[ray0 + pool + lane]) >> 32));
                 }
                 __syncwarp();
             }
@@ -384,7 +385,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                     c = f4_xyz(q0); inv = f4_xyz(q3);
                     sp = 0; sbase = 0;
                     bool go = (__float_as_uint(q3.w) & RAY_VALID) != 0;
-                    if (best) {                              // windowed pass: t = distance / |m|
+                    if (WINDOWED) {                          // windowed pass: t = distance / |m|
                         const float ml = q0.w;
                         const bool sane = ml > 0.0f && ml <= XP_FLT_MAX;
                         t_lo = sane ? __fdiv_rn(d_lo, ml) : 0.0f;
@@ -418,7 +419,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                     const int got = __shfl_sync(FULL, give, from);
                     const float cx = __shfl_sync(FULL, c.x, from), cy = __shfl_sync(FULL, c.y, from), cz = __shfl_sync(FULL, c.z, from);
                     const float ix = __shfl_sync(FULL, inv.x, from), iy = __shfl_sync(FULL, inv.y, from), iz = __shfl_sync(FULL, inv.z, from);
-                    const float lo_ = __shfl_sync(FULL, t_lo, from), hi_ = __shfl_sync(FULL, t_hi, from);
+                    const float lo_ = WINDOWED ? __shfl_sync(FULL, t_lo, from) : 0.0f, hi_ = WINDOWED ? __shfl_sync(FULL, t_hi, from) : INFINITY;
                     const unsigned ray_ = __shfl_sync(FULL, my_ray, from);
                     if (thief) {
                         node = got; c = {cx, cy, cz}; inv = {ix, iy, iz}; t_lo = lo_; t_hi = hi_; my_ray = ray_;
@@ -452,10 +453,12 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
             bool hit_b = slab2(c, inv, horizon, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tb, fb);
             // window: a subtree matters if the ray is inside its box somewhere in [t_lo, t_hi);
             // a leaf is emitted by the one pass whose window holds its ENTRY time
-            hit_a = hit_a && ta < t_hi && fa >= t_lo;
-            hit_b = hit_b && tb < t_hi && fb >= t_lo;
-            if (hit_a && link.x < 0) { if (ta >= t_lo) leaf_a = ~link.x; hit_a = false; }
-            if (hit_b && link.y < 0) { if (tb >= t_lo) leaf_b = ~link.y; hit_b = false; }
+            if (WINDOWED) {
+                hit_a = hit_a && ta < t_hi && fa >= t_lo;
+                hit_b = hit_b && tb < t_hi && fb >= t_lo;
+            }
+            if (hit_a && link.x < 0) { if (!WINDOWED || ta >= t_lo) leaf_a = ~link.x; hit_a = false; }
+            if (hit_b && link.y < 0) { if (!WINDOWED || tb >= t_lo) leaf_b = ~link.y; hit_b = false; }
             if (hit_a && hit_b) {
                 node = link.x;
                 if (sp < STACK_DEPTH) stack[sp++] = link.y;
@@ -1171,8 +1174,12 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
             else if (q4)
                 k_broadphase4<<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes4.as<Node4>(), rays, pos, end, s->cur_horizon, ctr, pairs, cap);
             else
-                k_broadphase<<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                        d_lo, d_hi, windows ? best : nullptr);
+                if (windows)
+                    k_broadphase<true><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                                                                                  d_lo, d_hi, best);
+                else
+                    k_broadphase<false><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                                                                                   0.0f, INFINITY, nullptr);
             ++s->stats.kernel_launches;
         }
         {
@@ -1401,7 +1408,7 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
         XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
         if (s->method != XP_METHOD_WIDE_FUSED && s->method != XP_METHOD_WIDE_PAIRS)
-            k_broadphase<<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
+            k_broadphase<false><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
                                                                   s->cur_horizon, ctr, pairs, buf_cap, 0.0f, INFINITY, nullptr);
         else
             k_sweep<ExactOps, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
