@@ -783,6 +783,9 @@ k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__re
 #ifndef XP_NP_LDG256
 #define XP_NP_LDG256 1
 #endif
+#ifndef XP_NP_GRID
+#define XP_NP_GRID 8              // blocks per SM in the grid (4 are resident)
+#endif
 template <class O, bool FILTER>
 __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec *__restrict__ recs,
                                                       const RayRec *__restrict__ rays,
@@ -800,7 +803,10 @@ __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec
     unsigned kept = 0;
     // a block works through contiguous spans of the pair list (the broadphase writes it in runs that
     // share rays and triangles), so the gathers below find most of their lines already in L1
-    constexpr unsigned long long NP_SPAN = 2048;
+#ifndef XP_NP_SPAN
+#define XP_NP_SPAN 2048
+#endif
+    constexpr unsigned long long NP_SPAN = XP_NP_SPAN;
     for (unsigned long long s0 = blockIdx.x * NP_SPAN; s0 < n; s0 += (unsigned long long)gridDim.x * NP_SPAN)
     for (unsigned long long p = s0 + threadIdx.x; p < n && p < s0 + NP_SPAN; p += blockDim.x) {
         const uint2 pr = __ldcs(&pairs[p]);              // read once: streaming
@@ -1184,8 +1190,8 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
         }
         {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
-            if (q4) k_narrow_pairs<O, true><<<148 * 8, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
-            else k_narrow_pairs<O, false><<<148 * 8, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
+            if (q4) k_narrow_pairs<O, true><<<148 * XP_NP_GRID, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
+            else k_narrow_pairs<O, false><<<148 * XP_NP_GRID, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
             ++s->stats.kernel_launches;
         }
         if (s->safe_pairs) {                 // synchronous mode: check the fill after every chunk
