@@ -33,6 +33,9 @@ extern "C" {
     fn xp_scene_build(s: *mut XpScene) -> c_int;
     fn xp_detect_batch(s: *mut XpScene, input: *const Response, n: u64, horizon_mode: u32, out: *mut Collision,
                        hit: *mut u8, tri_index: *mut u32, status: *mut u32) -> c_int;
+    fn xp_detect_batch_submit(s: *mut XpScene, input: *const Response, n: u64, horizon_mode: u32, out: *mut Collision,
+                              hit: *mut u8, tri_index: *mut u32, status: *mut u32, ticket: *mut c_int) -> c_int;
+    fn xp_detect_batch_wait(s: *mut XpScene, ticket: c_int) -> c_int;
     fn xp_collision_response_batch(s: *mut XpScene, input: *const Response, n: u64, max_iter: u32, horizon_mode: u32,
                                    out: *mut Response, iterations: *mut u32, status: *mut u32,
                                    last_slide_normal: *mut Vec3f) -> c_int;
@@ -53,6 +56,23 @@ impl Scene {
             assert_eq!(xp_scene_build(raw), 0, "xp_scene_build");
         }
         Scene { raw }
+    }
+    /// Stream of batches: queue one batch (copies and sweep run asynchronously, up to 2 in flight) and get a
+    /// ticket.  Safety: `input` and the four output slices must stay alive and untouched until `wait(ticket)`
+    /// returns, and should be page-locked for the copies to be truly asynchronous.
+    pub unsafe fn submit(&self, input: &[Response], out: &mut [Collision], hit: &mut [u8], tri_index: &mut [u32],
+                         status: &mut [u32]) -> i32 {
+        let n = input.len();
+        assert!(out.len() >= n && hit.len() >= n && tri_index.len() >= n && status.len() >= n);
+        let mut ticket: c_int = -1;
+        let rc = xp_detect_batch_submit(self.raw, input.as_ptr(), n as u64, 0, out.as_mut_ptr(), hit.as_mut_ptr(),
+                                        tri_index.as_mut_ptr(), status.as_mut_ptr(), &mut ticket);
+        assert_eq!(rc, 0, "xp_detect_batch_submit");
+        ticket
+    }
+    pub fn wait(&self, ticket: i32) {
+        let rc = unsafe { xp_detect_batch_wait(self.raw, ticket) };
+        assert_eq!(rc, 0, "xp_detect_batch_wait");
     }
     pub fn from_positions(device: i32, soup: &[Vec3f]) -> Scene {
         let mut raw = std::ptr::null_mut();
