@@ -36,8 +36,10 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "xp-game-engine_b200")]
 
 NX, NZ = 708, 707                 # 2 * 708 * 707 = 1 001 112 triangles
 N_SPHERES = 1 << 20
-# algorithmic flops per narrowphase test by code path
-PATH_FLOPS = {"cull": 5, "far": 16, "face_hit": 86, "full": 245, "full_pit": 298}
+# algorithmic flops per narrowphase test by code path (full 245, full+PIT 298),
+# minus the 14 flops of the two squared edge lengths that are stored with the triangle at upload (like n and
+# the plane constant, they depend on the triangle only) and no longer computed per test
+PATH_FLOPS = {"cull": 5, "far": 16, "face_hit": 86, "full": 231, "full_pit": 284}
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4
 
 
@@ -299,7 +301,7 @@ def run_b200(args):
                 "frac": achieved / peak if peak else None, "peak_source": peak_src, "kernel_ms": np_ms,
                 "algorithmic_flops_per_launch": flops, "flops_per_test_by_path": PATH_FLOPS, "path_mix": paths,
                 "traffic": TRAFFIC_NARROW, "traffic_source": TRAFFIC_SOURCE,
-                "note": "245 algorithmic flops are ~630 issued instructions (17 IEEE div, 12 IEEE sqrt); "
+                "note": "231 algorithmic flops are ~580 issued instructions (11 IEEE div, 10 IEEE sqrt); "
                         "ncu (profiles/r01g_ncu_full.txt): issue slots 78% busy, L1 data pipe 62% busy, FMA pipe 42% busy, 30.3/32 lanes active"}
     # the broadphase is the longest kernel of the step and is memory-latency / L1-bound, not compute
     tests_step = float(np.mean([s["narrowphase_tests"] for s in stats]))

@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
     r.q0 = make_float4(v0.x, v0.y, v0.z, d.n.x);
     r.q1 = make_float4(v1.x, v1.y, v1.z, d.n.y);
     r.q2 = make_float4(v2.x, v2.y, v2.z, d.n.z);
-    r.q3 = make_float4(d.pc, 0.0f, 0.0f, __uint_as_float(i));
+    // the squared lengths of edges (v0,v1) and (v1,v2), op for op what the edge test computes per test
+    r.q3 = make_float4(d.pc, xp_edge_len2<ExactOps>(v0, v1), xp_edge_len2<ExactOps>(v1, v2), __uint_as_float(i));
     recs[j] = r;
     leaf_lo[j] = make_float4(lo.x, lo.y, lo.z, 0.0f);
     leaf_hi[j] = make_float4(hi.x, hi.y, hi.z, 0.0f);

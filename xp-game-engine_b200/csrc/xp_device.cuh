@@ -2,7 +2,7 @@
 //
 // HBM layout (all fp32, 16-byte aligned float4 planes so every access is one LDG.128):
 //   TriRec[T]  64 B  leaf j (Morton order): q0=(v0, n.x) q1=(v1, n.y) q2=(v2, n.z)
-//                    q3=(plane_constant, 0, 0, bits(upload index))
+//                    q3=(plane_constant, |v1-v0|^2, |v2-v1|^2, bits(upload index))
 //   Node[T-1]  64 B  internal node i: both child AABBs (already inflated by 1+1e-4) and the two
 //                    child links (>= 0 internal, < 0 leaf ~c); node 0 is the root
 //   RayRec[S]  64 B  per sphere per sweep: q0=(c, |m|) q1=(m, |m|^2) q2=(m/|m|, horizon)

@@ -831,7 +831,8 @@ __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec
         }
         const Ray ray = ray_from(r0, r1, __ldg(rp + 2));
         float t;
-        if (xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t)) {
+        const float els01[2] = {t3.y, t3.z};             // stored with the triangle: |v1-v0|^2, |v2-v1|^2
+        if (xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t, nullptr, els01)) {
             const unsigned long long key =
                 ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(~__float_as_uint(t3.w));
             atomicMin(&best[pr.x], key);
