@@ -1018,6 +1018,9 @@ __global__ void __launch_bounds__(256) k_respond(const RayRec *__restrict__ rays
                                                  uint32_t *__restrict__ status, xp_vec3 *__restrict__ normal,
                                                  uint32_t *__restrict__ next_active,
                                                  DeviceCounters *__restrict__ ctr) {
+    // the optimistic two-stage sweep dropped candidates: best[] is incomplete, apply nothing -- the host sees
+    // the flag in the same read-back that fetches the next active count and redoes the iteration
+    if (ctr->pair_overflow) return;
     const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool again = false;
@@ -1328,9 +1331,12 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
                          uint32_t *d_status, xp_vec3 *d_normal) {
     cudaStream_t st = s->stream;
     XP_TRY(zero_counters(s));
-    // the loop reads the active count back every iteration anyway: use the synchronous pair mode
+    // One host read-back per iteration: the next active count and the overflow flag of the optimistic pair
+    // buffer travel together (k_respond applies nothing when the flag is up); only an iteration that did
+    // overflow is redone in the synchronous chunk-halving mode.
     struct SafeGuard { xp_scene *s; bool old; ~SafeGuard() { s->safe_pairs = old; } } guard{s, s->safe_pairs};
-    s->safe_pairs = true;
+    bool force_safe = s->safe_pairs;
+    unsigned long long acc_tests = 0, acc_pairs = 0;      // device accounting at the start of the iteration
     DeviceCounters *ctr = s->counters.as<DeviceCounters>();
     if (d_out != d_in) XP_TRY(cudaMemcpyAsync(d_out, d_in, n * sizeof(xp_response), cudaMemcpyDeviceToDevice, st));
     if (d_iter) XP_TRY(cudaMemsetAsync(d_iter, 0, n * 4, st));
@@ -1362,8 +1368,8 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
                 break;
             }
             XP_TRY(ray_setup(s, cur, active, na, horizon, status));
+            s->safe_pairs = force_safe;
             XP_TRY(closest(s, na));
-            s->swept_rays += na;
             XP_TRY(cudaMemsetAsync(&ctr->next_active, 0, sizeof(unsigned), st));
             {
                 StageTimer t(s, XP_STAGE_RESPONSE);
@@ -1375,9 +1381,20 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
                     k_respond<ExactOps><<<grid_for(na, 256), 256, 0, st>>>(rays, best, active, na, cur, iter, status, normal, next, ctr);
                 ++s->stats.kernel_launches;
             }
-            unsigned h_next = 0;
-            XP_TRY(cudaMemcpyAsync(&h_next, &ctr->next_active, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            XP_TRY(cudaStreamSynchronize(st));
+            DeviceCounters h;
+            XP_TRY(fetch_counters(s, &h));
+            if (h.pair_overflow) {             // rare: nothing was applied; same iteration again, synchronously
+                XP_TRY(cudaMemsetAsync(&ctr->pair_overflow, 0, sizeof(unsigned), st));
+                XP_TRY(cudaMemcpyAsync(&ctr->tests, &acc_tests, 8, cudaMemcpyHostToDevice, st));
+                XP_TRY(cudaMemcpyAsync(&ctr->pairs_total, &acc_pairs, 8, cudaMemcpyHostToDevice, st));
+                XP_TRY(cudaStreamSynchronize(st));
+                force_safe = true;
+                continue;
+            }
+            acc_tests = h.tests;
+            acc_pairs = h.pairs_total;
+            s->swept_rays += na;
+            const unsigned h_next = h.next_active;
             ++it;
             if (it > s->stats.iterations_run) s->stats.iterations_run = it;
             na = h_next;
