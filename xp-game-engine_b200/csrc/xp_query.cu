@@ -96,6 +96,9 @@ __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
 // same quarter) hit 8 different 16 B bank groups -- no padding, no conflicts (the earlier 80 B
 // stride was conflict-free for the loads only: ncu counted 2 wavefronts per 8 stored lanes).
 // idx < 0 = this lane wants nothing.  stage: 32 x 4 float4 per warp.
+#ifndef XP_GATHER_ASYNC
+#define XP_GATHER_ASYNC 1          // 1: cp.async.ca, 2: cp.async.cg (L2 only), 0: LDG + STS
+#endif
 static constexpr int GATHER_STRIDE = 4;            // float4 per staged record
 __device__ __forceinline__ void warp_gather64(const float4 *__restrict__ base, int idx, float4 *stage,
                                               float4 &o0, float4 &o1, float4 &o2, float4 &o3) {
@@ -103,11 +106,26 @@ __device__ __forceinline__ void warp_gather64(const float4 *__restrict__ base, i
     const int want = idx < 0 ? 0 : idx;             // idle lanes fetch record 0 (hot in L1): no predication needed
     const float4 *src = base + (lane & 3);
     float4 *dst = stage + (lane & ~3) + ((lane & 3) ^ ((lane >> 3) & 3));      // record lane>>2 (+ 8 per round)
+#if XP_GATHER_ASYNC
+    // cp.async (LDGSTS): global -> shared without the round trip through registers and the STS wavefronts
+    const unsigned dst_s = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int rec = __shfl_sync(0xffffffffu, want, (lane >> 2) + 8 * r);
+#if XP_GATHER_ASYNC == 2
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_s + 512u * r), "l"(src + (size_t)(unsigned)rec * 4) : "memory");
+#else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst_s + 512u * r), "l"(src + (size_t)(unsigned)rec * 4) : "memory");
+#endif
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#else
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int rec = __shfl_sync(0xffffffffu, want, (lane >> 2) + 8 * r);
         dst[32 * r] = __ldg(src + (size_t)(unsigned)rec * 4);
     }
+#endif
     __syncwarp();
     const float4 *mine = stage + lane * 4;
     const int sw = (lane >> 1) & 3;
@@ -304,7 +322,7 @@ static constexpr int BP_WARPS = BP_THREADS / 32;
 static constexpr int BP_SPAN = XP_BP_SPAN;          // pairs written per flush: long coherent runs help the narrowphase's L1
 static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at most 64 appended per step
 #ifndef XP_BP_BLOCKS
-#define XP_BP_BLOCKS 3
+#define XP_BP_BLOCKS 4
 #endif
 #ifndef XP_BP_GATHER
 #define XP_BP_GATHER 1
@@ -313,7 +331,8 @@ static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at 
 #define XP_BP_STEAL 1
 #endif
 // Measured on config 2 (stage-1 ms, before the swizzled gather): 2 blocks/SM 1.34, 3: 1.22, 4: 1.26, 5: 1.32,
-// 6: 1.38, 7 (spills): 1.59; with it 3: 0.95, 4: 0.98, 5: 1.06.
+// 6: 1.38, 7 (spills): 1.59; with it 3: 0.95, 4: 0.98, 5: 1.06; with work stealing and the cp.async gather
+// 2: 0.93, 3: 0.745, 4: 0.727, 5: 0.765, 6: 0.98.
 // Fewer resident warps leave more of the 228 KB to L1 (3 x 27 KB of staging -> ~148 KB of L1), and the node
 // walk gains more from cache hits than from extra warps.
 static constexpr int BP_BLOCKS_PER_SM = XP_BP_BLOCKS;
