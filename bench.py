@@ -302,7 +302,7 @@ def run_b200(args):
                 "algorithmic_flops_per_launch": flops, "flops_per_test_by_path": PATH_FLOPS, "path_mix": paths,
                 "traffic": TRAFFIC_NARROW, "traffic_source": TRAFFIC_SOURCE,
                 "note": "231 algorithmic flops are ~580 issued instructions (11 IEEE div, 10 IEEE sqrt); "
-                        "ncu (profiles/r01g_ncu_full.txt): issue slots 78% busy, L1 data pipe 62% busy, FMA pipe 42% busy, 30.3/32 lanes active"}
+                        "ncu (profiles/r01h_ncu_full.txt): issue slots 77% busy, L1 data pipe 65% busy, FMA pipe 42% busy, 30.1/32 lanes active"}
     # the broadphase is the longest kernel of the step and is memory-latency / L1-bound, not compute
     tests_step = float(np.mean([s["narrowphase_tests"] for s in stats]))
     bp_bytes = 64.0 * n + 8.0 * tests_step                       # ray records in + candidate pairs out
@@ -315,7 +315,7 @@ def run_b200(args):
                     "traffic_source": TRAFFIC_SOURCE,
                     "note": "64 B ray record per sphere + 8 B per candidate pair; the 64 B nodes it chases "
                             "(83 M visits) are L1/L2 hits (scene is L2-resident), so the kernel is bound by L1 "
-                            "throughput and the latency of one dependent L2 access per step (ncu: L1 data pipe 91% busy, issue slots 48%, 28 of 32 lanes active, DRAM 4%), not by HBM"}
+                            "throughput and the latency of one dependent L2 access per step (ncu: L1 data pipe 87% busy, issue slots 55%, 28 of 32 lanes active, DRAM 4%), not by HBM"}
 
     # e2e: the host-pointer C-ABI call, pinned host buffers, H2D + D2H inside the timed region
     h_in = torch.from_numpy(resps.view(np.float32).reshape(n, 7)).pin_memory()
@@ -460,10 +460,10 @@ def run_b200(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
-# same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r01g_ncu_full.txt
-TRAFFIC_NARROW = 619.5e6         # k_narrow_pairs: ~600 MB read + ~20 MB written (315 MB of the reads is the pair list)
-TRAFFIC_BROADPHASE = 402.8e6     # k_broadphase: ~128 MB read + ~277 MB written (the pair list)
-TRAFFIC_SOURCE = "profiles/r01g_ncu_full.txt"
+# same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r01h_ncu_full.txt
+TRAFFIC_NARROW = 628.5e6         # k_narrow_pairs: ~600 MB read + ~20 MB written (315 MB of the reads is the pair list)
+TRAFFIC_BROADPHASE = 414.7e6     # k_broadphase: ~128 MB read + ~277 MB written (the pair list)
+TRAFFIC_SOURCE = "profiles/r01h_ncu_full.txt"
 
 
 def measured_hbm_gbs():
