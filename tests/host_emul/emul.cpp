@@ -11,16 +11,17 @@ using namespace xp;
 
 extern "C" {
 
-// resp: 7 floats (c, r, m); tri: 9 floats; out: 8 floats (collision). returns 1/0/-1
+// resp: 7 floats (c, r, m); tri: 9 floats; out: 8 floats (collision). returns 1/0/-1.  fast = mode (0 / 1)
 int emul_detect(const float *resp, const float *tri, float *out, int fast) {
     if (!(resp[3] == 1.0f)) return -1;
     V3 c = {resp[0], resp[1], resp[2]}, m = {resp[4], resp[5], resp[6]};
     V3 v0 = {tri[0], tri[1], tri[2]}, v1 = {tri[3], tri[4], tri[5]}, v2 = {tri[6], tri[7], tri[8]};
     TriDerived d = xp_tri_derive(v0, v1, v2);
-    (void)fast;
     Ray ray = xp_ray_setup<ExactOps>(c, m);
     float t;
-    if (!xp_detect<ExactOps>(ray, v0, v1, v2, d.n, d.pc, t)) return 0;
+    // mode 1: the two squared edge lengths come precomputed, as k_pack stores them in the triangle record
+    const float els01[2] = {xp_edge_len2<ExactOps>(v0, v1), xp_edge_len2<ExactOps>(v1, v2)};
+    if (!xp_detect<ExactOps>(ray, v0, v1, v2, d.n, d.pc, t, nullptr, fast == 1 ? els01 : nullptr)) return 0;
     Contact k = xp_make_collision<ExactOps>(ray, t);
     out[0] = k.time_to; out[1] = k.distance_to;
     out[2] = k.position.x; out[3] = k.position.y; out[4] = k.position.z;

@@ -15,9 +15,9 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def _emul_detect(E, resp, tri):
+def _emul_detect(E, resp, tri, mode=0):
     out = np.zeros(8, np.float32)
-    r = E.emul_detect(_p(resp), _p(tri), _p(out), 0)
+    r = E.emul_detect(_p(resp), _p(tri), _p(out), mode)
     return r, out
 
 
@@ -82,6 +82,25 @@ def test_detect_lean_equals_oracle_bitwise(oracle):
             w = np.concatenate([[want["time_to"], want["distance_to"]], want["position"], want["intersection"]])
             assert_bits_equal(got, w.astype(np.float32), "collision fields")
     assert n_hit > 1000
+
+
+def test_detect_with_stored_edge_lengths_equals_oracle_bitwise(oracle):
+    """k_narrow_pairs reads |v1-v0|^2 and |v2-v1|^2 from the triangle record (k_pack computes them with
+    xp_edge_len2); the result must not change by a bit."""
+    E = emul_lib()
+    n_hit = 0
+    for c, m, tri in _cases(13, 20000):
+        resp = oracle.make_responses([c], [m])
+        want = oracle.detect(resp, tri)
+        r, got = _emul_detect(E, resp, tri, mode=1)
+        r0, got0 = _emul_detect(E, resp, tri, mode=0)
+        assert r == r0 and np.array_equal(got.view(np.uint32), got0.view(np.uint32))
+        assert (want is not None) == (r == 1), (c, m, tri)
+        if want is not None:
+            n_hit += 1
+            w = np.concatenate([[want["time_to"], want["distance_to"]], want["position"], want["intersection"]])
+            assert_bits_equal(got, w.astype(np.float32), "collision fields")
+    assert n_hit > 700
 
 
 def test_detect_lean_equals_oracle_on_terrain(oracle):
