@@ -103,7 +103,6 @@ static constexpr int GATHER_STRIDE = 4;            // float4 per staged record
 __device__ __forceinline__ void warp_gather64(const float4 *__restrict__ base, int idx, float4 *stage,
                                               float4 &o0, float4 &o1, float4 &o2, float4 &o3) {
     const int lane = threadIdx.x & 31;
-    const int want = idx < 0 ? 0 : idx;             // idle lanes fetch record 0 (hot in L1): no predication needed
     const float4 *src = base + (lane & 3);
     float4 *dst = stage + (lane & ~3) + ((lane & 3) ^ ((lane >> 3) & 3));      // record lane>>2 (+ 8 per round)
 #if XP_GATHER_ASYNC
@@ -111,7 +110,8 @@ __device__ __forceinline__ void warp_gather64(const float4 *__restrict__ base, i
     const unsigned dst_s = (unsigned)__cvta_generic_to_shared(dst);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const int rec = __shfl_sync(0xffffffffu, want, (lane >> 2) + 8 * r);
+        const int rec = __shfl_sync(0xffffffffu, idx, (lane >> 2) + 8 * r);
+        if (rec < 0) continue;                      // that lane wants nothing: no copy, its staging slot stays stale
 #if XP_GATHER_ASYNC == 2
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_s + 512u * r), "l"(src + (size_t)(unsigned)rec * 4) : "memory");
 #else
@@ -120,6 +120,7 @@ __device__ __forceinline__ void warp_gather64(const float4 *__restrict__ base, i
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
 #else
+    const int want = idx < 0 ? 0 : idx;             // idle lanes fetch record 0 (hot in L1): no predication needed
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int rec = __shfl_sync(0xffffffffu, want, (lane >> 2) + 8 * r);
