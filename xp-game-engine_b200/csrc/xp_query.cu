@@ -7,7 +7,7 @@
 // for a batch of independent spheres.
 //
 // closest() implementations selected by XP_OPT_METHOD:
-//   WIDE_FUSED k_sweep: one WARP per sphere over the 32-wide implicit tree (default; see k_sweep)
+//   WIDE_FUSED k_sweep: one WARP per sphere over the 32-wide implicit tree (see k_sweep)
 //   LBVH_PAIRS k_broadphase (persistent warps over the binary LBVH) writes the pairs of P to HBM,
 //              k_narrow_pairs tests them (default; see k_broadphase)
 //   Q4_PAIRS   k_broadphase4 over the quantised 4-wide collapse, k_narrow_pairs<FILTER> re-checks P
@@ -310,7 +310,7 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
 // stage 1 of the two-stage sweep: broadphase only (binary LBVH, persistent warps)
 // ------------------------------------------------------------------------------------------
 // The traversal is pointer chasing, so this kernel is built around the memory system: a persistent
-// grid of 3 blocks per SM (L1 capacity beats occupancy here), lanes that pull their next ray as soon as
+// grid of BP_BLOCKS_PER_SM blocks per SM (measured; L1 capacity limits it), lanes that pull their next ray as soon as
 // they finish one (warps grab 32 Morton-consecutive rays at a time from a global cursor), a cooperative
 // conflict-free gather of the 64 B nodes (warp_gather64), and, once the cursor has run dry, idle lanes
 // that take over pending subtrees of their warp's busy lanes.  Leaves whose box passes P are staged in a
