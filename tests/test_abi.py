@@ -61,6 +61,30 @@ def test_argument_validation_without_a_device(L):
     L.xp_scene_destroy(None)
 
 
+def test_new_entry_points_validate_arguments_without_a_device(L):
+    t = C.c_int(-1)
+    assert L.xp_detect_batch_submit(None, None, 0, 0, None, None, None, None, C.byref(t)) == _lib.XP_EINVAL
+    assert L.xp_detect_batch_wait(None, 0) == _lib.XP_EINVAL
+    assert L.xp_scene_set_exchange_stream(None, None) == _lib.XP_EINVAL
+    assert L.xp_detect_contacts_exchange_submit(None, None, 0, 0, None, 0, -1, 0, C.byref(t)) == _lib.XP_EINVAL
+    assert L.xp_detect_contacts_exchange_wait(None, 0) == _lib.XP_EINVAL
+    assert L.xp_detect_contacts_multicast_dev(None, None, 0, 0, None, 0) == _lib.XP_EINVAL
+    assert L.xp_scene_set_clipmap(None, None, 0, 0, None, 0, 2.0) == _lib.XP_EINVAL
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99, not only as C++."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        import pytest
+        pytest.skip("no C compiler")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", _lib.HEADER],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_no_cpu_fallback(L):
     """Without a CUDA device the product refuses to work instead of computing on the CPU."""
     n = C.c_int(-1)
