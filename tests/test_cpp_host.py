@@ -1,0 +1,36 @@
+"""The header-only C++ host mirror (xp-game-engine_b200/cpp/xp_physics.hpp) from a native program:
+builds on the CPU tier, runs its self-check on the GPU tier (no Python between the program and the C ABI)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from xp_physics_cuda import _lib
+
+CPP = os.path.normpath(os.path.join(_lib.CSRC, "..", "cpp"))
+
+
+def build_example(tmp_path):
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    _lib.lib()                                   # raises if the product library has not been built
+    exe = str(tmp_path / "xp_example")
+    r = subprocess.run([cxx, "-std=c++17", "-Wall", "-Werror", "-O1", os.path.join(CPP, "example.cpp"), "-L" + _lib.CSRC,
+                        "-lxp_physics_cuda", "-Wl,-rpath," + _lib.CSRC, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_example_builds_and_links(tmp_path):
+    exe = build_example(tmp_path)
+    assert os.path.getsize(exe) > 0
+
+
+@pytest.mark.gpu
+def test_cpp_example_self_check(tmp_path):
+    exe = build_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout
