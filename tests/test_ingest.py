@@ -220,6 +220,16 @@ def test_chunk_number_and_offset_kat():
     assert f(-1, 32) == (-1, 31) and f(-32, 32) == (-1, 0) and f(-33, 32) == (-2, 32)   # the `% (n + 1)` quirk
 
 
+def test_position_to_chunk_kat():
+    f = ingest.World.position_to_chunk                     # chunks.rs:137-162 `position_to_chunk_test` (32, 0.1)
+    assert f([0.0001] * 3) == [0, 0, 0]
+    assert f([-0.0001] * 3) == [-1, -1, -1]
+    assert f([3.1999] * 3) == [0, 0, 0]
+    assert f([3.2001] * 3) == [1, 1, 1]
+    assert f([-3.1999] * 3) == [-1, -1, -1]
+    assert f([-3.2001] * 3) == [-2, -2, -2]
+
+
 def visible_faces(grid):
     """Unit faces world.rs:262-279 exposes: (axis, plane, a, b, sign) for every voxel side whose neighbour is
     empty, out of the grid, or of a DIFFERENT colour id."""

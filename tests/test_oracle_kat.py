@@ -28,6 +28,22 @@ def test_detect_where_collision_against_edge(oracle):
     assert c is not None and c["time_to"] == np.float32(0.5)
 
 
+def test_triangle_normal_orientation(oracle):
+    # low_poly_nice_graphics/src/mesh/mesh.rs:342-359 (`check_understanding_normal_calculation_0/1`): the same
+    # cross(p1 - p0, p2 - p0) orientation as glm::triangle_normal (triangle.rs:44-46); counter-clockwise -> +y
+    import ctypes as C
+
+    class V3(C.Structure):
+        _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+    L = oracle.lib()
+    L.xpo_triangle_normal.restype = V3
+    L.xpo_triangle_normal.argtypes = [C.c_void_p]
+    for tri in ([[0, 0, 0], [0, 0, 1], [1, 0, 0]], [[-1, 0, -1], [0, 0, 0], [0, 0, -1]]):
+        t = np.asarray(tri, np.float32)
+        n = L.xpo_triangle_normal(t.ctypes.data_as(C.c_void_p))
+        assert (n.x, n.y, n.z) == (0.0, 1.0, 0.0)
+
+
 def test_point_in_triangle(oracle):
     # xp_physics/src/triangle.rs:62-76
     t = ([-1, 0, 0], [0, 1, 1], [1, 0, 0])

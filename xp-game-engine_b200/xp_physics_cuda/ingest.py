@@ -518,6 +518,13 @@ class World:
         offset = chunk_size - ((-start) % (chunk_size + 1))
         return chunk_number, offset
 
+    @classmethod
+    def position_to_chunk(cls, position, chunk_size: int | None = None, voxel_size=None) -> list[int]:
+        """chunks.rs:60-65 (`Chunks::position_to_chunk`): the chunk a world position falls into."""
+        cs = np.float32(cls.CHUNK_SIZE if chunk_size is None else chunk_size)
+        vs = cls.VOXEL if voxel_size is None else np.float32(voxel_size)
+        return [int(np.floor(np.float32(p) / (cs * vs))) for p in position]
+
     def add(self, vox: Vox, position) -> None:
         """world.rs:86-136: remember which part of the model lands in which chunk (a later model
         replaces an earlier one chunk by chunk, as the HashMap insert does)."""
