@@ -10,12 +10,15 @@ collision_response is called).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
 N > 1 is launched by torchrun (one rank per GPU): the sphere batch is sharded (weak scaling:
-2^20 spheres per GPU, scene + LBVH replicated), each rank writes 40 B contact records straight
-into its slot of the gather buffer and one NCCL all_gather assembles the global contact list.
+2^20 spheres per GPU, scene + LBVH replicated) and the global list of 40 B contact records is
+assembled in every rank's gather buffer over NVLink peer memory (NCCL all_gather as the fallback).
 
-Prints ONE JSON line (rank 0).  `value` = narrowphase tests/s with inputs resident in HBM;
-`e2e` = the same metric through the host-pointer C-ABI call (pinned host buffers, H2D + D2H inside
-the timed region); `roofline` = the dominant kernel against the measured fp32 FFMA peak;
+Prints ONE JSON line (rank 0).  `value` = narrowphase tests/s with inputs resident in HBM, measured
+over a loop of steps with two in flight (step i's contact build + exchange on a second stream under
+step i+1's sweep; `single_step` = one synchronous step with an L2 flush in between);
+`e2e` = the same metric through the host-pointer C ABI for a stream of batches (pinned host buffers,
+every step's H2D + D2H inside the timed region, two batches in flight; `e2e.single_call` = one
+synchronous call per step); `roofline` = the dominant kernel against the measured fp32 FFMA peak;
 `cpu_baseline` = the CPU oracle (a port of the reference's algorithm: brute force over every
 triangle) timed on this box's host cores on a bounded sample.
 """
