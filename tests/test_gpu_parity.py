@@ -650,3 +650,33 @@ def test_async_exchange_loop_single_process(terrain, oracle):
         assert_bits_equal(rec["time_to"][hm], w[0]["time_to"][hm], f"async exchange step {k}")
         assert_bits_equal(rec["position"][hm], w[0]["position"][hm], f"async exchange step {k}")
         assert_bits_equal(rec["intersection"][hm], w[0]["intersection"][hm], f"async exchange step {k}")
+
+
+# ---- ill-conditioned triangles: the reference's face test reports hits the geometric broadphase never offers
+SLIVER = [[-0.7752354741096497, -0.6470972299575806, 5.695098400115967],
+          [-0.21221216022968292, -0.4316372871398926, 5.311792373657227],
+          [0.3508111536502838, -0.21617737412452698, 4.928485870361328]]      # v1 = fl((v0 + v2) / 2): nearly collinear
+SLIVER_SPHERES = [([7.1984725, 3.6347277, -6.416019], [1.4218696, -0.8297933, -0.7164174]),
+                  ([7.556139, 4.7300577, -2.830135], [0.78011984, -2.0790448, 0.52724224]),
+                  ([5.215561, 3.7503188, 2.4745898], [0.48196483, -1.0705745, 0.48744422])]
+
+
+@pytest.mark.parametrize("method,prune", METHODS)
+def test_sliver_triangle_far_face_hits(oracle, method, prune):
+    """Found by tools/stress_parity.py: with a rounding-dominated normal the reference 'hits' this sliver from far
+    outside its inflated box.  The library lists such triangles at build time and sweeps them exhaustively."""
+    rng = np.random.default_rng(3)
+    others = (rng.uniform(-6, 6, (200, 1, 3)) + rng.normal(0, 1.0, (200, 3, 3))).astype(np.float32)
+    tris = np.concatenate([others[:3], np.asarray([SLIVER], np.float32), others[3:]])
+    extra = xp.make_responses(rng.uniform(-8, 8, (1500, 3)).astype(np.float32), rng.normal(0, 1, (1500, 3)).astype(np.float32))
+    resps = np.concatenate([xp.make_responses([c for c, m in SLIVER_SPHERES], [m for c, m in SLIVER_SPHERES]), extra])
+    want = oracle.detect_batch(resps, tris)
+    assert want[1][:3].all() and (want[2][:2] == 3).all()             # the reference hits the sliver (index 3)
+    assert not oracle.broadphase_pairs(resps[:3], tris[3:4])[0].size  # ... although P rejects those pairs
+    w = oracle.collision_response_batch(resps, tris, max_iter=3)
+    with xp.Scene(0, tris, method=method, prune=prune) as s:
+        got = s.detect_batch(resps)
+        out, it, st, ln = s.collision_response_batch(resps, max_iter=3)
+    check_detect_exact(got, want, f"sliver {method}")
+    assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
+    assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"sliver response {method}")

@@ -90,7 +90,7 @@ void xp_scene_destroy(xp_scene *s) {
     for (auto &x : s->ex_slot) if (x.busy) cudaEventSynchronize(x.fin);
     DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_lo, &s->node_hi, &s->leaf_lo, &s->leaf_hi,
                       &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
-                      &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->rays, &s->best, &s->active_a,
+                      &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->degen, &s->rays, &s->best, &s->active_a,
                       &s->active_b, &s->inv_order, &s->pairs, &s->counters, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
                       &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
     for (DevBuf *b : bufs) b->release();
@@ -233,8 +233,12 @@ int xp_scene_build(xp_scene *s) {
     if (!s) return XP_EINVAL;
     XP_BIND(s);
     reset_stats(s);
+    s->n_degen = 0;
     XP_API_TRY(build_lbvh(s));
+    uint32_t nd = 0;
+    if (s->n_tris > 0) XP_API_TRY(cudaMemcpyAsync(&nd, s->degen.p, sizeof nd, cudaMemcpyDeviceToHost, s->stream));
     XP_API_TRY(cudaStreamSynchronize(s->stream));
+    s->n_degen = nd;
     resolve_stage_timers(s);
     return XP_OK;
 }

@@ -385,7 +385,7 @@ cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *
 __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uint64_t n,
                                               const uint32_t *__restrict__ sorted_idx,
                                               TriRec *__restrict__ recs, float4 *__restrict__ leaf_lo,
-                                              float4 *__restrict__ leaf_hi) {
+                                              float4 *__restrict__ leaf_hi, uint32_t *__restrict__ degen) {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint32_t i = sorted_idx[j];
@@ -400,6 +400,20 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
     // the squared lengths of edges (v0,v1) and (v1,v2), op for op what the edge test computes per test
     r.q3 = make_float4(d.pc, xp_edge_len2<ExactOps>(v0, v1), xp_edge_len2<ExactOps>(v1, v2), __uint_as_float(i));
     recs[j] = r;
+    // Ill-conditioned triangles.  When the edges at v0 are (nearly) parallel -- sin^2 of their angle <= 1e-4 --
+    // the reference's normal and the denominator of its point-in-triangle test (triangle.rs:11-32) are
+    // dominated by rounding, and its face test can report a "collision" arbitrarily far from the triangle;
+    // the broadphase predicate P, which is geometric, would never offer that pair.  Such triangles (and any
+    // with non-finite terms) are listed here and swept against every sphere instead (k_sweep_degenerate), as
+    // the reference sweeps every triangle.  Exactly collinear ones have a NaN normal and only their geometric
+    // vertex / edge tests can hit; listing them too keeps the rule simple.
+    {
+        const V3 e1 = {v1.x - v0.x, v1.y - v0.y, v1.z - v0.z}, e2 = {v2.x - v0.x, v2.y - v0.y, v2.z - v0.z};
+        const V3 c = {e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x};
+        const float cc = c.x * c.x + c.y * c.y + c.z * c.z;
+        const float ee = (e1.x * e1.x + e1.y * e1.y + e1.z * e1.z) * (e2.x * e2.x + e2.y * e2.y + e2.z * e2.z);
+        if (!(cc > 1e-4f * ee)) degen[1 + atomicAdd(&degen[0], 1u)] = (uint32_t)j;
+    }
     leaf_lo[j] = make_float4(lo.x, lo.y, lo.z, 0.0f);
     leaf_hi[j] = make_float4(hi.x, hi.y, hi.z, 0.0f);
 }
@@ -704,8 +718,10 @@ cudaError_t build_lbvh(xp_scene *s) {
     const uint32_t *vals = s->vals_a.as<uint32_t>();
     {
         StageTimer t(s, XP_STAGE_BUILD_PACK);
+        XP_TRY(s->degen.reserve((n + 1) * sizeof(uint32_t)));
+        XP_TRY(cudaMemsetAsync(s->degen.p, 0, sizeof(uint32_t), st));
         k_pack<<<grid_for(n, 256), 256, 0, st>>>(aos, n, vals, s->recs.as<TriRec>(),
-                                                s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>());
+                                                s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>(), s->degen.as<uint32_t>());
         ++s->stats.kernel_launches;
     }
     if (n == 1) {

@@ -111,6 +111,8 @@ struct xp_scene {
     xp::DevBuf bounds;        // 6 ordered-int floats: scene AABB of triangle centres
     xp::DevBuf wide, wide_lo, wide_hi;               // 32-wide implicit tree planes + per-node union boxes
     xp::DevBuf nodes4;                               // Node4[max(T-1,1)], indexed like the binary nodes
+    xp::DevBuf degen;                                // uint32[1 + T]: count, then the leaves of ill-conditioned triangles
+    uint64_t n_degen = 0;                            // (swept exhaustively, see k_pack / k_sweep_degenerate)
     xp::WideTree wide_tree = {};
     // per-call workspaces
     xp::DevBuf rays, best, active_a, active_b, inv_order, pairs, counters;

@@ -1130,9 +1130,53 @@ static cudaError_t ray_setup_t(xp_scene *s, const xp_response *cur, const uint32
     return cudaGetLastError();
 }
 
+// The ill-conditioned triangles listed at build time (k_pack) against EVERY ray, like the reference's loop over
+// all triangles: one thread per ray, the records are read by whole warps at once (broadcast).  Normally the
+// list is empty and this is never launched.
+template <class O>
+__global__ void __launch_bounds__(256) k_sweep_degenerate(const TriRec *__restrict__ recs,
+                                                          const uint32_t *__restrict__ list, uint32_t n_list,
+                                                          const RayRec *__restrict__ rays, uint64_t na,
+                                                          unsigned long long *__restrict__ best,
+                                                          DeviceCounters *__restrict__ ctr) {
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (k == 0) atomicAdd(&ctr->tests, (unsigned long long)na * n_list);
+    if (k >= na) return;
+    const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
+    if (!(__float_as_uint(__ldg(rp + 3).w) & RAY_VALID)) return;
+    const Ray ray = ray_from(__ldg(rp + 0), __ldg(rp + 1), __ldg(rp + 2));
+    unsigned long long mine = BEST_NONE;
+    for (uint32_t e = 0; e < n_list; ++e) {
+        const float4 *tp = reinterpret_cast<const float4 *>(recs + __ldg(&list[1 + e]));
+        const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
+        float t;
+        if (xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t)) {
+            const unsigned long long key =
+                ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(~__float_as_uint(t3.w));
+            mine = key < mine ? key : mine;
+        }
+    }
+    if (mine != BEST_NONE) atomicMin(&best[k], mine);
+}
+
+template <class O> static cudaError_t closest_main_t(xp_scene *s, uint64_t na);
+
 // closest collision for rays[0..na): fills best[0..na)
 template <class O>
 static cudaError_t closest_t(xp_scene *s, uint64_t na) {
+    XP_TRY(closest_main_t<O>(s, na));
+    if (na == 0 || s->n_degen == 0 || s->method == XP_METHOD_BRUTE) return cudaSuccess;
+    StageTimer t(s, XP_STAGE_NARROWPHASE);
+    k_sweep_degenerate<O><<<grid_for(na, 256), 256, 0, s->stream>>>(s->recs.as<TriRec>(), s->degen.as<uint32_t>(),
+                                                                  (uint32_t)s->n_degen, s->rays.as<RayRec>(), na,
+                                                                  s->best.as<unsigned long long>(),
+                                                                  s->counters.as<DeviceCounters>());
+    ++s->stats.kernel_launches;
+    return cudaGetLastError();
+}
+
+template <class O>
+static cudaError_t closest_main_t(xp_scene *s, uint64_t na) {
     if (na == 0 || s->n_tris == 0) return cudaSuccess;
     XP_TRY(build_aux(s));
     cudaStream_t st = s->stream;
