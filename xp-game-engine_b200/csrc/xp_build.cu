@@ -406,13 +406,17 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
     // the broadphase predicate P, which is geometric, would never offer that pair.  Such triangles (and any
     // with non-finite terms) are listed here and swept against every sphere instead (k_sweep_degenerate), as
     // the reference sweeps every triangle.  Exactly collinear ones have a NaN normal and only their geometric
-    // vertex / edge tests can hit; listing them too keeps the rule simple.
+    // vertex / edge tests can hit; listing them too keeps the rule simple.  The second, scale-aware rule lists
+    // long thin triangles: the point-in-triangle rounding can accept a face contact about
+    // 6e-8 * L^2 / w outside a triangle of length L and width w = |cross| / L; beyond L^2 / w ~ 400 that is no
+    // longer small against the 1e-4 by which P inflates the box.
     {
         const V3 e1 = {v1.x - v0.x, v1.y - v0.y, v1.z - v0.z}, e2 = {v2.x - v0.x, v2.y - v0.y, v2.z - v0.z};
         const V3 c = {e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x};
         const float cc = c.x * c.x + c.y * c.y + c.z * c.z;
-        const float ee = (e1.x * e1.x + e1.y * e1.y + e1.z * e1.z) * (e2.x * e2.x + e2.y * e2.y + e2.z * e2.z);
-        if (!(cc > 1e-4f * ee)) degen[1 + atomicAdd(&degen[0], 1u)] = (uint32_t)j;
+        const float l1 = e1.x * e1.x + e1.y * e1.y + e1.z * e1.z, l2 = e2.x * e2.x + e2.y * e2.y + e2.z * e2.z;
+        const float m2 = fmaxf(l1, l2);
+        if (!(cc > 1e-4f * (l1 * l2)) || !(cc * 1.7e5f > m2 * m2 * m2)) degen[1 + atomicAdd(&degen[0], 1u)] = (uint32_t)j;
     }
     leaf_lo[j] = make_float4(lo.x, lo.y, lo.z, 0.0f);
     leaf_hi[j] = make_float4(hi.x, hi.y, hi.z, 0.0f);
