@@ -87,6 +87,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=12)
     ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--max-iter", type=int, default=3, help="response iterations (0 = unbounded like the reference)")
     ap.add_argument("--kinds", default="", help="comma list of case kinds 0..5 to cycle through (default: all)")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
@@ -97,14 +98,14 @@ def main():
             tris, resps = make_case(rng, kinds[k % len(kinds)])
             t0 = time.time()
             want = oracle.detect_batch(resps, tris)
-            wres = oracle.collision_response_batch(resps, tris, max_iter=3)
+            wres = oracle.collision_response_batch(resps, tris, max_iter=args.max_iter)
             t_cpu = time.time() - t0
             s.set_options(method="lbvh_pairs", prune=bool(k % 3 == 2))
             s.set_triangles(tris)
             s.build()
             t0 = time.time()
             got = s.detect_batch(resps)
-            out, it, st, ln = s.collision_response_batch(resps, max_iter=3)
+            out, it, st, ln = s.collision_response_batch(resps, max_iter=args.max_iter)
             t_gpu = time.time() - t0
             h = want[1].astype(bool)
             ok = (np.array_equal(got[1], want[1]) and np.array_equal(bits(fields(got[0])[h]), bits(fields(want[0])[h]))
