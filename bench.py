@@ -171,6 +171,8 @@ def run_b200(args):
     tris, resps = build_workload(seed=1 + rank)
     n = len(resps)
     scene = xp.Scene(local, arith=args.arith, method=args.method, prune=bool(args.prune), timing=True)
+    if args.far_exact:
+        scene.set_options(far_exact=True)
     stream = torch.cuda.current_stream()
     scene.set_stream(stream.cuda_stream)
     scene.set_triangles(tris)
@@ -428,7 +430,7 @@ def run_b200(args):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": dict(workload_config(world), arith=args.arith, method=args.method,
-                                                    prune=bool(args.prune),
+                                                    prune=bool(args.prune), far_exact=bool(args.far_exact),
                                                     l2=("not flushed inside the loop (steps overlap): one step's inputs -- 128 MB of "
                                                         "scene records + 29 MB of spheres -- exceed the 126 MB L2 and a step streams "
                                                         "~0.5 GB through it; single_step is the same step with an explicit L2 flush"
@@ -485,6 +487,7 @@ def main():
     ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
     ap.add_argument("--method", default="lbvh_pairs", choices=["wide_fused", "wide_pairs", "lbvh_fused", "lbvh_pairs", "brute", "q4_pairs"])
     ap.add_argument("--prune", type=int, default=0)
+    ap.add_argument("--far-exact", type=int, default=0, help="1: XP_OPT_FAR_EXACT (also reproduce the reference's far-range grazing noise)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

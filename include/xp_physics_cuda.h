@@ -75,6 +75,12 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                 when a sphere has hundreds of candidates (volumetric scenes: 8.5x on config 3), costs
                                 ~15 % on terrain.  tri_index may differ among exactly equal times.
                                 2: auto for LBVH_PAIRS: windows only after a sweep saw > 96 candidates per sphere */
+#define XP_OPT_FAR_EXACT  7  /* 1: also reproduce the reference's far-range grazing noise.  Its vertex / edge quadratics
+                                lose ~3e-7 * D^2 of miss distance at range D, so beyond D ~ 18 it can report a hit on
+                                a triangle whose (1 + 1e-4)-inflated box the path never enters; with this option a
+                                second pass re-walks the spheres whose best hit lies more than 10 units away (or that
+                                have none) with every box inflated by 8e-7 * D^2 and tests what that adds.  Default 0:
+                                hit/miss can differ from the brute-force reference for exactly those contacts. */
 
 #define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical */
 #define XP_ARITH_FAST     1  /* FMA contraction allowed                          */

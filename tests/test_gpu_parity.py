@@ -680,3 +680,54 @@ def test_sliver_triangle_far_face_hits(oracle, method, prune):
     check_detect_exact(got, want, f"sliver {method}")
     assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
     assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"sliver response {method}")
+
+
+# ---- far-range grazing: the reference's quadratics lose ~3e-7 D^2 of miss distance ----------
+def far_grazing_case(seed=4):
+    rng = np.random.default_rng(seed)
+    tris = (rng.uniform(-4, 4, (8, 1, 3)) + rng.normal(0, 0.05, (8, 3, 3))).astype(np.float32)
+    cs, ms = [], []
+    for D in (30.0, 100.0, 300.0, 1000.0):
+        ns = 1500
+        k = rng.integers(0, 8, ns)
+        axis, sgn = rng.integers(0, 3, ns), rng.choice([-1.0, 1.0], ns)
+        d = 1.0 + rng.uniform(-0.2, 1.5, ns) * 6e-8 * D * D / 2 + rng.uniform(0, 2e-4, ns)
+        off = np.zeros((ns, 3))
+        off[np.arange(ns), axis] = sgn * d                       # closest approach: next to vertex 0 of triangle k, along an axis
+        dirs = rng.normal(0, 1, (ns, 3))
+        dirs[np.arange(ns), axis] = 0
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        cs.append(tris[k, 0].astype(np.float64) + off - dirs * D)
+        ms.append(dirs * rng.uniform(0.05, 2.0, (ns, 1)))
+    return tris, xp.make_responses(np.concatenate(cs).astype(np.float32), np.concatenate(ms).astype(np.float32))
+
+
+def test_far_exact_reproduces_the_references_far_grazing_noise(oracle):
+    tris, resps = far_grazing_case()
+    want = oracle.detect_batch(resps, tris)
+    w = oracle.collision_response_batch(resps, tris, max_iter=2)
+    with xp.Scene(0, tris) as s:
+        plain = s.detect_batch(resps)
+        s.set_options(far_exact=True)
+        got = s.detect_batch(resps)
+        tests_far = s.stats()["narrowphase_tests"]
+        out, it, st, ln = s.collision_response_batch(resps, max_iter=2)
+    # default mode: the documented gap -- the reference "hits" triangles whose inflated box the path never enters
+    n_gap = int((plain[1] != want[1]).sum())
+    print("far-grazing rows where the default mode differs from the reference:", n_gap, "of", len(resps))
+    assert n_gap > 0
+    assert not (plain[1].astype(bool) & ~want[1].astype(bool)).any()        # never the other way round
+    # XP_OPT_FAR_EXACT closes it, bit for bit
+    check_detect_exact(got, want, "far exact")
+    assert tests_far > 0
+    assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
+    assert_bits_equal(resp_fields(out), resp_fields(w[0]), "far exact response")
+    # and changes nothing where there is no far noise
+    tris2, h = scenes.sine_terrain(40, 40, seed=31)
+    resps2 = scenes.terrain_spheres(h, 3000, seed=32)
+    with xp.Scene(0, tris2) as s:
+        a = s.detect_batch(resps2)
+        s.set_options(far_exact=True)
+        b = s.detect_batch(resps2)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))

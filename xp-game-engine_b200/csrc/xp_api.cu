@@ -142,6 +142,7 @@ int xp_scene_set_option(xp_scene *s, int option, int64_t value) {
     case XP_OPT_PRUNE:
         if (value < 0 || value > 2) return XP_EINVAL;
         s->prune = (int)value; s->cand_per_ray = 0.0; return XP_OK;
+    case XP_OPT_FAR_EXACT: s->far_exact = value ? 1 : 0; return XP_OK;
     default: return XP_EINVAL;
     }
 }

@@ -90,6 +90,7 @@ struct xp_scene {
     int prune = 0;
     int timing = 0;
     int sort_spheres = 1;
+    int far_exact = 0;                 // XP_OPT_FAR_EXACT: second pass for far-range grazing noise of the reference
     uint64_t max_pairs = 1ull << 26;
     float cur_horizon = 0.0f;          // horizon of the rays currently in `rays`
     bool safe_pairs = false;           // two-stage methods: read the pair count back after every chunk

@@ -338,7 +338,12 @@ static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at 
 // walk gains more from cache hits than from extra warps.
 static constexpr int BP_BLOCKS_PER_SM = XP_BP_BLOCKS;
 
-template <bool WINDOWED>
+// MODE 0: the exhaustive sweep.  MODE 1: one distance window of the pruned sweep.  MODE 2: the far pass of
+// XP_OPT_FAR_EXACT -- only spheres whose best hit so far lies beyond d_lo (or that have none), boxes inflated
+// by XP_FAR_K * D^2 with D the farthest a closer hit could be, every leaf the ray is inside of after d_lo and
+// before its best hit (see closest_t).
+static constexpr float XP_FAR_K = 8e-7f;
+template <int MODE>
 __global__ void __launch_bounds__(BP_THREADS, BP_BLOCKS_PER_SM)
 k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
              float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap,
@@ -363,7 +368,9 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     const unsigned ray0 = (unsigned)ray_base;
 
     V3 c = {0, 0, 0}, inv = {0, 0, 0};
+    constexpr bool WINDOWED = MODE != 0;
     float t_lo = 0.0f, t_hi = 0.0f;        // this ray's window in units of its own t
+    float grow = 0.0f;                     // MODE 2: extra inflation of every box for this ray
     unsigned my_ray = 0;
     int node = -1;                         // internal node to visit next; -1 = lane needs a ray
     int stack[STACK_DEPTH];
@@ -413,6 +420,19 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                         if (!sane && d_lo > 0.0f) go = false;
                         const float bt = rbest[mine - pool_base];        // best t so far, NaN = no hit yet
                         if (bt <= t_lo) go = false;         // nothing entered at or after t_lo can beat it
+                        if (MODE == 2 && go) {
+                            // D = how far away a closer hit can be: the best hit so far, or the far corner of the scene
+                            const float4 r0 = __ldg(reinterpret_cast<const float4 *>(nodes) + 0), r1 = __ldg(reinterpret_cast<const float4 *>(nodes) + 1);
+                            const float4 r2 = __ldg(reinterpret_cast<const float4 *>(nodes) + 2);
+                            const float lx = fminf(r0.x, r1.z), ly = fminf(r0.y, r1.w), lz = fminf(r0.z, r2.x);
+                            const float hx = fmaxf(r0.w, r2.y), hy = fmaxf(r1.x, r2.z), hz = fmaxf(r1.y, r2.w);
+                            const float dx = fmaxf(fabsf(lx - c.x), fabsf(hx - c.x)), dy = fmaxf(fabsf(ly - c.y), fabsf(hy - c.y));
+                            const float dz = fmaxf(fabsf(lz - c.z), fabsf(hz - c.z));
+                            float D = sqrtf(dx * dx + dy * dy + dz * dz);
+                            if (bt == bt) { D = fminf(D, bt * ml); t_hi = bt; }   // entered after the best hit: cannot beat it
+                            grow = XP_FAR_K * D * D;
+                            if (!(grow >= 0.0f)) grow = INFINITY;
+                        }
                     } else {
                         t_lo = 0.0f; t_hi = INFINITY;
                     }
@@ -440,9 +460,10 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                     const float cx = __shfl_sync(FULL, c.x, from), cy = __shfl_sync(FULL, c.y, from), cz = __shfl_sync(FULL, c.z, from);
                     const float ix = __shfl_sync(FULL, inv.x, from), iy = __shfl_sync(FULL, inv.y, from), iz = __shfl_sync(FULL, inv.z, from);
                     const float lo_ = WINDOWED ? __shfl_sync(FULL, t_lo, from) : 0.0f, hi_ = WINDOWED ? __shfl_sync(FULL, t_hi, from) : INFINITY;
+                    const float grow_ = MODE == 2 ? __shfl_sync(FULL, grow, from) : 0.0f;
                     const unsigned ray_ = __shfl_sync(FULL, my_ray, from);
                     if (thief) {
-                        node = got; c = {cx, cy, cz}; inv = {ix, iy, iz}; t_lo = lo_; t_hi = hi_; my_ray = ray_;
+                        node = got; c = {cx, cy, cz}; inv = {ix, iy, iz}; t_lo = lo_; t_hi = hi_; my_ray = ray_; grow = grow_;
                         sp = 0; sbase = 0;
                     }
                 }
@@ -469,16 +490,22 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         if (node >= 0) {
             const int2 link = make_int2(__float_as_int(n3.x), __float_as_int(n3.y));
             float ta, tb, fa, fb;
-            bool hit_a = slab2(c, inv, horizon, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ta, fa);
-            bool hit_b = slab2(c, inv, horizon, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tb, fb);
+            bool hit_a, hit_b;
+            if (MODE == 2) {
+                hit_a = slab2(c, inv, horizon, n0.x - grow, n0.y - grow, n0.z - grow, n0.w + grow, n1.x + grow, n1.y + grow, ta, fa);
+                hit_b = slab2(c, inv, horizon, n1.z - grow, n1.w - grow, n2.x - grow, n2.y + grow, n2.z + grow, n2.w + grow, tb, fb);
+            } else {
+                hit_a = slab2(c, inv, horizon, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ta, fa);
+                hit_b = slab2(c, inv, horizon, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tb, fb);
+            }
             // window: a subtree matters if the ray is inside its box somewhere in [t_lo, t_hi);
-            // a leaf is emitted by the one pass whose window holds its ENTRY time
+            // a leaf is emitted by the one pass whose window holds its ENTRY time (far pass: any leaf it overlaps)
             if (WINDOWED) {
                 hit_a = hit_a && ta < t_hi && fa >= t_lo;
                 hit_b = hit_b && tb < t_hi && fb >= t_lo;
             }
-            if (hit_a && link.x < 0) { if (!WINDOWED || ta >= t_lo) leaf_a = ~link.x; hit_a = false; }
-            if (hit_b && link.y < 0) { if (!WINDOWED || tb >= t_lo) leaf_b = ~link.y; hit_b = false; }
+            if (hit_a && link.x < 0) { if (MODE != 1 || ta >= t_lo) leaf_a = ~link.x; hit_a = false; }
+            if (hit_b && link.y < 0) { if (MODE != 1 || tb >= t_lo) leaf_b = ~link.y; hit_b = false; }
             if (hit_a && hit_b) {
                 node = link.x;
                 if (sp < STACK_DEPTH) stack[sp++] = link.y;
@@ -1159,12 +1186,17 @@ __global__ void __launch_bounds__(256) k_sweep_degenerate(const TriRec *__restri
     if (mine != BEST_NONE) atomicMin(&best[k], mine);
 }
 
-template <class O> static cudaError_t closest_main_t(xp_scene *s, uint64_t na);
+template <class O> static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far);
 
 // closest collision for rays[0..na): fills best[0..na)
 template <class O>
 static cudaError_t closest_t(xp_scene *s, uint64_t na) {
-    XP_TRY(closest_main_t<O>(s, na));
+    XP_TRY(closest_main_t<O>(s, na, false));
+    // XP_OPT_FAR_EXACT: the reference's quadratics lose ~3e-7 * D^2 of miss distance at range D, so beyond D ~ 18
+    // it can report grazing hits on triangles whose (1 + 1e-4)-inflated box the path never enters.  A second
+    // pass re-walks the spheres whose best hit lies beyond XP_FAR_D0 (or that have none) with every box
+    // inflated by XP_FAR_K * D^2 and tests whatever that adds.
+    if (s->far_exact && na > 0 && s->method != XP_METHOD_BRUTE) XP_TRY(closest_main_t<O>(s, na, true));
     if (na == 0 || s->n_degen == 0 || s->method == XP_METHOD_BRUTE) return cudaSuccess;
     StageTimer t(s, XP_STAGE_NARROWPHASE);
     k_sweep_degenerate<O><<<grid_for(na, 256), 256, 0, s->stream>>>(s->recs.as<TriRec>(), s->degen.as<uint32_t>(),
@@ -1175,8 +1207,9 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
     return cudaGetLastError();
 }
 
+static constexpr float XP_FAR_D0 = 10.0f;
 template <class O>
-static cudaError_t closest_main_t(xp_scene *s, uint64_t na) {
+static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
     if (na == 0 || s->n_tris == 0) return cudaSuccess;
     XP_TRY(build_aux(s));
     cudaStream_t st = s->stream;
@@ -1185,7 +1218,7 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na) {
     const RayRec *rays = s->rays.as<RayRec>();
     unsigned long long *best = s->best.as<unsigned long long>();
     DeviceCounters *ctr = s->counters.as<DeviceCounters>();
-    if (s->method == XP_METHOD_BRUTE) {
+    if (!far && s->method == XP_METHOD_BRUTE) {
         StageTimer t(s, XP_STAGE_NARROWPHASE);
         dim3 grid(grid_for(s->n_tris, BRUTE_THREADS), grid_for(na, BRUTE_RAY_CHUNK));
         k_brute<O><<<grid, BRUTE_THREADS, 0, st>>>(recs, s->n_tris, rays, na, best);
@@ -1193,7 +1226,7 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na) {
         s->stats.narrowphase_tests += na * s->n_tris;
         return cudaGetLastError();
     }
-    if (s->method == XP_METHOD_LBVH_FUSED) {
+    if (!far && s->method == XP_METHOD_LBVH_FUSED) {
         StageTimer t(s, XP_STAGE_TRAVERSE);
         const unsigned blocks = grid_for(na, TRAV_THREADS);
         if (s->prune) k_traverse<O, true><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, best, ctr, s->timing);
@@ -1201,7 +1234,7 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na) {
         ++s->stats.kernel_launches;
         return cudaGetLastError();
     }
-    if (s->method == XP_METHOD_WIDE_FUSED) {
+    if (!far && s->method == XP_METHOD_WIDE_FUSED) {
         StageTimer t(s, XP_STAGE_TRAVERSE);
         const unsigned blocks = grid_for(na, SWEEP_THREADS);
         if (s->prune) k_sweep<O, true, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
@@ -1210,8 +1243,8 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na) {
         return cudaGetLastError();
     }
     // two-stage methods: chunks of rays sized so the pair buffer holds the candidates
-    const bool wide = s->method == XP_METHOD_WIDE_PAIRS;
-    const bool q4 = s->method == XP_METHOD_Q4_PAIRS;
+    const bool wide = !far && s->method == XP_METHOD_WIDE_PAIRS;
+    const bool q4 = !far && s->method == XP_METHOD_Q4_PAIRS;
     const uint64_t cap = s->max_pairs;
     XP_TRY(s->pairs.reserve(cap * sizeof(uint2)));
     uint2 *pairs = s->pairs.as<uint2>();
@@ -1224,7 +1257,7 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na) {
     // on the volumetric config-3 scene).  No read-back between passes: a pass over finished spheres only
     // costs their ray fetch.
     static const float kWin[] = {0.0f, 4.0f, 16.0f, 64.0f, 256.0f, 1024.0f, INFINITY};
-    const bool windows = s->method == XP_METHOD_LBVH_PAIRS && (s->prune == 1 || (s->prune == 2 && s->cand_per_ray > 96.0));
+    const bool windows = !far && s->method == XP_METHOD_LBVH_PAIRS && (s->prune == 1 || (s->prune == 2 && s->cand_per_ray > 96.0));
     const int n_pass = windows ? 6 : 1;
     uint64_t pos = 0;
     unsigned long long snap_tests = 0, snap_pairs = 0;   // synchronous mode: accounting before the current chunk
@@ -1247,13 +1280,16 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na) {
                     s->wide_tree, recs, rays, pos, end, best, ctr, pairs, cap, 0);
             else if (q4)
                 k_broadphase4<<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes4.as<Node4>(), rays, pos, end, s->cur_horizon, ctr, pairs, cap);
+            else if (far)
+                k_broadphase<2><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                                                                           XP_FAR_D0, INFINITY, best);
             else
                 if (windows)
-                    k_broadphase<true><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                    k_broadphase<1><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
                                                                                   d_lo, d_hi, best);
                 else
-                    k_broadphase<false><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                                   0.0f, INFINITY, nullptr);
+                    k_broadphase<0><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                                                                               0.0f, INFINITY, nullptr);
             ++s->stats.kernel_launches;
         }
         {
@@ -1496,7 +1532,7 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
         XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
         if (s->method != XP_METHOD_WIDE_FUSED && s->method != XP_METHOD_WIDE_PAIRS)
-            k_broadphase<false><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
+            k_broadphase<0><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
                                                                   s->cur_horizon, ctr, pairs, buf_cap, 0.0f, INFINITY, nullptr);
         else
             k_sweep<ExactOps, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(

@@ -18,7 +18,7 @@ HEADER = os.path.normpath(os.path.join(_PKG, "..", "..", "include", "xp_physics_
 XP_OK, XP_EINVAL, XP_ECUDA, XP_ENOMEM, XP_ESTATE, XP_ECAP = 0, -1, -2, -3, -4, -5
 ST_RADIUS_NE_1, ST_ASSERT_NEG_DISTANCE, ST_ITER_CAP = 1, 2, 4
 HORIZON_INF, HORIZON_UNIT = 0, 1
-OPT_ARITH, OPT_METHOD, OPT_TIMING, OPT_SORT_SPHERES, OPT_MAX_PAIRS, OPT_PRUNE = 1, 2, 3, 4, 5, 6
+OPT_ARITH, OPT_METHOD, OPT_TIMING, OPT_SORT_SPHERES, OPT_MAX_PAIRS, OPT_PRUNE, OPT_FAR_EXACT = 1, 2, 3, 4, 5, 6, 7
 ARITH_EXACT, ARITH_FAST = 0, 1
 METHODS = {"wide_fused": 0, "lbvh_fused": 1, "lbvh_pairs": 2, "brute": 3, "wide_pairs": 4, "q4_pairs": 5}
 STAGE_NAMES = ["build_bounds", "build_morton", "build_sort", "build_pack", "build_tree", "build_refit",

@@ -134,7 +134,8 @@ class Scene:
         self.close()
 
     # -- options
-    def set_options(self, *, arith=None, method=None, prune=None, sort_spheres=None, timing=None, max_pairs=None):
+    def set_options(self, *, arith=None, method=None, prune=None, sort_spheres=None, timing=None, max_pairs=None,
+                    far_exact=None):
         L, h = self._L, self._h
         if arith is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_ARITH, {"exact": 0, "fast": 1}[arith]))
@@ -148,6 +149,8 @@ class Scene:
             check(L.xp_scene_set_option(h, _lib.OPT_TIMING, int(bool(timing))))
         if max_pairs is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_MAX_PAIRS, int(max_pairs)))
+        if far_exact is not None:
+            check(L.xp_scene_set_option(h, _lib.OPT_FAR_EXACT, int(bool(far_exact))))
 
     def set_stream(self, cuda_stream_ptr: int):
         check(self._L.xp_scene_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
