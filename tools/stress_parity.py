@@ -88,6 +88,7 @@ def main():
     ap.add_argument("--cases", type=int, default=12)
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--max-iter", type=int, default=3, help="response iterations (0 = unbounded like the reference)")
+    ap.add_argument("--far-exact", type=int, default=0, help="1: run with XP_OPT_FAR_EXACT")
     ap.add_argument("--kinds", default="", help="comma list of case kinds 0..5 to cycle through (default: all)")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
@@ -100,7 +101,7 @@ def main():
             want = oracle.detect_batch(resps, tris)
             wres = oracle.collision_response_batch(resps, tris, max_iter=args.max_iter)
             t_cpu = time.time() - t0
-            s.set_options(method="lbvh_pairs", prune=bool(k % 3 == 2))
+            s.set_options(method="lbvh_pairs", prune=bool(k % 3 == 2), far_exact=bool(args.far_exact))
             s.set_triangles(tris)
             s.build()
             t0 = time.time()
