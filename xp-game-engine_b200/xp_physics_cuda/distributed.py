@@ -170,7 +170,17 @@ class ContactExchange:
             self._side = torch.cuda.Stream(device=self.device)
             self.scene.set_exchange_stream(self._side.cuda_stream)
             self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self._release = torch.zeros(1, dtype=torch.float32, device=self.device)
         half = self._half_i = (getattr(self, "_half_i", 1) + 1) % 2
+        if not self.solo:
+            # Release barrier: this step overwrites the gather buffer of the step before last ON EVERY RANK, so no
+            # rank may start its exchange before all ranks have finished reading that buffer.  Whatever the caller
+            # has queued on its stream so far (its reads) is ordered before this rank joins the barrier.
+            read_done = torch.cuda.Event()
+            read_done.record(torch.cuda.current_stream(self.device))
+            self._side.wait_event(read_done)
+            with torch.cuda.stream(self._side):
+                dist.all_reduce(self._release, group=self.group)
         ticket = self.scene.detect_contacts_exchange_submit(
             d_in_ptr, n_local, self.bufs, half * self.half + self.rank * self.cap, horizon,
             self_index=self.rank if os.environ.get("XP_EXCHANGE_COPY", "1") != "0" else -1)
@@ -183,8 +193,9 @@ class ContactExchange:
         return ticket
 
     def wait(self, ticket: int):
-        """Complete a queued step; returns its gather buffer [world, cap, 10] (valid until the step after the
-        next one is queued)."""
+        """Complete a queued step; returns its gather buffer [world, cap, 10].  It stays valid until this rank
+        queues the step after the next one: reads queued on the current stream before that call are safe on every
+        rank (sweep_async orders a cross-rank release barrier behind them)."""
         ev, half = self._done.pop(ticket)
         ok = self.scene.detect_contacts_exchange_wait(ticket)
         ev.synchronize()
