@@ -77,6 +77,8 @@ class ContactExchange:
     on 8 B200s (exchange stage 0.43 vs 0.44 ms for 336 MB of records, step 2.51 vs 2.56 ms).
     `ok` is False when the transport could not be set up on every rank (callers fall back to NCCL)."""
 
+    N_BUF = 4
+
     def __init__(self, scene: Scene, cap: int, device, group=None):
         import torch
         import torch.distributed as dist
@@ -85,12 +87,12 @@ class ContactExchange:
         self.world = 1 if self.solo else dist.get_world_size(group)
         self.rank = 0 if self.solo else dist.get_rank(group)
         self.cap = cap + (cap & 1)                   # even slots: 16-byte aligned spans
-        self.half = self.world * self.cap            # records per gather buffer; there are two (steps alternate)
-        self.nbytes = 2 * self.half * 4 * CONTACT_FLOATS
+        self.half = self.world * self.cap            # records per gather buffer; there are N_BUF (steps use them round robin)
+        self.nbytes = self.N_BUF * self.half * 4 * CONTACT_FLOATS
         self.ptr, self.bufs, self.ok, self.mode = 0, [], True, "p2p"
         self.mc_ptr, self._symm = 0, None
         self._side, self._done, self._flag = None, {}, None
-        shape = (2, self.world, self.cap, CONTACT_FLOATS)
+        shape = (self.N_BUF, self.world, self.cap, CONTACT_FLOATS)
         if (not self.solo and os.environ.get("XP_EXCHANGE_MULTICAST", "0") == "1"
                 and self._try_multicast(torch, dist, device, shape)):
             self.mode = "multicast"
@@ -160,8 +162,8 @@ class ContactExchange:
     # -- a loop of steps: step i's exchange runs under step i+1's sweep -----------------------------
     def sweep_async(self, d_in_ptr: int, n_local: int, horizon: str = "inf") -> int:
         """Queue one step: the sweep on the scene's stream, the record build + exchange on a second stream,
-        the cross-rank barrier (a one-element NCCL all-reduce) behind it on that stream.  Steps alternate
-        between the two gather buffers; `wait(ticket)` returns the buffer of that step."""
+        the cross-rank barrier (a one-element NCCL all-reduce) behind it on that stream.  Steps go round robin
+        through the gather buffers; `wait(ticket)` returns the buffer of that step."""
         import torch
         import torch.distributed as dist
         if self.mode != "p2p":
@@ -170,17 +172,13 @@ class ContactExchange:
             self._side = torch.cuda.Stream(device=self.device)
             self.scene.set_exchange_stream(self._side.cuda_stream)
             self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
-            self._release = torch.zeros(1, dtype=torch.float32, device=self.device)
-        half = self._half_i = (getattr(self, "_half_i", 1) + 1) % 2
-        if not self.solo:
-            # Release barrier: this step overwrites the gather buffer of the step before last ON EVERY RANK, so no
-            # rank may start its exchange before all ranks have finished reading that buffer.  Whatever the caller
-            # has queued on its stream so far (its reads) is ordered before this rank joins the barrier.
-            read_done = torch.cuda.Event()
-            read_done.record(torch.cuda.current_stream(self.device))
-            self._side.wait_event(read_done)
-            with torch.cuda.stream(self._side):
-                dist.all_reduce(self._release, group=self.group)
+        # Four gather buffers, used round robin, make an explicit "buffer free" handshake unnecessary: step i+4
+        # overwrites the buffer of step i on every rank, and a rank starts its exchange of step i+4 only after its
+        # wait(i+2), i.e. after the barrier behind every rank's exchange of step i+2 -- which every rank queued after
+        # the reads of buffer i it had put on its stream (wait(i) precedes submit(i+2): two steps in flight).  With
+        # two buffers a fast rank's step i+2 could overwrite a buffer a slow rank was still reading (seen by
+        # tools/check_exchange.py); an extra release all-reduce per step fixed that too but cost 0.25 ms on 8 GPUs.
+        half = self._half_i = (getattr(self, "_half_i", self.N_BUF - 1) + 1) % self.N_BUF
         ticket = self.scene.detect_contacts_exchange_submit(
             d_in_ptr, n_local, self.bufs, half * self.half + self.rank * self.cap, horizon,
             self_index=self.rank if os.environ.get("XP_EXCHANGE_COPY", "1") != "0" else -1)
@@ -194,8 +192,8 @@ class ContactExchange:
 
     def wait(self, ticket: int):
         """Complete a queued step; returns its gather buffer [world, cap, 10].  It stays valid until this rank
-        queues the step after the next one: reads queued on the current stream before that call are safe on every
-        rank (sweep_async orders a cross-rank release barrier behind them)."""
+        queues the step after the next one: reads queued on the scene's stream (or done synchronously) before that
+        call are safe on every rank (four buffers, see sweep_async)."""
         ev, half = self._done.pop(ticket)
         ok = self.scene.detect_contacts_exchange_wait(ticket)
         ev.synchronize()
