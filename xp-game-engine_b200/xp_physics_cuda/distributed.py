@@ -153,7 +153,7 @@ class ContactExchange:
 
     def sweep(self, d_in_ptr: int, n_local: int, horizon: str = "inf"):
         """Sweep this rank's spheres; their contact records land in slot `rank` of EVERY rank's buffer
-        (`view`, the first of the two gather buffers).  Synchronous; the caller adds the barrier."""
+        (`view`, the first of the gather buffers).  Synchronous; the caller adds the barrier."""
         if self.mode == "multicast":
             self.scene.detect_contacts_multicast_dev(d_in_ptr, n_local, self.mc_ptr, self.rank * self.cap, horizon)
         else:
