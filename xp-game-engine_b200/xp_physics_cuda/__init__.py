@@ -13,7 +13,7 @@ from .api import (COLLISION_DTYPE, CONTACT_DTYPE, RESPONSE_DTYPE, Collision, Res
                   make_responses, probe_fp32_peak, sphere_triangle_calculate_response,
                   sphere_triangle_detect_collision)
 
-from . import clipmap, controller, distributed, ingest, scenes   # noqa: E402,F401  (host-side glue: caller mirror, sharding, asset loaders, generators)
+from . import clipmap, controller, distributed, fauerby, ingest, scenes   # noqa: E402,F401  (host-side glue: caller mirror, sharding, asset loaders, generators)
 
 __all__ = ["Scene", "Sphere", "Triangle", "Response", "Collision", "collision_response",
            "collision_response_non_trianulated", "sphere_triangle_detect_collision",
