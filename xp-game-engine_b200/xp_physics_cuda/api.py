@@ -104,13 +104,14 @@ class Scene:
     """Owns an xp_scene (device triangle records + LBVH) on one GPU."""
 
     def __init__(self, device: int = 0, triangles=None, *, arith: str = "exact", method: str = "lbvh_pairs",
-                 prune: bool = False, sort_spheres: bool = True, timing: bool = False):
+                 prune: bool = False, sort_spheres: bool = True, timing: bool = False, far_exact: bool = False):
         self._L = _lib.lib()
         h = C.c_void_p()
         check(self._L.xp_scene_create(device, C.byref(h)), "xp_scene_create")
         self._h = h
         self.device = device
-        self.set_options(arith=arith, method=method, prune=prune, sort_spheres=sort_spheres, timing=timing)
+        self.set_options(arith=arith, method=method, prune=prune, sort_spheres=sort_spheres, timing=timing,
+                         far_exact=far_exact)
         if triangles is not None:
             self.set_triangles(triangles)
             self.build()
