@@ -80,7 +80,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.strip().split(",")])
                 except Exception:
                     pass
-                self.stop.wait(0.2)
+                self.stop.wait(0.05)
         self.t = threading.Thread(target=run, daemon=True)
         self.t.start()
         return self
@@ -248,8 +248,8 @@ def run_b200(args):
             out.append(scene.stats())
         return out
 
-    sync_ms, sync_stats = timed(step_device, args.steps, max(args.warmup, 3))     # one synchronous call per step, L2 flushed
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:                      # nvidia-smi samples while both timed regions run
+        sync_ms, sync_stats = timed(step_device, args.steps, max(args.warmup, 3))     # one synchronous call per step, L2 flushed
         if pipelined:
             loop_device(max(args.warmup, 3))
             if world > 1:
