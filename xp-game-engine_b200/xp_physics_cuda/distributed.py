@@ -65,7 +65,8 @@ class _DeviceArray:
 
 
 class ContactExchange:
-    """One gather buffer per rank ([world, cap, 10] float32) that a kernel on any rank can store into.
+    """N_BUF gather buffers per rank (each [world, cap, 10] float32) that a kernel on any rank can store into;
+    synchronous steps use the first, a loop of steps (sweep_async) goes through them round robin.
 
     Two transports (`mode` says which one is live):
       "p2p":       every rank maps every other rank's buffer through CUDA IPC and the kernel stores each
