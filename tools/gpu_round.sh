@@ -1,5 +1,6 @@
 #!/bin/bash
-# One gpurun call: smoke, GPU parity tests, bench, then (only if the plain bench exited 0) the ncu
+# One gpurun call: smoke, GPU parity tests, bench, optionally (`stress`) the stress-parity tool, then (only if
+# the plain bench exited 0 and neither `noncu` nor `stress` was given) the ncu
 # launch list and one --set full capture of the dominant kernel.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
@@ -15,7 +16,12 @@ if [ "$1" = "variants" ] || [ "$2" = "variants" ]; then
     tail -c 1500 "gpurun_out/bench_$(echo $v | tr -d ' -').json"
   done
 fi
-if [ $BRC -eq 0 ] && [ "$1" != "noncu" ]; then
+if [ "$1" = "stress" ] || [ "$2" = "stress" ]; then
+  echo "== stress parity (mid-size adversarial scenes against the oracle)"
+  timeout 900 python tools/stress_parity.py --cases 18 --seed $RANDOM 2>&1 | tail -4 | tee gpurun_out/stress.log
+  timeout 600 python tools/stress_parity.py --cases 12 --seed $RANDOM --far-exact 1 --kinds 2,4,5 2>&1 | tail -2 | tee -a gpurun_out/stress.log
+fi
+if [ $BRC -eq 0 ] && [ "$1" != "noncu" ] && [ "$1" != "stress" ]; then
   echo "== ncu launch list"
   timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 &&
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
