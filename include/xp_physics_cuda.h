@@ -67,14 +67,15 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                 and count narrowphase tests per code path */
 #define XP_OPT_SORT_SPHERES 4 /* 1: process spheres in Morton order of their centre (default 1) */
 #define XP_OPT_MAX_PAIRS  5  /* capacity (pairs) of the two-stage candidate buffer per chunk */
-#define XP_OPT_PRUNE      6  /* 0 (default): evaluate detect on EVERY pair passing P, so narrowphase_tests == |P| and the
+#define XP_OPT_PRUNE      6  /* 0: evaluate detect on EVERY pair passing P, so narrowphase_tests == |P| and the
                                 tested set is the bit-exact candidate set.
                                 1: find the same closest collision with fewer tests: the fused methods skip subtrees
                                 entered after the best t so far; LBVH_PAIRS sweeps growing distance windows
                                 [0,4) [4,16) ... [1024,inf) and drops spheres already hit before the window.  Pays off
                                 when a sphere has hundreds of candidates (volumetric scenes: 8.5x on config 3), costs
                                 ~15 % on terrain.  tri_index may differ among exactly equal times.
-                                2: auto for LBVH_PAIRS: windows only after a sweep saw > 96 candidates per sphere */
+                                2 (default): auto for LBVH_PAIRS: like 0 until a sweep saw > 96 candidates per sphere
+                                (volumetric scenes), like 1 from then on; terrain-like scenes therefore run as 0 */
 #define XP_OPT_FAR_EXACT  7  /* 1: also reproduce the reference's far-range grazing noise.  Its vertex / edge quadratics
                                 lose ~3e-7 * D^2 of miss distance at range D, so beyond D ~ 18 it can report a hit on
                                 a triangle whose (1 + 1e-4)-inflated box the path never enters; with this option a
@@ -90,7 +91,7 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                    leaf hits go to a warp-shared queue in shared memory that is drained 32 pairs at
                                    a time through the narrowphase */
 #define XP_METHOD_LBVH_FUSED  1  /* binary Karras LBVH, one LANE per sphere with a private stack, same warp queue */
-#define XP_METHOD_LBVH_PAIRS  2  /* default. Persistent-warp binary LBVH traversal (<= 32 registers) emits every pair passing P to HBM; narrowphase over the pairs */
+#define XP_METHOD_LBVH_PAIRS  2  /* default. Persistent-warp binary LBVH traversal (4 blocks of 256 per SM, 60 registers) emits every pair passing P to HBM; narrowphase over the pairs */
 #define XP_METHOD_BRUTE       3  /* the reference's literal algorithm: every triangle for every sphere (lib.rs:33-35) */
 #define XP_METHOD_WIDE_PAIRS  4  /* 32-wide tree traversal emits the pairs to HBM; narrowphase over the pairs */
 #define XP_METHOD_Q4_PAIRS    5  /* quantised 4-wide collapse of the LBVH (64 B nodes, 8-bit boxes rounded outward):

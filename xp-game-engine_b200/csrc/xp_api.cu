@@ -77,6 +77,8 @@ int xp_scene_create(int device, xp_scene **out) {
     xp_scene *s = new (std::nothrow) xp_scene();
     if (!s) return XP_ENOMEM;
     s->device = device;
+    int n_sm = 0;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n_sm > 0) s->n_sm = n_sm;
     reset_stats(s);
     *out = s;
     return XP_OK;
@@ -495,8 +497,7 @@ int xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint3
     a.out = out; a.hit_out = hit; a.tri_out = tri_index; a.status_out = status;
     a.launches = 0;
     *ticket = slot;
-    a.busy = true;
-    if (n == 0) { memset(a.h_ctr, 0, sizeof(DeviceCounters)); return XP_OK; }
+    if (n == 0) { memset(a.h_ctr, 0, sizeof(DeviceCounters)); a.busy = true; return XP_OK; }
     cudaStream_t st = s->stream;
     XP_API_TRY(a.in.reserve(n * sizeof(xp_response)));
     XP_API_TRY(a.col.reserve(n * sizeof(xp_collision)));
@@ -517,7 +518,7 @@ int xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint3
     s->timing = timing;
     s->counters_live = false;
     a.launches = s->stats.kernel_launches - before;
-    if (e != cudaSuccess) { a.busy = false; return fail_cuda(e); }
+    if (e != cudaSuccess) return fail_cuda(e);
     XP_API_TRY(cudaMemcpyAsync(a.h_ctr, s->counters.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
     XP_API_TRY(cudaEventRecord(a.done, st));
     cudaStream_t so = s->copy_out;
@@ -527,6 +528,7 @@ int xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint3
     if (tri_index) XP_API_TRY(cudaMemcpyAsync(tri_index, a.tri.p, n * 4, cudaMemcpyDeviceToHost, so));
     if (status) XP_API_TRY(cudaMemcpyAsync(status, a.status.p, n * 4, cudaMemcpyDeviceToHost, so));
     XP_API_TRY(cudaEventRecord(a.d2h, so));
+    a.busy = true;                                   // only now: an error return above leaves the slot free
     return XP_OK;
 }
 

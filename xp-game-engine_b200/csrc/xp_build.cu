@@ -698,7 +698,7 @@ cudaError_t build_lbvh(xp_scene *s) {
         StageTimer t(s, XP_STAGE_BUILD_BOUNDS);
         k_bounds_init<<<1, 32, 0, st>>>(bounds);
         unsigned blocks = grid_for(n, 256);
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks > (unsigned)s->n_sm * 8) blocks = (unsigned)s->n_sm * 8;
         k_bounds<<<blocks, 256, 0, st>>>(aos, n, bounds);
         s->stats.kernel_launches += 2;
     }

@@ -83,11 +83,12 @@ struct DeviceCounters {           // one small block of device memory, zeroed pe
 
 struct xp_scene {
     int device = 0;
+    int n_sm = 1;                      // multiProcessorCount of the device (persistent grids are sized from it)
     cudaStream_t stream = nullptr;
     // options
     int arith = XP_ARITH_EXACT;
     int method = XP_METHOD_LBVH_PAIRS;
-    int prune = 0;
+    int prune = 2;                     // XP_OPT_PRUNE: auto (distance windows once a sweep saw > 96 candidates per sphere)
     int timing = 0;
     int sort_spheres = 1;
     int far_exact = 0;                 // XP_OPT_FAR_EXACT: second pass for far-range grazing noise of the reference

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_ray_setup(const xp_response *__restrict
                                                    const uint32_t *__restrict__ active, uint64_t na,
                                                    float horizon, RayRec *__restrict__ rays,
                                                    unsigned long long *__restrict__ best,
-                                                   uint32_t *__restrict__ status) {
+                                                   uint32_t *__restrict__ status, int have_tris) {
     const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (k >= na) return;
     const uint64_t i = active ? active[k] : k;
@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(256) k_ray_setup(const xp_response *__restrict
     uint32_t flags = RAY_VALID;
     if (!(r == 1.0f)) {
         flags = 0;
-        if (status) status[i] |= XP_ST_RADIUS_NE_1;
+        // the assert sits inside sphere_triangle_detect_collision (collision_detect.rs:161), which the loop over an
+        // EMPTY triangle slice (lib.rs:33-35) never calls: no triangles, no panic
+        if (status && have_tris) status[i] |= XP_ST_RADIUS_NE_1;
     }
     const Ray ray = xp_ray_setup<O>(c, m);
     RayRec rr;
@@ -1127,9 +1129,9 @@ __global__ void k_translate_pairs(const uint2 *__restrict__ pairs, uint64_t n, u
 // XP_HORIZON_INF is FLT_MAX, not +inf: the branch-free slab test turns "m_k == 0 and outside the
 // slab" into an entry time of +inf, which must reject (predicate P)
 // persistent grid: BP_BLOCKS_PER_SM blocks of 256 threads per SM, never more blocks than work
-static unsigned bp_grid(uint64_t n_rays) {
+static unsigned bp_grid(const xp_scene *s, uint64_t n_rays) {
     const uint64_t want = (n_rays + BP_THREADS - 1) / BP_THREADS;
-    const uint64_t full = 148ull * BP_BLOCKS_PER_SM;
+    const uint64_t full = (uint64_t)s->n_sm * BP_BLOCKS_PER_SM;
     return (unsigned)(want < full ? (want ? want : 1) : full);
 }
 
@@ -1152,7 +1154,7 @@ static cudaError_t ray_setup_t(xp_scene *s, const xp_response *cur, const uint32
     StageTimer t(s, XP_STAGE_RAY_SETUP);
     s->cur_horizon = horizon;
     k_ray_setup<O><<<grid_for(na, 256), 256, 0, s->stream>>>(cur, active, na, horizon, s->rays.as<RayRec>(),
-                                                            s->best.as<unsigned long long>(), status);
+                                                            s->best.as<unsigned long long>(), status, s->n_tris > 0);
     ++s->stats.kernel_launches;
     return cudaGetLastError();
 }
@@ -1229,7 +1231,7 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
     if (!far && s->method == XP_METHOD_LBVH_FUSED) {
         StageTimer t(s, XP_STAGE_TRAVERSE);
         const unsigned blocks = grid_for(na, TRAV_THREADS);
-        if (s->prune) k_traverse<O, true><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, best, ctr, s->timing);
+        if (s->prune == 1) k_traverse<O, true><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, best, ctr, s->timing);
         else k_traverse<O, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, best, ctr, s->timing);
         ++s->stats.kernel_launches;
         return cudaGetLastError();
@@ -1237,7 +1239,7 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
     if (!far && s->method == XP_METHOD_WIDE_FUSED) {
         StageTimer t(s, XP_STAGE_TRAVERSE);
         const unsigned blocks = grid_for(na, SWEEP_THREADS);
-        if (s->prune) k_sweep<O, true, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
+        if (s->prune == 1) k_sweep<O, true, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
         else k_sweep<O, false, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
         ++s->stats.kernel_launches;
         return cudaGetLastError();
@@ -1279,23 +1281,23 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
                 k_sweep<O, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
                     s->wide_tree, recs, rays, pos, end, best, ctr, pairs, cap, 0);
             else if (q4)
-                k_broadphase4<<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes4.as<Node4>(), rays, pos, end, s->cur_horizon, ctr, pairs, cap);
+                k_broadphase4<<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes4.as<Node4>(), rays, pos, end, s->cur_horizon, ctr, pairs, cap);
             else if (far)
-                k_broadphase<2><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                k_broadphase<2><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
                                                                            XP_FAR_D0, INFINITY, best);
             else
                 if (windows)
-                    k_broadphase<1><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                    k_broadphase<1><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
                                                                                   d_lo, d_hi, best);
                 else
-                    k_broadphase<0><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                    k_broadphase<0><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
                                                                                0.0f, INFINITY, nullptr);
             ++s->stats.kernel_launches;
         }
         {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
-            if (q4) k_narrow_pairs<O, true><<<148 * XP_NP_GRID, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
-            else k_narrow_pairs<O, false><<<148 * XP_NP_GRID, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
+            if (q4) k_narrow_pairs<O, true><<<s->n_sm * XP_NP_GRID, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
+            else k_narrow_pairs<O, false><<<s->n_sm * XP_NP_GRID, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
             ++s->stats.kernel_launches;
         }
         if (s->safe_pairs) {                 // synchronous mode: check the fill after every chunk
@@ -1532,7 +1534,7 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
         XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
         if (s->method != XP_METHOD_WIDE_FUSED && s->method != XP_METHOD_WIDE_PAIRS)
-            k_broadphase<0><<<bp_grid(end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
+            k_broadphase<0><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
                                                                   s->cur_horizon, ctr, pairs, buf_cap, 0.0f, INFINITY, nullptr);
         else
             k_sweep<ExactOps, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
@@ -1640,11 +1642,14 @@ __global__ void __launch_bounds__(256) k_ffma_probe(float *out, int iters, float
 }
 
 cudaError_t probe_fp32(double *tflops) {
+    int dev = 0, n_sm = 1;
+    XP_TRY(cudaGetDevice(&dev));
+    XP_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     float *d = nullptr;
     XP_TRY(cudaMalloc(&d, 4));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int blocks = 148 * 8, iters = 4096;
+    const int blocks = n_sm * 8, iters = 4096;
     k_ffma_probe<<<blocks, 256>>>(d, iters / 8, 1.0000001f, 1e-7f);   // warm-up
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {

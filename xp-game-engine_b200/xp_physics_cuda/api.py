@@ -104,7 +104,7 @@ class Scene:
     """Owns an xp_scene (device triangle records + LBVH) on one GPU."""
 
     def __init__(self, device: int = 0, triangles=None, *, arith: str = "exact", method: str = "lbvh_pairs",
-                 prune: bool = False, sort_spheres: bool = True, timing: bool = False, far_exact: bool = False):
+                 prune="auto", sort_spheres: bool = True, timing: bool = False, far_exact: bool = False):
         self._L = _lib.lib()
         h = C.c_void_p()
         check(self._L.xp_scene_create(device, C.byref(h)), "xp_scene_create")
