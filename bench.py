@@ -170,7 +170,7 @@ def run_b200(args):
 
     tris, resps = build_workload(seed=1 + rank)
     n = len(resps)
-    scene = xp.Scene(local, arith=args.arith, method=args.method, prune=bool(args.prune), timing=True)
+    scene = xp.Scene(local, arith=args.arith, method=args.method, prune=args.prune, timing=True)
     if args.far_exact:
         scene.set_options(far_exact=True)
     stream = torch.cuda.current_stream()
@@ -290,7 +290,7 @@ def run_b200(args):
     scene.set_options(method="lbvh_fused", prune=False)
     scene.detect_contacts_dev(d_in.data_ptr(), n, mine.data_ptr())
     paths = {k: float(v) for k, v in scene.stats()["path_tests"].items()}
-    scene.set_options(method=args.method, prune=bool(args.prune))
+    scene.set_options(method=args.method, prune=args.prune)
     flops = sum(paths[k] * PATH_FLOPS[k] for k in PATH_FLOPS)
     try:
         peak = xp.probe_fp32_peak(local)
@@ -484,7 +484,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--arith", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--arith", default="exact", choices=["exact", "fast", "exact_literal", "fast_literal"])
     ap.add_argument("--method", default="lbvh_pairs", choices=["wide_fused", "wide_pairs", "lbvh_fused", "lbvh_pairs", "brute", "q4_pairs"])
     ap.add_argument("--prune", type=int, default=0)
     ap.add_argument("--far-exact", type=int, default=0, help="1: XP_OPT_FAR_EXACT (also reproduce the reference's far-range grazing noise)")

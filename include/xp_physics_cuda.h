@@ -83,8 +83,10 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                 have none) with every box inflated by 8e-7 * D^2 and tests what that adds.  Default 0:
                                 hit/miss can differ from the brute-force reference for exactly those contacts. */
 
-#define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical */
-#define XP_ARITH_FAST     1  /* FMA contraction allowed                          */
+#define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical to the reference's results         */
+#define XP_ARITH_FAST     1  /* tolerance mode: FMA, hardware reciprocal / square root, reduced quadratics (<= 1e-5) */
+#define XP_ARITH_EXACT_LITERAL 2 /* same results as 0 through the compiler's IEEE div / sqrt (the round-1 kernel; A/B)  */
+#define XP_ARITH_FAST_LITERAL  3 /* the literal formulas with FMA contraction only (the round-1 fast mode; A/B)        */
 
 #define XP_METHOD_WIDE_FUSED  0  /* 32-wide implicit tree over the Morton-sorted triangles; one WARP per
                                    sphere: the 32 lanes test a node's 32 child boxes (six coalesced 128 B loads),
@@ -263,6 +265,14 @@ int  xp_detect_contacts_exchange_submit(xp_scene *s, const xp_response *d_in, ui
                                         void *const *bufs, int n_bufs, int self_index, uint64_t slot_first,
                                         int *ticket);
 int  xp_detect_contacts_exchange_wait(xp_scene *s, int ticket);
+
+/* ---- device self-check of the narrowphase's arithmetic building blocks (csrc/xp_debug.cu) ----
+ * The exact mode's division / square-root sequences against the compiler's IEEE intrinsics on every square-root
+ * input of the guarded range and on n_random hashed + structured operand pairs, and the operand-side decisions
+ * (edge parameter, face interval, shared-denominator minimum) against the quotient-side ones of the reference.
+ * counters[0..5] = mismatches per check (sqrt, div random, div per mantissa, edge parameter, face interval,
+ * vertex minimum); all zero = the hand-rolled forms are exact. */
+int  xp_debug_check_arith(int device, uint64_t n_random, uint64_t seed, uint64_t counters[8]);
 
 /* ---- measurement helpers ---- */
 /* Dependent-free FFMA loop on every SM: the fp32 CUDA-core peak used as roofline denominator. */

@@ -22,6 +22,8 @@ def lib():
     L.emul_respond.restype = C.c_int
     L.emul_broadphase.argtypes = [vp, vp, C.c_float]
     L.emul_broadphase.restype = C.c_int
-    L.emul_detect_many.argtypes = [vp, vp, C.c_long, vp, vp]
+    L.emul_detect_many.argtypes = [vp, vp, C.c_long, vp, vp, C.c_int]
     L.emul_detect_many.restype = None
+    L.emul_bad_count.argtypes = [C.c_int]
+    L.emul_bad_count.restype = C.c_long
     return L

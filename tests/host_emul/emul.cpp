@@ -9,7 +9,11 @@
 
 using namespace xp;
 
+static long g_bad = 0;       // tests of modes 2 / 3 that fell back to the literal form
+
 extern "C" {
+
+long emul_bad_count(int reset) { const long v = g_bad; if (reset) g_bad = 0; return v; }
 
 // resp: 7 floats (c, r, m); tri: 9 floats; out: 8 floats (collision). returns 1/0/-1.  fast = mode (0 / 1)
 int emul_detect(const float *resp, const float *tri, float *out, int fast) {
@@ -21,6 +25,19 @@ int emul_detect(const float *resp, const float *tri, float *out, int fast) {
     float t;
     // mode 1: the two squared edge lengths come precomputed, as k_pack stores them in the triangle record
     const float els01[2] = {xp_edge_len2<ExactOps>(v0, v1), xp_edge_len2<ExactOps>(v1, v2)};
+    if (fast == 2 || fast == 3) {
+        // modes 2 / 3: the production forms xp_detect_x / xp_detect_f exactly as k_narrow_pairs calls them (per-ray
+        // operand from xp_ray_r2a, +inf marker for an irregular triangle, literal form when `bad`); the host build
+        // substitutes IEEE division / square root for the device sequences (see the header)
+        const float r2a = xp_ray_r2a<ExactOps>(ray);
+        const float e0 = xp_tri_regular(v0, v1, v2) ? els01[0] : XP_INF;
+        bool bad = false;
+        bool hit = fast == 2 ? xp_detect_x(ray, r2a, v0, v1, v2, d.n, d.pc, e0, els01[1], t, bad)
+                             : xp_detect_f(ray, r2a, v0, v1, v2, d.n, d.pc, e0, els01[1], t, bad);
+        g_bad += bad ? 1 : 0;
+        if (bad) hit = xp_detect<ExactOps>(ray, v0, v1, v2, d.n, d.pc, t);
+        if (!hit) return 0;
+    } else
     if (!xp_detect<ExactOps>(ray, v0, v1, v2, d.n, d.pc, t, nullptr, fast == 1 ? els01 : nullptr)) return 0;
     Contact k = xp_make_collision<ExactOps>(ray, t);
     out[0] = k.time_to; out[1] = k.distance_to;
@@ -67,10 +84,10 @@ int emul_broadphase(const float *resp, const float *tri, float horizon) {
     return r;
 }
 
-void emul_detect_many(const float *resp, const float *tris, long n_tris, float *out_t, int *out_hit) {
+void emul_detect_many(const float *resp, const float *tris, long n_tris, float *out_t, int *out_hit, int mode) {
     for (long j = 0; j < n_tris; ++j) {
         float col[8];
-        int r = emul_detect(resp, tris + 9 * j, col, 0);
+        int r = emul_detect(resp, tris + 9 * j, col, mode);
         out_hit[j] = r;
         out_t[j] = (r == 1) ? col[0] : 0.0f;
     }

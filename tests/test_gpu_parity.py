@@ -230,6 +230,19 @@ def test_empty_and_tiny_inputs(oracle):
         out, it, st, ln = s.collision_response_batch(resps)
         assert_bits_equal(resp_fields(out), resp_fields(resps), "no triangles: unchanged")
         assert not it.any()
+        # r != 1 against an EMPTY slice: the assert of collision_detect.rs:161 sits inside the per-triangle call,
+        # which the loop of lib.rs:33-35 never reaches -- the reference returns the Response unchanged
+        odd = resps.copy()
+        odd["r"][::2] = 0.5
+        col, hit, tri, st = s.detect_batch(odd)
+        w = oracle.detect_batch(odd, tris[:0])
+        assert not hit.any() and np.array_equal(st, w[3]) and not st.any()
+        out, it, st, ln = s.collision_response_batch(odd)
+        w = oracle.collision_response_batch(odd, tris[:0])
+        assert np.array_equal(st, w[2]) and not st.any() and not it.any()
+        assert_bits_equal(resp_fields(out), resp_fields(odd), "no triangles, r != 1: unchanged")
+    r = xp.Response(xp.Sphere([0, 3, 0], 0.5), [0, -1, 0])
+    assert xp.collision_response(r, tris[:0]) == r            # no panic, like the reference
     for n in (1, 2, 3, 5):
         with xp.Scene(0, tris[:n]) as s:
             got = s.detect_batch(resps)
@@ -488,6 +501,30 @@ def test_full_size_properties(full_scene, oracle):
     idx = np.flatnonzero(hh)[:: max(1, hh.sum() // 64)][:64]
     sub = oracle.detect_batch(resps[idx], tris, threads=0)          # brute force: 64 x 1M tests on the CPU
     check_detect_exact(tuple(x[idx] for x in a), sub, "64-sphere sample vs brute-force oracle")
+
+
+@pytest.fixture(scope="module")
+def full_brute(full_scene):
+    """The reference's literal algorithm (lib.rs:33-35: every triangle for every sphere) on the DEVICE for the
+    whole benchmark workload: 2^20 x 1 001 112 = 1.05e12 evaluations of a11 (k_brute, itself bit-compared with
+    the oracle at small size by test_detect_exact_bitwise[brute])."""
+    tris, h, resps = full_scene
+    with xp.Scene(0, tris, method="brute") as s:
+        return s.detect_batch(resps)
+
+
+@pytest.mark.parametrize("far_exact", [False, True])
+@pytest.mark.parametrize("arith", ["exact"])
+def test_full_size_every_sphere_against_brute_force(full_scene, full_brute, far_exact, arith):
+    """Predicate P + the LBVH are conservative on the benchmark workload itself: the two-stage sweep agrees with
+    the all-pairs sweep for ALL 2^20 spheres -- hit, triangle, every bit of the collision -- with and without the
+    far-exact pass."""
+    tris, h, resps = full_scene
+    with xp.Scene(0, tris, far_exact=far_exact, arith=arith) as s:
+        got = s.detect_batch(resps)
+        pairs = s.stats()["narrowphase_tests"]
+    check_detect_exact(got, full_brute, f"lbvh_pairs(far_exact={far_exact}) vs brute, all spheres")
+    assert pairs < len(resps) * 200                                    # ... with ~1e-5 of the all-pairs work
 
 
 def test_full_size_host_batch_above_pipeline_threshold(full_scene):

@@ -112,7 +112,7 @@ def test_detect_lean_equals_oracle_on_terrain(oracle):
     flat = np.ascontiguousarray(tris.reshape(-1, 9))
     total_hits = 0
     for i in range(len(resps)):
-        E.emul_detect_many(_p(resps[i:i + 1]), _p(flat), len(tris), _p(out_t), _p(out_hit))
+        E.emul_detect_many(_p(resps[i:i + 1]), _p(flat), len(tris), _p(out_t), _p(out_hit), 0)
         for j in range(len(tris)):
             w = oracle.detect(resps[i:i + 1], tris[j])
             assert (w is not None) == (out_hit[j] == 1)
@@ -120,6 +120,78 @@ def test_detect_lean_equals_oracle_on_terrain(oracle):
                 total_hits += 1
                 assert bits(np.float32(w["time_to"])) == bits(out_t[j])
     assert total_hits > 200
+
+
+def test_detect_x_equals_oracle_bitwise(oracle):
+    """xp_detect_x (comparison-based face interval and edge parameter, one vertex division, accumulated range
+    guards, literal form when `bad`) against the oracle on the same adversarial cases as the literal form --
+    NaN / inf / zero movement / overflow / lattice ties included.  The host build substitutes IEEE division and
+    square root for the device sequences, so this checks the RESTRUCTURING and the guards; the device
+    sequences themselves are checked against __fdiv_rn / __fsqrt_rn on the GPU (tests/test_gpu_arith.py)."""
+    E = emul_lib()
+    E.emul_bad_count(1)
+    n_hit = n = 0
+    for seed, count in ((11, 30000), (23, 30000)):
+        for c, m, tri in _cases(seed, count):
+            resp = oracle.make_responses([c], [m])
+            want = oracle.detect(resp, tri)
+            r, got = _emul_detect(E, resp, tri, mode=2)
+            n += 1
+            assert (want is not None) == (r == 1), (c, m, tri)
+            if want is not None:
+                n_hit += 1
+                w = np.concatenate([[want["time_to"], want["distance_to"]], want["position"], want["intersection"]])
+                assert_bits_equal(got, w.astype(np.float32), "collision fields")
+    bad = E.emul_bad_count(1)
+    print(f"x path: {n} adversarial cases, {n_hit} hits, {bad} took the literal form")
+    assert n_hit > 2000
+    assert bad < 0.6 * n             # kinds 6-10 (zero movement, 1e20 coordinates, NaN, ...) are SUPPOSED to fall back
+
+
+def test_detect_x_on_terrain_without_fallback(oracle):
+    """On an ordinary scene every pair stays on the guarded path (no fallback) and every result is the oracle's."""
+    E = emul_lib()
+    tris, h = scenes.sine_terrain(24, 24, seed=3)
+    resps = scenes.terrain_spheres(h, 96, seed=5)
+    flat = np.ascontiguousarray(tris.reshape(-1, 9))
+    out_t, out_hit = np.zeros(len(tris), np.float32), np.zeros(len(tris), np.int32)
+    ref_t, ref_hit = np.zeros(len(tris), np.float32), np.zeros(len(tris), np.int32)
+    E.emul_bad_count(1)
+    hits = 0
+    for i in range(len(resps)):
+        E.emul_detect_many(_p(resps[i:i + 1]), _p(flat), len(tris), _p(ref_t), _p(ref_hit), 0)   # literal form == oracle (above)
+        E.emul_detect_many(_p(resps[i:i + 1]), _p(flat), len(tris), _p(out_t), _p(out_hit), 2)
+        assert np.array_equal(out_hit, ref_hit)
+        assert np.array_equal(out_t.view(np.uint32), ref_t.view(np.uint32))
+        hits += int((ref_hit == 1).sum())
+    assert hits > 1000
+    assert E.emul_bad_count(1) <= 2, "ordinary terrain pairs must not need the literal form"
+
+
+def test_detect_f_within_tolerance(oracle):
+    """xp_detect_f (contracted arithmetic, half-b quadratics) on terrain: same hit / miss as the literal form except
+    on a small fraction of grazing pairs, times of impact within 1e-5 relative on all but a small tail."""
+    E = emul_lib()
+    tris, h = scenes.sine_terrain(24, 24, seed=3)
+    resps = scenes.terrain_spheres(h, 96, seed=5)
+    flat = np.ascontiguousarray(tris.reshape(-1, 9))
+    out_t, out_hit = np.zeros(len(tris), np.float32), np.zeros(len(tris), np.int32)
+    ref_t, ref_hit = np.zeros(len(tris), np.float32), np.zeros(len(tris), np.int32)
+    n = differ = beyond = both = 0
+    worst = 0.0
+    for i in range(len(resps)):
+        E.emul_detect_many(_p(resps[i:i + 1]), _p(flat), len(tris), _p(ref_t), _p(ref_hit), 0)
+        E.emul_detect_many(_p(resps[i:i + 1]), _p(flat), len(tris), _p(out_t), _p(out_hit), 3)
+        n += len(tris)
+        differ += int((out_hit != ref_hit).sum())
+        b = (out_hit == 1) & (ref_hit == 1)
+        rel = np.abs(out_t[b] - ref_t[b]) / np.maximum(1.0, np.abs(ref_t[b]))
+        both += int(b.sum())
+        beyond += int((rel > 1e-5).sum())
+        worst = max(worst, float(rel.max()) if len(rel) else 0.0)
+    print(f"f path (host emulation): {n} pairs, hit/miss differs on {differ}, {beyond} of {both} common hits beyond 1e-5 (worst {worst:.2e})")
+    assert differ < 2e-4 * n
+    assert beyond < 0.01 * both and worst < 5e-3
 
 
 def test_respond_equals_oracle_bitwise(oracle):

@@ -131,7 +131,7 @@ int xp_scene_set_option(xp_scene *s, int option, int64_t value) {
     if (!s) return XP_EINVAL;
     switch (option) {
     case XP_OPT_ARITH:
-        if (value != XP_ARITH_EXACT && value != XP_ARITH_FAST) return XP_EINVAL;
+        if (value < XP_ARITH_EXACT || value > XP_ARITH_FAST_LITERAL) return XP_EINVAL;
         s->arith = (int)value; return XP_OK;
     case XP_OPT_METHOD:
         if (value < XP_METHOD_WIDE_FUSED || value > XP_METHOD_Q4_PAIRS) return XP_EINVAL;
@@ -762,6 +762,14 @@ int xp_sphere_triangle_calculate_response(int device, const xp_response *respons
     int result = 0;
     XP_API_TRY(single_respond_dev(response, collision, out, &result));
     return result;
+}
+
+int xp_debug_check_arith(int device, uint64_t n_random, uint64_t seed, uint64_t counters[8]) {
+    if (!counters) return XP_EINVAL;
+    XP_API_TRY(cudaSetDevice(device));
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
+    XP_API_TRY(check_arith(n_random, seed, reinterpret_cast<unsigned long long *>(counters)));
+    return XP_OK;
 }
 
 int xp_probe_fp32_peak(int device, double *tflops) {

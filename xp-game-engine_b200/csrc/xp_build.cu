@@ -398,7 +398,9 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
     r.q1 = make_float4(v1.x, v1.y, v1.z, d.n.y);
     r.q2 = make_float4(v2.x, v2.y, v2.z, d.n.z);
     // the squared lengths of edges (v0,v1) and (v1,v2), op for op what the edge test computes per test
-    r.q3 = make_float4(d.pc, xp_edge_len2<ExactOps>(v0, v1), xp_edge_len2<ExactOps>(v1, v2), __uint_as_float(i));
+    // (+inf instead of the first one marks a triangle outside the narrowphase's regular domain: literal path)
+    r.q3 = make_float4(d.pc, xp_tri_regular(v0, v1, v2) ? xp_edge_len2<ExactOps>(v0, v1) : INFINITY,
+                       xp_edge_len2<ExactOps>(v1, v2), __uint_as_float(i));
     recs[j] = r;
     // Ill-conditioned triangles.  When the edges at v0 are (nearly) parallel -- sin^2 of their angle <= 1e-4 --
     // the reference's normal and the denominator of its point-in-triangle test (triangle.rs:11-32) are

@@ -73,6 +73,7 @@ struct DeviceCounters {           // one small block of device memory, zeroed pe
     unsigned long long path[5];   // tests per code path (XP_PATH_*), only with XP_OPT_TIMING=1
     unsigned long long ray_cursor;  // k_broadphase: next unclaimed run of 32 rays
     unsigned long long pairs_total; // candidates over all chunks of the call
+    unsigned long long redone;      // narrowphase tests redone with the literal form (operands outside the guarded range)
     unsigned int next_active;
     unsigned int stack_overflow;
     unsigned int pair_overflow;     // a chunk produced more candidates than the pair buffer holds

@@ -63,4 +63,7 @@ cudaError_t single_respond_dev(const xp_response *h_resp, const xp_collision *h_
                                xp_response *h_out, int *result);
 cudaError_t probe_fp32(double *tflops);
 
+// ---- xp_debug.cu ----
+cudaError_t check_arith(uint64_t n_random, uint64_t seed, unsigned long long *h_bad /* [8] */);
+
 }  // namespace xp

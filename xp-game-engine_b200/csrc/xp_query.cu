@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(256) k_ray_setup(const xp_response *__restrict
     RayRec rr;
     rr.q0 = make_float4(c.x, c.y, c.z, ray.ml);
     rr.q1 = make_float4(m.x, m.y, m.z, ray.msl);
-    rr.q2 = make_float4(ray.mh.x, ray.mh.y, ray.mh.z, horizon);
+    // q2.w: the per-ray operand of the narrowphase's one vertex-root division (+inf = irregular ray, literal path)
+    rr.q2 = make_float4(ray.mh.x, ray.mh.y, ray.mh.z, xp_ray_r2a<O>(ray));
     rr.q3 = make_float4(fdiv(1.0f, m.x), fdiv(1.0f, m.y), fdiv(1.0f, m.z), __uint_as_float(flags));
     rays[k] = rr;
     best[k] = BEST_NONE;
@@ -219,7 +220,7 @@ __device__ __forceinline__ bool slab2(const V3 &c, const V3 &inv, float horizon,
 template <class O, bool PRUNE>
 __global__ void __launch_bounds__(TRAV_THREADS)
 k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
-           const RayRec *__restrict__ rays, uint64_t na,
+           const RayRec *__restrict__ rays, uint64_t na, const float horizon,
            unsigned long long *__restrict__ best, DeviceCounters *__restrict__ ctr, int count_paths) {
     __shared__ WarpShared sh[TRAV_WARPS];
     unsigned long long *path_ctr = count_paths ? ctr->path : nullptr;
@@ -228,13 +229,12 @@ k_traverse(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
     const uint64_t k = blockIdx.x * (uint64_t)TRAV_THREADS + threadIdx.x;
 
     V3 c = {0, 0, 0}, inv = {0, 0, 0};
-    float horizon = 0.0f;
     int node = -1;                       // internal node to visit next, -1 = this lane is done
     if (k < na) {
         const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
         const float4 q0 = __ldg(rp + 0), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
         ws.ray[0][lane] = q0; ws.ray[1][lane] = q1; ws.ray[2][lane] = q2;
-        c = f4_xyz(q0); inv = f4_xyz(q3); horizon = q2.w;
+        c = f4_xyz(q0); inv = f4_xyz(q3);
         if (__float_as_uint(q3.w) & RAY_VALID) node = 0;
     }
     ws.best[lane] = BEST_NONE;
@@ -691,7 +691,7 @@ struct SweepShared {
 template <class O, bool PRUNE, bool EMIT>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__restrict__ rays,
-        uint64_t ray_base, uint64_t na, unsigned long long *__restrict__ best,
+        uint64_t ray_base, uint64_t na, const float horizon, unsigned long long *__restrict__ best,
         DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap, int count_paths) {
     __shared__ SweepShared sh[SWEEP_WARPS];
     const int lane = threadIdx.x & 31;
@@ -732,7 +732,6 @@ k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__re
         todo &= todo - 1;
         const float4 q0 = ws.ray[0][r], q3 = ws.ray[3][r];          // broadcast reads
         const V3 c = f4_xyz(q0), inv = f4_xyz(q3);
-        const float horizon = ws.ray[2][r].w;
 
         // slab test of this lane's child of (level, node); returns the warp's hit mask
         auto test = [&](int lvl, unsigned node) -> unsigned {
@@ -835,7 +834,12 @@ k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__re
 #ifndef XP_NP_GRID
 #define XP_NP_GRID 8              // blocks per SM in the grid (4 are resident)
 #endif
-template <class O, bool FILTER>
+// NP_LITERAL_*: the round-1 kernels (xp_detect<O>: IEEE div / sqrt intrinsics, one branch per operation), kept as
+// the A/B baseline and as the definition the other two are tested against.  NP_X: xp_detect_x, bit-identical to
+// NP_LITERAL_EXACT at ~2/3 of its instructions (a pair whose operands leave the guarded range is redone with the
+// literal form in place).  NP_F: xp_detect_f, the tolerance mode.
+enum { NP_LITERAL_EXACT = 0, NP_LITERAL_FAST = 1, NP_X = 2, NP_F = 3 };
+template <int MODE, bool FILTER>
 __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec *__restrict__ recs,
                                                       const RayRec *__restrict__ rays,
                                                       const uint2 *__restrict__ pairs,
@@ -849,7 +853,7 @@ __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec
         atomicAdd(&ctr->pairs_total, n);
     }
     if (n > pair_cap) n = pair_cap;
-    unsigned kept = 0;
+    unsigned kept = 0, redone = 0;
     // a block works through contiguous spans of the pair list (the broadphase writes it in runs that
     // share rays and triangles), so the gathers below find most of their lines already in L1
 #ifndef XP_NP_SPAN
@@ -878,10 +882,26 @@ __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec
             if (!slab(f4_xyz(r0), f4_xyz(r3), horizon, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, tn)) continue;
             ++kept;
         }
-        const Ray ray = ray_from(r0, r1, __ldg(rp + 2));
+        const float4 r2 = __ldg(rp + 2);
+        const Ray ray = ray_from(r0, r1, r2);
+        const V3 v0 = f4_xyz(t0), v1 = f4_xyz(t1), v2 = f4_xyz(t2), nrm = {t0.w, t1.w, t2.w};
         float t;
-        const float els01[2] = {t3.y, t3.z};             // stored with the triangle: |v1-v0|^2, |v2-v1|^2
-        if (xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t, nullptr, els01)) {
+        bool hit;
+        if (MODE == NP_X || MODE == NP_F) {
+            bool bad;
+            hit = MODE == NP_X ? xp_detect_x(ray, r2.w, v0, v1, v2, nrm, t3.x, t3.y, t3.z, t, bad)
+                               : xp_detect_f(ray, r2.w, v0, v1, v2, nrm, t3.x, t3.y, t3.z, t, bad);
+            if (bad) {                                   // an operand outside the guarded range (rare): as written
+                hit = MODE == NP_X ? xp_detect<ExactOps>(ray, v0, v1, v2, nrm, t3.x, t) : xp_detect<FastOps>(ray, v0, v1, v2, nrm, t3.x, t);
+                ++redone;
+            }
+        } else {
+            const float els01[2] = {t3.y, t3.z};         // stored with the triangle: |v1-v0|^2, |v2-v1|^2
+            const bool stored = t3.y <= XP_ELS_HI;       // +inf marks an irregular triangle: recompute
+            hit = MODE == NP_LITERAL_FAST ? xp_detect<FastOps>(ray, v0, v1, v2, nrm, t3.x, t, nullptr, stored ? els01 : nullptr)
+                                          : xp_detect<ExactOps>(ray, v0, v1, v2, nrm, t3.x, t, nullptr, stored ? els01 : nullptr);
+        }
+        if (hit) {
             const unsigned long long key =
                 ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(~__float_as_uint(t3.w));
             atomicMin(&best[pr.x], key);
@@ -890,6 +910,13 @@ __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec
     if (FILTER) {
         for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(FULL, kept, o);
         if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&ctr->tests, (unsigned long long)kept);
+    }
+    if (MODE == NP_X || MODE == NP_F) {
+        const unsigned any = __ballot_sync(FULL, redone != 0);
+        if (any) {
+            for (int o = 16; o > 0; o >>= 1) redone += __shfl_xor_sync(FULL, redone, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->redone, (unsigned long long)redone);
+        }
     }
 }
 
@@ -1135,6 +1162,7 @@ static unsigned bp_grid(const xp_scene *s, uint64_t n_rays) {
     return (unsigned)(want < full ? (want ? want : 1) : full);
 }
 
+static bool arith_fast(const xp_scene *s) { return s->arith == XP_ARITH_FAST || s->arith == XP_ARITH_FAST_LITERAL; }
 static float horizon_of(uint32_t mode) { return mode == XP_HORIZON_UNIT ? 1.0f : 3.402823466e+38f; }
 
 static cudaError_t zero_counters(xp_scene *s) {
@@ -1231,16 +1259,16 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
     if (!far && s->method == XP_METHOD_LBVH_FUSED) {
         StageTimer t(s, XP_STAGE_TRAVERSE);
         const unsigned blocks = grid_for(na, TRAV_THREADS);
-        if (s->prune == 1) k_traverse<O, true><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, best, ctr, s->timing);
-        else k_traverse<O, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, best, ctr, s->timing);
+        if (s->prune == 1) k_traverse<O, true><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, s->cur_horizon, best, ctr, s->timing);
+        else k_traverse<O, false><<<blocks, TRAV_THREADS, 0, st>>>(nodes, recs, rays, na, s->cur_horizon, best, ctr, s->timing);
         ++s->stats.kernel_launches;
         return cudaGetLastError();
     }
     if (!far && s->method == XP_METHOD_WIDE_FUSED) {
         StageTimer t(s, XP_STAGE_TRAVERSE);
         const unsigned blocks = grid_for(na, SWEEP_THREADS);
-        if (s->prune == 1) k_sweep<O, true, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
-        else k_sweep<O, false, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, best, ctr, nullptr, 0, s->timing);
+        if (s->prune == 1) k_sweep<O, true, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, s->cur_horizon, best, ctr, nullptr, 0, s->timing);
+        else k_sweep<O, false, false><<<blocks, SWEEP_THREADS, 0, st>>>(s->wide_tree, recs, rays, 0, na, s->cur_horizon, best, ctr, nullptr, 0, s->timing);
         ++s->stats.kernel_launches;
         return cudaGetLastError();
     }
@@ -1279,7 +1307,7 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
             StageTimer t(s, XP_STAGE_TRAVERSE);
             if (wide)
                 k_sweep<O, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
-                    s->wide_tree, recs, rays, pos, end, best, ctr, pairs, cap, 0);
+                    s->wide_tree, recs, rays, pos, end, s->cur_horizon, best, ctr, pairs, cap, 0);
             else if (q4)
                 k_broadphase4<<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes4.as<Node4>(), rays, pos, end, s->cur_horizon, ctr, pairs, cap);
             else if (far)
@@ -1296,8 +1324,16 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
         }
         {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
-            if (q4) k_narrow_pairs<O, true><<<s->n_sm * XP_NP_GRID, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
-            else k_narrow_pairs<O, false><<<s->n_sm * XP_NP_GRID, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
+            const unsigned ng = (unsigned)s->n_sm * XP_NP_GRID;
+#define XP_NP_LAUNCH(M) do { if (q4) k_narrow_pairs<M, true><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
+                             else k_narrow_pairs<M, false><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); } while (0)
+            switch (s->arith) {
+            case XP_ARITH_FAST: XP_NP_LAUNCH(NP_F); break;
+            case XP_ARITH_EXACT_LITERAL: XP_NP_LAUNCH(NP_LITERAL_EXACT); break;
+            case XP_ARITH_FAST_LITERAL: XP_NP_LAUNCH(NP_LITERAL_FAST); break;
+            default: XP_NP_LAUNCH(NP_X); break;
+            }
+#undef XP_NP_LAUNCH
             ++s->stats.kernel_launches;
         }
         if (s->safe_pairs) {                 // synchronous mode: check the fill after every chunk
@@ -1327,11 +1363,11 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
 }
 
 static cudaError_t closest(xp_scene *s, uint64_t na) {
-    return s->arith == XP_ARITH_FAST ? closest_t<FastOps>(s, na) : closest_t<ExactOps>(s, na);
+    return arith_fast(s) ? closest_t<FastOps>(s, na) : closest_t<ExactOps>(s, na);
 }
 static cudaError_t ray_setup(xp_scene *s, const xp_response *cur, const uint32_t *active, uint64_t na,
                              float horizon, uint32_t *status) {
-    return s->arith == XP_ARITH_FAST ? ray_setup_t<FastOps>(s, cur, active, na, horizon, status)
+    return arith_fast(s) ? ray_setup_t<FastOps>(s, cur, active, na, horizon, status)
                                      : ray_setup_t<ExactOps>(s, cur, active, na, horizon, status);
 }
 
@@ -1401,7 +1437,7 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
                 const int self = out.copy_self_plus1 - 1;
                 PeerBufs kp = peers;
                 if (self >= 0) { kp.n = 1; kp.rot = 0; kp.p[0] = peers.p[self]; }       // the kernel fills this rank's buffer only
-                if (s->arith == XP_ARITH_FAST)
+                if (arith_fast(s))
                     k_finalize_exchange<FastOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
                 else
                     k_finalize_exchange<ExactOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
@@ -1415,7 +1451,7 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
                         XP_TRY(cudaMemcpyAsync(peers.p[p] + slot, src, m * sizeof(xp_contact), cudaMemcpyDeviceToDevice, s->stream));
                     }
                 }
-            } else if (s->arith == XP_ARITH_FAST)
+            } else if (arith_fast(s))
                 k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
             else
                 k_finalize_detect<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
@@ -1477,7 +1513,7 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
                 StageTimer t(s, XP_STAGE_RESPONSE);
                 const RayRec *rays = s->rays.as<RayRec>();
                 const unsigned long long *best = s->best.as<unsigned long long>();
-                if (s->arith == XP_ARITH_FAST)
+                if (arith_fast(s))
                     k_respond<FastOps><<<grid_for(na, 256), 256, 0, st>>>(rays, best, active, na, cur, iter, status, normal, next, ctr);
                 else
                     k_respond<ExactOps><<<grid_for(na, 256), 256, 0, st>>>(rays, best, active, na, cur, iter, status, normal, next, ctr);
@@ -1538,7 +1574,7 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
                                                                   s->cur_horizon, ctr, pairs, buf_cap, 0.0f, INFINITY, nullptr);
         else
             k_sweep<ExactOps, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
-                s->wide_tree, s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end,
+                s->wide_tree, s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end, s->cur_horizon,
                 s->best.as<unsigned long long>(), ctr, pairs, buf_cap, 0);
         ++s->stats.kernel_launches;
         DeviceCounters h;

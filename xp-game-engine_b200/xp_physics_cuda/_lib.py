@@ -19,7 +19,8 @@ XP_OK, XP_EINVAL, XP_ECUDA, XP_ENOMEM, XP_ESTATE, XP_ECAP = 0, -1, -2, -3, -4, -
 ST_RADIUS_NE_1, ST_ASSERT_NEG_DISTANCE, ST_ITER_CAP = 1, 2, 4
 HORIZON_INF, HORIZON_UNIT = 0, 1
 OPT_ARITH, OPT_METHOD, OPT_TIMING, OPT_SORT_SPHERES, OPT_MAX_PAIRS, OPT_PRUNE, OPT_FAR_EXACT = 1, 2, 3, 4, 5, 6, 7
-ARITH_EXACT, ARITH_FAST = 0, 1
+ARITH_EXACT, ARITH_FAST, ARITH_EXACT_LITERAL, ARITH_FAST_LITERAL = 0, 1, 2, 3
+ARITH = {"exact": 0, "fast": 1, "exact_literal": 2, "fast_literal": 3}
 METHODS = {"wide_fused": 0, "lbvh_fused": 1, "lbvh_pairs": 2, "brute": 3, "wide_pairs": 4, "q4_pairs": 5}
 STAGE_NAMES = ["build_bounds", "build_morton", "build_sort", "build_pack", "build_tree", "build_refit",
                "ray_setup", "traverse", "narrowphase", "response", "finalize", "sphere_sort"]
@@ -96,6 +97,7 @@ def lib() -> C.CDLL:
         "xp_detect_contacts_exchange_submit": ([vp, vp, u64, u32, vp, i32, i32, u64, vp], i32),
         "xp_detect_contacts_exchange_wait": ([vp, i32], i32),
         "xp_probe_fp32_peak": ([i32, vp], i32),
+        "xp_debug_check_arith": ([i32, u64, u64, vp], i32),
         "xp_strerror": ([i32], C.c_char_p),
         "xp_last_cuda_error": ([], C.c_char_p),
         "xp_version": ([], C.c_char_p),
@@ -117,7 +119,7 @@ EXPORTED_SYMBOLS = [
     "xp_sphere_triangle_calculate_response", "xp_broadphase_pairs", "xp_scene_debug_tree",
     "xp_detect_contacts_dev", "xp_exchange_alloc", "xp_exchange_free", "xp_exchange_open", "xp_exchange_close",
     "xp_detect_contacts_exchange_dev", "xp_detect_contacts_multicast_dev", "xp_scene_set_exchange_stream",
-    "xp_detect_contacts_exchange_submit", "xp_detect_contacts_exchange_wait", "xp_probe_fp32_peak", "xp_strerror", "xp_last_cuda_error", "xp_version",
+    "xp_detect_contacts_exchange_submit", "xp_detect_contacts_exchange_wait", "xp_probe_fp32_peak", "xp_debug_check_arith", "xp_strerror", "xp_last_cuda_error", "xp_version",
 ]
 
 

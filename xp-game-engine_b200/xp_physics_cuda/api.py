@@ -139,7 +139,7 @@ class Scene:
                     far_exact=None):
         L, h = self._L, self._h
         if arith is not None:
-            check(L.xp_scene_set_option(h, _lib.OPT_ARITH, {"exact": 0, "fast": 1}[arith]))
+            check(L.xp_scene_set_option(h, _lib.OPT_ARITH, _lib.ARITH[arith]))
         if method is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_METHOD, _lib.METHODS[method]))
         if prune is not None:
@@ -414,6 +414,15 @@ def probe_fp32_peak(device: int = 0) -> float:
     v = C.c_double()
     check(_lib.lib().xp_probe_fp32_peak(device, C.byref(v)), "xp_probe_fp32_peak")
     return float(v.value)
+
+
+def debug_check_arith(device: int = 0, n_random: int = 1 << 32, seed: int = 1) -> dict:
+    """Device self-check of the exact mode's hand-rolled division / square root and operand-side decisions
+    (xp_debug_check_arith): mismatch counters per check, all zero when they are exact."""
+    c = (C.c_uint64 * 8)()
+    check(_lib.lib().xp_debug_check_arith(device, n_random, seed, c), "xp_debug_check_arith")
+    names = ("sqrt", "div_random", "div_mantissa", "edge_param", "face_interval", "vertex_min")
+    return {k: int(c[i]) for i, k in enumerate(names)}
 
 
 def device_count() -> int:
