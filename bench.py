@@ -46,11 +46,11 @@ PATH_FLOPS = {"cull": 5, "far": 16, "face_hit": 86, "full": 231, "full_pit": 284
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4
 
 
-def build_workload(seed: int, n_spheres: int = N_SPHERES):
+def build_workload(seed: int, n_spheres: int = N_SPHERES, with_heights: bool = False):
     from xp_physics_cuda import scenes
     tris, heights = scenes.sine_terrain(NX, NZ, seed=1)
     resps = scenes.terrain_spheres(heights, n_spheres, seed=seed)
-    return tris, resps
+    return (tris, resps, heights) if with_heights else (tris, resps)
 
 
 def workload_config(n_gpus: int) -> dict:
@@ -168,14 +168,17 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    tris, resps = build_workload(seed=1 + rank)
+    tris, resps, heights = build_workload(seed=1 + rank, with_heights=True)
     n = len(resps)
     scene = xp.Scene(local, arith=args.arith, method=args.method, prune=args.prune, timing=True)
     if args.far_exact:
         scene.set_options(far_exact=True)
     stream = torch.cuda.current_stream()
     scene.set_stream(stream.cuda_stream)
-    scene.set_triangles(tris)
+    if args.scene == "heightmap":
+        scene.set_heightmap(heights)              # the terrain as the reference holds it: a height grid (emitted on the device)
+    else:
+        scene.set_triangles(tris)                 # the same terrain as an anonymous triangle soup: LBVH walk
     scene.build()
     build_stats = scene.stats()
 
@@ -429,7 +432,7 @@ def run_b200(args):
         line = {"metric": "narrowphase_tests_per_sec", "value": value, "unit": "tests/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": dict(workload_config(world), arith=args.arith, method=args.method,
+                "data": "synthetic", "config": dict(workload_config(world), arith=args.arith, method=args.method, scene=args.scene,
                                                     prune=bool(args.prune), far_exact=bool(args.far_exact),
                                                     l2=("not flushed inside the loop (steps overlap): one step's inputs -- 128 MB of "
                                                         "scene records + 29 MB of spheres -- exceed the 126 MB L2 and a step streams "
@@ -487,6 +490,8 @@ def main():
     ap.add_argument("--arith", default="exact", choices=["exact", "fast", "exact_literal", "fast_literal"])
     ap.add_argument("--method", default="lbvh_pairs", choices=["wide_fused", "wide_pairs", "lbvh_fused", "lbvh_pairs", "brute", "q4_pairs"])
     ap.add_argument("--prune", type=int, default=0)
+    ap.add_argument("--scene", default="heightmap", choices=["heightmap", "soup"],
+                    help="how the config-2 terrain is handed over: xp_scene_set_heightmap (grid walk) or xp_scene_set_triangles (LBVH walk)")
     ap.add_argument("--far-exact", type=int, default=0, help="1: XP_OPT_FAR_EXACT (also reproduce the reference's far-range grazing noise)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -83,6 +83,11 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                 have none) with every box inflated by 8e-7 * D^2 and tests what that adds.  Default 0:
                                 hit/miss can differ from the brute-force reference for exactly those contacts. */
 
+#define XP_OPT_GRID_WALK  8  /* 1 (default): a scene set with xp_scene_set_heightmap is swept by walking the height grid
+                                itself (computed cell addresses, no tree; csrc/xp_gridwalk.cuh) instead of the LBVH.
+                                Same candidate set, bit for bit; applies to XP_METHOD_LBVH_PAIRS without distance
+                                windows.  0: always the LBVH. */
+
 #define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical to the reference's results         */
 #define XP_ARITH_FAST     1  /* tolerance mode: FMA, hardware reciprocal / square root, reduced quadratics (<= 1e-5) */
 #define XP_ARITH_EXACT_LITERAL 2 /* same results as 0 through the compiler's IEEE div / sqrt (the round-1 kernel; A/B)  */

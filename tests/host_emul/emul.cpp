@@ -6,6 +6,7 @@
 // Build: g++ -O2 -ffp-contract=off -fno-fast-math -shared -fPIC (see tests/host_emul/__init__.py)
 #include <cstring>
 #include "../../xp-game-engine_b200/csrc/xp_narrowphase.cuh"
+#include "../../xp-game-engine_b200/csrc/xp_gridwalk.cuh"
 
 using namespace xp;
 
@@ -82,6 +83,36 @@ int emul_broadphase(const float *resp, const float *tri, float horizon) {
     int r = xp_slab_hit(s, lo, hi, tn) ? 1 : 0;
     if (slab_branchfree(c, s.inv, s.horizon, lo, hi)) r |= 2;
     return r;
+}
+
+// The height-grid walk of k_broadphase_grid as plain nested loops over the same functions (xp_gridwalk.cuh):
+// every (column, cell) the ray enumerates, the two triangles' predicate P.  Writes the upload indices of the
+// candidates; returns their number (cells tested in *cells).
+long emul_grid_walk(const float *heights, unsigned nx, unsigned nz, float x0, float z0, float sp, int pad,
+                    const float *resp, float horizon, unsigned *out_tris, long cap, long *cells) {
+    GridDesc g;
+    g.h = heights; g.nx = nx; g.nz = nz; g.x0 = x0; g.z0 = z0; g.sp = sp; g.inv_sp = 1.0f / sp; g.pad = pad;
+    float ymin = heights[0], ymax = heights[0];
+    for (unsigned long i = 0; i < (unsigned long)(nx + 1) * (nz + 1); ++i) { ymin = fminf(ymin, heights[i]); ymax = fmaxf(ymax, heights[i]); }
+    const V3 c = {resp[0], resp[1], resp[2]}, m = {resp[4], resp[5], resp[6]};
+    const SlabRay sr = xp_slab_setup(c, m, horizon);          // 1/m and the FLT_MAX-clamped horizon, as k_ray_setup stores them
+    GridRay r;
+    long n = 0;
+    *cells = 0;
+    if (!grid_ray_setup(g, ymin, ymax, c, m, sr.inv, sr.horizon, r)) return 0;
+    const unsigned row = nz + 1;
+    for (int ix = r.ix; ix <= r.ix_hi; ++ix) {
+        GridCol col;
+        if (!grid_col_setup(g, r, ix, col)) continue;
+        for (int iz = col.iz; iz <= col.iz_hi; ++iz) {
+            const float *p = heights + (unsigned long)ix * row + iz;
+            const unsigned hit = grid_cell_test(r, col, grid_coord(z0, sp, iz), grid_coord(z0, sp, iz + 1), p[0], p[1], p[row], p[row + 1]);
+            ++*cells;
+            for (unsigned k = 0; k < 2; ++k)
+                if ((hit >> k) & 1u) { if (n < cap) out_tris[n] = 2u * ((unsigned)ix * nz + (unsigned)iz) + k; ++n; }
+        }
+    }
+    return n;
 }
 
 void emul_detect_many(const float *resp, const float *tris, long n_tris, float *out_t, int *out_hit, int mode) {

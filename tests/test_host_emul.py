@@ -258,3 +258,57 @@ def test_P_is_conservative(oracle):
                 assert (i, j) in P
     assert hits > 1000
     assert len(P) < 0.2 * len(resps) * len(tris)
+
+
+def _grid_pad(x0, z0, sp, nx, nz):
+    """xp_scene_set_heightmap's choice (xp_api.cu)"""
+    big = max(abs(x0) + sp * nx, abs(z0) + sp * nz) + 2.0
+    err = 32.0 * 1.1920929e-7 * big
+    assert err < 8.0 * sp
+    return 1 + int(err / sp + 0.75)
+
+
+@pytest.mark.parametrize("case", ["config2-like", "offset-fine", "coarse", "far-origin"])
+def test_grid_walk_enumerates_exactly_predicate_P(oracle, case):
+    """The height-grid walk (csrc/xp_gridwalk.cuh, the functions k_broadphase_grid runs) against the oracle's
+    predicate P over the emitted triangle soup: the same candidate set for every ray -- rays inside, outside,
+    along grid lines, with zero components, vertical, pointing away, unit and infinite horizon."""
+    E = emul_lib()
+    nx, nz, x0, z0, sp, seed = {"config2-like": (40, 37, 0.0, 0.0, 1.0, 3), "offset-fine": (33, 29, -5.5, 2.25, 0.37, 4),
+                                "coarse": (9, 12, 100.0, -50.0, 7.5, 5), "far-origin": (24, 24, 4000.0, -3000.0, 1.0, 6)}[case]
+    h = scenes.sine_terrain_heights(nx, nz, seed=seed)
+    tris = scenes.heightmap_from_heights(h, x0=x0, z0=z0, spacing=sp)
+    pad = _grid_pad(x0, z0, sp, nx, nz)
+    rng = np.random.default_rng(seed)
+    n = 400
+    resps = scenes.terrain_spheres(h, n, seed=seed + 10)
+    resps["c"][:, 0] = resps["c"][:, 0] * sp + x0
+    resps["c"][:, 2] = resps["c"][:, 2] * sp + z0
+    k = np.arange(n)
+    resps["movement"][k % 9 == 1, 0] = 0.0                            # movement inside a z-column
+    resps["movement"][k % 9 == 2, 2] = 0.0
+    resps["movement"][k % 9 == 3, 0::2] = 0.0                         # vertical
+    resps["movement"][k % 9 == 4] = 0.0                               # zero movement
+    resps["movement"][k % 9 == 5, 1] *= -1.0                          # upwards
+    resps["c"][k % 9 == 6] += rng.uniform(-3, 3, ((k % 9 == 6).sum(), 3)).astype(np.float32) * np.float32([nx * sp, 1, nz * sp])   # outside
+    on_line = k % 9 == 7                                              # centres exactly on grid lines / inflated faces
+    resps["c"][on_line, 0] = (x0 + sp * rng.integers(0, nx + 1, on_line.sum())).astype(np.float32)
+    resps["c"][k % 9 == 8, 2] = np.float32(z0 - 1.0001)
+    resps["movement"][k % 9 == 8, 2] = 0.0
+    hf = np.ascontiguousarray(h, np.float32)
+    cap = 1 << 16
+    out = np.zeros(cap, np.uint32)
+    cells = C.c_long(0)
+    total = tested = 0
+    for horizon in (np.inf, 1.0):
+        wi, wj = oracle.broadphase_pairs(resps, tris, horizon=horizon)
+        for i in range(n):
+            cnt = E.emul_grid_walk(_p(hf), nx, nz, x0, z0, sp, pad, _p(resps[i:i + 1]), horizon, _p(out), cap, C.byref(cells))
+            assert cnt <= cap
+            got = np.sort(out[:cnt])
+            want = np.sort(wj[wi == i])
+            assert np.array_equal(got, want), (case, horizon, i, resps[i], len(got), len(want))
+            total += cnt
+            tested += cells.value
+    print(f"{case}: {total} candidates, {2 * tested} triangle boxes tested ({2 * tested / max(total, 1):.2f} per candidate)")
+    assert total > 800

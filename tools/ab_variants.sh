@@ -11,7 +11,7 @@ if [ "$1" = "build" ]; then
     name=$1; flags=$2; shift 2
     /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --prec-div=true --prec-sqrt=true \
       --ftz=false -Xcompiler -fPIC -Xcompiler -fvisibility=default -Xptxas -v $flags -shared \
-      -o build_ab/libxp_$name.so $CS/xp_api.cu $CS/xp_build.cu $CS/xp_query.cu 2> build_ab/build_$name.log \
+      -o build_ab/libxp_$name.so $CS/xp_api.cu $CS/xp_build.cu $CS/xp_query.cu $CS/xp_debug.cu 2> build_ab/build_$name.log \
       || { tail -20 build_ab/build_$name.log; exit 1; }
     echo "built $name ($flags)"
   done

@@ -3,6 +3,7 @@
 // that computes launches kernels, and fails with XP_ECUDA when no CUDA device is usable.
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 
@@ -92,7 +93,7 @@ void xp_scene_destroy(xp_scene *s) {
     for (auto &x : s->ex_slot) if (x.busy) cudaEventSynchronize(x.fin);
     DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_lo, &s->node_hi, &s->leaf_lo, &s->leaf_hi,
                       &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
-                      &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->degen, &s->rays, &s->best, &s->active_a,
+                      &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->degen, &s->grid_h, &s->grid_yrange, &s->recs_grid, &s->rays, &s->best, &s->active_a,
                       &s->active_b, &s->inv_order, &s->pairs, &s->counters, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
                       &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
     for (DevBuf *b : bufs) b->release();
@@ -145,6 +146,7 @@ int xp_scene_set_option(xp_scene *s, int option, int64_t value) {
         if (value < 0 || value > 2) return XP_EINVAL;
         s->prune = (int)value; s->cand_per_ray = 0.0; return XP_OK;
     case XP_OPT_FAR_EXACT: s->far_exact = value ? 1 : 0; return XP_OK;
+    case XP_OPT_GRID_WALK: s->use_grid = value ? 1 : 0; return XP_OK;
     default: return XP_EINVAL;
     }
 }
@@ -161,6 +163,7 @@ int xp_scene_set_triangles(xp_scene *s, const xp_triangle *aos, uint64_t n) {
     if (!s || (!aos && n)) return XP_EINVAL;
     XP_BIND(s);
     s->built = false;
+    s->grid_valid = false;
     s->n_tris = 0;
     if (n) {
         XP_API_TRY(s->tris_aos.reserve(n * sizeof(xp_triangle)));
@@ -175,6 +178,7 @@ int xp_scene_set_triangles_dev(xp_scene *s, const xp_triangle *d_aos, uint64_t n
     if (!s || (!d_aos && n)) return XP_EINVAL;
     XP_BIND(s);
     s->built = false;
+    s->grid_valid = false;
     s->n_tris = 0;
     if (n) {
         XP_API_TRY(s->tris_aos.reserve(n * sizeof(xp_triangle)));
@@ -192,12 +196,25 @@ int xp_scene_set_heightmap(xp_scene *s, const float *heights, uint32_t nx, uint3
     XP_BIND(s);
     s->built = false;
     s->n_tris = 0;
-    const uint64_t hbytes = ((uint64_t)nx + 1) * ((uint64_t)nz + 1) * sizeof(float);
-    XP_API_TRY(s->io_in.reserve(hbytes));
-    XP_API_TRY(cudaMemcpyAsync(s->io_in.p, heights, hbytes, cudaMemcpyHostToDevice, s->stream));
-    XP_API_TRY(emit_heightmap(s, s->io_in.as<float>(), nx, nz, x0, z0, spacing));
+    const uint64_t hcount = ((uint64_t)nx + 1) * ((uint64_t)nz + 1), hbytes = hcount * sizeof(float);
+    s->grid_valid = false;
+    XP_API_TRY(s->grid_h.reserve(hbytes));               // kept: the height grid doubles as the broadphase structure
+    XP_API_TRY(cudaMemcpyAsync(s->grid_h.p, heights, hbytes, cudaMemcpyHostToDevice, s->stream));
+    XP_API_TRY(emit_heightmap(s, s->grid_h.as<float>(), nx, nz, x0, z0, spacing));
+    XP_API_TRY(height_range(s, s->grid_h.as<float>(), hcount));
     XP_API_TRY(cudaStreamSynchronize(s->stream));
     s->n_tris = n;
+    // The grid walk (xp_gridwalk.cuh) needs a regular grid: finite origin, positive spacing, grid lines that really
+    // advance in fp32, and coordinates small enough that `pad` cells cover the rounding of an enumerated position
+    // (~32 ulp of the largest coordinate).  Anything else simply keeps the LBVH walk.
+    const double xmax = fabs((double)x0) + (double)spacing * nx, zmax = fabs((double)z0) + (double)spacing * nz;
+    const double big = (xmax > zmax ? xmax : zmax) + 2.0;
+    const double err = 32.0 * 1.1920929e-7 * big;
+    if (spacing > 0.0f && spacing <= 3.0e38f && x0 == x0 && z0 == z0 && big < 1.0e30 && err < 8.0 * spacing) {
+        s->grid_nx = nx; s->grid_nz = nz; s->grid_x0 = x0; s->grid_z0 = z0; s->grid_sp = spacing;
+        s->grid_pad = 1 + (int)(err / spacing + 0.75);
+        s->grid_valid = true;
+    }
     return XP_OK;
 }
 
@@ -214,6 +231,7 @@ int xp_scene_set_clipmap(xp_scene *s, const float *heights, uint32_t levels, uin
     if (n == 0 || n >= (1ull << 27)) return XP_EINVAL;
     XP_BIND(s);
     s->built = false;
+    s->grid_valid = false;
     s->n_tris = 0;
     const uint64_t hbytes = (uint64_t)levels * size * size * sizeof(float), pbytes = (uint64_t)n_parts * 8 * sizeof(int32_t);
     XP_API_TRY(s->io_in.reserve(hbytes + pbytes));

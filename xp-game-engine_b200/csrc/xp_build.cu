@@ -385,7 +385,8 @@ cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *
 __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uint64_t n,
                                               const uint32_t *__restrict__ sorted_idx,
                                               TriRec *__restrict__ recs, float4 *__restrict__ leaf_lo,
-                                              float4 *__restrict__ leaf_hi, uint32_t *__restrict__ degen) {
+                                              float4 *__restrict__ leaf_hi, uint32_t *__restrict__ degen,
+                                              TriRec *__restrict__ recs_upload) {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint32_t i = sorted_idx[j];
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
     r.q3 = make_float4(d.pc, xp_tri_regular(v0, v1, v2) ? xp_edge_len2<ExactOps>(v0, v1) : INFINITY,
                        xp_edge_len2<ExactOps>(v1, v2), __uint_as_float(i));
     recs[j] = r;
+    if (recs_upload) recs_upload[i] = r;          // heightmap scenes: a second copy in upload (cell-major) order for the grid walk
     // Ill-conditioned triangles.  When the edges at v0 are (nearly) parallel -- sin^2 of their angle <= 1e-4 --
     // the reference's normal and the denominator of its point-in-triangle test (triangle.rs:11-32) are
     // dominated by rounding, and its face test can report a "collision" arbitrarily far from the triangle;
@@ -620,7 +622,38 @@ __global__ void __launch_bounds__(256) k_emit_heightmap(const float *__restrict_
     o[9] = xa; o[10] = h00; o[11] = za; o[12] = xb; o[13] = h11; o[14] = zb; o[15] = xb; o[16] = h10; o[17] = za;
 }
 
+// min / max of the height grid (the y extent of the scene box the grid walk clips rays against): ordered-int
+// atomics, decoded in place by the second kernel
+__global__ void __launch_bounds__(256) k_height_range(const float *__restrict__ h, uint64_t n, unsigned *__restrict__ out) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(h + i);
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], enc_f(mn)); atomicMax(&out[1], enc_f(mx)); }
+}
+__global__ void k_height_range_decode(unsigned *io) {
+    if (threadIdx.x < 2) reinterpret_cast<float *>(io)[threadIdx.x] = dec_f(io[threadIdx.x]);
+}
+
 #define XP_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
+
+cudaError_t height_range(xp_scene *s, const float *d_heights, uint64_t n) {
+    XP_TRY(s->grid_yrange.reserve(2 * sizeof(float)));
+    unsigned *out = s->grid_yrange.as<unsigned>();
+    const unsigned init[2] = {0xFFFFFFFFu, 0u};
+    XP_TRY(cudaMemcpyAsync(out, init, sizeof init, cudaMemcpyHostToDevice, s->stream));
+    unsigned blocks = grid_for(n, 256);
+    if (blocks > (unsigned)s->n_sm * 8) blocks = (unsigned)s->n_sm * 8;
+    k_height_range<<<blocks, 256, 0, s->stream>>>(d_heights, n, out);
+    k_height_range_decode<<<1, 32, 0, s->stream>>>(out);
+    s->stats.kernel_launches += 2;
+    return cudaGetLastError();
+}
 
 cudaError_t emit_heightmap(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz, float x0, float z0,
                            float spacing) {
@@ -726,8 +759,10 @@ cudaError_t build_lbvh(xp_scene *s) {
         StageTimer t(s, XP_STAGE_BUILD_PACK);
         XP_TRY(s->degen.reserve((n + 1) * sizeof(uint32_t)));
         XP_TRY(cudaMemsetAsync(s->degen.p, 0, sizeof(uint32_t), st));
+        if (s->grid_valid) XP_TRY(s->recs_grid.reserve(n * sizeof(TriRec)));
         k_pack<<<grid_for(n, 256), 256, 0, st>>>(aos, n, vals, s->recs.as<TriRec>(),
-                                                s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>(), s->degen.as<uint32_t>());
+                                                s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>(), s->degen.as<uint32_t>(),
+                                                s->grid_valid ? s->recs_grid.as<TriRec>() : nullptr);
         ++s->stats.kernel_launches;
     }
     if (n == 1) {

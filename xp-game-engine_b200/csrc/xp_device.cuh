@@ -34,6 +34,7 @@ static constexpr int Q4_EMPTY = (int)0x80000000;
 
 static constexpr unsigned long long BEST_NONE = 0xFFFFFFFFFFFFFFFFull;
 static constexpr uint32_t RAY_VALID = 1u;
+static constexpr uint32_t RAY_GRID_OK = 2u;      // centre and movement finite: the height-grid walk may take this ray
 static constexpr uint32_t HARD_ITER_CAP = 65536u;
 
 // Growable device buffer (never shrinks; freed with the scene).
@@ -77,7 +78,7 @@ struct DeviceCounters {           // one small block of device memory, zeroed pe
     unsigned int next_active;
     unsigned int stack_overflow;
     unsigned int pair_overflow;     // a chunk produced more candidates than the pair buffer holds
-    unsigned int pad;
+    unsigned int irregular_rays;    // rays the height-grid walk left to the LBVH walk (non-finite centre / movement)
 };
 
 }  // namespace xp
@@ -115,6 +116,15 @@ struct xp_scene {
     xp::DevBuf wide, wide_lo, wide_hi;               // 32-wide implicit tree planes + per-node union boxes
     xp::DevBuf nodes4;                               // Node4[max(T-1,1)], indexed like the binary nodes
     xp::DevBuf degen;                                // uint32[1 + T]: count, then the leaves of ill-conditioned triangles
+    // heightmap scenes (xp_scene_set_heightmap): the height grid itself is the broadphase structure (xp_gridwalk.cuh)
+    bool grid_valid = false;                         // the triangles are exactly the soup of this grid
+    int use_grid = 1;                                // XP_OPT_GRID_WALK
+    unsigned grid_nx = 0, grid_nz = 0;
+    float grid_x0 = 0, grid_z0 = 0, grid_sp = 0;
+    int grid_pad = 1;
+    xp::DevBuf grid_h;                               // (nx+1) x (nz+1) heights
+    xp::DevBuf grid_yrange;                          // 2 floats: min / max height (2 ordered ints while being reduced)
+    xp::DevBuf recs_grid;                            // TriRec[T] in UPLOAD order (cell-major): what the grid walk's pairs index
     uint64_t n_degen = 0;                            // (swept exhaustively, see k_pack / k_sweep_degenerate)
     xp::WideTree wide_tree = {};
     // per-call workspaces

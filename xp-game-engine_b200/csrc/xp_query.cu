@@ -26,6 +26,7 @@
 
 #include "xp_internal.h"
 #include "xp_narrowphase.cuh"
+#include "xp_gridwalk.cuh"
 
 namespace xp {
 
@@ -56,6 +57,10 @@ __global__ void __launch_bounds__(256) k_ray_setup(const xp_response *__restrict
     const float r = p[3];
     const V3 m = {p[4], p[5], p[6]};
     uint32_t flags = RAY_VALID;
+    {   // finite centre and movement: the height-grid walk can enumerate this ray's cells (anything else walks the LBVH)
+        const float big = fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fabsf(c.z)), fmaxf(fmaxf(fabsf(m.x), fabsf(m.y)), fabsf(m.z)));
+        if (big <= XP_FLT_MAX && c.x == c.x && c.y == c.y && c.z == c.z && m.x == m.x && m.y == m.y && m.z == m.z) flags |= RAY_GRID_OK;
+    }
     if (!(r == 1.0f)) {
         flags = 0;
         // the assert sits inside sphere_triangle_detect_collision (collision_detect.rs:161), which the loop over an
@@ -349,7 +354,10 @@ template <int MODE>
 __global__ void __launch_bounds__(BP_THREADS, BP_BLOCKS_PER_SM)
 k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
              float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap,
-             float d_lo, float d_hi, const unsigned long long *__restrict__ best) {
+             float d_lo, float d_hi, const unsigned long long *__restrict__ best, const uint32_t *__restrict__ leaf_to_tri) {
+    // MODE 3: the rays the height-grid walk could not take (non-finite centre / movement) -- usually none, and then
+    // this launch ends at once; its pairs go into the same list and therefore name the triangle by UPLOAD index
+    if (MODE == 3 && ctr->irregular_rays == 0u) return;
     // Distance window [d_lo, d_hi) of this pass (pruned sweeps, see closest_t): only leaves whose box the
     // ray ENTERS inside the window are emitted, and spheres whose best hit so far lies before the window
     // are skipped.  The exhaustive sweep is the single window [0, +inf) with best == nullptr.
@@ -370,7 +378,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     const unsigned ray0 = (unsigned)ray_base;
 
     V3 c = {0, 0, 0}, inv = {0, 0, 0};
-    constexpr bool WINDOWED = MODE != 0;
+    constexpr bool WINDOWED = MODE == 1 || MODE == 2;
     float t_lo = 0.0f, t_hi = 0.0f;        // this ray's window in units of its own t
     float grow = 0.0f;                     // MODE 2: extra inflation of every box for this ray
     unsigned my_ray = 0;
@@ -414,6 +422,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                     c = f4_xyz(q0); inv = f4_xyz(q3);
                     sp = 0; sbase = 0;
                     bool go = (__float_as_uint(q3.w) & RAY_VALID) != 0;
+                    if (MODE == 3) go = go && !(__float_as_uint(q3.w) & RAY_GRID_OK);
                     if (WINDOWED) {                          // windowed pass: t = distance / |m|
                         const float ml = q0.w;
                         const bool sane = ml > 0.0f && ml <= XP_FLT_MAX;
@@ -521,6 +530,10 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
         const unsigned mb = __ballot_sync(FULL, leaf_b >= 0);
         if (ma | mb) {
             const unsigned na = __popc(ma);
+            if (MODE == 3) {
+                if (leaf_a >= 0) leaf_a = (int)__ldg(&leaf_to_tri[leaf_a]);
+                if (leaf_b >= 0) leaf_b = (int)__ldg(&leaf_to_tri[leaf_b]);
+            }
             if (leaf_a >= 0) q[count + __popc(ma & lt_mask)] = make_uint2(ray0 + my_ray, (uint32_t)leaf_a);
             if (leaf_b >= 0) q[count + na + __popc(mb & lt_mask)] = make_uint2(ray0 + my_ray, (uint32_t)leaf_b);
             count += na + __popc(mb);
@@ -545,6 +558,154 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
             if (base + w < pair_cap) __stcs(&pairs_out[base + w], q[w]);
     }
     if (lane == 0) atomicAdd(&ctr->node_visits, (unsigned long long)n_nodes);
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1 for heightmap scenes: the ray walks the height grid (xp_gridwalk.cuh), no tree
+// ------------------------------------------------------------------------------------------
+// Same persistent-warp frame as k_broadphase (warps claim runs of 32 Morton-consecutive rays, a lane takes its
+// next ray the moment it has finished one), but a lane's state is (column, cell) instead of a node stack, the
+// data it reads are 4 B heights at computed addresses -- consecutive along a column -- and nothing is
+// pointer-chased.  Per outer iteration a lane tests up to GW_CELLS cells (2 triangles each) with uniform control
+// flow, then the warp writes the hits out with each LANE's hits contiguous: a run of pairs that share the ray and
+// name consecutive triangles of one column, i.e. consecutive 64 B records of the upload-order record array.  That
+// is what the narrowphase wants: its gathers are bound by L1 wavefronts (one per distinct line per instruction),
+// and such runs put ~4 rays and ~16 triangle lines under a warp instead of 32 and 32.
+#ifndef XP_GW_CELLS
+#define XP_GW_CELLS 8
+#endif
+#ifndef XP_GW_BLOCKS
+#define XP_GW_BLOCKS 4
+#endif
+static constexpr int GW_CELLS = XP_GW_CELLS;
+static constexpr int GW_QUEUE = 32 * 2 * GW_CELLS;
+
+__global__ void __launch_bounds__(BP_THREADS, XP_GW_BLOCKS)
+k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayRec *__restrict__ rays, uint64_t ray_base,
+                  uint64_t ray_end, float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out,
+                  uint64_t pair_cap) {
+    __shared__ uint2 queue[BP_WARPS][GW_QUEUE];
+    __shared__ float4 rpool_all[BP_WARPS][96];          // the warp's current run of rays: (c,|m|)[32], (m,|m|^2)[32], (1/m,flags)[32]
+    uint2 *q = queue[threadIdx.x >> 5];
+    float4 *rpool = rpool_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    rays += ray_base;
+    const unsigned n_rays = (unsigned)(ray_end - ray_base);
+    const unsigned ray0 = (unsigned)ray_base;
+    const float ymin = __ldg(yrange), ymax = __ldg(yrange + 1);
+    const unsigned row = g.nz + 1;
+
+    GridRay r;
+    r.ix = 0; r.ix_hi = -1;
+    GridCol col;
+    col.iz = 0; col.iz_hi = -1; col.tx_lo = 0.0f; col.tx_hi = 0.0f;
+    int cur_ix = 0;                          // the column col belongs to
+    float h00 = 0.0f, h10 = 0.0f, z_lo = 0.0f;      // carried from cell to cell along the column
+    unsigned my_ray = 0;
+    unsigned pool = 0, pool_end = 0, pool_base = 0;
+    bool drained = false;
+    unsigned n_cells = 0, n_irregular = 0;
+
+    for (;;) {
+        // ---- lanes that have finished their ray take the next one of the warp's run
+        const bool done = col.iz > col.iz_hi && r.ix > r.ix_hi;
+        const unsigned idle = __ballot_sync(FULL, done);
+        if (idle) {
+            if (pool >= pool_end && !drained) {
+                unsigned start = 0;
+                if (lane == 0) start = (unsigned)atomicAdd(&ctr->ray_cursor, 32ull);
+                start = __shfl_sync(FULL, start, 0);
+                pool = start < n_rays ? start : n_rays;
+                pool_end = pool + 32 < n_rays ? pool + 32 : n_rays;
+                drained = pool >= n_rays;
+                pool_base = pool;
+                __syncwarp();
+                if (pool + lane < pool_end) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(rays + pool + lane);
+                    rpool[lane] = __ldcs(rp + 0);
+                    rpool[32 + lane] = __ldcs(rp + 1);
+                    rpool[64 + lane] = __ldcs(rp + 3);
+                }
+                __syncwarp();
+            }
+            if (pool < pool_end) {
+                const unsigned mine = pool + __popc(idle & lt_mask);
+                if (done && mine < pool_end) {
+                    my_ray = mine;
+                    const float4 q0 = rpool[mine - pool_base], q1 = rpool[32 + mine - pool_base], q3 = rpool[64 + mine - pool_base];
+                    const unsigned flags = __float_as_uint(q3.w);
+                    if ((flags & (RAY_VALID | RAY_GRID_OK)) == (RAY_VALID | RAY_GRID_OK))
+                        grid_ray_setup(g, ymin, ymax, f4_xyz(q0), f4_xyz(q1), f4_xyz(q3), horizon, r);
+                    else if (flags & RAY_VALID) ++n_irregular;           // left to k_broadphase<3>
+                }
+                pool = min(pool + __popc(idle), pool_end);
+            } else if (idle == FULL) {
+                break;
+            }
+        }
+        // ---- lanes whose column is exhausted move to their next column that can hold a candidate
+#pragma unroll 1
+        for (int tries = 0; tries < 3; ++tries) {
+            const bool need = col.iz > col.iz_hi && r.ix <= r.ix_hi;
+            if (!__any_sync(FULL, need)) break;
+            if (need) {
+                cur_ix = r.ix++;
+                if (grid_col_setup(g, r, cur_ix, col)) {
+                    const float *p = g.h + (size_t)cur_ix * row + col.iz;
+                    h00 = __ldg(p); h10 = __ldg(p + row);
+                    z_lo = grid_coord(g.z0, g.sp, col.iz);
+                }
+            }
+        }
+        // ---- up to GW_CELLS cells of the column, two triangles each
+        unsigned mask = 0;
+        const unsigned first_tri = 2u * ((unsigned)cur_ix * g.nz + (unsigned)col.iz);
+        {
+            const float *p = g.h + (size_t)cur_ix * row + col.iz + 1;
+#pragma unroll
+            for (int k = 0; k < GW_CELLS; ++k) {
+                if (col.iz <= col.iz_hi) {
+                    const float h01 = __ldg(p + k), h11 = __ldg(p + row + k);
+                    const float z_hi = grid_coord(g.z0, g.sp, col.iz + 1);
+                    mask |= grid_cell_test(r, col, z_lo, z_hi, h00, h01, h10, h11) << (2 * k);
+                    h00 = h01; h10 = h11; z_lo = z_hi;
+                    ++col.iz;
+                    ++n_cells;
+                }
+            }
+        }
+        // ---- write the hits out, each lane's as one contiguous run (same ray, consecutive triangles)
+        if (__any_sync(FULL, mask != 0u)) {
+            const unsigned cnt = __popc(mask);
+            unsigned inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += y; }
+            const unsigned total = __shfl_sync(FULL, inc, 31);
+            unsigned pos = inc - cnt;
+            const unsigned ray_id = ray0 + my_ray;
+            while (mask) {
+                const unsigned b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                q[pos++] = make_uint2(ray_id, first_tri + b);           // bit 2k+s <-> triangle 2 (cell0 + k) + s
+            }
+            __syncwarp();
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)total);
+            base = __shfl_sync(FULL, base, 0);
+            for (unsigned w = lane; w < total; w += 32)
+                if (base + w < pair_cap) __stcs(&pairs_out[base + w], q[w]);
+            __syncwarp();
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_cells += __shfl_xor_sync(FULL, n_cells, o);
+        n_irregular += __shfl_xor_sync(FULL, n_irregular, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&ctr->node_visits, (unsigned long long)n_cells);
+        if (n_irregular) atomicAdd(&ctr->irregular_rays, n_irregular);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1145,7 +1306,7 @@ __global__ void k_translate_pairs(const uint2 *__restrict__ pairs, uint64_t n, u
     if (p >= n || out_base + p >= cap) return;
     const uint2 pr = pairs[p];
     sphere_idx[out_base + p] = active ? active[pr.x] : pr.x;
-    tri_idx[out_base + p] = __float_as_uint(recs[pr.y].q3.w);
+    tri_idx[out_base + p] = recs ? __float_as_uint(recs[pr.y].q3.w) : pr.y;      // null: the pairs already hold upload indices
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1163,6 +1324,30 @@ static unsigned bp_grid(const xp_scene *s, uint64_t n_rays) {
 }
 
 static bool arith_fast(const xp_scene *s) { return s->arith == XP_ARITH_FAST || s->arith == XP_ARITH_FAST_LITERAL; }
+static bool grid_walk_on(const xp_scene *s) { return s->grid_valid && s->use_grid && s->method == XP_METHOD_LBVH_PAIRS; }
+static GridDesc grid_desc(const xp_scene *s) {
+    GridDesc g;
+    g.h = s->grid_h.as<float>();
+    g.nx = s->grid_nx; g.nz = s->grid_nz;
+    g.x0 = s->grid_x0; g.z0 = s->grid_z0; g.sp = s->grid_sp; g.inv_sp = 1.0f / s->grid_sp;
+    g.pad = s->grid_pad;
+    return g;
+}
+// stage 1 of a heightmap scene: the grid walk, then the LBVH walk for whatever rays it could not take (normally none:
+// that launch returns at once).  Both append to the same pair list, triangles named by upload index.
+static cudaError_t launch_grid_broadphase(xp_scene *s, uint64_t pos, uint64_t end, uint2 *pairs, uint64_t cap) {
+    cudaStream_t st = s->stream;
+    DeviceCounters *ctr = s->counters.as<DeviceCounters>();
+    const uint64_t want = (end - pos + BP_THREADS - 1) / BP_THREADS, full = (uint64_t)s->n_sm * XP_GW_BLOCKS;
+    const unsigned grid = (unsigned)(want < full ? (want ? want : 1) : full);
+    k_broadphase_grid<<<grid, BP_THREADS, 0, st>>>(grid_desc(s), s->grid_yrange.as<float>(), s->rays.as<RayRec>(), pos, end,
+                                                  s->cur_horizon, ctr, pairs, cap);
+    XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
+    k_broadphase<3><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end, s->cur_horizon,
+                                                               ctr, pairs, cap, 0.0f, INFINITY, nullptr, s->vals_a.as<uint32_t>());
+    s->stats.kernel_launches += 2;
+    return cudaGetLastError();
+}
 static float horizon_of(uint32_t mode) { return mode == XP_HORIZON_UNIT ? 1.0f : 3.402823466e+38f; }
 
 static cudaError_t zero_counters(xp_scene *s) {
@@ -1289,6 +1474,8 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
     static const float kWin[] = {0.0f, 4.0f, 16.0f, 64.0f, 256.0f, 1024.0f, INFINITY};
     const bool windows = !far && s->method == XP_METHOD_LBVH_PAIRS && (s->prune == 1 || (s->prune == 2 && s->cand_per_ray > 96.0));
     const int n_pass = windows ? 6 : 1;
+    const bool grid = !far && !windows && grid_walk_on(s);
+    if (grid) recs = s->recs_grid.as<TriRec>();      // the grid walk names triangles by upload index
     uint64_t pos = 0;
     unsigned long long snap_tests = 0, snap_pairs = 0;   // synchronous mode: accounting before the current chunk
     if (s->safe_pairs) {
@@ -1310,17 +1497,19 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
                     s->wide_tree, recs, rays, pos, end, s->cur_horizon, best, ctr, pairs, cap, 0);
             else if (q4)
                 k_broadphase4<<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes4.as<Node4>(), rays, pos, end, s->cur_horizon, ctr, pairs, cap);
+            else if (grid)
+                XP_TRY(launch_grid_broadphase(s, pos, end, pairs, cap));
             else if (far)
                 k_broadphase<2><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                           XP_FAR_D0, INFINITY, best);
+                                                                           XP_FAR_D0, INFINITY, best, nullptr);
             else
                 if (windows)
                     k_broadphase<1><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                                  d_lo, d_hi, best);
+                                                                                  d_lo, d_hi, best, nullptr);
                 else
                     k_broadphase<0><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                               0.0f, INFINITY, nullptr);
-            ++s->stats.kernel_launches;
+                                                                               0.0f, INFINITY, nullptr, nullptr);
+            if (!grid) ++s->stats.kernel_launches;
         }
         {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
@@ -1569,9 +1758,12 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
         const uint64_t end = (pos + chunk < n) ? pos + chunk : n;
         XP_TRY(cudaMemsetAsync(&ctr->pairs, 0, sizeof(unsigned long long), st));
         XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
-        if (s->method != XP_METHOD_WIDE_FUSED && s->method != XP_METHOD_WIDE_PAIRS)
+        if (grid_walk_on(s)) {
+            XP_TRY(launch_grid_broadphase(s, pos, end, pairs, buf_cap));
+            --s->stats.kernel_launches;
+        } else if (s->method != XP_METHOD_WIDE_FUSED && s->method != XP_METHOD_WIDE_PAIRS)
             k_broadphase<0><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
-                                                                  s->cur_horizon, ctr, pairs, buf_cap, 0.0f, INFINITY, nullptr);
+                                                                  s->cur_horizon, ctr, pairs, buf_cap, 0.0f, INFINITY, nullptr, nullptr);
         else
             k_sweep<ExactOps, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
                 s->wide_tree, s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end, s->cur_horizon,
@@ -1587,7 +1779,7 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
         }
         if (h.pairs > 0 && total < cap) {
             k_translate_pairs<<<grid_for(h.pairs, 256), 256, 0, st>>>(pairs, h.pairs, total, nullptr,
-                                                                     s->recs.as<TriRec>(), d_sphere, d_tri, cap);
+                                                                     grid_walk_on(s) ? nullptr : s->recs.as<TriRec>(), d_sphere, d_tri, cap);
             ++s->stats.kernel_launches;
         }
         total += h.pairs;

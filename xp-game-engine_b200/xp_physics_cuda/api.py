@@ -136,7 +136,7 @@ class Scene:
 
     # -- options
     def set_options(self, *, arith=None, method=None, prune=None, sort_spheres=None, timing=None, max_pairs=None,
-                    far_exact=None):
+                    far_exact=None, grid_walk=None):
         L, h = self._L, self._h
         if arith is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_ARITH, _lib.ARITH[arith]))
@@ -152,6 +152,8 @@ class Scene:
             check(L.xp_scene_set_option(h, _lib.OPT_MAX_PAIRS, int(max_pairs)))
         if far_exact is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_FAR_EXACT, int(bool(far_exact))))
+        if grid_walk is not None:
+            check(L.xp_scene_set_option(h, _lib.OPT_GRID_WALK, int(bool(grid_walk))))
 
     def set_stream(self, cuda_stream_ptr: int):
         check(self._L.xp_scene_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
