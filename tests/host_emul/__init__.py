@@ -25,7 +25,7 @@ def lib():
     L.emul_broadphase.restype = C.c_int
     L.emul_detect_many.argtypes = [vp, vp, C.c_long, vp, vp, C.c_int]
     L.emul_detect_many.restype = None
-    L.emul_grid_walk.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_int, vp, C.c_float, vp, C.c_long, vp]
+    L.emul_grid_walk.argtypes = [vp, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_float, vp, C.c_float, vp, C.c_long, vp]
     L.emul_grid_walk.restype = C.c_long
     L.emul_bad_count.argtypes = [C.c_int]
     L.emul_bad_count.restype = C.c_long

@@ -88,10 +88,10 @@ int emul_broadphase(const float *resp, const float *tri, float horizon) {
 // The height-grid walk of k_broadphase_grid as plain nested loops over the same functions (xp_gridwalk.cuh):
 // every (column, cell) the ray enumerates, the two triangles' predicate P.  Writes the upload indices of the
 // candidates; returns their number (cells tested in *cells).
-long emul_grid_walk(const float *heights, unsigned nx, unsigned nz, float x0, float z0, float sp, int pad,
+long emul_grid_walk(const float *heights, unsigned nx, unsigned nz, float x0, float z0, float sp, float eps,
                     const float *resp, float horizon, unsigned *out_tris, long cap, long *cells) {
     GridDesc g;
-    g.h = heights; g.nx = nx; g.nz = nz; g.x0 = x0; g.z0 = z0; g.sp = sp; g.inv_sp = 1.0f / sp; g.pad = pad;
+    g.h = heights; g.nx = nx; g.nz = nz; g.x0 = x0; g.z0 = z0; g.sp = sp; g.inv_sp = 1.0f / sp; g.eps = eps; g.mm = nullptr;
     float ymin = heights[0], ymax = heights[0];
     for (unsigned long i = 0; i < (unsigned long)(nx + 1) * (nz + 1); ++i) { ymin = fminf(ymin, heights[i]); ymax = fmaxf(ymax, heights[i]); }
     const V3 c = {resp[0], resp[1], resp[2]}, m = {resp[4], resp[5], resp[6]};
@@ -105,6 +105,14 @@ long emul_grid_walk(const float *heights, unsigned nx, unsigned nz, float x0, fl
         GridCol col;
         if (!grid_col_setup(g, r, ix, col)) continue;
         for (int iz = col.iz; iz <= col.iz_hi; ++iz) {
+            if ((iz - col.iz) % XP_GW_WINDOW == 0) {          // a new window of cells: k_height_windows' (min, max), then the cull
+                float hmin = HUGE_VALF, hmax = -HUGE_VALF;
+                for (unsigned j = (unsigned)iz; j <= ((unsigned)iz + XP_GW_WINDOW < nz ? (unsigned)iz + XP_GW_WINDOW : nz); ++j) {
+                    const float a = heights[(unsigned long)ix * row + j], b = heights[(unsigned long)(ix + 1) * row + j];
+                    hmin = fminf(hmin, fminf(a, b)); hmax = fmaxf(hmax, fmaxf(a, b));
+                }
+                if (!grid_window_test(r, col, hmin, hmax)) { iz += XP_GW_WINDOW - 1; continue; }
+            }
             const float *p = heights + (unsigned long)ix * row + iz;
             const unsigned hit = grid_cell_test(r, col, grid_coord(z0, sp, iz), grid_coord(z0, sp, iz + 1), p[0], p[1], p[row], p[row + 1]);
             ++*cells;

@@ -198,6 +198,33 @@ def test_collision_response_exact_bitwise(terrain, oracle, method, prune):
     assert want_it.max() >= 3
 
 
+def test_response_loop_runs_on_the_device_and_survives_overflow(terrain, oracle, monkeypatch):
+    """The device-resident loop (no host read-back between iterations; live counts, next rays and lists stay on
+    the GPU) gives the synchronous loop's answer bit for bit -- bounded, unbounded (one look per 8 iterations), and
+    when a sweep overflows the optimistic candidate buffer mid-loop (the call is redone from a copy of the input)."""
+    tris, h, resps, _ = terrain
+    for max_iter in (0, 2, 5, 11):
+        w = oracle.collision_response_batch(resps, tris, max_iter=max_iter)
+        with xp.Scene(0, tris, timing=True) as s:
+            out, it, st, ln = s.collision_response_batch(resps, max_iter=max_iter)
+            stats = s.stats()
+        assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
+        assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"device loop max_iter={max_iter}")
+        assert_bits_equal(ln, w[3], "slide normal")
+        assert w[1].max() <= stats["iterations_run"] <= w[1].max() + 1
+    w = oracle.collision_response_batch(resps, tris, max_iter=4)
+    with xp.Scene(0, tris) as s:
+        s.set_options(max_pairs=4096)                      # every sweep overflows: the redo path
+        out, it, st, ln = s.collision_response_batch(resps, max_iter=4)
+    assert np.array_equal(it, w[1]) and np.array_equal(st, w[2])
+    assert_bits_equal(resp_fields(out), resp_fields(w[0]), "device loop, overflow redo")
+    monkeypatch.setenv("XP_RESPONSE_SYNC", "1")             # read once per process: only effective if set before the first call
+    with xp.Scene(0, tris) as s:
+        out2 = s.collision_response_batch(resps, max_iter=4)
+    monkeypatch.delenv("XP_RESPONSE_SYNC")
+    assert_bits_equal(resp_fields(out2[0]), resp_fields(w[0]), "loop (either form)")
+
+
 def test_response_status_bits(oracle):
     tri = np.array([[[-2, 2, -2], [-2, 2, 2], [2, 2, 0]]], np.float32)
     resps = xp.make_responses([[0, 4, 0], [0, 4, 0], [0.1, 3.2, 0.05], [0, 9, 0]],

@@ -260,12 +260,12 @@ def test_P_is_conservative(oracle):
     assert len(P) < 0.2 * len(resps) * len(tris)
 
 
-def _grid_pad(x0, z0, sp, nx, nz):
+def _grid_eps(x0, z0, sp, nx, nz):
     """xp_scene_set_heightmap's choice (xp_api.cu)"""
     big = max(abs(x0) + sp * nx, abs(z0) + sp * nz) + 2.0
     err = 32.0 * 1.1920929e-7 * big
-    assert err < 8.0 * sp
-    return 1 + int(err / sp + 0.75)
+    assert err < 0.25 * sp
+    return float(np.float32(err))
 
 
 @pytest.mark.parametrize("case", ["config2-like", "offset-fine", "coarse", "far-origin"])
@@ -278,7 +278,7 @@ def test_grid_walk_enumerates_exactly_predicate_P(oracle, case):
                                 "coarse": (9, 12, 100.0, -50.0, 7.5, 5), "far-origin": (24, 24, 4000.0, -3000.0, 1.0, 6)}[case]
     h = scenes.sine_terrain_heights(nx, nz, seed=seed)
     tris = scenes.heightmap_from_heights(h, x0=x0, z0=z0, spacing=sp)
-    pad = _grid_pad(x0, z0, sp, nx, nz)
+    eps = _grid_eps(x0, z0, sp, nx, nz)
     rng = np.random.default_rng(seed)
     n = 400
     resps = scenes.terrain_spheres(h, n, seed=seed + 10)
@@ -303,7 +303,7 @@ def test_grid_walk_enumerates_exactly_predicate_P(oracle, case):
     for horizon in (np.inf, 1.0):
         wi, wj = oracle.broadphase_pairs(resps, tris, horizon=horizon)
         for i in range(n):
-            cnt = E.emul_grid_walk(_p(hf), nx, nz, x0, z0, sp, pad, _p(resps[i:i + 1]), horizon, _p(out), cap, C.byref(cells))
+            cnt = E.emul_grid_walk(_p(hf), nx, nz, x0, z0, sp, eps, _p(resps[i:i + 1]), horizon, _p(out), cap, C.byref(cells))
             assert cnt <= cap
             got = np.sort(out[:cnt])
             want = np.sort(wj[wi == i])

@@ -93,8 +93,8 @@ void xp_scene_destroy(xp_scene *s) {
     for (auto &x : s->ex_slot) if (x.busy) cudaEventSynchronize(x.fin);
     DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_lo, &s->node_hi, &s->leaf_lo, &s->leaf_hi,
                       &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
-                      &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->degen, &s->grid_h, &s->grid_yrange, &s->recs_grid, &s->rays, &s->best, &s->active_a,
-                      &s->active_b, &s->inv_order, &s->pairs, &s->counters, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
+                      &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->degen, &s->grid_h, &s->grid_yrange, &s->grid_mm, &s->recs_grid, &s->rays, &s->best, &s->active_a,
+                      &s->active_b, &s->inv_order, &s->pairs, &s->counters, &s->rays2, &s->best2, &s->active_c, &s->io_backup, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
                       &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
     for (DevBuf *b : bufs) b->release();
     for (auto &a : s->async_slot) {
@@ -202,17 +202,18 @@ int xp_scene_set_heightmap(xp_scene *s, const float *heights, uint32_t nx, uint3
     XP_API_TRY(cudaMemcpyAsync(s->grid_h.p, heights, hbytes, cudaMemcpyHostToDevice, s->stream));
     XP_API_TRY(emit_heightmap(s, s->grid_h.as<float>(), nx, nz, x0, z0, spacing));
     XP_API_TRY(height_range(s, s->grid_h.as<float>(), hcount));
+    XP_API_TRY(height_windows(s, s->grid_h.as<float>(), nx, nz, 8));
     XP_API_TRY(cudaStreamSynchronize(s->stream));
     s->n_tris = n;
     // The grid walk (xp_gridwalk.cuh) needs a regular grid: finite origin, positive spacing, grid lines that really
-    // advance in fp32, and coordinates small enough that `pad` cells cover the rounding of an enumerated position
-    // (~32 ulp of the largest coordinate).  Anything else simply keeps the LBVH walk.
+    // advance in fp32, and coordinates small enough that the rounding of an enumerated position (~32 ulp of the
+    // largest coordinate, the slack `eps`) stays a fraction of a cell.  Anything else simply keeps the LBVH walk.
     const double xmax = fabs((double)x0) + (double)spacing * nx, zmax = fabs((double)z0) + (double)spacing * nz;
     const double big = (xmax > zmax ? xmax : zmax) + 2.0;
     const double err = 32.0 * 1.1920929e-7 * big;
-    if (spacing > 0.0f && spacing <= 3.0e38f && x0 == x0 && z0 == z0 && big < 1.0e30 && err < 8.0 * spacing) {
+    if (spacing > 0.0f && spacing <= 3.0e38f && x0 == x0 && z0 == z0 && big < 1.0e30 && err < 0.25 * spacing) {
         s->grid_nx = nx; s->grid_nz = nz; s->grid_x0 = x0; s->grid_z0 = z0; s->grid_sp = spacing;
-        s->grid_pad = 1 + (int)(err / spacing + 0.75);
+        s->grid_eps = (float)err;
         s->grid_valid = true;
     }
     return XP_OK;

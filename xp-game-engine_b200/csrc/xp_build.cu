@@ -640,7 +640,32 @@ __global__ void k_height_range_decode(unsigned *io) {
     if (threadIdx.x < 2) reinterpret_cast<float *>(io)[threadIdx.x] = dec_f(io[threadIdx.x]);
 }
 
+// mm[(ix, iz)] = (min, max) of h[ix .. ix+1][iz .. iz + W], the heights under the W cells (ix, iz .. iz+W-1): the grid
+// walk skips such a window when the ray misses the box of its height range
+__global__ void __launch_bounds__(256) k_height_windows(const float *__restrict__ h, unsigned nx, unsigned nz, int window,
+                                                        float2 *__restrict__ mm) {
+    const uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (q >= (uint64_t)nx * nz) return;
+    const unsigned ix = (unsigned)(q / nz), iz = (unsigned)(q % nz);
+    const uint64_t row = (uint64_t)nz + 1;
+    const unsigned last = min(iz + (unsigned)window, nz);
+    float mn = INFINITY, mx = -INFINITY;
+    for (unsigned j = iz; j <= last; ++j) {
+        const float a = __ldg(h + ix * row + j), b = __ldg(h + (ix + 1) * row + j);
+        mn = fminf(mn, fminf(a, b)); mx = fmaxf(mx, fmaxf(a, b));
+    }
+    mm[q] = make_float2(mn, mx);
+}
+
 #define XP_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
+
+cudaError_t height_windows(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz, int window) {
+    const uint64_t cells = (uint64_t)nx * nz;
+    XP_TRY(s->grid_mm.reserve(cells * sizeof(float2)));
+    k_height_windows<<<grid_for(cells, 256), 256, 0, s->stream>>>(d_heights, nx, nz, window, s->grid_mm.as<float2>());
+    ++s->stats.kernel_launches;
+    return cudaGetLastError();
+}
 
 cudaError_t height_range(xp_scene *s, const float *d_heights, uint64_t n) {
     XP_TRY(s->grid_yrange.reserve(2 * sizeof(float)));

@@ -79,6 +79,10 @@ struct DeviceCounters {           // one small block of device memory, zeroed pe
     unsigned int stack_overflow;
     unsigned int pair_overflow;     // a chunk produced more candidates than the pair buffer holds
     unsigned int irregular_rays;    // rays the height-grid walk left to the LBVH walk (non-finite centre / movement)
+    unsigned int active[2];         // response loop: live spheres of the current / next iteration (double-buffered)
+    unsigned int iters_done;        // response loop: iterations that had work
+    unsigned int pad0;
+    unsigned long long rays_swept;  // response loop: sum of the live counts over its iterations
 };
 
 }  // namespace xp
@@ -99,6 +103,7 @@ struct xp_scene {
     bool safe_pairs = false;           // two-stage methods: read the pair count back after every chunk
     bool pair_overflowed = false;      // optimistic mode dropped candidates: results must be recomputed
     bool counters_live = false;        // device counters hold uncollected statistics
+    const unsigned *na_dev = nullptr;  // response loop: device address of the live ray count (null: the host knows it)
     uint64_t swept_rays = 0;           // rays swept since the counters were zeroed
     double cand_per_ray = 0.0;         // candidates per sphere of the last exhaustive sweep (XP_OPT_PRUNE = 2)
     // geometry
@@ -121,7 +126,8 @@ struct xp_scene {
     int use_grid = 1;                                // XP_OPT_GRID_WALK
     unsigned grid_nx = 0, grid_nz = 0;
     float grid_x0 = 0, grid_z0 = 0, grid_sp = 0;
-    int grid_pad = 1;
+    float grid_eps = 0.0f;                           // slack on enumerated positions (~32 ulp of the largest coordinate)
+    xp::DevBuf grid_mm;                              // nx x nz (min, max) of the heights under windows of 8 cells along z
     xp::DevBuf grid_h;                               // (nx+1) x (nz+1) heights
     xp::DevBuf grid_yrange;                          // 2 floats: min / max height (2 ordered ints while being reduced)
     xp::DevBuf recs_grid;                            // TriRec[T] in UPLOAD order (cell-major): what the grid walk's pairs index
@@ -129,6 +135,7 @@ struct xp_scene {
     xp::WideTree wide_tree = {};
     // per-call workspaces
     xp::DevBuf rays, best, active_a, active_b, inv_order, pairs, counters;
+    xp::DevBuf rays2, best2, active_c, io_backup;       // response loop: next iteration's rays / keys / list, and the input kept for a redo
     xp::DevBuf sort_ka, sort_kb;   // sphere Morton keys (ping-pong)
     xp::DevBuf io_in, io_out, io_hit, io_tri, io_status, io_iter, io_normal, io_col;
     // stats

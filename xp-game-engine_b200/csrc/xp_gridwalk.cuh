@@ -10,9 +10,12 @@
 // The candidate set stays bit-exact: the DECISION for a triangle is the very slab test of predicate P (same
 // operations on the same box values k_pack would derive from the emitted vertices), evaluated axis by axis --
 // max / min are associative, so hoisting the x axis per column and the z axis per cell changes no value.  The
-// ENUMERATION only has to be a superset; its positions are padded by `pad` cells (set from the grid's coordinate
-// magnitude at upload) against rounding.  Compiles for the host too: tests/host_emul runs the same functions
-// against the oracle's P on the CPU.
+// ENUMERATION only has to be a superset; its positions are widened by `eps` (a distance set from the grid's
+// coordinate magnitude at upload, ~32 ulp of the largest coordinate) against rounding.  Runs of GW_WINDOW cells
+// are skipped wholesale when the ray misses the box of their height range (mm: sliding-window min / max, the
+// implicit "mip" level of this hierarchy) -- again predicate P's own slab test on an enclosing box, so nothing
+// that P accepts is ever skipped.  Compiles for the host too: tests/host_emul runs the same functions against
+// the oracle's P on the CPU.
 #pragma once
 
 #include "xp_narrowphase.cuh"
@@ -23,8 +26,10 @@ struct GridDesc {
     const float *h;            // (nx+1) x (nz+1) heights, x-major: h[ix * (nz+1) + iz]
     unsigned nx, nz;           // quads per axis
     float x0, z0, sp, inv_sp;  // vertex (ix, iz) = (x0 + sp*ix, h, z0 + sp*iz), as k_emit_heightmap forms it
-    int pad;                   // cells of slack on every enumerated range (>= 1)
+    float eps;                 // slack (a distance) on every enumerated position
+    const float *mm;           // nx x nz pairs (min, max) of the heights under cells (ix, iz .. iz + GW_WINDOW - 1): h[ix..ix+1][iz..iz+GW_WINDOW]
 };
+#define XP_GW_WINDOW 8
 
 // coordinate of grid line i exactly as the emitted triangles carry it (k_emit_heightmap)
 XP_HD float grid_coord(float org, float sp, int i) { return ExactOps::add(org, ExactOps::mul(sp, (float)i)); }
@@ -64,9 +69,10 @@ XP_HD bool grid_ray_setup(const GridDesc &g, float ymin, float ymax, V3 c, V3 m,
     if (!(tmin <= tmax)) return false;
     const float xa = c.x + tmin * m.x, xb = c.x + tmax * m.x;
     const float xlo = fminf(xa, xb), xhi = fmaxf(xa, xb);
-    // cell ix overlaps [xlo, xhi] iff X(ix+1) + R >= xlo and X(ix) - R <= xhi
-    r.ix = grid_floor_clamped((xlo - XP_INFLATE - g.x0) * g.inv_sp, -(1 << 28), (int)g.nx) - 1 - g.pad;
-    r.ix_hi = grid_floor_clamped((xhi + XP_INFLATE - g.x0) * g.inv_sp, -(1 << 28), (int)g.nx) + g.pad;
+    // cell ix overlaps [xlo, xhi] iff X(ix+1) + R >= xlo and X(ix) - R <= xhi, i.e. u - 1 <= ix <= v with
+    // u = (xlo - R - x0) / sp, v = (xhi + R - x0) / sp; floor(u - eps/sp) <= ceil(u - 1) for any eps > 0
+    r.ix = grid_floor_clamped((xlo - (XP_INFLATE + g.eps) - g.x0) * g.inv_sp, -(1 << 28), (int)g.nx);
+    r.ix_hi = grid_floor_clamped((xhi + (XP_INFLATE + g.eps) - g.x0) * g.inv_sp, -(1 << 28), (int)g.nx);
     if (r.ix < 0) r.ix = 0;
     if (r.ix_hi > (int)g.nx - 1) r.ix_hi = (int)g.nx - 1;
     return r.ix <= r.ix_hi;
@@ -90,11 +96,19 @@ XP_HD bool grid_col_setup(const GridDesc &g, const GridRay &r, int ix, GridCol &
     if (!(t0 <= t1)) return false;
     const float za = r.c.z + t0 * r.m.z, zb = r.c.z + t1 * r.m.z;
     const float zlo = fminf(za, zb), zhi = fmaxf(za, zb);
-    col.iz = grid_floor_clamped((zlo - XP_INFLATE - g.z0) * g.inv_sp, -(1 << 28), (int)g.nz) - 1 - g.pad;
-    col.iz_hi = grid_floor_clamped((zhi + XP_INFLATE - g.z0) * g.inv_sp, -(1 << 28), (int)g.nz) + g.pad;
+    col.iz = grid_floor_clamped((zlo - (XP_INFLATE + g.eps) - g.z0) * g.inv_sp, -(1 << 28), (int)g.nz);
+    col.iz_hi = grid_floor_clamped((zhi + (XP_INFLATE + g.eps) - g.z0) * g.inv_sp, -(1 << 28), (int)g.nz);
     if (col.iz < 0) col.iz = 0;
     if (col.iz_hi > (int)g.nz - 1) col.iz_hi = (int)g.nz - 1;
     return col.iz <= col.iz_hi;
+}
+
+// Can any triangle of cells (ix, iz .. iz + GW_WINDOW - 1) pass?  P's x and y axes on the box of the window's height
+// range (hmin, hmax from g.mm): every triangle box of the window lies inside it, and the slab test is monotone.
+XP_HD bool grid_window_test(const GridRay &r, const GridCol &col, float hmin, float hmax) {
+    float tmin = col.tx_lo, tmax = col.tx_hi;
+    grid_slab_axis(r.c.y, r.inv.y, ExactOps::sub(hmin, XP_INFLATE), ExactOps::add(hmax, XP_INFLATE), tmin, tmax);
+    return tmin <= tmax;
 }
 
 // Predicate P for the two triangles of cell (ix, iz): bit 0 = (p00, p01, p11), bit 1 = (p00, p11, p10).

@@ -23,6 +23,9 @@
 //   BRUTE      k_brute: the reference's literal all-pairs loop, one thread per triangle, rays
 //              staged in shared memory.
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <utility>
 
 #include "xp_internal.h"
 #include "xp_narrowphase.cuh"
@@ -43,29 +46,13 @@ __device__ __forceinline__ V3 f4_xyz(float4 q) { return {q.x, q.y, q.z}; }
 // ray setup: collision_detect.rs:161 (r == 1), :163 (normalised movement), :179-180 (|m|, |m|^2)
 // plus the slab reciprocals of predicate P
 // ------------------------------------------------------------------------------------------
+// The 64 B record of one sphere for one sweep (layout in xp_device.cuh).  valid: the r == 1 assert held.
 template <class O>
-__global__ void __launch_bounds__(256) k_ray_setup(const xp_response *__restrict__ cur,
-                                                   const uint32_t *__restrict__ active, uint64_t na,
-                                                   float horizon, RayRec *__restrict__ rays,
-                                                   unsigned long long *__restrict__ best,
-                                                   uint32_t *__restrict__ status, int have_tris) {
-    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (k >= na) return;
-    const uint64_t i = active ? active[k] : k;
-    const float *p = reinterpret_cast<const float *>(cur) + i * 7;
-    const V3 c = {p[0], p[1], p[2]};
-    const float r = p[3];
-    const V3 m = {p[4], p[5], p[6]};
-    uint32_t flags = RAY_VALID;
+__device__ __forceinline__ RayRec make_ray_rec(V3 c, V3 m, bool valid) {
+    uint32_t flags = valid ? RAY_VALID : 0u;
     {   // finite centre and movement: the height-grid walk can enumerate this ray's cells (anything else walks the LBVH)
         const float big = fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fabsf(c.z)), fmaxf(fmaxf(fabsf(m.x), fabsf(m.y)), fabsf(m.z)));
         if (big <= XP_FLT_MAX && c.x == c.x && c.y == c.y && c.z == c.z && m.x == m.x && m.y == m.y && m.z == m.z) flags |= RAY_GRID_OK;
-    }
-    if (!(r == 1.0f)) {
-        flags = 0;
-        // the assert sits inside sphere_triangle_detect_collision (collision_detect.rs:161), which the loop over an
-        // EMPTY triangle slice (lib.rs:33-35) never calls: no triangles, no panic
-        if (status && have_tris) status[i] |= XP_ST_RADIUS_NE_1;
     }
     const Ray ray = xp_ray_setup<O>(c, m);
     RayRec rr;
@@ -74,7 +61,31 @@ __global__ void __launch_bounds__(256) k_ray_setup(const xp_response *__restrict
     // q2.w: the per-ray operand of the narrowphase's one vertex-root division (+inf = irregular ray, literal path)
     rr.q2 = make_float4(ray.mh.x, ray.mh.y, ray.mh.z, xp_ray_r2a<O>(ray));
     rr.q3 = make_float4(fdiv(1.0f, m.x), fdiv(1.0f, m.y), fdiv(1.0f, m.z), __uint_as_float(flags));
-    rays[k] = rr;
+    return rr;
+}
+
+// n_active (nullable): the number of live entries, on the DEVICE -- the response loop runs without the host ever
+// learning how many spheres are still moving; launches are sized for the upper bound and clamp here.
+template <class O>
+__global__ void __launch_bounds__(256) k_ray_setup(const xp_response *__restrict__ cur,
+                                                   const uint32_t *__restrict__ active, uint64_t na,
+                                                   float horizon, RayRec *__restrict__ rays,
+                                                   unsigned long long *__restrict__ best,
+                                                   uint32_t *__restrict__ status, int have_tris,
+                                                   const unsigned *__restrict__ n_active) {
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (n_active && na > *n_active) na = *n_active;
+    if (k >= na) return;
+    const uint64_t i = active ? active[k] : k;
+    const float *p = reinterpret_cast<const float *>(cur) + i * 7;
+    const V3 c = {p[0], p[1], p[2]};
+    const float r = p[3];
+    const V3 m = {p[4], p[5], p[6]};
+    const bool valid = r == 1.0f;
+    // the assert sits inside sphere_triangle_detect_collision (collision_detect.rs:161), which the loop over an
+    // EMPTY triangle slice (lib.rs:33-35) never calls: no triangles, no panic
+    if (!valid && status && have_tris) status[i] |= XP_ST_RADIUS_NE_1;
+    rays[k] = make_ray_rec<O>(c, m, valid);
     best[k] = BEST_NONE;
 }
 
@@ -354,7 +365,8 @@ template <int MODE>
 __global__ void __launch_bounds__(BP_THREADS, BP_BLOCKS_PER_SM)
 k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
              float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap,
-             float d_lo, float d_hi, const unsigned long long *__restrict__ best, const uint32_t *__restrict__ leaf_to_tri) {
+             float d_lo, float d_hi, const unsigned long long *__restrict__ best, const uint32_t *__restrict__ leaf_to_tri,
+             const unsigned *__restrict__ n_active) {
     // MODE 3: the rays the height-grid walk could not take (non-finite centre / movement) -- usually none, and then
     // this launch ends at once; its pairs go into the same list and therefore name the triangle by UPLOAD index
     if (MODE == 3 && ctr->irregular_rays == 0u) return;
@@ -373,6 +385,11 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     float *rbest = rbest_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+    if (n_active) {                                      // the live ray count sits on the device (response loop)
+        const uint64_t live = *n_active;
+        if (ray_end > live) ray_end = live;
+        if (ray_base > ray_end) ray_base = ray_end;
+    }
     rays += ray_base;                                   // 32-bit ray indices relative to the chunk
     const unsigned n_rays = (unsigned)(ray_end - ray_base);
     const unsigned ray0 = (unsigned)ray_base;
@@ -578,18 +595,24 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
 #define XP_GW_BLOCKS 4
 #endif
 static constexpr int GW_CELLS = XP_GW_CELLS;
+static_assert(XP_GW_CELLS == XP_GW_WINDOW, "one outer iteration walks exactly the cells one height window covers");
 static constexpr int GW_QUEUE = 32 * 2 * GW_CELLS;
 
 __global__ void __launch_bounds__(BP_THREADS, XP_GW_BLOCKS)
 k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayRec *__restrict__ rays, uint64_t ray_base,
                   uint64_t ray_end, float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out,
-                  uint64_t pair_cap) {
+                  uint64_t pair_cap, const unsigned *__restrict__ n_active) {
     __shared__ uint2 queue[BP_WARPS][GW_QUEUE];
     __shared__ float4 rpool_all[BP_WARPS][96];          // the warp's current run of rays: (c,|m|)[32], (m,|m|^2)[32], (1/m,flags)[32]
     uint2 *q = queue[threadIdx.x >> 5];
     float4 *rpool = rpool_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+    if (n_active) {
+        const uint64_t live = *n_active;
+        if (ray_end > live) ray_end = live;
+        if (ray_base > ray_end) ray_base = ray_end;
+    }
     rays += ray_base;
     const unsigned n_rays = (unsigned)(ray_end - ray_base);
     const unsigned ray0 = (unsigned)ray_base;
@@ -645,18 +668,29 @@ k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayR
             }
         }
         // ---- lanes whose column is exhausted move to their next column that can hold a candidate
+        // ... and past the windows of GW_WINDOW cells whose height range the ray misses (the cull of this implicit
+        // hierarchy: one 8 B read decides 16 triangles)
+        bool ready = false;                    // the window at col.iz has been tested and may hold candidates
 #pragma unroll 1
-        for (int tries = 0; tries < 3; ++tries) {
-            const bool need = col.iz > col.iz_hi && r.ix <= r.ix_hi;
+        for (int tries = 0; tries < 4; ++tries) {
+            const bool need = !ready && (col.iz <= col.iz_hi || r.ix <= r.ix_hi);
             if (!__any_sync(FULL, need)) break;
             if (need) {
-                cur_ix = r.ix++;
-                if (grid_col_setup(g, r, cur_ix, col)) {
-                    const float *p = g.h + (size_t)cur_ix * row + col.iz;
-                    h00 = __ldg(p); h10 = __ldg(p + row);
-                    z_lo = grid_coord(g.z0, g.sp, col.iz);
+                if (col.iz > col.iz_hi) {
+                    cur_ix = r.ix++;
+                    grid_col_setup(g, r, cur_ix, col);
+                }
+                if (col.iz <= col.iz_hi) {
+                    const float2 w = __ldg(reinterpret_cast<const float2 *>(g.mm) + (size_t)cur_ix * g.nz + col.iz);
+                    if (grid_window_test(r, col, w.x, w.y)) ready = true;
+                    else col.iz += XP_GW_WINDOW;
                 }
             }
+        }
+        if (ready) {
+            const float *p = g.h + (size_t)cur_ix * row + col.iz;
+            h00 = __ldg(p); h10 = __ldg(p + row);
+            z_lo = grid_coord(g.z0, g.sp, col.iz);
         }
         // ---- up to GW_CELLS cells of the column, two triangles each
         unsigned mask = 0;
@@ -665,7 +699,7 @@ k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayR
             const float *p = g.h + (size_t)cur_ix * row + col.iz + 1;
 #pragma unroll
             for (int k = 0; k < GW_CELLS; ++k) {
-                if (col.iz <= col.iz_hi) {
+                if (ready && col.iz <= col.iz_hi) {
                     const float h01 = __ldg(p + k), h11 = __ldg(p + row + k);
                     const float z_hi = grid_coord(g.z0, g.sp, col.iz + 1);
                     mask |= grid_cell_test(r, col, z_lo, z_hi, h00, h01, h10, h11) << (2 * k);
@@ -1293,8 +1327,71 @@ __global__ void __launch_bounds__(256) k_respond(const RayRec *__restrict__ rays
     }
 }
 
-__global__ void k_mark_cap(const uint32_t *__restrict__ active, uint64_t na, uint32_t *__restrict__ status) {
+// The same step for the device-resident loop: the live count comes from the device (n_active), the sphere that
+// iterates again gets its NEXT ray record written right here (the ray setup of the following sweep is fused into the
+// response), and the next live count is accumulated where the next iteration's kernels will read it -- the host never
+// learns how many spheres are still moving.
+template <class O>
+__global__ void __launch_bounds__(256) k_respond_setup(const RayRec *__restrict__ rays,
+                                                       const unsigned long long *__restrict__ best,
+                                                       const uint32_t *__restrict__ active, uint64_t na,
+                                                       const unsigned *__restrict__ n_active,
+                                                       xp_response *__restrict__ cur, uint32_t *__restrict__ iterations,
+                                                       uint32_t *__restrict__ status, xp_vec3 *__restrict__ normal,
+                                                       uint32_t *__restrict__ next_active, RayRec *__restrict__ next_rays,
+                                                       unsigned long long *__restrict__ next_best,
+                                                       DeviceCounters *__restrict__ ctr, unsigned *__restrict__ next_count,
+                                                       unsigned iter_no) {
+    // candidates were dropped somewhere in this call: best[] is incomplete, apply nothing.  The next live count stays
+    // zero, so the iterations already queued behind this one are empty; the host redoes the call from its input.
+    if (ctr->pair_overflow) return;
+    if (n_active && na > *n_active) na = *n_active;
     const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (k == 0 && na > 0) { ctr->iters_done = iter_no + 1u; ctr->rays_swept += na; }
+    bool again = false;
+    uint32_t i = 0;
+    V3 nc = {0, 0, 0}, nm = {0, 0, 0};
+    if (k < na) {
+        i = active ? active[k] : (uint32_t)k;
+        const unsigned long long b = best[k];
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
+        const float4 q3 = rp[3];
+        if (b != BEST_NONE && (__float_as_uint(q3.w) & RAY_VALID)) {          // Some(closest) lib.rs:44
+            const Ray ray = ray_from(rp[0], rp[1], rp[2]);
+            const Contact ct = xp_make_collision<O>(ray, __uint_as_float((unsigned)(b >> 32)));
+            V3 sn;
+            const bool ok = xp_respond<O>(ray.c, ray.m, ct.position, ct.intersection, nc, nm, sn);
+            if (normal) { normal[i].x = sn.x; normal[i].y = sn.y; normal[i].z = sn.z; }
+            if (!ok) {
+                if (status) status[i] |= XP_ST_ASSERT_NEG_DISTANCE;           // collision_response.rs:22
+            } else {
+                float *o = reinterpret_cast<float *>(cur) + (uint64_t)i * 7;
+                o[0] = nc.x; o[1] = nc.y; o[2] = nc.z; o[3] = 1.0f;           // collision_response.rs:29-32
+                o[4] = nm.x; o[5] = nm.y; o[6] = nm.z;
+                if (iterations) iterations[i] += 1;                           // lib.rs:45
+                again = !(len<O>(nm) < 0.001f);                               // lib.rs:55, collision.rs:3
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(FULL, again);
+    if (m) {
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(next_count, (unsigned)__popc(m));
+        base = __shfl_sync(FULL, base, __ffs(m) - 1);
+        if (again) {
+            const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+            next_active[pos] = i;
+            next_rays[pos] = make_ray_rec<O>(nc, nm, true);                   // r = 1.0 by construction
+            next_best[pos] = BEST_NONE;
+        }
+    }
+}
+
+__global__ void k_mark_cap(const uint32_t *__restrict__ active, uint64_t na, uint32_t *__restrict__ status,
+                           const unsigned *__restrict__ n_active) {
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (n_active && na > *n_active) na = *n_active;
     if (k < na && status) status[active ? active[k] : k] |= XP_ST_ITER_CAP;
 }
 
@@ -1330,7 +1427,8 @@ static GridDesc grid_desc(const xp_scene *s) {
     g.h = s->grid_h.as<float>();
     g.nx = s->grid_nx; g.nz = s->grid_nz;
     g.x0 = s->grid_x0; g.z0 = s->grid_z0; g.sp = s->grid_sp; g.inv_sp = 1.0f / s->grid_sp;
-    g.pad = s->grid_pad;
+    g.eps = s->grid_eps;
+    g.mm = s->grid_mm.as<float>();
     return g;
 }
 // stage 1 of a heightmap scene: the grid walk, then the LBVH walk for whatever rays it could not take (normally none:
@@ -1341,15 +1439,20 @@ static cudaError_t launch_grid_broadphase(xp_scene *s, uint64_t pos, uint64_t en
     const uint64_t want = (end - pos + BP_THREADS - 1) / BP_THREADS, full = (uint64_t)s->n_sm * XP_GW_BLOCKS;
     const unsigned grid = (unsigned)(want < full ? (want ? want : 1) : full);
     k_broadphase_grid<<<grid, BP_THREADS, 0, st>>>(grid_desc(s), s->grid_yrange.as<float>(), s->rays.as<RayRec>(), pos, end,
-                                                  s->cur_horizon, ctr, pairs, cap);
+                                                  s->cur_horizon, ctr, pairs, cap, s->na_dev);
     XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
     k_broadphase<3><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end, s->cur_horizon,
-                                                               ctr, pairs, cap, 0.0f, INFINITY, nullptr, s->vals_a.as<uint32_t>());
+                                                               ctr, pairs, cap, 0.0f, INFINITY, nullptr, s->vals_a.as<uint32_t>(), s->na_dev);
     s->stats.kernel_launches += 2;
     return cudaGetLastError();
 }
 static float horizon_of(uint32_t mode) { return mode == XP_HORIZON_UNIT ? 1.0f : 3.402823466e+38f; }
 
+static void reset_call_stats(xp_scene *s) {
+    const uint32_t launches = s->stats.kernel_launches;
+    memset(&s->stats, 0, sizeof s->stats);
+    s->stats.kernel_launches = launches;
+}
 static cudaError_t zero_counters(xp_scene *s) {
     s->swept_rays = 0;
     XP_TRY(s->counters.reserve(sizeof(DeviceCounters)));
@@ -1367,7 +1470,7 @@ static cudaError_t ray_setup_t(xp_scene *s, const xp_response *cur, const uint32
     StageTimer t(s, XP_STAGE_RAY_SETUP);
     s->cur_horizon = horizon;
     k_ray_setup<O><<<grid_for(na, 256), 256, 0, s->stream>>>(cur, active, na, horizon, s->rays.as<RayRec>(),
-                                                            s->best.as<unsigned long long>(), status, s->n_tris > 0);
+                                                            s->best.as<unsigned long long>(), status, s->n_tris > 0, s->na_dev);
     ++s->stats.kernel_launches;
     return cudaGetLastError();
 }
@@ -1380,8 +1483,9 @@ __global__ void __launch_bounds__(256) k_sweep_degenerate(const TriRec *__restri
                                                           const uint32_t *__restrict__ list, uint32_t n_list,
                                                           const RayRec *__restrict__ rays, uint64_t na,
                                                           unsigned long long *__restrict__ best,
-                                                          DeviceCounters *__restrict__ ctr) {
+                                                          DeviceCounters *__restrict__ ctr, const unsigned *__restrict__ n_active) {
     const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (n_active && na > *n_active) na = *n_active;
     if (k == 0) atomicAdd(&ctr->tests, (unsigned long long)na * n_list);
     if (k >= na) return;
     const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
@@ -1417,7 +1521,7 @@ static cudaError_t closest_t(xp_scene *s, uint64_t na) {
     k_sweep_degenerate<O><<<grid_for(na, 256), 256, 0, s->stream>>>(s->recs.as<TriRec>(), s->degen.as<uint32_t>(),
                                                                   (uint32_t)s->n_degen, s->rays.as<RayRec>(), na,
                                                                   s->best.as<unsigned long long>(),
-                                                                  s->counters.as<DeviceCounters>());
+                                                                  s->counters.as<DeviceCounters>(), s->na_dev);
     ++s->stats.kernel_launches;
     return cudaGetLastError();
 }
@@ -1501,14 +1605,14 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
                 XP_TRY(launch_grid_broadphase(s, pos, end, pairs, cap));
             else if (far)
                 k_broadphase<2><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                           XP_FAR_D0, INFINITY, best, nullptr);
+                                                                           XP_FAR_D0, INFINITY, best, nullptr, s->na_dev);
             else
                 if (windows)
                     k_broadphase<1><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                                  d_lo, d_hi, best, nullptr);
+                                                                                  d_lo, d_hi, best, nullptr, s->na_dev);
                 else
                     k_broadphase<0><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                               0.0f, INFINITY, nullptr, nullptr);
+                                                                               0.0f, INFINITY, nullptr, nullptr, s->na_dev);
             if (!grid) ++s->stats.kernel_launches;
         }
         {
@@ -1567,6 +1671,8 @@ static cudaError_t collect_counters(xp_scene *s) {
     s->stats.broadphase_pairs += h.pairs_total;
     s->stats.node_visits += h.node_visits;
     if (h.pair_overflow) s->pair_overflowed = true;
+    if (h.iters_done > s->stats.iterations_run) s->stats.iterations_run = h.iters_done;
+    s->swept_rays += h.rays_swept;
     // XP_OPT_PRUNE = 2 (auto): remember how many candidates a sphere had in the exhaustive sweep
     if (s->swept_rays && h.pairs_total && !(s->prune == 2 && s->cand_per_ray > 96.0))
         s->cand_per_ray = (double)h.pairs_total / (double)s->swept_rays;
@@ -1653,6 +1759,63 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
     return collect_counters(s);
 }
 
+// collision_response (lib.rs:29-62) for one chunk of spheres WITHOUT a host round trip per iteration: every kernel of
+// an iteration takes the live count from the device, launches are sized for the upper bound m, the sphere order of
+// the first sweep (Morton order of the start positions) is kept -- centres move one unit per iteration -- and the
+// response kernel writes the next iteration's ray records itself.  With a bounded max_iter <= 8 the host queues
+// everything and returns; an unbounded loop looks at the live count once per 8 iterations.
+static cudaError_t response_chunk_device(xp_scene *s, xp_response *cur, uint64_t m, uint32_t cap_iter, float horizon,
+                                         uint32_t *iter, uint32_t *status, xp_vec3 *normal, bool *overflowed) {
+    cudaStream_t st = s->stream;
+    DeviceCounters *ctr = s->counters.as<DeviceCounters>();
+    XP_TRY(s->rays.reserve(m * sizeof(RayRec)));  XP_TRY(s->rays2.reserve(m * sizeof(RayRec)));
+    XP_TRY(s->best.reserve(m * 8));               XP_TRY(s->best2.reserve(m * 8));
+    XP_TRY(s->active_a.reserve(m * 4)); XP_TRY(s->active_b.reserve(m * 4)); XP_TRY(s->active_c.reserve(m * 4));
+    uint32_t *order = nullptr;
+    if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, cur, m, &order, nullptr));
+    const uint32_t *list = order;                                   // null = identity
+    uint32_t *spare[2] = {(order == s->active_b.as<uint32_t>()) ? s->active_a.as<uint32_t>() : s->active_b.as<uint32_t>(),
+                          s->active_c.as<uint32_t>()};
+    struct Guard { xp_scene *s; ~Guard() { s->na_dev = nullptr; } } guard{s};
+    s->na_dev = nullptr;
+    XP_TRY(ray_setup(s, cur, list, m, horizon, status));
+    uint32_t it = 0;
+    bool live = true;
+    while (live && it < cap_iter) {
+        for (int b = 0; b < 8 && it < cap_iter; ++b, ++it) {
+            s->na_dev = it == 0 ? nullptr : &ctr->active[it & 1u];
+            XP_TRY(closest(s, m));
+            unsigned *next_count = &ctr->active[(it + 1u) & 1u];
+            XP_TRY(cudaMemsetAsync(next_count, 0, sizeof(unsigned), st));
+            uint32_t *next = spare[it & 1u];
+            {
+                StageTimer t(s, XP_STAGE_RESPONSE);
+                if (arith_fast(s))
+                    k_respond_setup<FastOps><<<grid_for(m, 256), 256, 0, st>>>(s->rays.as<RayRec>(), s->best.as<unsigned long long>(), list, m, s->na_dev, cur, iter, status,
+                                                                              normal, next, s->rays2.as<RayRec>(), s->best2.as<unsigned long long>(), ctr, next_count, it);
+                else
+                    k_respond_setup<ExactOps><<<grid_for(m, 256), 256, 0, st>>>(s->rays.as<RayRec>(), s->best.as<unsigned long long>(), list, m, s->na_dev, cur, iter, status,
+                                                                               normal, next, s->rays2.as<RayRec>(), s->best2.as<unsigned long long>(), ctr, next_count, it);
+                ++s->stats.kernel_launches;
+            }
+            std::swap(s->rays, s->rays2);
+            std::swap(s->best, s->best2);
+            list = next;
+        }
+        if (it >= cap_iter) break;
+        DeviceCounters h;                                           // unbounded loop: one look per 8 iterations
+        XP_TRY(fetch_counters(s, &h));
+        if (h.pair_overflow) { *overflowed = true; return cudaSuccess; }
+        live = h.active[it & 1u] != 0u;
+    }
+    if (live && it >= cap_iter) {                                   // whoever is still moving hit the cap
+        s->na_dev = &ctr->active[it & 1u];
+        k_mark_cap<<<grid_for(m, 256), 256, 0, st>>>(list, m, status, s->na_dev);
+        ++s->stats.kernel_launches;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t max_iter,
                          uint32_t horizon_mode, xp_response *d_out, uint32_t *d_iter,
                          uint32_t *d_status, xp_vec3 *d_normal) {
@@ -1671,6 +1834,33 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
     if (d_normal) XP_TRY(cudaMemsetAsync(d_normal, 0, n * sizeof(xp_vec3), st));
     const uint32_t cap_iter = max_iter ? max_iter : HARD_ITER_CAP;
     const float horizon = horizon_of(horizon_mode);
+    // The device-resident loop (default for the two-stage LBVH / grid sweep).  Its candidate buffer is optimistic: if a
+    // sweep overflowed it, nothing after that point was applied and the whole call is redone from a copy of the input
+    // with the synchronous loop below (chunk-halving pair mode).
+    static const bool force_sync = getenv("XP_RESPONSE_SYNC") != nullptr;
+    if (s->method == XP_METHOD_LBVH_PAIRS && !s->safe_pairs && !force_sync) {
+        XP_TRY(s->io_backup.reserve(n * sizeof(xp_response)));
+        XP_TRY(cudaMemcpyAsync(s->io_backup.p, d_out, n * sizeof(xp_response), cudaMemcpyDeviceToDevice, st));
+        bool overflowed = false;
+        for (uint64_t off = 0; off < n && !overflowed; off += SPHERE_CHUNK) {
+            const uint64_t m = (n - off < SPHERE_CHUNK) ? n - off : SPHERE_CHUNK;
+            XP_TRY(response_chunk_device(s, d_out + off, m, cap_iter, horizon, d_iter ? d_iter + off : nullptr,
+                                         d_status ? d_status + off : nullptr, d_normal ? d_normal + off : nullptr, &overflowed));
+        }
+        if (!overflowed) {
+            const cudaError_t e = collect_counters(s);
+            if (e != cudaSuccess || !s->pair_overflowed) return e;
+        }
+        // rare: start over, synchronously
+        s->pair_overflowed = false;
+        force_safe = true;
+        reset_call_stats(s);
+        XP_TRY(zero_counters(s));
+        XP_TRY(cudaMemcpyAsync(d_out, s->io_backup.p, n * sizeof(xp_response), cudaMemcpyDeviceToDevice, st));
+        if (d_iter) XP_TRY(cudaMemsetAsync(d_iter, 0, n * 4, st));
+        if (d_status) XP_TRY(cudaMemsetAsync(d_status, 0, n * 4, st));
+        if (d_normal) XP_TRY(cudaMemsetAsync(d_normal, 0, n * sizeof(xp_vec3), st));
+    }
     for (uint64_t off = 0; off < n; off += SPHERE_CHUNK) {
         const uint64_t m = (n - off < SPHERE_CHUNK) ? n - off : SPHERE_CHUNK;
         xp_response *cur = d_out + off;
@@ -1690,7 +1880,7 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
         uint32_t it = 0;
         while (na > 0) {
             if (it >= cap_iter) {
-                k_mark_cap<<<grid_for(na, 256), 256, 0, st>>>(active, na, status);
+                k_mark_cap<<<grid_for(na, 256), 256, 0, st>>>(active, na, status, nullptr);
                 ++s->stats.kernel_launches;
                 break;
             }
@@ -1763,7 +1953,7 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
             --s->stats.kernel_launches;
         } else if (s->method != XP_METHOD_WIDE_FUSED && s->method != XP_METHOD_WIDE_PAIRS)
             k_broadphase<0><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
-                                                                  s->cur_horizon, ctr, pairs, buf_cap, 0.0f, INFINITY, nullptr, nullptr);
+                                                                  s->cur_horizon, ctr, pairs, buf_cap, 0.0f, INFINITY, nullptr, nullptr, nullptr);
         else
             k_sweep<ExactOps, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(
                 s->wide_tree, s->recs.as<TriRec>(), s->rays.as<RayRec>(), pos, end, s->cur_horizon,
