@@ -189,6 +189,21 @@ int  xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint
                             int *ticket);
 int  xp_detect_batch_wait(xp_scene *s, int ticket);
 
+/* ---- compact results: 8 B per sphere over the host link instead of 41 B ----
+ * All four fields of the reference's Collision are functions of (c, m, t) alone (collision_detect.rs:188-194:
+ * position = c + m*t, distance_to = |m|*t, intersection = position + m/|m|*r), so a caller that keeps its own
+ * Responses only needs t and the triangle: out[i] = { time_to, tri_index } with tri_index = 0xFFFFFFFF for "no
+ * collision" (time_to is then 0).  cpp/xp_physics.hpp (xp::collision_from_hit) and xp_physics_cuda.api
+ * (collision_from_hit) rebuild the full Collision from it, bit for bit.  status (nullable) as in xp_detect_batch.
+ * The _submit form shares tickets, slots and xp_detect_batch_wait with xp_detect_batch_submit. */
+typedef struct { float time_to; uint32_t tri_index; } xp_hit;
+int  xp_detect_batch_compact(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                             xp_hit *out, uint32_t *status);
+int  xp_detect_batch_compact_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                                 xp_hit *d_out, uint32_t *d_status);
+int  xp_detect_batch_compact_submit(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                                    xp_hit *out, uint32_t *status, int *ticket);
+
 /* ---- a16: collision_response (lib.rs:29-62) for a batch of independent spheres.
  * max_iter == 0: unbounded like the reference (an internal guard of 65536 iterations sets
  * XP_ST_ITER_CAP).  out[i] = the Response the reference returns; where a panic site is hit

@@ -17,7 +17,7 @@ def build_example(tmp_path):
         pytest.skip("no g++")
     _lib.lib()                                   # raises if the product library has not been built
     exe = str(tmp_path / "xp_example")
-    r = subprocess.run([cxx, "-std=c++17", "-Wall", "-Werror", "-O1", os.path.join(CPP, "example.cpp"), "-L" + _lib.CSRC,
+    r = subprocess.run([cxx, "-std=c++17", "-Wall", "-Werror", "-O1", "-ffp-contract=off", os.path.join(CPP, "example.cpp"), "-L" + _lib.CSRC,
                         "-lxp_physics_cuda", "-Wl,-rpath," + _lib.CSRC, "-o", exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe

@@ -169,6 +169,28 @@ def test_pair_buffer_overflow_is_recovered(terrain):
             assert it.max() == 2
 
 
+def test_compact_results_rebuild_the_full_collision(terrain, oracle):
+    """xp_detect_batch_compact (8 B per sphere: time_to, tri_index) + collision_from_hit == xp_detect_batch, bit for bit;
+    the asynchronous compact form shares tickets with the full one."""
+    import torch
+    tris, h, resps, want = terrain
+    with xp.Scene(0, tris) as s:
+        full = s.detect_batch(resps)
+        hits, st = s.detect_batch_compact(resps)
+        n = len(resps)
+        h_in = torch.from_numpy(resps.view(np.float32).reshape(n, 7).copy()).pin_memory()
+        h_out = [torch.zeros((n, 2), dtype=torch.int32).pin_memory() for _ in range(2)]
+        t0 = s.detect_batch_compact_submit(h_in.data_ptr(), n, h_out[0].data_ptr())
+        t1 = s.detect_batch_compact_submit(h_in.data_ptr(), n, h_out[1].data_ptr())
+        s.detect_batch_wait(t0); s.detect_batch_wait(t1)
+    col, hit = xp.collision_from_hit(resps, hits)
+    check_detect_exact((col, hit, hits["tri_index"], st), want, "compact + collision_from_hit")
+    check_detect_exact((col, hit, hits["tri_index"], st), full, "compact vs full records")
+    assert (hits["time_to"][hit == 0] == 0).all()
+    for o in h_out:
+        assert np.array_equal(o.numpy().view(np.uint32), hits.view(np.uint32).reshape(n, 2))
+
+
 def test_host_pipeline_chunks(terrain, monkeypatch):
     """the host-pointer sweep cut into H2D / compute / D2H pipeline chunks gives the same answer as one piece"""
     tris, h, resps, want = terrain

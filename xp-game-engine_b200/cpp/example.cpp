@@ -61,6 +61,14 @@ int main() {
             if (a.hit[i] && std::memcmp(&b->collision[i], &a.collision[i], sizeof(Collision)) != 0) return fail("async collision differs");
         }
 
+    // compact results (8 B per sphere) + collision_from_hit rebuild the full records bit for bit
+    auto compact = scene.detect_batch_compact(spheres);
+    for (size_t i = 0; i < spheres.size(); ++i) {
+        auto c = collision_from_hit(spheres[i], compact[i]);
+        if (c.has_value() != (a.hit[i] != 0) || compact[i].tri_index != a.tri_index[i]) return fail("compact hit / triangle differs");
+        if (c && std::memcmp(&*c, &a.collision[i], sizeof(Collision)) != 0) return fail("collision_from_hit differs from the device's record");
+    }
+
     // the response loop agrees with the single-sphere reference-shaped call
     auto res = scene.collision_response_batch(spheres, 3);
     for (size_t i = 0; i < 8; ++i) {

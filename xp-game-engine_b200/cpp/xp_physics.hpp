@@ -7,6 +7,7 @@
 // per-sphere status instead.  All arithmetic happens on the GPU in libxp_physics_cuda.so.
 #pragma once
 
+#include <cmath>
 #include <cstdint>
 #include <optional>
 #include <stdexcept>
@@ -70,6 +71,20 @@ class Scene {
         return ticket;
     }
     void detect_batch_wait(int ticket) { check(xp_detect_batch_wait(s_, ticket), "xp_detect_batch_wait"); }
+    // the same sweep with compact results: 8 B (time_to, tri_index) per sphere cross the host link instead of 41 B;
+    // collision_from_hit() below rebuilds the reference's Collision where a caller wants it
+    std::vector<xp_hit> detect_batch_compact(const std::vector<Response> &in, uint32_t horizon = XP_HORIZON_INF) {
+        std::vector<xp_hit> out(in.size());
+        check(xp_detect_batch_compact(s_, reinterpret_cast<const xp_response *>(in.data()), in.size(), horizon, out.data(), nullptr),
+              "xp_detect_batch_compact");
+        return out;
+    }
+    int detect_batch_compact_submit(const Response *in, size_t n, xp_hit *out, uint32_t horizon = XP_HORIZON_INF) {
+        int ticket = -1;
+        check(xp_detect_batch_compact_submit(s_, reinterpret_cast<const xp_response *>(in), n, horizon, out, nullptr, &ticket),
+              "xp_detect_batch_compact_submit");
+        return ticket;
+    }
 
     struct Resolved { std::vector<Response> response; std::vector<uint32_t> iterations, status; std::vector<Vec3> slide_normal; };
     Resolved collision_response_batch(const std::vector<Response> &in, uint32_t max_iter = 0,
@@ -86,6 +101,26 @@ class Scene {
   private:
     xp_scene *s_ = nullptr;
 };
+
+// The reference's Collision from the compact result (collision_detect.rs:188-194 / :203-209): every field is a function
+// of (c, m, t).  Same operations in the same order as the device (and the reference): compile the including
+// translation unit without floating-point contraction (-ffp-contract=off) and the fields are bit-identical to what
+// xp_detect_batch returns.  nullopt = no collision.
+inline std::optional<Collision> collision_from_hit(const Response &r, const xp_hit &h) {
+    if (h.tri_index == 0xFFFFFFFFu) return std::nullopt;
+    const Vec3 &c = r.sphere.c, &m = r.movement;
+    const float t = h.time_to;
+    const float ml = std::sqrt((m.x * m.x + m.y * m.y) + m.z * m.z);          // nalgebra's 3-vector dot order
+    Collision k;
+    k.time_to = t;
+    k.distance_to = ml * t;
+    const float px = m.x * t, py = m.y * t, pz = m.z * t;
+    k.position = Vec3{c.x + px, c.y + py, c.z + pz};
+    const float nx = m.x / ml, ny = m.y / ml, nz = m.z / ml;
+    const float ix = nx * r.sphere.r, iy = ny * r.sphere.r, iz = nz * r.sphere.r;
+    k.intersection = Vec3{k.position.x + ix, k.position.y + iy, k.position.z + iz};
+    return k;
+}
 
 inline void raise_status(uint32_t st) {
     if (st & XP_ST_RADIUS_NE_1) throw std::logic_error("assertion failed: sphere.r == 1.0 (collision_detect.rs:161)");

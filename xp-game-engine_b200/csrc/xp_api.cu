@@ -98,7 +98,7 @@ void xp_scene_destroy(xp_scene *s) {
                       &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
     for (DevBuf *b : bufs) b->release();
     for (auto &a : s->async_slot) {
-        DevBuf *ab[] = {&a.in, &a.col, &a.hit, &a.tri, &a.status};
+        DevBuf *ab[] = {&a.in, &a.col, &a.hit, &a.tri, &a.status, &a.compact};
         for (DevBuf *b : ab) b->release();
         if (a.h2d) cudaEventDestroy(a.h2d);
         if (a.done) cudaEventDestroy(a.done);
@@ -499,8 +499,8 @@ static int ensure_async(xp_scene *s) {
     return XP_OK;
 }
 
-int xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
-                           xp_collision *out, uint8_t *hit, uint32_t *tri_index, uint32_t *status, int *ticket) {
+static int submit_impl(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode, xp_collision *out,
+                       uint8_t *hit, uint32_t *tri_index, uint32_t *status, xp_hit *compact, int *ticket) {
     int rc = check_query(s, in, n);
     if (rc) return rc;
     if (!ticket) return XP_EINVAL;
@@ -513,22 +513,24 @@ int xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint3
     if (slot < 0) return XP_ESTATE;                  // every slot is in flight: wait for a ticket first
     xp_scene::AsyncSlot &a = s->async_slot[slot];
     a.h_in = in; a.n = n; a.horizon_mode = horizon_mode;
-    a.out = out; a.hit_out = hit; a.tri_out = tri_index; a.status_out = status;
+    a.out = out; a.hit_out = hit; a.tri_out = tri_index; a.status_out = status; a.compact_out = compact;
     a.launches = 0;
     *ticket = slot;
     if (n == 0) { memset(a.h_ctr, 0, sizeof(DeviceCounters)); a.busy = true; return XP_OK; }
     cudaStream_t st = s->stream;
     XP_API_TRY(a.in.reserve(n * sizeof(xp_response)));
-    XP_API_TRY(a.col.reserve(n * sizeof(xp_collision)));
-    XP_API_TRY(a.hit.reserve(n));
-    XP_API_TRY(a.tri.reserve(n * 4));
+    if (out) XP_API_TRY(a.col.reserve(n * sizeof(xp_collision)));
+    if (hit) XP_API_TRY(a.hit.reserve(n));
+    if (tri_index) XP_API_TRY(a.tri.reserve(n * 4));
+    if (compact) XP_API_TRY(a.compact.reserve(n * sizeof(xp_hit)));
     XP_API_TRY(a.status.reserve(n * 4));
     XP_API_TRY(cudaMemcpyAsync(a.in.p, in, n * sizeof(xp_response), cudaMemcpyHostToDevice, s->copy_in));
     XP_API_TRY(cudaEventRecord(a.h2d, s->copy_in));
     XP_API_TRY(cudaStreamWaitEvent(st, a.h2d, 0));
     if (out) XP_API_TRY(cudaMemsetAsync(a.col.p, 0, n * sizeof(xp_collision), st));
-    QueryOut q = {out ? a.col.as<xp_collision>() : nullptr, a.hit.as<uint8_t>(), tri_index ? a.tri.as<uint32_t>() : nullptr,
+    QueryOut q = {out ? a.col.as<xp_collision>() : nullptr, hit ? a.hit.as<uint8_t>() : nullptr, tri_index ? a.tri.as<uint32_t>() : nullptr,
                   a.status.as<uint32_t>(), nullptr, {}, 0};
+    q.compact = compact ? a.compact.as<xp_hit>() : nullptr;
     const int timing = s->timing;
     s->timing = 0;                                   // stage events are resolved by synchronous calls only
     s->counters_live = false;                        // this batch gets freshly zeroed counters
@@ -546,8 +548,56 @@ int xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint3
     if (hit) XP_API_TRY(cudaMemcpyAsync(hit, a.hit.p, n, cudaMemcpyDeviceToHost, so));
     if (tri_index) XP_API_TRY(cudaMemcpyAsync(tri_index, a.tri.p, n * 4, cudaMemcpyDeviceToHost, so));
     if (status) XP_API_TRY(cudaMemcpyAsync(status, a.status.p, n * 4, cudaMemcpyDeviceToHost, so));
+    if (compact) XP_API_TRY(cudaMemcpyAsync(compact, a.compact.p, n * sizeof(xp_hit), cudaMemcpyDeviceToHost, so));
     XP_API_TRY(cudaEventRecord(a.d2h, so));
     a.busy = true;                                   // only now: an error return above leaves the slot free
+    return XP_OK;
+}
+
+int xp_detect_batch_submit(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                           xp_collision *out, uint8_t *hit, uint32_t *tri_index, uint32_t *status, int *ticket) {
+    return submit_impl(s, in, n, horizon_mode, out, hit, tri_index, status, nullptr, ticket);
+}
+
+int xp_detect_batch_compact_submit(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                                   xp_hit *out, uint32_t *status, int *ticket) {
+    if (!out && n) return XP_EINVAL;
+    return submit_impl(s, in, n, horizon_mode, nullptr, nullptr, nullptr, status, out, ticket);
+}
+
+int xp_detect_batch_compact_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
+                                xp_hit *d_out, uint32_t *d_status) {
+    int rc = check_query(s, d_in, n);
+    if (rc) return rc;
+    if (!d_out && n) return XP_EINVAL;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    QueryOut q = {nullptr, nullptr, nullptr, d_status, nullptr, {}, 0};
+    q.compact = d_out;
+    XP_API_TRY(detect_retry(s, d_in, n, horizon_mode, q));
+    return XP_OK;
+}
+
+int xp_detect_batch_compact(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode,
+                            xp_hit *out, uint32_t *status) {
+    int rc = check_query(s, in, n);
+    if (rc) return rc;
+    if (!out && n) return XP_EINVAL;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    cudaStream_t st = s->stream;
+    XP_API_TRY(s->io_in.reserve(n * sizeof(xp_response)));
+    XP_API_TRY(s->io_col.reserve(n * sizeof(xp_hit)));
+    XP_API_TRY(s->io_status.reserve(n * 4));
+    XP_API_TRY(cudaMemcpyAsync(s->io_in.p, in, n * sizeof(xp_response), cudaMemcpyHostToDevice, st));
+    QueryOut q = {nullptr, nullptr, nullptr, s->io_status.as<uint32_t>(), nullptr, {}, 0};
+    q.compact = s->io_col.as<xp_hit>();
+    XP_API_TRY(detect_retry(s, s->io_in.as<xp_response>(), n, horizon_mode, q));
+    XP_API_TRY(cudaMemcpyAsync(out, s->io_col.p, n * sizeof(xp_hit), cudaMemcpyDeviceToHost, st));
+    if (status) XP_API_TRY(cudaMemcpyAsync(status, s->io_status.p, n * 4, cudaMemcpyDeviceToHost, st));
+    XP_API_TRY(cudaStreamSynchronize(st));
     return XP_OK;
 }
 
@@ -563,6 +613,7 @@ int xp_detect_batch_wait(xp_scene *s, int ticket) {
     const DeviceCounters &h = *a.h_ctr;
     if (h.stack_overflow) return fail_cuda(cudaErrorAssert);
     if (h.pair_overflow) {                           // rare: candidates were dropped -- redo this batch synchronously
+        if (a.compact_out) return xp_detect_batch_compact(s, a.h_in, a.n, a.horizon_mode, a.compact_out, a.status_out);
         return xp_detect_batch(s, a.h_in, a.n, a.horizon_mode, a.out, a.hit_out, a.tri_out, a.status_out);
     }
     s->stats.narrowphase_tests = h.tests;

@@ -156,7 +156,7 @@ struct xp_scene {
     // one batch's copies overlap another batch's kernels
     static constexpr int ASYNC_SLOTS = 2;
     struct AsyncSlot {
-        xp::DevBuf in, col, hit, tri, status;
+        xp::DevBuf in, col, hit, tri, status, compact;
         cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
         xp::DeviceCounters *h_ctr = nullptr;     // pinned snapshot of the device counters of this batch
         bool busy = false;
@@ -166,6 +166,7 @@ struct xp_scene {
         xp_collision *out = nullptr;
         uint8_t *hit_out = nullptr;
         uint32_t *tri_out = nullptr, *status_out = nullptr;
+        xp_hit *compact_out = nullptr;           // compact form (xp_detect_batch_compact_submit)
     };
     AsyncSlot async_slot[ASYNC_SLOTS];
     bool async_ready = false;

@@ -47,6 +47,7 @@ struct QueryOut {            // device pointers, any may be null
     // asynchronous steps with copy_self >= 0: the kernel writes only peers.p[copy_self] (this rank's buffer)
     // and the copy engines push that span to the other buffers, so no SM waits on NVLink
     int copy_self_plus1;
+    xp_hit *compact;         // 8 B per sphere: (time_to, tri_index or 0xFFFFFFFF)
 };
 // collect = false: leave the statistics on the device (no host synchronisation); the caller ends
 // the batch with collect_stats().  After collecting, s->pair_overflowed tells whether the

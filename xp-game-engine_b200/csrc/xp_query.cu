@@ -1034,8 +1034,29 @@ k_sweep(const WideTree tree, const TriRec *__restrict__ recs, const RayRec *__re
 // NP_LITERAL_EXACT at ~2/3 of its instructions (a pair whose operands leave the guarded range is redone with the
 // literal form in place).  NP_F: xp_detect_f, the tolerance mode.
 enum { NP_LITERAL_EXACT = 0, NP_LITERAL_FAST = 1, NP_X = 2, NP_F = 3 };
+// The literal form behind a real call: it runs for a handful of pairs per million, and inlined it would set the
+// register budget (and with it the occupancy) of the kernel that almost never executes it.
+// (It reloads its operands from the pair instead of taking them as arguments, so the caller need not keep 28 registers
+// of ray and triangle alive across its fast path.)
+template <class O>
+__device__ __noinline__ bool detect_literal_call(const RayRec *__restrict__ rays, const TriRec *__restrict__ recs, uint2 pr, float *t_out) {
+    const float4 *rp = reinterpret_cast<const float4 *>(rays + pr.x);
+    const float4 *tp = reinterpret_cast<const float4 *>(recs + pr.y);
+    const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
+    float t;
+    const bool hit = xp_detect<O>(ray_from(__ldg(rp + 0), __ldg(rp + 1), __ldg(rp + 2)), f4_xyz(t0), f4_xyz(t1), f4_xyz(t2),
+                                  V3{t0.w, t1.w, t2.w}, t3.x, t);
+    *t_out = t;
+    return hit;
+}
+#ifndef XP_NP_BLOCKS_X
+#define XP_NP_BLOCKS_X 4
+#endif
+#ifndef XP_NP_BLOCKS_F
+#define XP_NP_BLOCKS_F 4
+#endif
 template <int MODE, bool FILTER>
-__global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec *__restrict__ recs,
+__global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == NP_F ? XP_NP_BLOCKS_F : XP_NP_BLOCKS) k_narrow_pairs(const TriRec *__restrict__ recs,
                                                       const RayRec *__restrict__ rays,
                                                       const uint2 *__restrict__ pairs,
                                                       DeviceCounters *__restrict__ ctr,
@@ -1087,7 +1108,7 @@ __global__ void __launch_bounds__(256, XP_NP_BLOCKS) k_narrow_pairs(const TriRec
             hit = MODE == NP_X ? xp_detect_x(ray, r2.w, v0, v1, v2, nrm, t3.x, t3.y, t3.z, t, bad)
                                : xp_detect_f(ray, r2.w, v0, v1, v2, nrm, t3.x, t3.y, t3.z, t, bad);
             if (bad) {                                   // an operand outside the guarded range (rare): as written
-                hit = MODE == NP_X ? xp_detect<ExactOps>(ray, v0, v1, v2, nrm, t3.x, t) : xp_detect<FastOps>(ray, v0, v1, v2, nrm, t3.x, t);
+                hit = MODE == NP_X ? detect_literal_call<ExactOps>(rays, recs, pr, &t) : detect_literal_call<FastOps>(rays, recs, pr, &t);
                 ++redone;
             }
         } else {
@@ -1174,13 +1195,18 @@ __global__ void __launch_bounds__(256) k_finalize_detect(const RayRec *__restric
                                                          xp_collision *__restrict__ col, uint8_t *__restrict__ hit,
                                                          uint32_t *__restrict__ tri_index,
                                                          const uint32_t *__restrict__ status,
-                                                         xp_contact *__restrict__ contact, int col_vec) {
+                                                         xp_contact *__restrict__ contact, int col_vec,
+                                                         xp_hit *__restrict__ compact) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= na) return;
     const uint64_t k = inv_order ? inv_order[i] : i;
     const unsigned long long b = best[k];
     const bool h = b != BEST_NONE;
     const uint32_t tri = h ? ~(uint32_t)(b & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+    if (compact) {                                   // (t, triangle) is all a caller with its own Responses needs
+        reinterpret_cast<uint2 *>(compact)[i] = make_uint2(h ? (unsigned)(b >> 32) : 0u, tri);
+        if (!col && !hit && !tri_index && !contact) return;
+    }
     Contact ct = {0.0f, 0.0f, {0, 0, 0}, {0, 0, 0}};
     if (h) {
         const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
@@ -1617,7 +1643,8 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
         }
         {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
-            const unsigned ng = (unsigned)s->n_sm * XP_NP_GRID;
+            const int np_blocks = s->arith == XP_ARITH_EXACT ? XP_NP_BLOCKS_X : s->arith == XP_ARITH_FAST ? XP_NP_BLOCKS_F : XP_NP_BLOCKS;
+            const unsigned ng = (unsigned)s->n_sm * 2u * (unsigned)np_blocks;          // two waves of resident blocks
 #define XP_NP_LAUNCH(M) do { if (q4) k_narrow_pairs<M, true><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
                              else k_narrow_pairs<M, false><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); } while (0)
             switch (s->arith) {
@@ -1747,9 +1774,9 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
                     }
                 }
             } else if (arith_fast(s))
-                k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
+                k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec, out.compact ? out.compact + off : nullptr);
             else
-                k_finalize_detect<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec);
+                k_finalize_detect<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec, out.compact ? out.compact + off : nullptr);
             ++s->stats.kernel_launches;
         }
         if (out.finalize_stream) XP_TRY(cudaEventRecord(out.ev_fin, s->stream));

@@ -80,6 +80,9 @@ def lib() -> C.CDLL:
         "xp_detect_batch_dev": ([vp, vp, u64, u32, vp, vp, vp, vp], i32),
         "xp_detect_batch_submit": ([vp, vp, u64, u32, vp, vp, vp, vp, vp], i32),
         "xp_detect_batch_wait": ([vp, i32], i32),
+        "xp_detect_batch_compact": ([vp, vp, u64, u32, vp, vp], i32),
+        "xp_detect_batch_compact_dev": ([vp, vp, u64, u32, vp, vp], i32),
+        "xp_detect_batch_compact_submit": ([vp, vp, u64, u32, vp, vp, vp], i32),
         "xp_collision_response_batch": ([vp, vp, u64, u32, u32, vp, vp, vp, vp], i32),
         "xp_collision_response_batch_dev": ([vp, vp, u64, u32, u32, vp, vp, vp, vp], i32),
         "xp_sphere_triangle_detect_collision": ([i32, vp, vp, vp], i32),
@@ -114,7 +117,7 @@ EXPORTED_SYMBOLS = [
     "xp_device_count", "xp_scene_create", "xp_scene_destroy", "xp_scene_set_stream", "xp_scene_set_option",
     "xp_scene_get_stats", "xp_scene_set_triangles", "xp_scene_set_triangles_dev", "xp_scene_set_positions", "xp_scene_set_heightmap", "xp_scene_set_clipmap",
     "xp_scene_build", "xp_scene_triangle_count", "xp_detect_batch", "xp_detect_batch_dev",
-    "xp_detect_batch_submit", "xp_detect_batch_wait",
+    "xp_detect_batch_submit", "xp_detect_batch_wait", "xp_detect_batch_compact", "xp_detect_batch_compact_dev", "xp_detect_batch_compact_submit",
     "xp_collision_response_batch", "xp_collision_response_batch_dev", "xp_sphere_triangle_detect_collision",
     "xp_sphere_triangle_calculate_response", "xp_broadphase_pairs", "xp_scene_debug_tree",
     "xp_detect_contacts_dev", "xp_exchange_alloc", "xp_exchange_free", "xp_exchange_open", "xp_exchange_close",

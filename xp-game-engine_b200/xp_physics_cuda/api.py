@@ -26,6 +26,7 @@ from ._lib import check
 RESPONSE_DTYPE = np.dtype([("c", "<f4", (3,)), ("r", "<f4"), ("movement", "<f4", (3,))])
 COLLISION_DTYPE = np.dtype([("time_to", "<f4"), ("distance_to", "<f4"),
                             ("position", "<f4", (3,)), ("intersection", "<f4", (3,))])
+HIT_DTYPE = np.dtype([("time_to", "<f4"), ("tri_index", "<u4")])       # xp_hit: the compact result, 8 B
 CONTACT_DTYPE = np.dtype([("time_to", "<f4"), ("distance_to", "<f4"), ("position", "<f4", (3,)),
                           ("intersection", "<f4", (3,)), ("tri_index", "<u4"), ("flags", "<u4")])
 assert RESPONSE_DTYPE.itemsize == 28 and COLLISION_DTYPE.itemsize == 32 and CONTACT_DTYPE.itemsize == 40
@@ -234,6 +235,30 @@ class Scene:
                                              C.byref(ticket)), "xp_detect_batch_submit")
         return ticket.value
 
+    def detect_batch_compact(self, responses: np.ndarray, horizon: str = "inf"):
+        """Closest collision per sphere in the compact form (xp_hit: time_to, tri_index; 0xFFFFFFFF = none).
+        Returns (hits, status); `collision_from_hit` rebuilds the reference's Collision."""
+        r = np.ascontiguousarray(responses, RESPONSE_DTYPE)
+        out = np.zeros(len(r), HIT_DTYPE)
+        st = np.zeros(len(r), np.uint32)
+        check(self._L.xp_detect_batch_compact(self._h, _p(r), len(r), _horizon(horizon), _p(out), _p(st)),
+              "xp_detect_batch_compact")
+        return out, st
+
+    def detect_batch_compact_dev(self, d_in: int, n: int, d_out: int, d_status: int = 0, horizon: str = "inf"):
+        vp = C.c_void_p
+        check(self._L.xp_detect_batch_compact_dev(self._h, vp(d_in), n, _horizon(horizon), vp(d_out), vp(d_status or None)),
+              "xp_detect_batch_compact_dev")
+
+    def detect_batch_compact_submit(self, h_in: int, n: int, h_out: int, h_status: int = 0, horizon: str = "inf") -> int:
+        """Queue one batch with compact results (8 B per sphere back over the host link); same tickets and
+        `detect_batch_wait` as `detect_batch_submit`."""
+        vp = C.c_void_p
+        ticket = C.c_int(-1)
+        check(self._L.xp_detect_batch_compact_submit(self._h, vp(h_in), n, _horizon(horizon), vp(h_out), vp(h_status or None),
+                                                     C.byref(ticket)), "xp_detect_batch_compact_submit")
+        return ticket.value
+
     def detect_batch_wait(self, ticket: int) -> None:
         """Block until the batch behind `ticket` is in the caller's buffers; `stats()` then describes it."""
         check(self._L.xp_detect_batch_wait(self._h, ticket), "xp_detect_batch_wait")
@@ -351,6 +376,25 @@ class Scene:
         check(self._L.xp_collision_response_batch_dev(self._h, vp(d_in), n, max_iter, _horizon(horizon), vp(d_out),
                                                       vp(d_iter or None), vp(d_status or None), vp(d_normal or None)),
               "xp_collision_response_batch_dev")
+
+
+def collision_from_hit(responses: np.ndarray, hits: np.ndarray):
+    """The reference's Collision from the compact result (collision_detect.rs:188-194 / :203-209): position = c + m*t,
+    distance_to = |m|*t, intersection = position + m/|m| * r -- float32, unfused, in the reference's operation
+    order, so the fields equal the ones xp_detect_batch returns bit for bit.  Returns (collisions, hit)."""
+    r = np.ascontiguousarray(responses, RESPONSE_DTYPE)
+    h = np.ascontiguousarray(hits, HIT_DTYPE)
+    hit = h["tri_index"] != 0xFFFFFFFF
+    col = np.zeros(len(r), COLLISION_DTYPE)
+    c, m, t = r["c"][hit], r["movement"][hit], h["time_to"][hit][:, None]
+    with np.errstate(all="ignore"):
+        ml = np.sqrt(((m[:, 0] * m[:, 0] + m[:, 1] * m[:, 1]) + m[:, 2] * m[:, 2]).astype(np.float32))[:, None]   # nalgebra dot order
+        pos = (c + (m * t).astype(np.float32)).astype(np.float32)
+        col["time_to"][hit] = t[:, 0]
+        col["distance_to"][hit] = (ml * t)[:, 0]
+        col["position"][hit] = pos
+        col["intersection"][hit] = pos + ((m / ml).astype(np.float32) * r["r"][hit][:, None]).astype(np.float32)
+    return col, hit.astype(np.uint8)
 
 
 def _horizon(h) -> int:

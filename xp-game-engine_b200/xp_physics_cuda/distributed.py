@@ -80,10 +80,12 @@ class ContactExchange:
 
     N_BUF = 4
 
-    def __init__(self, scene: Scene, cap: int, device, group=None):
+    def __init__(self, scene: Scene, cap: int, device, group=None, n_buf: int = 0):
         import torch
         import torch.distributed as dist
         self.scene, self.group, self.device = scene, group, device
+        if n_buf:
+            self.N_BUF = n_buf                      # 1 is enough for synchronous steps (sweep); sweep_async needs 4
         self.solo = not (dist.is_available() and dist.is_initialized())        # one process, no peers
         self.world = 1 if self.solo else dist.get_world_size(group)
         self.rank = 0 if self.solo else dist.get_rank(group)
@@ -169,6 +171,8 @@ class ContactExchange:
         import torch.distributed as dist
         if self.mode != "p2p":
             raise RuntimeError("sweep_async uses the P2P transport")
+        if self.N_BUF < 4:
+            raise RuntimeError("sweep_async needs four gather buffers (see below)")
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
             self.scene.set_exchange_stream(self._side.cuda_stream)
