@@ -218,6 +218,22 @@ int  xp_collision_response_batch_dev(xp_scene *s, const xp_response *d_in, uint6
                                      xp_response *d_out, uint32_t *d_iterations,
                                      uint32_t *d_status, xp_vec3 *d_last_slide_normal);
 
+/* ---- row f4 of SURVEY.md section 8 (beyond the reference): Fauerby's collide-and-slide on the device ----
+ * What the author's note at collision_response.rs:9-14 points at, for a batch: every sphere moves by its velocity;
+ * only contacts inside the step count (t <= 1: the sweep runs with XP_HORIZON_UNIT); the sphere stops 0.005 short of
+ * the first contact and continues with its velocity projected onto the sliding plane through the TRUE contact point
+ * (the closest point of the hit triangle to the sphere centre at the time of impact), up to max_iter times
+ * (0 = 5).  radii (nullable): an ellipsoid's radii -- positions and velocities are taken to its space, in which it
+ * is the unit sphere the sweep requires (collision_detect.rs:161), and back; the scene's triangles must already be
+ * in that space.  out_velocity = what is left of the step (zero for a sphere that came to rest or ran free),
+ * handled (nullable) = contacts handled per sphere.  XP_METHOD_LBVH_PAIRS only (the default method). */
+int  xp_collide_and_slide_batch(xp_scene *s, const xp_vec3 *position, const xp_vec3 *velocity, uint64_t n,
+                                uint32_t max_iter, const float radii[3], xp_vec3 *out_position,
+                                xp_vec3 *out_velocity, uint32_t *handled);
+int  xp_collide_and_slide_batch_dev(xp_scene *s, const xp_vec3 *d_position, const xp_vec3 *d_velocity, uint64_t n,
+                                    uint32_t max_iter, const float radii[3], xp_vec3 *d_out_position,
+                                    xp_vec3 *d_out_velocity, uint32_t *d_handled);
+
 /* ---- the 1-sphere calls with the reference's exact shapes (host pointers) ----
  * sphere_triangle_detect_collision (collision_detect.rs:155): returns 1 = Some, 0 = None,
  * XP_EINVAL where the reference panics on r != 1.  Evaluated on the device. */

@@ -753,6 +753,51 @@ int xp_collision_response_batch(xp_scene *s, const xp_response *in, uint64_t n, 
     return XP_OK;
 }
 
+static int check_slide(xp_scene *s, const void *a, const void *b, const void *c, const void *d_, uint64_t n, const float *radii) {
+    int rc = check_query(s, a, n);
+    if (rc) return rc;
+    if (n && (!b || !c || !d_)) return XP_EINVAL;
+    if (s->method != XP_METHOD_LBVH_PAIRS) return XP_EINVAL;
+    if (radii && !(radii[0] > 0.0f && radii[1] > 0.0f && radii[2] > 0.0f)) return XP_EINVAL;
+    return XP_OK;
+}
+
+int xp_collide_and_slide_batch_dev(xp_scene *s, const xp_vec3 *d_position, const xp_vec3 *d_velocity, uint64_t n,
+                                   uint32_t max_iter, const float radii[3], xp_vec3 *d_out_position,
+                                   xp_vec3 *d_out_velocity, uint32_t *d_handled) {
+    int rc = check_slide(s, d_position, d_velocity, d_out_position, d_out_velocity, n, radii);
+    if (rc) return rc;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    XP_API_TRY(slide_dev(s, d_position, d_velocity, n, max_iter, radii, d_out_position, d_out_velocity, d_handled));
+    return XP_OK;
+}
+
+int xp_collide_and_slide_batch(xp_scene *s, const xp_vec3 *position, const xp_vec3 *velocity, uint64_t n,
+                               uint32_t max_iter, const float radii[3], xp_vec3 *out_position,
+                               xp_vec3 *out_velocity, uint32_t *handled) {
+    int rc = check_slide(s, position, velocity, out_position, out_velocity, n, radii);
+    if (rc) return rc;
+    XP_BIND(s);
+    reset_stats(s);
+    if (n == 0) return XP_OK;
+    cudaStream_t st = s->stream;
+    const size_t vb = n * sizeof(xp_vec3);
+    XP_API_TRY(s->io_in.reserve(2 * vb));
+    XP_API_TRY(s->io_col.reserve(2 * vb));
+    XP_API_TRY(s->io_iter.reserve(n * 4));
+    xp_vec3 *d_p = s->io_in.as<xp_vec3>(), *d_v = d_p + n, *o_p = s->io_col.as<xp_vec3>(), *o_v = o_p + n;
+    XP_API_TRY(cudaMemcpyAsync(d_p, position, vb, cudaMemcpyHostToDevice, st));
+    XP_API_TRY(cudaMemcpyAsync(d_v, velocity, vb, cudaMemcpyHostToDevice, st));
+    XP_API_TRY(slide_dev(s, d_p, d_v, n, max_iter, radii, o_p, o_v, s->io_iter.as<uint32_t>()));
+    XP_API_TRY(cudaMemcpyAsync(out_position, o_p, vb, cudaMemcpyDeviceToHost, st));
+    XP_API_TRY(cudaMemcpyAsync(out_velocity, o_v, vb, cudaMemcpyDeviceToHost, st));
+    if (handled) XP_API_TRY(cudaMemcpyAsync(handled, s->io_iter.p, n * 4, cudaMemcpyDeviceToHost, st));
+    XP_API_TRY(cudaStreamSynchronize(st));
+    return XP_OK;
+}
+
 int xp_broadphase_pairs(xp_scene *s, const xp_response *in, uint64_t n, uint32_t horizon_mode, uint64_t cap,
                         uint32_t *sphere_idx, uint32_t *tri_idx, uint64_t *count) {
     int rc = check_query(s, in, n);

@@ -58,6 +58,8 @@ cudaError_t collect_stats(xp_scene *s);
 cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t max_iter,
                          uint32_t horizon_mode, xp_response *d_out, uint32_t *d_iter,
                          uint32_t *d_status, xp_vec3 *d_normal);
+cudaError_t slide_dev(xp_scene *s, const xp_vec3 *d_pos, const xp_vec3 *d_vel, uint64_t n, uint32_t max_iter, const float *radii,
+                      xp_vec3 *d_out_pos, xp_vec3 *d_out_vel, uint32_t *d_handled);
 cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,
                       uint64_t cap, uint32_t *d_sphere, uint32_t *d_tri, uint64_t *h_count);
 cudaError_t single_detect_dev(const xp_response *h_resp, const xp_triangle *h_tri,

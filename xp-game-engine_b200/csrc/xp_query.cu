@@ -1414,6 +1414,132 @@ __global__ void __launch_bounds__(256) k_respond_setup(const RayRec *__restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Row f4 (beyond the reference): Fauerby's collide-and-slide step with the TRUE contact point
+// ------------------------------------------------------------------------------------------
+// What the author's note at collision_response.rs:9-14 points at: only contacts inside the step count (t <= 1, the
+// sweep runs with the unit horizon), the sphere stops VERY_CLOSE short of the contact, and the sliding plane passes
+// through the closest point of the hit TRIANGLE to the sphere centre at the time of impact, with the normal from
+// that point to the centre.  No reference arithmetic exists for this step (plain fp32, contraction allowed); it is
+// checked by geometric invariants and against the float64 host form (xp_physics_cuda/fauerby.py).
+static constexpr float SLIDE_VERY_CLOSE = 0.005f;
+
+// Ericson, Real-Time Collision Detection 5.1.5
+__device__ __forceinline__ V3 closest_point_on_triangle(V3 p, V3 a, V3 b, V3 c) {
+    const V3 ab = {b.x - a.x, b.y - a.y, b.z - a.z}, ac = {c.x - a.x, c.y - a.y, c.z - a.z}, ap = {p.x - a.x, p.y - a.y, p.z - a.z};
+    const float d1 = ab.x * ap.x + ab.y * ap.y + ab.z * ap.z, d2 = ac.x * ap.x + ac.y * ap.y + ac.z * ap.z;
+    if (d1 <= 0.0f && d2 <= 0.0f) return a;
+    const V3 bp = {p.x - b.x, p.y - b.y, p.z - b.z};
+    const float d3 = ab.x * bp.x + ab.y * bp.y + ab.z * bp.z, d4 = ac.x * bp.x + ac.y * bp.y + ac.z * bp.z;
+    if (d3 >= 0.0f && d4 <= d3) return b;
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) { const float v = d1 / (d1 - d3); return {a.x + v * ab.x, a.y + v * ab.y, a.z + v * ab.z}; }
+    const V3 cp = {p.x - c.x, p.y - c.y, p.z - c.z};
+    const float d5 = ab.x * cp.x + ab.y * cp.y + ab.z * cp.z, d6 = ac.x * cp.x + ac.y * cp.y + ac.z * cp.z;
+    if (d6 >= 0.0f && d5 <= d6) return c;
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) { const float w = d2 / (d2 - d6); return {a.x + w * ac.x, a.y + w * ac.y, a.z + w * ac.z}; }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        return {b.x + w * (c.x - b.x), b.y + w * (c.y - b.y), b.z + w * (c.z - b.z)};
+    }
+    const float denom = 1.0f / (va + vb + vc);
+    const float v = vb * denom, w = vc * denom;
+    const V3 q = {a.x + ab.x * v + ac.x * w, a.y + ab.y * v + ac.y * w, a.z + ab.z * v + ac.z * w};
+    return (q.x == q.x && q.y == q.y && q.z == q.z && fabsf(q.x) <= XP_FLT_MAX && fabsf(q.y) <= XP_FLT_MAX && fabsf(q.z) <= XP_FLT_MAX) ? q : a;
+}
+
+// One collide-and-slide iteration for the live spheres (same frame as k_respond_setup: live count on the device, next
+// ray records written here).  cur[i] = (position, 1, remaining velocity) in / out.
+template <class O>
+__global__ void __launch_bounds__(256) k_slide_setup(const RayRec *__restrict__ rays, const unsigned long long *__restrict__ best,
+                                                     const uint32_t *__restrict__ active, uint64_t na,
+                                                     const unsigned *__restrict__ n_active, const xp_triangle *__restrict__ tris,
+                                                     xp_response *__restrict__ cur, uint32_t *__restrict__ handled,
+                                                     uint32_t *__restrict__ next_active, RayRec *__restrict__ next_rays,
+                                                     unsigned long long *__restrict__ next_best, DeviceCounters *__restrict__ ctr,
+                                                     unsigned *__restrict__ next_count, unsigned iter_no) {
+    if (ctr->pair_overflow) return;
+    if (n_active && na > *n_active) na = *n_active;
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (k == 0 && na > 0) { ctr->iters_done = iter_no + 1u; ctr->rays_swept += na; }
+    bool again = false;
+    uint32_t i = 0;
+    V3 np_ = {0, 0, 0}, nv = {0, 0, 0};
+    if (k < na) {
+        i = active ? active[k] : (uint32_t)k;
+        const unsigned long long b = best[k];
+        const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
+        const float4 q0 = rp[0], q1 = rp[1];
+        const V3 p = f4_xyz(q0), v = f4_xyz(q1);
+        const float vlen = q0.w;
+        const float t = __uint_as_float((unsigned)(b >> 32));
+        if (!(vlen > SLIDE_VERY_CLOSE)) {
+            // (almost) no velocity: nothing to do; a sphere that arrives here after a slide has been stopped already
+        } else if (b == BEST_NONE || !(t <= 1.0f)) {
+            np_ = {p.x + v.x, p.y + v.y, p.z + v.z};                          // nothing in the way: take the step
+            float *o = reinterpret_cast<float *>(cur) + (uint64_t)i * 7;
+            o[0] = np_.x; o[1] = np_.y; o[2] = np_.z; o[4] = 0.0f; o[5] = 0.0f; o[6] = 0.0f;
+        } else {
+            const float *tv = reinterpret_cast<const float *>(tris + ~(uint32_t)(b & 0xFFFFFFFFull));
+            const V3 a = {tv[0], tv[1], tv[2]}, bb = {tv[3], tv[4], tv[5]}, c = {tv[6], tv[7], tv[8]};
+            const float dist = vlen * t;
+            const V3 centre = {p.x + v.x * t, p.y + v.y * t, p.z + v.z * t};  // sphere centre at the time of impact
+            V3 cp = closest_point_on_triangle(centre, a, bb, c);
+            const float inv_len = 1.0f / vlen;
+            const V3 vhat = {v.x * inv_len, v.y * inv_len, v.z * inv_len};
+            const bool moved = dist >= SLIDE_VERY_CLOSE;                      // stop VERY_CLOSE short, pull the contact point back too
+            const float shrt = fmaxf(dist - SLIDE_VERY_CLOSE, 0.0f);
+            np_ = moved ? V3{p.x + vhat.x * shrt, p.y + vhat.y * shrt, p.z + vhat.z * shrt} : p;
+            if (moved) cp = {cp.x - vhat.x * SLIDE_VERY_CLOSE, cp.y - vhat.y * SLIDE_VERY_CLOSE, cp.z - vhat.z * SLIDE_VERY_CLOSE};
+            V3 n = {np_.x - cp.x, np_.y - cp.y, np_.z - cp.z};               // sliding plane: through cp, normal towards the centre
+            const float nl = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+            const float inl = nl > 0.0f ? 1.0f / nl : 0.0f;
+            n = {n.x * inl, n.y * inl, n.z * inl};
+            const V3 dest = {p.x + v.x, p.y + v.y, p.z + v.z};
+            const float sd = (dest.x - cp.x) * n.x + (dest.y - cp.y) * n.y + (dest.z - cp.z) * n.z;
+            nv = {dest.x - sd * n.x - cp.x, dest.y - sd * n.y - cp.y, dest.z - sd * n.z - cp.z};
+            again = !(sqrtf(nv.x * nv.x + nv.y * nv.y + nv.z * nv.z) < SLIDE_VERY_CLOSE);
+            if (!again) nv = {0.0f, 0.0f, 0.0f};
+            float *o = reinterpret_cast<float *>(cur) + (uint64_t)i * 7;
+            o[0] = np_.x; o[1] = np_.y; o[2] = np_.z; o[4] = nv.x; o[5] = nv.y; o[6] = nv.z;
+            if (handled) handled[i] += 1;
+        }
+    }
+    const unsigned m = __ballot_sync(FULL, again);
+    if (m) {
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(next_count, (unsigned)__popc(m));
+        base = __shfl_sync(FULL, base, __ffs(m) - 1);
+        if (again) {
+            const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+            next_active[pos] = i;
+            next_rays[pos] = make_ray_rec<O>(np_, nv, true);
+            next_best[pos] = BEST_NONE;
+        }
+    }
+}
+
+// positions / velocities (optionally an ellipsoid's: divided by its radii) <-> the loop's Response array
+__global__ void __launch_bounds__(256) k_slide_pack(const xp_vec3 *__restrict__ pos, const xp_vec3 *__restrict__ vel, uint64_t n,
+                                                    float rx, float ry, float rz, xp_response *__restrict__ cur) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float *o = reinterpret_cast<float *>(cur) + i * 7;
+    o[0] = pos[i].x / rx; o[1] = pos[i].y / ry; o[2] = pos[i].z / rz; o[3] = 1.0f;
+    o[4] = vel[i].x / rx; o[5] = vel[i].y / ry; o[6] = vel[i].z / rz;
+}
+__global__ void __launch_bounds__(256) k_slide_unpack(const xp_response *__restrict__ cur, uint64_t n, float rx, float ry, float rz,
+                                                      xp_vec3 *__restrict__ pos, xp_vec3 *__restrict__ vel) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = reinterpret_cast<const float *>(cur) + i * 7;
+    pos[i].x = p[0] * rx; pos[i].y = p[1] * ry; pos[i].z = p[2] * rz;
+    vel[i].x = p[4] * rx; vel[i].y = p[5] * ry; vel[i].z = p[6] * rz;
+}
+
 __global__ void k_mark_cap(const uint32_t *__restrict__ active, uint64_t na, uint32_t *__restrict__ status,
                            const unsigned *__restrict__ n_active) {
     const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -1792,7 +1918,7 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
 // response kernel writes the next iteration's ray records itself.  With a bounded max_iter <= 8 the host queues
 // everything and returns; an unbounded loop looks at the live count once per 8 iterations.
 static cudaError_t response_chunk_device(xp_scene *s, xp_response *cur, uint64_t m, uint32_t cap_iter, float horizon,
-                                         uint32_t *iter, uint32_t *status, xp_vec3 *normal, bool *overflowed) {
+                                         uint32_t *iter, uint32_t *status, xp_vec3 *normal, bool *overflowed, bool slide = false) {
     cudaStream_t st = s->stream;
     DeviceCounters *ctr = s->counters.as<DeviceCounters>();
     XP_TRY(s->rays.reserve(m * sizeof(RayRec)));  XP_TRY(s->rays2.reserve(m * sizeof(RayRec)));
@@ -1817,7 +1943,11 @@ static cudaError_t response_chunk_device(xp_scene *s, xp_response *cur, uint64_t
             uint32_t *next = spare[it & 1u];
             {
                 StageTimer t(s, XP_STAGE_RESPONSE);
-                if (arith_fast(s))
+                if (slide)          // row f4: `iter` counts the contacts handled
+                    k_slide_setup<ExactOps><<<grid_for(m, 256), 256, 0, st>>>(s->rays.as<RayRec>(), s->best.as<unsigned long long>(), list, m, s->na_dev,
+                                                                             s->tris_aos.as<xp_triangle>(), cur, iter, next, s->rays2.as<RayRec>(),
+                                                                             s->best2.as<unsigned long long>(), ctr, next_count, it);
+                else if (arith_fast(s))
                     k_respond_setup<FastOps><<<grid_for(m, 256), 256, 0, st>>>(s->rays.as<RayRec>(), s->best.as<unsigned long long>(), list, m, s->na_dev, cur, iter, status,
                                                                               normal, next, s->rays2.as<RayRec>(), s->best2.as<unsigned long long>(), ctr, next_count, it);
                 else
@@ -1835,7 +1965,7 @@ static cudaError_t response_chunk_device(xp_scene *s, xp_response *cur, uint64_t
         if (h.pair_overflow) { *overflowed = true; return cudaSuccess; }
         live = h.active[it & 1u] != 0u;
     }
-    if (live && it >= cap_iter) {                                   // whoever is still moving hit the cap
+    if (live && it >= cap_iter && !slide) {                         // whoever is still moving hit the cap
         s->na_dev = &ctr->active[it & 1u];
         k_mark_cap<<<grid_for(m, 256), 256, 0, st>>>(list, m, status, s->na_dev);
         ++s->stats.kernel_launches;
@@ -1952,6 +2082,41 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
     }
     XP_TRY(cudaGetLastError());
     return collect_counters(s);
+}
+
+// Row f4: collide-and-slide for a batch (device pointers).  radii: the ellipsoid's, or null for the unit sphere; the
+// scene's triangles must already be in that ellipsoid space.  Runs on the device-resident loop of the reference's
+// response (same sweeps, same live-count plumbing), with the unit horizon and k_slide_setup as the response step.
+cudaError_t slide_dev(xp_scene *s, const xp_vec3 *d_pos, const xp_vec3 *d_vel, uint64_t n, uint32_t max_iter, const float *radii,
+                      xp_vec3 *d_out_pos, xp_vec3 *d_out_vel, uint32_t *d_handled) {
+    cudaStream_t st = s->stream;
+    const float rx = radii ? radii[0] : 1.0f, ry = radii ? radii[1] : 1.0f, rz = radii ? radii[2] : 1.0f;
+    struct SafeGuard { xp_scene *s; bool old; ~SafeGuard() { s->safe_pairs = old; } } guard{s, s->safe_pairs};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        XP_TRY(zero_counters(s));
+        XP_TRY(s->io_out.reserve(n * sizeof(xp_response)));
+        xp_response *cur = s->io_out.as<xp_response>();
+        k_slide_pack<<<grid_for(n, 256), 256, 0, st>>>(d_pos, d_vel, n, rx, ry, rz, cur);
+        ++s->stats.kernel_launches;
+        if (d_handled) XP_TRY(cudaMemsetAsync(d_handled, 0, n * 4, st));
+        bool overflowed = false;
+        for (uint64_t off = 0; off < n && !overflowed; off += SPHERE_CHUNK) {
+            const uint64_t m = (n - off < SPHERE_CHUNK) ? n - off : SPHERE_CHUNK;
+            XP_TRY(response_chunk_device(s, cur + off, m, max_iter ? max_iter : 5u, horizon_of(XP_HORIZON_UNIT), d_handled ? d_handled + off : nullptr,
+                                         nullptr, nullptr, &overflowed, /*slide=*/true));
+        }
+        if (!overflowed) {
+            k_slide_unpack<<<grid_for(n, 256), 256, 0, st>>>(cur, n, rx, ry, rz, d_out_pos, d_out_vel);
+            ++s->stats.kernel_launches;
+            XP_TRY(collect_counters(s));
+            if (!s->pair_overflowed) return cudaSuccess;
+        }
+        // the optimistic candidate buffer overflowed: once more from the inputs with the synchronous pair mode
+        s->pair_overflowed = false;
+        s->safe_pairs = true;
+        reset_call_stats(s);
+    }
+    return cudaErrorMemoryAllocation;
 }
 
 cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,

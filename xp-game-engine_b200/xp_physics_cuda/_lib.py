@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
         "xp_detect_batch_compact_submit": ([vp, vp, u64, u32, vp, vp, vp], i32),
         "xp_collision_response_batch": ([vp, vp, u64, u32, u32, vp, vp, vp, vp], i32),
         "xp_collision_response_batch_dev": ([vp, vp, u64, u32, u32, vp, vp, vp, vp], i32),
+        "xp_collide_and_slide_batch": ([vp, vp, vp, u64, u32, vp, vp, vp, vp], i32),
+        "xp_collide_and_slide_batch_dev": ([vp, vp, vp, u64, u32, vp, vp, vp, vp], i32),
         "xp_sphere_triangle_detect_collision": ([i32, vp, vp, vp], i32),
         "xp_sphere_triangle_calculate_response": ([i32, vp, vp, vp], i32),
         "xp_broadphase_pairs": ([vp, vp, u64, u32, u64, vp, vp, vp], i32),
@@ -118,7 +120,7 @@ EXPORTED_SYMBOLS = [
     "xp_scene_get_stats", "xp_scene_set_triangles", "xp_scene_set_triangles_dev", "xp_scene_set_positions", "xp_scene_set_heightmap", "xp_scene_set_clipmap",
     "xp_scene_build", "xp_scene_triangle_count", "xp_detect_batch", "xp_detect_batch_dev",
     "xp_detect_batch_submit", "xp_detect_batch_wait", "xp_detect_batch_compact", "xp_detect_batch_compact_dev", "xp_detect_batch_compact_submit",
-    "xp_collision_response_batch", "xp_collision_response_batch_dev", "xp_sphere_triangle_detect_collision",
+    "xp_collision_response_batch", "xp_collision_response_batch_dev", "xp_collide_and_slide_batch", "xp_collide_and_slide_batch_dev", "xp_sphere_triangle_detect_collision",
     "xp_sphere_triangle_calculate_response", "xp_broadphase_pairs", "xp_scene_debug_tree",
     "xp_detect_contacts_dev", "xp_exchange_alloc", "xp_exchange_free", "xp_exchange_open", "xp_exchange_close",
     "xp_detect_contacts_exchange_dev", "xp_detect_contacts_multicast_dev", "xp_scene_set_exchange_stream",

@@ -276,6 +276,20 @@ class Scene:
                                                   _p(it), _p(st), _p(ln)), "xp_collision_response_batch")
         return out, it, st, ln
 
+    def collide_and_slide_batch(self, position, velocity, max_iter: int = 5, radii=None):
+        """Row f4 on the device (xp_collide_and_slide_batch): Fauerby's collide-and-slide with the true contact point,
+        unit horizon and optional ellipsoid radii (the scene must be in that ellipsoid's space).
+        Returns (position, remaining velocity, contacts handled), like fauerby.collide_and_slide."""
+        p = np.ascontiguousarray(np.asarray(position, np.float32).reshape(-1, 3))
+        v = np.ascontiguousarray(np.asarray(velocity, np.float32).reshape(-1, 3))
+        assert p.shape == v.shape
+        op, ov = np.zeros_like(p), np.zeros_like(v)
+        handled = np.zeros(len(p), np.uint32)
+        rad = None if radii is None else np.ascontiguousarray(np.broadcast_to(np.asarray(radii, np.float32).reshape(-1), (3,)))
+        check(self._L.xp_collide_and_slide_batch(self._h, _p(p), _p(v), len(p), max_iter, _p(rad), _p(op), _p(ov), _p(handled)),
+              "xp_collide_and_slide_batch")
+        return op, ov, handled.astype(np.int32)
+
     def broadphase_pairs(self, responses: np.ndarray, horizon: str = "inf", cap: Optional[int] = None):
         r = np.ascontiguousarray(responses, RESPONSE_DTYPE)
         cap = int(cap if cap is not None else max(1024, min(len(r) * max(self.triangle_count, 1), 1 << 26)))
