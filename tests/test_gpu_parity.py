@@ -169,6 +169,31 @@ def test_pair_buffer_overflow_is_recovered(terrain):
             assert it.max() == 2
 
 
+@pytest.mark.parametrize("scene_kind", ["soup", "heightmap"])
+def test_entry_time_cull_changes_no_contact(oracle, scene_kind):
+    """XP_OPT_PRUNE = 1 on the two-stage sweep: distance windows (LBVH) + the narrowphase's entry-time cull skip pairs the
+    ray enters after the sphere's best hit -- fewer tests, the same closest collision and the same triangle, bit for bit."""
+    h = scenes.sine_terrain_heights(90, 80, seed=21)
+    tris = scenes.heightmap_from_heights(h)
+    resps = scenes.terrain_spheres(h, 20000, seed=22)
+    want = oracle.detect_batch(resps[:3000], tris)
+    with xp.Scene(0, prune=False) as s:
+        if scene_kind == "heightmap":
+            s.set_heightmap(h)
+        else:
+            s.set_triangles(tris)
+        s.build()
+        a = s.detect_batch(resps)
+        tests_all = s.stats()["narrowphase_tests"]
+        s.set_options(prune=True)
+        b = s.detect_batch(resps)
+        tests_cull = s.stats()["narrowphase_tests"]
+    check_detect_exact(tuple(x[:3000] for x in a), want, "exhaustive")
+    check_detect_exact(b, a, f"entry-time cull ({scene_kind})")
+    print(f"{scene_kind}: {tests_all} tests exhaustive, {tests_cull} with the cull ({tests_cull / tests_all:.2%})")
+    assert tests_cull < 0.9 * tests_all
+
+
 def test_compact_results_rebuild_the_full_collision(terrain, oracle):
     """xp_detect_batch_compact (8 B per sphere: time_to, tri_index) + collision_from_hit == xp_detect_batch, bit for bit;
     the asynchronous compact form shares tickets with the full one."""

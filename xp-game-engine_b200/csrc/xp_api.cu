@@ -202,7 +202,7 @@ int xp_scene_set_heightmap(xp_scene *s, const float *heights, uint32_t nx, uint3
     XP_API_TRY(cudaMemcpyAsync(s->grid_h.p, heights, hbytes, cudaMemcpyHostToDevice, s->stream));
     XP_API_TRY(emit_heightmap(s, s->grid_h.as<float>(), nx, nz, x0, z0, spacing));
     XP_API_TRY(height_range(s, s->grid_h.as<float>(), hcount));
-    XP_API_TRY(height_windows(s, s->grid_h.as<float>(), nx, nz, 8));
+    XP_API_TRY(height_windows(s, s->grid_h.as<float>(), nx, nz));
     XP_API_TRY(cudaStreamSynchronize(s->stream));
     s->n_tris = n;
     // The grid walk (xp_gridwalk.cuh) needs a regular grid: finite origin, positive spacing, grid lines that really

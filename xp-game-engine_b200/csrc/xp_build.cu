@@ -17,6 +17,7 @@
 
 #include "xp_internal.h"
 #include "xp_narrowphase.cuh"
+#include "xp_gridwalk.cuh"
 
 namespace xp {
 
@@ -659,7 +660,8 @@ __global__ void __launch_bounds__(256) k_height_windows(const float *__restrict_
 
 #define XP_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return _e; } while (0)
 
-cudaError_t height_windows(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz, int window) {
+cudaError_t height_windows(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz) {
+    const int window = XP_GW_WINDOW;
     const uint64_t cells = (uint64_t)nx * nz;
     XP_TRY(s->grid_mm.reserve(cells * sizeof(float2)));
     k_height_windows<<<grid_for(cells, 256), 256, 0, s->stream>>>(d_heights, nx, nz, window, s->grid_mm.as<float2>());

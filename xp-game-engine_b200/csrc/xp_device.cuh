@@ -104,6 +104,7 @@ struct xp_scene {
     bool pair_overflowed = false;      // optimistic mode dropped candidates: results must be recomputed
     bool counters_live = false;        // device counters hold uncollected statistics
     const unsigned *na_dev = nullptr;  // response loop: device address of the live ray count (null: the host knows it)
+    bool in_response_loop = false;     // sweeps of a response / slide loop: XP_OPT_PRUNE = 2 (auto) turns the entry-time cull on
     uint64_t swept_rays = 0;           // rays swept since the counters were zeroed
     double cand_per_ray = 0.0;         // candidates per sphere of the last exhaustive sweep (XP_OPT_PRUNE = 2)
     // geometry

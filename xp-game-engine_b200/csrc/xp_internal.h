@@ -26,7 +26,7 @@ cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *
 cudaError_t build_lbvh(xp_scene *s);
 cudaError_t emit_heightmap(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz, float x0, float z0, float spacing);
 cudaError_t height_range(xp_scene *s, const float *d_heights, uint64_t n);     // -> s->grid_yrange
-cudaError_t height_windows(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz, int window);   // -> s->grid_mm
+cudaError_t height_windows(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz);   // -> s->grid_mm
 cudaError_t emit_clipmap(xp_scene *s, const float *d_heights, unsigned size, const int *d_parts, unsigned n_parts,
                          float unit0, uint64_t n_tris);
 cudaError_t build_aux(xp_scene *s);      // Node4 / 32-wide planes, on first use by the method that needs them
