@@ -114,8 +114,7 @@ long emul_grid_walk(const float *heights, unsigned nx, unsigned nz, float x0, fl
                 if (!grid_window_test(r, col, hmin, hmax)) { iz += XP_GW_WINDOW - 1; continue; }
             }
             const float *p = heights + (unsigned long)ix * row + iz;
-            float t_cell;
-            const unsigned hit = grid_cell_test(r, col, grid_coord(z0, sp, iz), grid_coord(z0, sp, iz + 1), p[0], p[1], p[row], p[row + 1], t_cell);
+            const unsigned hit = grid_cell_test(r, col, grid_coord(z0, sp, iz), grid_coord(z0, sp, iz + 1), p[0], p[1], p[row], p[row + 1]);
             ++*cells;
             for (unsigned k = 0; k < 2; ++k)
                 if ((hit >> k) & 1u) { if (n < cap) out_tris[n] = 2u * ((unsigned)ix * nz + (unsigned)iz) + k; ++n; }

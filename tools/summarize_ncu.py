@@ -4,7 +4,7 @@
   python tools/summarize_ncu.py <tag>      e.g. r01b
 
   gpurun_out/launches.csv            -> profiles/<tag>_launches.csv (per-kernel totals + share of the step)
-  gpurun_out/prof_r02c.ncu-rep   -> profiles/<tag>_ncu_full.txt (selected --set full metrics per kernel)
+  gpurun_out/prof_r02g_build.ncu-rep   -> profiles/<tag>_ncu_full.txt (selected --set full metrics per kernel)
 """
 import collections
 import csv
@@ -60,7 +60,7 @@ def launches(tag):
     print("wrote", f"{tag}_launches.csv")
 
 
-def full(tag, rep="prof_r02c.ncu-rep"):
+def full(tag, rep="prof_r02g_build.ncu-rep"):
     src = os.path.join(SCR, rep)
     if not os.path.exists(src):
         return
@@ -84,4 +84,4 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
-    full(tag, sys.argv[2] if len(sys.argv) > 2 else "prof_r02c.ncu-rep")
+    full(tag, sys.argv[2] if len(sys.argv) > 2 else "prof_r02g_build.ncu-rep")

@@ -91,7 +91,7 @@ void xp_scene_destroy(xp_scene *s) {
     cudaStreamSynchronize(s->stream);
     if (s->io_ready) { cudaStreamSynchronize(s->copy_in); cudaStreamSynchronize(s->copy_out); }   // batches still in flight
     for (auto &x : s->ex_slot) if (x.busy) cudaEventSynchronize(x.fin);
-    DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_lo, &s->node_hi, &s->leaf_lo, &s->leaf_hi,
+    DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_box, &s->leaf_box,
                       &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
                       &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->degen, &s->grid_h, &s->grid_yrange, &s->grid_mm, &s->recs_grid, &s->rays, &s->best, &s->active_a,
                       &s->active_b, &s->inv_order, &s->pairs, &s->counters, &s->rays2, &s->best2, &s->active_c, &s->io_backup, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
@@ -847,14 +847,14 @@ int xp_scene_debug_tree(xp_scene *s, uint32_t *sorted_tri, uint32_t *morton, int
         if (e != cudaSuccess) return fail_cuda(e);
     }
     if (node_lo || node_hi) {
-        float4 *h = new (std::nothrow) float4[ni];
+        float4 *h = new (std::nothrow) float4[2 * ni];
         if (!h) return XP_ENOMEM;
+        cudaError_t e = cudaMemcpy(h, s->node_box.p, 2 * ni * sizeof(float4), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { delete[] h; return fail_cuda(e); }
         for (int pass = 0; pass < 2; ++pass) {
             xp_vec3 *dst = pass ? node_hi : node_lo;
             if (!dst) continue;
-            cudaError_t e = cudaMemcpy(h, pass ? s->node_hi.p : s->node_lo.p, ni * sizeof(float4), cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) { delete[] h; return fail_cuda(e); }
-            for (uint64_t i = 0; i < ni; ++i) { dst[i].x = h[i].x; dst[i].y = h[i].y; dst[i].z = h[i].z; }
+            for (uint64_t i = 0; i < ni; ++i) { dst[i].x = h[2 * i + pass].x; dst[i].y = h[2 * i + pass].y; dst[i].z = h[2 * i + pass].z; }
         }
         delete[] h;
     }

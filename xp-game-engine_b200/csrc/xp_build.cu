@@ -206,22 +206,28 @@ static constexpr int RS_ITEMS = 16;
 static constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 keys per block
 static constexpr int RS_WARPS = RS_THREADS / 32;
 static constexpr int RS_SEG = RS_TILE / RS_WARPS;       // 512 consecutive keys per warp
+#ifndef XP_RS_BITS
+#define XP_RS_BITS 10
+#endif
+static constexpr int RS_BITS = XP_RS_BITS;              // digit width: 10 bits = three passes over the 30-bit Morton codes
+static constexpr int RS_BINS = 1 << RS_BITS;
+static constexpr unsigned RS_MASK = RS_BINS - 1;
 
 // per-tile digit histogram, stored digit-major so one flat exclusive scan yields the bases
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t *__restrict__ keys, uint64_t n,
                                                         int shift, uint32_t *__restrict__ hist,
                                                         unsigned num_tiles) {
-    __shared__ unsigned h[256];
-    h[threadIdx.x] = 0;
+    __shared__ unsigned h[RS_BINS];
+    for (int b = threadIdx.x; b < RS_BINS; b += RS_THREADS) h[b] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
 #pragma unroll 4
     for (int c = 0; c < RS_ITEMS; ++c) {
         uint64_t idx = base + (uint64_t)c * RS_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & RS_MASK], 1u);
     }
     __syncthreads();
-    hist[(uint64_t)threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
+    for (int b = threadIdx.x; b < RS_BINS; b += RS_THREADS) hist[(uint64_t)b * num_tiles + blockIdx.x] = h[b];
 }
 
 // stable scatter: warp w owns keys [w*512, (w+1)*512) of the tile, processed in chunks of 32.
@@ -232,9 +238,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__res
                                                            uint32_t *__restrict__ vals_out, uint64_t n,
                                                            int shift, const uint32_t *__restrict__ scanned,
                                                            unsigned num_tiles, uint32_t *__restrict__ inv_out) {
-    __shared__ unsigned cnt[RS_WARPS][256];
+    __shared__ unsigned cnt[RS_WARPS][RS_BINS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)w * RS_SEG;
     uint32_t k[RS_ITEMS], v[RS_ITEMS];
@@ -247,15 +253,14 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__res
         v[c] = valid ? vals_in[idx] : 0u;
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
         if (valid) {
-            const unsigned d = (k[c] >> shift) & 255u;
+            const unsigned d = (k[c] >> shift) & RS_MASK;
             const unsigned peers = __match_any_sync(vm, d);
             if (lane == (31 - __clz(peers))) cnt[w][d] += __popc(peers);
         }
         __syncwarp();
     }
     __syncthreads();
-    {   // exclusive prefix over warps, seeded with this tile's global base for the digit
-        const unsigned d = threadIdx.x;
+    for (unsigned d = threadIdx.x; d < (unsigned)RS_BINS; d += RS_THREADS) {   // exclusive prefix over warps, seeded with this tile's global base for the digit
         unsigned run = scanned[(uint64_t)d * num_tiles + blockIdx.x];
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ++ww) {
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__res
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
         unsigned d = 0, peers = 0;
         if (valid) {
-            d = (k[c] >> shift) & 255u;
+            d = (k[c] >> shift) & RS_MASK;
             peers = __match_any_sync(vm, d);
             const unsigned pos = cnt[w][d] + __popc(peers & ((1u << lane) - 1u));
             keys_out[pos] = k[c];
@@ -360,20 +365,20 @@ cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *
     *in_a = true;
     if (n == 0) return cudaSuccess;
     const unsigned tiles = grid_for(n, RS_TILE);
-    const uint64_t hist_n = (uint64_t)tiles * 256;
+    const uint64_t hist_n = (uint64_t)tiles * RS_BINS;
     // histogram + scan scratch (geometric series of block sums: < hist_n/2047 + 64)
     cudaError_t e = s->hist.reserve((hist_n + hist_n / 1024 + 4096) * sizeof(uint32_t));
     if (e != cudaSuccess) return e;
     uint32_t *hist = s->hist.as<uint32_t>();
     uint32_t *scratch = hist + hist_n;
     uint32_t *ki = ka, *ko = kb, *vi = va, *vo = vb;
-    for (int shift = 0; shift < bits; shift += 8) {
+    for (int shift = 0; shift < bits; shift += RS_BITS) {
         k_rs_hist<<<tiles, RS_THREADS, 0, s->stream>>>(ki, n, shift, hist, tiles);
         ++s->stats.kernel_launches;
         e = exclusive_scan_u32(hist, hist_n, scratch, s->stream, &s->stats.kernel_launches);
         if (e != cudaSuccess) return e;
         k_rs_scatter<<<tiles, RS_THREADS, 0, s->stream>>>(ki, vi, ko, vo, n, shift, hist, tiles,
-                                                          shift + 8 >= bits ? inv_out : nullptr);
+                                                          shift + RS_BITS >= bits ? inv_out : nullptr);
         ++s->stats.kernel_launches;
         uint32_t *t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;
@@ -385,9 +390,8 @@ cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *
 // K1 -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uint64_t n,
                                               const uint32_t *__restrict__ sorted_idx,
-                                              TriRec *__restrict__ recs, float4 *__restrict__ leaf_lo,
-                                              float4 *__restrict__ leaf_hi, uint32_t *__restrict__ degen,
-                                              TriRec *__restrict__ recs_upload) {
+                                              TriRec *__restrict__ recs, float4 *__restrict__ leaf_box,
+                                              uint32_t *__restrict__ degen, TriRec *__restrict__ recs_upload) {
     uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint32_t i = sorted_idx[j];
@@ -423,8 +427,8 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
         const float m2 = fmaxf(l1, l2);
         if (!(cc > 1e-4f * (l1 * l2)) || !(cc * 1.7e5f > m2 * m2 * m2)) degen[1 + atomicAdd(&degen[0], 1u)] = (uint32_t)j;
     }
-    leaf_lo[j] = make_float4(lo.x, lo.y, lo.z, 0.0f);
-    leaf_hi[j] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    leaf_box[2 * j] = make_float4(lo.x, lo.y, lo.z, 0.0f);          // (lo, hi) side by side: one 32 B sector per box for the refit
+    leaf_box[2 * j + 1] = make_float4(hi.x, hi.y, hi.z, 0.0f);
 }
 
 // K4: Karras 2012 ------------------------------------------------------------------------------
@@ -468,9 +472,8 @@ __global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ key
 __global__ void __launch_bounds__(256) k_refit(int n, Node *__restrict__ nodes,
                                                const int *__restrict__ parent_internal,
                                                const int *__restrict__ parent_leaf,
-                                               const float4 *__restrict__ leaf_lo,
-                                               const float4 *__restrict__ leaf_hi, float4 *node_lo,
-                                               float4 *node_hi, unsigned *__restrict__ flags) {
+                                               const float4 *__restrict__ leaf_box, float4 *node_box,
+                                               unsigned *__restrict__ flags) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     int cur = parent_leaf[j];
@@ -478,15 +481,15 @@ __global__ void __launch_bounds__(256) k_refit(int n, Node *__restrict__ nodes,
         if (atomicAdd(&flags[cur], 1u) == 0u) return;     // first arrival: the sibling finishes
         const int4 link = nodes[cur].link;
         float4 lo0, hi0, lo1, hi1;
-        if (link.x < 0) { lo0 = leaf_lo[~link.x]; hi0 = leaf_hi[~link.x]; }
-        else { lo0 = __ldcg(&node_lo[link.x]); hi0 = __ldcg(&node_hi[link.x]); }
-        if (link.y < 0) { lo1 = leaf_lo[~link.y]; hi1 = leaf_hi[~link.y]; }
-        else { lo1 = __ldcg(&node_lo[link.y]); hi1 = __ldcg(&node_hi[link.y]); }
+        if (link.x < 0) { lo0 = leaf_box[2 * (~link.x)]; hi0 = leaf_box[2 * (~link.x) + 1]; }
+        else { lo0 = __ldcg(&node_box[2 * link.x]); hi0 = __ldcg(&node_box[2 * link.x + 1]); }
+        if (link.y < 0) { lo1 = leaf_box[2 * (~link.y)]; hi1 = leaf_box[2 * (~link.y) + 1]; }
+        else { lo1 = __ldcg(&node_box[2 * link.y]); hi1 = __ldcg(&node_box[2 * link.y + 1]); }
         nodes[cur].q0 = make_float4(lo0.x, lo0.y, lo0.z, hi0.x);
         nodes[cur].q1 = make_float4(hi0.y, hi0.z, lo1.x, lo1.y);
         nodes[cur].q2 = make_float4(lo1.z, hi1.x, hi1.y, hi1.z);
-        __stcg(&node_lo[cur], make_float4(fminf(lo0.x, lo1.x), fminf(lo0.y, lo1.y), fminf(lo0.z, lo1.z), 0.0f));
-        __stcg(&node_hi[cur], make_float4(fmaxf(hi0.x, hi1.x), fmaxf(hi0.y, hi1.y), fmaxf(hi0.z, hi1.z), 0.0f));
+        __stcg(&node_box[2 * cur], make_float4(fminf(lo0.x, lo1.x), fminf(lo0.y, lo1.y), fminf(lo0.z, lo1.z), 0.0f));
+        __stcg(&node_box[2 * cur + 1], make_float4(fmaxf(hi0.x, hi1.x), fmaxf(hi0.y, hi1.y), fmaxf(hi0.z, hi1.z), 0.0f));
         __threadfence();
         cur = parent_internal[cur];
     }
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(256) k_refit(int n, Node *__restrict__ nodes,
 // the union box that becomes the node's own entry one level up.  Missing children get the empty
 // box (+inf, -inf), which the slab test can never hit.
 __global__ void __launch_bounds__(256) k_wide_level(const float4 *__restrict__ src_lo,
-                                                    const float4 *__restrict__ src_hi, uint64_t n_src,
+                                                    const float4 *__restrict__ src_hi, int src_stride, uint64_t n_src,
                                                     float *__restrict__ planes, float4 *__restrict__ dst_lo,
                                                     float4 *__restrict__ dst_hi, uint64_t n_dst) {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(256) k_wide_level(const float4 *__restrict__ s
     const int lane = threadIdx.x & 31;
     float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
     float4 hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
-    if (t < n_src) { lo = src_lo[t]; hi = src_hi[t]; }
+    if (t < n_src) { lo = src_lo[t * src_stride]; hi = src_hi[t * src_stride]; }
     float *node = planes + (t >> 5) * WIDE_NODE_FLOATS;
     node[0 * 32 + lane] = lo.x; node[1 * 32 + lane] = lo.y; node[2 * 32 + lane] = lo.z;
     node[3 * 32 + lane] = hi.x; node[4 * 32 + lane] = hi.y; node[5 * 32 + lane] = hi.z;
@@ -592,15 +595,14 @@ __global__ void __launch_bounds__(256) k_collapse4(const Node *__restrict__ node
 }
 
 // a scene with one triangle: root = (leaf 0, empty); the empty box (+inf,-inf) can never be hit
-__global__ void k_single_root(Node *nodes, const float4 *leaf_lo, const float4 *leaf_hi,
-                              float4 *node_lo, float4 *node_hi) {
-    const float4 lo = leaf_lo[0], hi = leaf_hi[0];
+__global__ void k_single_root(Node *nodes, const float4 *leaf_box, float4 *node_box) {
+    const float4 lo = leaf_box[0], hi = leaf_box[1];
     const float inf = INFINITY;
     nodes[0].q0 = make_float4(lo.x, lo.y, lo.z, hi.x);
     nodes[0].q1 = make_float4(hi.y, hi.z, inf, inf);
     nodes[0].q2 = make_float4(inf, -inf, -inf, -inf);
     nodes[0].link = make_int4(~0, ~0, 0, 0);
-    node_lo[0] = lo; node_hi[0] = hi;
+    node_box[0] = lo; node_box[1] = hi;
 }
 
 // Row f2 of SURVEY.md section 8: heightmap terrain -> triangle soup ON THE DEVICE.  Emits, for every quad
@@ -751,8 +753,7 @@ cudaError_t build_lbvh(xp_scene *s) {
     XP_TRY(s->vals_a.reserve(n * 4)); XP_TRY(s->vals_b.reserve(n * 4));
     XP_TRY(s->recs.reserve(n * sizeof(TriRec)));
     XP_TRY(s->nodes.reserve((n > 1 ? n - 1 : 1) * sizeof(Node)));
-    XP_TRY(s->node_lo.reserve(n * 16)); XP_TRY(s->node_hi.reserve(n * 16));
-    XP_TRY(s->leaf_lo.reserve(n * 16)); XP_TRY(s->leaf_hi.reserve(n * 16));
+    XP_TRY(s->node_box.reserve(n * 32)); XP_TRY(s->leaf_box.reserve(n * 32));
     XP_TRY(s->parent_internal.reserve(n * 4)); XP_TRY(s->parent_leaf.reserve(n * 4));
     XP_TRY(s->refit_flags.reserve(n * 4));
     unsigned *bounds = s->bounds.as<unsigned>();
@@ -774,7 +775,7 @@ cudaError_t build_lbvh(xp_scene *s) {
     {
         StageTimer t(s, XP_STAGE_BUILD_SORT);
         XP_TRY(radix_sort_pairs(s, s->keys_a.as<uint32_t>(), s->keys_b.as<uint32_t>(),
-                                s->vals_a.as<uint32_t>(), s->vals_b.as<uint32_t>(), n, 32, &in_a));
+                                s->vals_a.as<uint32_t>(), s->vals_b.as<uint32_t>(), n, 30, &in_a));   // 30-bit Morton codes
     }
     if (!in_a) {   // keep the sorted arrays in *_a (scene invariant used by debug_tree and queries)
         xp::DevBuf t = s->keys_a; s->keys_a = s->keys_b; s->keys_b = t;
@@ -788,13 +789,12 @@ cudaError_t build_lbvh(xp_scene *s) {
         XP_TRY(cudaMemsetAsync(s->degen.p, 0, sizeof(uint32_t), st));
         if (s->grid_valid) XP_TRY(s->recs_grid.reserve(n * sizeof(TriRec)));
         k_pack<<<grid_for(n, 256), 256, 0, st>>>(aos, n, vals, s->recs.as<TriRec>(),
-                                                s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>(), s->degen.as<uint32_t>(),
+                                                s->leaf_box.as<float4>(), s->degen.as<uint32_t>(),
                                                 s->grid_valid ? s->recs_grid.as<TriRec>() : nullptr);
         ++s->stats.kernel_launches;
     }
     if (n == 1) {
-        k_single_root<<<1, 1, 0, st>>>(s->nodes.as<Node>(), s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>(),
-                                       s->node_lo.as<float4>(), s->node_hi.as<float4>());
+        k_single_root<<<1, 1, 0, st>>>(s->nodes.as<Node>(), s->leaf_box.as<float4>(), s->node_box.as<float4>());
         ++s->stats.kernel_launches;
     } else {
         {
@@ -809,8 +809,7 @@ cudaError_t build_lbvh(xp_scene *s) {
             XP_TRY(cudaMemsetAsync(s->refit_flags.p, 0, n * 4, st));
             k_refit<<<grid_for(n, 256), 256, 0, st>>>((int)n, s->nodes.as<Node>(),
                                                      s->parent_internal.as<int>(), s->parent_leaf.as<int>(),
-                                                     s->leaf_lo.as<float4>(), s->leaf_hi.as<float4>(),
-                                                     s->node_lo.as<float4>(), s->node_hi.as<float4>(),
+                                                     s->leaf_box.as<float4>(), s->node_box.as<float4>(),
                                                      s->refit_flags.as<unsigned>());
             ++s->stats.kernel_launches;
         }
@@ -854,15 +853,16 @@ cudaError_t build_aux(xp_scene *s) {
         XP_TRY(s->wide.reserve(total * WIDE_NODE_FLOATS * sizeof(float)));
         XP_TRY(s->wide_lo.reserve(total * 16));
         XP_TRY(s->wide_hi.reserve(total * 16));
-        const float4 *src_lo = s->leaf_lo.as<float4>(), *src_hi = s->leaf_hi.as<float4>();
+        const float4 *src_lo = s->leaf_box.as<float4>(), *src_hi = s->leaf_box.as<float4>() + 1;
+        int src_stride = 2;
         uint64_t n_src = n;
         for (int L = 0; L < levels; ++L) {
             float *planes = s->wide.as<float>() + (uint64_t)s->wide_tree.off[L] * WIDE_NODE_FLOATS;
             float4 *dlo = s->wide_lo.as<float4>() + s->wide_tree.off[L];
             float4 *dhi = s->wide_hi.as<float4>() + s->wide_tree.off[L];
-            k_wide_level<<<grid_for(cnt[L] * 32, 256), 256, 0, st>>>(src_lo, src_hi, n_src, planes, dlo, dhi, cnt[L]);
+            k_wide_level<<<grid_for(cnt[L] * 32, 256), 256, 0, st>>>(src_lo, src_hi, src_stride, n_src, planes, dlo, dhi, cnt[L]);
             ++s->stats.kernel_launches;
-            src_lo = dlo; src_hi = dhi; n_src = cnt[L];
+            src_lo = dlo; src_hi = dhi; src_stride = 1; n_src = cnt[L];
         }
         s->wide_tree.planes = s->wide.as<float>();
         s->wide_tree.top = levels - 1;

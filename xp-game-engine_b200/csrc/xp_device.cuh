@@ -104,7 +104,6 @@ struct xp_scene {
     bool pair_overflowed = false;      // optimistic mode dropped candidates: results must be recomputed
     bool counters_live = false;        // device counters hold uncollected statistics
     const unsigned *na_dev = nullptr;  // response loop: device address of the live ray count (null: the host knows it)
-    bool in_response_loop = false;     // sweeps of a response / slide loop: XP_OPT_PRUNE = 2 (auto) turns the entry-time cull on
     uint64_t swept_rays = 0;           // rays swept since the counters were zeroed
     double cand_per_ray = 0.0;         // candidates per sphere of the last exhaustive sweep (XP_OPT_PRUNE = 2)
     // geometry
@@ -114,7 +113,7 @@ struct xp_scene {
     xp::DevBuf tris_aos;      // xp_triangle[T], upload order
     xp::DevBuf recs;          // TriRec[T], Morton order
     xp::DevBuf nodes;         // Node[max(T-1,1)]
-    xp::DevBuf node_lo, node_hi, leaf_lo, leaf_hi;   // float4 boxes used by the refit
+    xp::DevBuf node_box, leaf_box;                   // float4 (lo, hi) pairs, 32 B per box, used by the refit
     xp::DevBuf parent_internal, parent_leaf, refit_flags;
     xp::DevBuf keys_a, keys_b, vals_a, vals_b;       // radix sort ping-pong (triangles / spheres)
     xp::DevBuf hist;          // radix histograms + scan scratch

@@ -115,12 +115,10 @@ XP_HD bool grid_window_test(const GridRay &r, const GridCol &col, float hmin, fl
 
 // Predicate P for the two triangles of cell (ix, iz): bit 0 = (p00, p01, p11), bit 1 = (p00, p11, p10).
 // z_lo / z_hi: grid_coord(z0, sp, iz), grid_coord(z0, sp, iz + 1) (carried from cell to cell by the caller).
-// t_cell: when the ray enters the cell's x-z footprint -- a lower bound of both triangles' box entry times.
 XP_HD unsigned grid_cell_test(const GridRay &r, const GridCol &col, float z_lo, float z_hi, float h00, float h01,
-                              float h10, float h11, float &t_cell) {
+                              float h10, float h11) {
     float tmin = col.tx_lo, tmax = col.tx_hi;
     grid_slab_axis(r.c.z, r.inv.z, ExactOps::sub(z_lo, XP_INFLATE), ExactOps::add(z_hi, XP_INFLATE), tmin, tmax);
-    t_cell = tmin;
     if (!(tmin <= tmax)) return 0u;
     float amin = tmin, amax = tmax, bmin = tmin, bmax = tmax;
     grid_slab_axis(r.c.y, r.inv.y, ExactOps::sub(x_min3(h00, h01, h11), XP_INFLATE), ExactOps::add(x_max3(h00, h01, h11), XP_INFLATE), amin, amax);

@@ -42,18 +42,6 @@ static constexpr uint32_t LEAF_MASK = (1u << 27) - 1u;
 
 __device__ __forceinline__ V3 f4_xyz(float4 q) { return {q.x, q.y, q.z}; }
 
-// A candidate pair is (ray slot, leaf / triangle) in 8 bytes.  Ray slots of one chunk fit 24 bits (chunks hold <= 2^24
-// rays), so the top byte of the first word carries a coarse, ROUNDED-DOWN code of the time at which the ray enters the
-// candidate's box (3 mantissa bits, exponents 2^-6 .. 2^25; 0 = "at once").  The narrowphase's entry-time cull
-// (k_narrow_pairs<.., CULL>) skips a pair whose entry time lies beyond the sphere's best hit so far: a contact with
-// that triangle happens inside its box, i.e. not before the ray enters it.
-static constexpr uint32_t PAIR_RAY_MASK = 0x00FFFFFFu;
-__device__ __forceinline__ uint32_t tn_quant(float tn) {
-    const int qv = (int)(__float_as_uint(tn) >> 20) - ((127 - 6) << 3);
-    return (uint32_t)min(255, max(0, qv));
-}
-__device__ __forceinline__ float tn_dequant(uint32_t qv) { return qv ? __uint_as_float((qv + ((127u - 6u) << 3)) << 20) : 0.0f; }
-
 // ------------------------------------------------------------------------------------------
 // ray setup: collision_detect.rs:161 (r == 1), :163 (normalised movement), :179-180 (|m|, |m|^2)
 // plus the slab reciprocals of predicate P
@@ -361,6 +349,9 @@ static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at 
 #ifndef XP_BP_STEAL
 #define XP_BP_STEAL 1
 #endif
+#ifndef XP_BP_LANESORT
+#define XP_BP_LANESORT 1           // write a span out grouped by emitting lane (per-ray runs for the narrowphase)
+#endif
 // Measured on config 2 (stage-1 ms, before the swizzled gather): 2 blocks/SM 1.34, 3: 1.22, 4: 1.26, 5: 1.32,
 // 6: 1.38, 7 (spills): 1.59; with it 3: 0.95, 4: 0.98, 5: 1.06; with work stealing and the cp.async gather
 // 2: 0.93, 3: 0.745, 4: 0.727, 5: 0.765, 6: 0.98.
@@ -529,7 +520,6 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
 #endif
         n_nodes += __popc(__ballot_sync(FULL, node >= 0));
         int leaf_a = -1, leaf_b = -1;
-        float tn_a = 0.0f, tn_b = 0.0f;        // entry times of the emitted leaves' boxes
         if (node >= 0) {
             const int2 link = make_int2(__float_as_int(n3.x), __float_as_int(n3.y));
             float ta, tb, fa, fb;
@@ -547,12 +537,11 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                 hit_a = hit_a && ta < t_hi && fa >= t_lo;
                 hit_b = hit_b && tb < t_hi && fb >= t_lo;
             }
-            if (hit_a && link.x < 0) { if (MODE != 1 || ta >= t_lo) { leaf_a = ~link.x; tn_a = ta; } hit_a = false; }
-            if (hit_b && link.y < 0) { if (MODE != 1 || tb >= t_lo) { leaf_b = ~link.y; tn_b = tb; } hit_b = false; }
+            if (hit_a && link.x < 0) { if (MODE != 1 || ta >= t_lo) leaf_a = ~link.x; hit_a = false; }
+            if (hit_b && link.y < 0) { if (MODE != 1 || tb >= t_lo) leaf_b = ~link.y; hit_b = false; }
             if (hit_a && hit_b) {
-                const bool a_first = ta <= tb;             // near child first: candidates come out roughly by entry time
-                node = a_first ? link.x : link.y;
-                if (sp < STACK_DEPTH) stack[sp++] = a_first ? link.y : link.x;
+                node = link.x;
+                if (sp < STACK_DEPTH) stack[sp++] = link.y;
                 else atomicExch(&ctr->stack_overflow, 1u);
             } else if (hit_a) node = link.x;
             else if (hit_b) node = link.y;
@@ -568,8 +557,8 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                 if (leaf_b >= 0) leaf_b = (int)__ldg(&leaf_to_tri[leaf_b]);
             }
             // (the emitting lane rides in the top 5 bits of the leaf word until the span is written out)
-            if (leaf_a >= 0) q[count + __popc(ma & lt_mask)] = make_uint2((ray0 + my_ray) | (tn_quant(tn_a) << 24), ((uint32_t)lane << 27) | (uint32_t)leaf_a);
-            if (leaf_b >= 0) q[count + na + __popc(mb & lt_mask)] = make_uint2((ray0 + my_ray) | (tn_quant(tn_b) << 24), ((uint32_t)lane << 27) | (uint32_t)leaf_b);
+            if (leaf_a >= 0) q[count + __popc(ma & lt_mask)] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)leaf_a);
+            if (leaf_b >= 0) q[count + na + __popc(mb & lt_mask)] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)leaf_b);
             count += na + __popc(mb);
             __syncwarp();
             if (count >= BP_SPAN) {
@@ -581,6 +570,12 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                 if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)BP_SPAN);
                 base = __shfl_sync(FULL, base, 0);
                 count -= BP_SPAN;
+#if !XP_BP_LANESORT
+#pragma unroll 4
+                for (int w = lane; w < BP_SPAN; w += 32)
+                    if (base + w < pair_cap) __stcs(&pairs_out[base + w], make_uint2(q[count + w].x, q[count + w].y & LEAF_MASK));
+                __syncwarp();
+#else
                 uint2 e[BP_SPAN / 32];
                 unsigned rank[BP_SPAN / 32];
                 bucket[lane] = 0u;
@@ -604,6 +599,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                     if (w < pair_cap) __stcs(&pairs_out[w], make_uint2(e[k].x, e[k].y & LEAF_MASK));   // streaming: keep the tree in L2
                 }
                 __syncwarp();
+#endif
             }
         }
     }
@@ -717,8 +713,7 @@ k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayR
             if (!__any_sync(FULL, need)) break;
             if (need) {
                 if (col.iz > col.iz_hi) {
-                    // columns in the ray's direction of travel: candidates reach the narrowphase roughly by entry time
-                    cur_ix = (r.m.x < 0.0f) ? r.ix_hi-- : r.ix++;
+                    cur_ix = r.ix++;
                     grid_col_setup(g, r, cur_ix, col);
                 }
                 if (col.iz <= col.iz_hi) {
@@ -734,7 +729,7 @@ k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayR
             z_lo = grid_coord(g.z0, g.sp, col.iz);
         }
         // ---- up to GW_CELLS cells of the column, two triangles each
-        unsigned mask = 0, tq0 = 0, tq1 = 0;                     // hit bits; 8-bit entry-time codes of cells 0-3 / 4-7
+        unsigned mask = 0;
         const unsigned first_tri = 2u * ((unsigned)cur_ix * g.nz + (unsigned)col.iz);
         {
             const float *p = g.h + (size_t)cur_ix * row + col.iz + 1;
@@ -743,9 +738,7 @@ k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayR
                 if (ready && col.iz <= col.iz_hi) {
                     const float h01 = __ldg(p + k), h11 = __ldg(p + row + k);
                     const float z_hi = grid_coord(g.z0, g.sp, col.iz + 1);
-                    float t_cell;
-                    mask |= grid_cell_test(r, col, z_lo, z_hi, h00, h01, h10, h11, t_cell) << (2 * k);
-                    if (k < 4) tq0 |= tn_quant(t_cell) << (8 * k); else tq1 |= tn_quant(t_cell) << (8 * (k - 4));
+                    mask |= grid_cell_test(r, col, z_lo, z_hi, h00, h01, h10, h11) << (2 * k);
                     h00 = h01; h10 = h11; z_lo = z_hi;
                     ++col.iz;
                     ++n_cells;
@@ -764,8 +757,7 @@ k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayR
             while (mask) {
                 const unsigned b = __ffs(mask) - 1;
                 mask &= mask - 1;
-                const unsigned code = ((b < 8 ? tq0 : tq1) >> (8 * ((b >> 1) & 3))) & 0xFFu;
-                q[pos++] = make_uint2(ray_id | (code << 24), first_tri + b);   // bit 2k+s <-> triangle 2 (cell0 + k) + s
+                q[pos++] = make_uint2(ray_id, first_tri + b);           // bit 2k+s <-> triangle 2 (cell0 + k) + s
             }
             __syncwarp();
             unsigned long long base = 0;
@@ -1099,9 +1091,7 @@ __device__ __noinline__ bool detect_literal_call(const RayRec *__restrict__ rays
 #ifndef XP_NP_BLOCKS_F
 #define XP_NP_BLOCKS_F 4
 #endif
-// CULL: skip a pair the ray enters after the sphere's best hit so far (XP_OPT_PRUNE; the response loop).  The closest
-// collision is unchanged -- a pair with t <= best is never skipped -- only fewer pairs are evaluated.
-template <int MODE, bool FILTER, bool CULL = false>
+template <int MODE, bool FILTER>
 __global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == NP_F ? XP_NP_BLOCKS_F : XP_NP_BLOCKS) k_narrow_pairs(const TriRec *__restrict__ recs,
                                                       const RayRec *__restrict__ rays,
                                                       const uint2 *__restrict__ pairs,
@@ -1111,7 +1101,7 @@ __global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == N
     unsigned long long n = ctr->pairs;
     if (blockIdx.x == 0 && threadIdx.x == 0) {       // accounting stays on the device: no host round trip per chunk
         if (n > pair_cap) ctr->pair_overflow = 1u;    // candidates were dropped: the host reruns with smaller chunks
-        if (!FILTER && !CULL) atomicAdd(&ctr->tests, n > pair_cap ? (unsigned long long)pair_cap : n);
+        if (!FILTER) atomicAdd(&ctr->tests, n > pair_cap ? (unsigned long long)pair_cap : n);
         atomicAdd(&ctr->pairs_total, n);
     }
     if (n > pair_cap) n = pair_cap;
@@ -1124,15 +1114,7 @@ __global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == N
     constexpr unsigned long long NP_SPAN = XP_NP_SPAN;
     for (unsigned long long s0 = blockIdx.x * NP_SPAN; s0 < n; s0 += (unsigned long long)gridDim.x * NP_SPAN)
     for (unsigned long long p = s0 + threadIdx.x; p < n && p < s0 + NP_SPAN; p += blockDim.x) {
-        uint2 pr = __ldcs(&pairs[p]);                    // read once: streaming
-        const uint32_t tn_code = pr.x >> 24;
-        pr.x &= PAIR_RAY_MASK;
-        if (CULL) {
-            // best so far (L2 copy: other blocks lower it concurrently; a stale value only culls less).  No hit yet = NaN.
-            const float bt = __uint_as_float((unsigned)(__ldcg(&best[pr.x]) >> 32));
-            if (tn_dequant(tn_code) > bt) continue;
-            ++kept;
-        }
+        const uint2 pr = __ldcs(&pairs[p]);              // read once: streaming
         const float4 *rp = reinterpret_cast<const float4 *>(rays + pr.x);
         const float4 *tp = reinterpret_cast<const float4 *>(recs + pr.y);
 #if XP_NP_LDG256
@@ -1177,7 +1159,7 @@ __global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == N
             atomicMin(&best[pr.x], key);
         }
     }
-    if (FILTER || CULL) {
+    if (FILTER) {
         for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(FULL, kept, o);
         if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&ctr->tests, (unsigned long long)kept);
     }
@@ -1608,7 +1590,7 @@ __global__ void k_translate_pairs(const uint2 *__restrict__ pairs, uint64_t n, u
     const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (p >= n || out_base + p >= cap) return;
     const uint2 pr = pairs[p];
-    sphere_idx[out_base + p] = active ? active[pr.x & PAIR_RAY_MASK] : (pr.x & PAIR_RAY_MASK);
+    sphere_idx[out_base + p] = active ? active[pr.x] : pr.x;
     tri_idx[out_base + p] = recs ? __float_as_uint(recs[pr.y].q3.w) : pr.y;      // null: the pairs already hold upload indices
 }
 
@@ -1782,9 +1764,9 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
     // on the volumetric config-3 scene).  No read-back between passes: a pass over finished spheres only
     // costs their ray fetch.
     static const float kWin[] = {0.0f, 4.0f, 16.0f, 64.0f, 256.0f, 1024.0f, INFINITY};
-    const bool grid = !far && grid_walk_on(s);        // a heightmap scene: the grid walk (pruning = the entry-time cull alone)
-    const bool windows = !far && !grid && s->method == XP_METHOD_LBVH_PAIRS && (s->prune == 1 || (s->prune == 2 && s->cand_per_ray > 96.0));
+    const bool windows = !far && s->method == XP_METHOD_LBVH_PAIRS && (s->prune == 1 || (s->prune == 2 && s->cand_per_ray > 96.0));
     const int n_pass = windows ? 6 : 1;
+    const bool grid = !far && !windows && grid_walk_on(s);
     if (grid) recs = s->recs_grid.as<TriRec>();      // the grid walk names triangles by upload index
     uint64_t pos = 0;
     unsigned long long snap_tests = 0, snap_pairs = 0;   // synchronous mode: accounting before the current chunk
@@ -1827,12 +1809,6 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
             const unsigned ng = (unsigned)s->n_sm * 2u * (unsigned)np_blocks;          // two waves of resident blocks
 #define XP_NP_LAUNCH(M) do { if (q4) k_narrow_pairs<M, true><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
                              else k_narrow_pairs<M, false><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); } while (0)
-            // entry-time cull: whenever pruning is in force (explicitly, by the auto rule's distance windows, or inside a
-            // response / slide loop, which reports no triangle and whose metric is spheres resolved)
-            const bool cull = !q4 && !far && (s->prune == 1 || windows || (s->prune == 2 && s->in_response_loop));
-            if (cull && s->arith == XP_ARITH_FAST) k_narrow_pairs<NP_F, false, true><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
-            else if (cull && s->arith == XP_ARITH_EXACT) k_narrow_pairs<NP_X, false, true><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best);
-            else
             switch (s->arith) {
             case XP_ARITH_FAST: XP_NP_LAUNCH(NP_F); break;
             case XP_ARITH_EXACT_LITERAL: XP_NP_LAUNCH(NP_LITERAL_EXACT); break;
@@ -1989,9 +1965,8 @@ static cudaError_t response_chunk_device(xp_scene *s, xp_response *cur, uint64_t
     const uint32_t *list = order;                                   // null = identity
     uint32_t *spare[2] = {(order == s->active_b.as<uint32_t>()) ? s->active_a.as<uint32_t>() : s->active_b.as<uint32_t>(),
                           s->active_c.as<uint32_t>()};
-    struct Guard { xp_scene *s; ~Guard() { s->na_dev = nullptr; s->in_response_loop = false; } } guard{s};
+    struct Guard { xp_scene *s; ~Guard() { s->na_dev = nullptr; } } guard{s};
     s->na_dev = nullptr;
-    s->in_response_loop = true;
     XP_TRY(ray_setup(s, cur, list, m, horizon, status));
     uint32_t it = 0;
     bool live = true;

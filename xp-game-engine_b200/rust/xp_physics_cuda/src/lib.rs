@@ -14,6 +14,19 @@ use std::os::raw::c_int;
 #[repr(C)] #[derive(Clone, Copy, Debug)] pub struct Collision {
     pub time_to: f32, pub distance_to: f32, pub position: Vec3f, pub intersection: Vec3f,
 }
+/// xp_hit: time of impact + triangle (u32::MAX = no collision)
+#[repr(C)] #[derive(Clone, Copy, Debug)] pub struct Hit { pub time_to: f32, pub tri_index: u32 }
+impl Collision {
+    /// collision_detect.rs:188-194: every field is a function of (c, m, t)
+    pub fn from_hit(r: &Response, h: &Hit) -> Option<Collision> {
+        if h.tri_index == u32::MAX { return None; }
+        let (c, m, t) = (r.sphere.c, r.movement, h.time_to);
+        let ml = ((m.x * m.x + m.y * m.y) + m.z * m.z).sqrt();
+        let position = Vec3f { x: c.x + m.x * t, y: c.y + m.y * t, z: c.z + m.z * t };
+        let intersection = Vec3f { x: position.x + m.x / ml * r.sphere.r, y: position.y + m.y / ml * r.sphere.r, z: position.z + m.z / ml * r.sphere.r };
+        Some(Collision { time_to: t, distance_to: ml * t, position, intersection })
+    }
+}
 impl From<Vec3> for Vec3f { fn from(v: Vec3) -> Self { Vec3f { x: v.x, y: v.y, z: v.z } } }
 impl From<Vec3f> for Vec3 { fn from(v: Vec3f) -> Self { nalgebra_glm::vec3(v.x, v.y, v.z) } }
 impl Sphere { pub fn new(c: Vec3, r: f32) -> Self { Sphere { c: c.into(), r } } }
@@ -36,6 +49,10 @@ extern "C" {
     fn xp_detect_batch_submit(s: *mut XpScene, input: *const Response, n: u64, horizon_mode: u32, out: *mut Collision,
                               hit: *mut u8, tri_index: *mut u32, status: *mut u32, ticket: *mut c_int) -> c_int;
     fn xp_detect_batch_wait(s: *mut XpScene, ticket: c_int) -> c_int;
+    // compact results (8 B per sphere over the host link); Collision::from_hit rebuilds the full record
+    fn xp_detect_batch_compact(s: *mut XpScene, input: *const Response, n: u64, horizon_mode: u32, out: *mut Hit,
+                               status: *mut u32) -> c_int;
+    fn xp_scene_set_heightmap(s: *mut XpScene, heights: *const f32, nx: u32, nz: u32, x0: f32, z0: f32, spacing: f32) -> c_int;
     fn xp_collision_response_batch(s: *mut XpScene, input: *const Response, n: u64, max_iter: u32, horizon_mode: u32,
                                    out: *mut Response, iterations: *mut u32, status: *mut u32,
                                    last_slide_normal: *mut Vec3f) -> c_int;
