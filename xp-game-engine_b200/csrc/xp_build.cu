@@ -18,6 +18,7 @@
 #include "xp_internal.h"
 #include "xp_narrowphase.cuh"
 #include "xp_gridwalk.cuh"
+#include "xp_rays.cuh"
 
 namespace xp {
 
@@ -173,9 +174,15 @@ __global__ void __launch_bounds__(1024) k_bin_offsets(uint32_t *__restrict__ bin
     if (threadIdx.x == 1023) group_tot[blockIdx.x] = ti;
 }
 
+// RAYS: the scatter also writes the sphere's ray record and an empty best key at its slot -- the ray setup of the
+// sweep that follows, fused (one launch and one gather of the Response less).
+template <class O, bool RAYS>
 __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict__ keys, uint64_t n,
                                                      uint32_t *__restrict__ offs, const uint32_t *__restrict__ group_tot,
-                                                     uint32_t *__restrict__ order, uint32_t *__restrict__ inv) {
+                                                     uint32_t *__restrict__ order, uint32_t *__restrict__ inv,
+                                                     const xp_response *__restrict__ in, RayRec *__restrict__ rays,
+                                                     unsigned long long *__restrict__ best, uint32_t *__restrict__ status,
+                                                     int have_tris) {
     __shared__ unsigned group_base[CS_GROUPS];
     if (threadIdx.x < 32) {                                  // exclusive prefix of the 64 group totals
         const unsigned a = group_tot[2 * threadIdx.x], b = group_tot[2 * threadIdx.x + 1];
@@ -198,6 +205,15 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict_
     const unsigned pos = base + __popc(peers & ((1u << lane) - 1u));
     order[pos] = (uint32_t)i;
     if (inv) inv[i] = pos;
+    if (RAYS) {
+        const float *p = reinterpret_cast<const float *>(in) + i * 7;
+        const V3 c = {__ldg(p + 0), __ldg(p + 1), __ldg(p + 2)};
+        const bool valid = __ldg(p + 3) == 1.0f;
+        const V3 m = {__ldg(p + 4), __ldg(p + 5), __ldg(p + 6)};
+        if (!valid && status && have_tris) status[i] |= XP_ST_RADIUS_NE_1;     // collision_detect.rs:161 (see k_ray_setup)
+        rays[pos] = make_ray_rec<O>(c, m, valid);
+        best[pos] = BEST_NONE;
+    }
 }
 
 // K3: radix sort -------------------------------------------------------------------------------
@@ -871,7 +887,9 @@ cudaError_t build_aux(xp_scene *s) {
     return cudaGetLastError();
 }
 
-cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order, uint32_t **inv_order) {
+cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order, uint32_t **inv_order,
+                                uint32_t *status_for_rays, bool *rays_done) {
+    if (rays_done) *rays_done = false;
     StageTimer t(s, XP_STAGE_SPHERE_SORT);
     XP_TRY(s->active_a.reserve(n * 4)); XP_TRY(s->active_b.reserve(n * 4));
     XP_TRY(s->sort_ka.reserve(n * 4)); XP_TRY(s->sort_kb.reserve(n * 4));
@@ -889,7 +907,16 @@ cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n
         XP_TRY(cudaMemsetAsync(bins, 0, CS_BINS * sizeof(uint32_t), s->stream));
         k_morton_spheres<<<grid_for(n, 256), 256, 0, s->stream>>>(d_in, n, s->bounds.as<unsigned>(), ka, va, key_mode, bins);
         k_bin_offsets<<<CS_GROUPS, 1024, 0, s->stream>>>(bins, bins + CS_BINS);
-        k_bin_scatter<<<grid_for(n, 256), 256, 0, s->stream>>>(ka, n, bins, bins + CS_BINS, va, inv);
+        if (rays_done) {             // the caller sweeps right away: write the ray records from here (s->rays / s->best are reserved)
+            RayRec *rays = s->rays.as<RayRec>();
+            unsigned long long *best = s->best.as<unsigned long long>();
+            const bool fast = s->arith == XP_ARITH_FAST || s->arith == XP_ARITH_FAST_LITERAL;
+            if (fast) k_bin_scatter<FastOps, true><<<grid_for(n, 256), 256, 0, s->stream>>>(ka, n, bins, bins + CS_BINS, va, inv, d_in, rays, best, status_for_rays, s->n_tris > 0);
+            else k_bin_scatter<ExactOps, true><<<grid_for(n, 256), 256, 0, s->stream>>>(ka, n, bins, bins + CS_BINS, va, inv, d_in, rays, best, status_for_rays, s->n_tris > 0);
+            *rays_done = true;
+        } else {
+            k_bin_scatter<ExactOps, false><<<grid_for(n, 256), 256, 0, s->stream>>>(ka, n, bins, bins + CS_BINS, va, inv, nullptr, nullptr, nullptr, nullptr, 0);
+        }
         s->stats.kernel_launches += 3;
         *order = va;
         return cudaGetLastError();

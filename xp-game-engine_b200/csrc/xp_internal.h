@@ -31,7 +31,10 @@ cudaError_t emit_clipmap(xp_scene *s, const float *d_heights, unsigned size, con
                          float unit0, uint64_t n_tris);
 cudaError_t build_aux(xp_scene *s);      // Node4 / 32-wide planes, on first use by the method that needs them
 // order[k] = index of the k-th sphere in Morton order of its centre (scene bounds).
-cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order, uint32_t **inv_order);
+// rays_done (nullable): when given, the ordering may also write the ray records + empty best keys of the sweep that
+// follows into s->rays / s->best (reserved by the caller) and reports whether it did; status_for_rays as in k_ray_setup.
+cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t **order, uint32_t **inv_order,
+                                uint32_t *status_for_rays = nullptr, bool *rays_done = nullptr);
 
 // ---- xp_query.cu ----
 static constexpr int XP_MAX_PEERS = 16;

@@ -30,6 +30,7 @@
 #include "xp_internal.h"
 #include "xp_narrowphase.cuh"
 #include "xp_gridwalk.cuh"
+#include "xp_rays.cuh"
 
 namespace xp {
 
@@ -46,24 +47,6 @@ __device__ __forceinline__ V3 f4_xyz(float4 q) { return {q.x, q.y, q.z}; }
 // ray setup: collision_detect.rs:161 (r == 1), :163 (normalised movement), :179-180 (|m|, |m|^2)
 // plus the slab reciprocals of predicate P
 // ------------------------------------------------------------------------------------------
-// The 64 B record of one sphere for one sweep (layout in xp_device.cuh).  valid: the r == 1 assert held.
-template <class O>
-__device__ __forceinline__ RayRec make_ray_rec(V3 c, V3 m, bool valid) {
-    uint32_t flags = valid ? RAY_VALID : 0u;
-    {   // finite centre and movement: the height-grid walk can enumerate this ray's cells (anything else walks the LBVH)
-        const float big = fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fabsf(c.z)), fmaxf(fmaxf(fabsf(m.x), fabsf(m.y)), fabsf(m.z)));
-        if (big <= XP_FLT_MAX && c.x == c.x && c.y == c.y && c.z == c.z && m.x == m.x && m.y == m.y && m.z == m.z) flags |= RAY_GRID_OK;
-    }
-    const Ray ray = xp_ray_setup<O>(c, m);
-    RayRec rr;
-    rr.q0 = make_float4(c.x, c.y, c.z, ray.ml);
-    rr.q1 = make_float4(m.x, m.y, m.z, ray.msl);
-    // q2.w: the per-ray operand of the narrowphase's one vertex-root division (+inf = irregular ray, literal path)
-    rr.q2 = make_float4(ray.mh.x, ray.mh.y, ray.mh.z, xp_ray_r2a<O>(ray));
-    rr.q3 = make_float4(fdiv(1.0f, m.x), fdiv(1.0f, m.y), fdiv(1.0f, m.z), __uint_as_float(flags));
-    return rr;
-}
-
 // n_active (nullable): the number of live entries, on the DEVICE -- the response loop runs without the host ever
 // learning how many spheres are still moving; launches are sized for the upper bound and clamp here.
 template <class O>
@@ -350,7 +333,7 @@ static constexpr int BP_QUEUE = BP_SPAN + 64;       // < BP_SPAN left over + at 
 #define XP_BP_STEAL 1
 #endif
 #ifndef XP_BP_LANESORT
-#define XP_BP_LANESORT 1           // write a span out grouped by emitting lane (per-ray runs for the narrowphase)
+#define XP_BP_LANESORT 0           // 1: write a span out grouped by emitting lane (per-ray runs for the narrowphase): -0.03 ms there (-0.10 fast), +0.05 ms here
 #endif
 // Measured on config 2 (stage-1 ms, before the swizzled gather): 2 blocks/SM 1.34, 3: 1.22, 4: 1.26, 5: 1.32,
 // 6: 1.38, 7 (spills): 1.59; with it 3: 0.95, 4: 0.98, 5: 1.06; with work stealing and the cp.async gather
@@ -1112,9 +1095,24 @@ __global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == N
 #define XP_NP_SPAN 2048
 #endif
     constexpr unsigned long long NP_SPAN = XP_NP_SPAN;
-    for (unsigned long long s0 = blockIdx.x * NP_SPAN; s0 < n; s0 += (unsigned long long)gridDim.x * NP_SPAN)
-    for (unsigned long long p = s0 + threadIdx.x; p < n && p < s0 + NP_SPAN; p += blockDim.x) {
+#ifndef XP_NP_PREFETCH
+#define XP_NP_PREFETCH 1
+#endif
+    for (unsigned long long s0 = blockIdx.x * NP_SPAN; s0 < n; s0 += (unsigned long long)gridDim.x * NP_SPAN) {
+    const unsigned long long s_end = (s0 + NP_SPAN < n) ? s0 + NP_SPAN : n;
+    unsigned long long p = s0 + threadIdx.x;
+#if XP_NP_PREFETCH
+    // the pair of the NEXT iteration is fetched before this one is evaluated: its two dependent gathers (ray, triangle)
+    // can then be issued the moment the iteration starts instead of one memory latency later
+    uint2 pr_next = p < s_end ? __ldcs(&pairs[p]) : make_uint2(0u, 0u);
+#endif
+    for (; p < s_end; p += blockDim.x) {
+#if XP_NP_PREFETCH
+        const uint2 pr = pr_next;
+        if (p + blockDim.x < s_end) pr_next = __ldcs(&pairs[p + blockDim.x]);
+#else
         const uint2 pr = __ldcs(&pairs[p]);              // read once: streaming
+#endif
         const float4 *rp = reinterpret_cast<const float4 *>(rays + pr.x);
         const float4 *tp = reinterpret_cast<const float4 *>(recs + pr.y);
 #if XP_NP_LDG256
@@ -1158,6 +1156,7 @@ __global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == N
                 ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(~__float_as_uint(t3.w));
             atomicMin(&best[pr.x], key);
         }
+    }
     }
     if (FILTER) {
         for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(FULL, kept, o);
@@ -1887,8 +1886,10 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
         uint32_t *status = out.status ? out.status + off : nullptr;
         if (status) XP_TRY(cudaMemsetAsync(status, 0, m * 4, s->stream));
         uint32_t *order = nullptr, *inv = nullptr;       // processing order and its inverse (null = identity)
-        if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, in, m, &order, &inv));
-        XP_TRY(ray_setup(s, in, order, m, horizon_of(horizon_mode), status));
+        bool rays_done = false;
+        s->cur_horizon = horizon_of(horizon_mode);
+        if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, in, m, &order, &inv, status, &rays_done));
+        if (!rays_done) XP_TRY(ray_setup(s, in, order, m, horizon_of(horizon_mode), status));
         XP_TRY(closest(s, m));
         s->swept_rays += m;
         // asynchronous steps: snapshot the counters, then hand the result kernel to the second stream
@@ -1961,13 +1962,15 @@ static cudaError_t response_chunk_device(xp_scene *s, xp_response *cur, uint64_t
     XP_TRY(s->best.reserve(m * 8));               XP_TRY(s->best2.reserve(m * 8));
     XP_TRY(s->active_a.reserve(m * 4)); XP_TRY(s->active_b.reserve(m * 4)); XP_TRY(s->active_c.reserve(m * 4));
     uint32_t *order = nullptr;
-    if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, cur, m, &order, nullptr));
+    bool rays_done = false;
+    s->cur_horizon = horizon;
+    if (s->sort_spheres && s->n_tris > 0 && m > 1024) XP_TRY(sphere_morton_order(s, cur, m, &order, nullptr, status, &rays_done));
     const uint32_t *list = order;                                   // null = identity
     uint32_t *spare[2] = {(order == s->active_b.as<uint32_t>()) ? s->active_a.as<uint32_t>() : s->active_b.as<uint32_t>(),
                           s->active_c.as<uint32_t>()};
     struct Guard { xp_scene *s; ~Guard() { s->na_dev = nullptr; } } guard{s};
     s->na_dev = nullptr;
-    XP_TRY(ray_setup(s, cur, list, m, horizon, status));
+    if (!rays_done) XP_TRY(ray_setup(s, cur, list, m, horizon, status));
     uint32_t it = 0;
     bool live = true;
     while (live && it < cap_iter) {
