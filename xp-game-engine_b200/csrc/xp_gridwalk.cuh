@@ -114,16 +114,22 @@ XP_HD bool grid_window_test(const GridRay &r, const GridCol &col, float hmin, fl
 }
 
 // Predicate P for the two triangles of cell (ix, iz): bit 0 = (p00, p01, p11), bit 1 = (p00, p11, p10).
-// z_lo / z_hi: grid_coord(z0, sp, iz), grid_coord(z0, sp, iz + 1) (carried from cell to cell by the caller).
-XP_HD unsigned grid_cell_test(const GridRay &r, const GridCol &col, float z_lo, float z_hi, float h00, float h01,
-                              float h10, float h11) {
-    float tmin = col.tx_lo, tmax = col.tx_hi;
-    grid_slab_axis(r.c.z, r.inv.z, ExactOps::sub(z_lo, XP_INFLATE), ExactOps::add(z_hi, XP_INFLATE), tmin, tmax);
+// z_lo / z_hi: grid_coord(z0, sp, iz), grid_coord(z0, sp, iz + 1); (tx_lo, tx_hi): P's running (tmin, tmax) after the x
+// axis of the column's boxes (GridCol).  The scalar form is what the cell-parallel walk calls: a lane that tests a
+// cell holds only these values of the ray, not the ray.
+XP_HD unsigned grid_cell_test_s(float cy, float inv_y, float cz, float inv_z, float tx_lo, float tx_hi, float z_lo, float z_hi,
+                                float h00, float h01, float h10, float h11) {
+    float tmin = tx_lo, tmax = tx_hi;
+    grid_slab_axis(cz, inv_z, ExactOps::sub(z_lo, XP_INFLATE), ExactOps::add(z_hi, XP_INFLATE), tmin, tmax);
     if (!(tmin <= tmax)) return 0u;
     float amin = tmin, amax = tmax, bmin = tmin, bmax = tmax;
-    grid_slab_axis(r.c.y, r.inv.y, ExactOps::sub(x_min3(h00, h01, h11), XP_INFLATE), ExactOps::add(x_max3(h00, h01, h11), XP_INFLATE), amin, amax);
-    grid_slab_axis(r.c.y, r.inv.y, ExactOps::sub(x_min3(h00, h11, h10), XP_INFLATE), ExactOps::add(x_max3(h00, h11, h10), XP_INFLATE), bmin, bmax);
+    grid_slab_axis(cy, inv_y, ExactOps::sub(x_min3(h00, h01, h11), XP_INFLATE), ExactOps::add(x_max3(h00, h01, h11), XP_INFLATE), amin, amax);
+    grid_slab_axis(cy, inv_y, ExactOps::sub(x_min3(h00, h11, h10), XP_INFLATE), ExactOps::add(x_max3(h00, h11, h10), XP_INFLATE), bmin, bmax);
     return (amin <= amax ? 1u : 0u) | (bmin <= bmax ? 2u : 0u);
+}
+XP_HD unsigned grid_cell_test(const GridRay &r, const GridCol &col, float z_lo, float z_hi, float h00, float h01,
+                              float h10, float h11) {
+    return grid_cell_test_s(r.c.y, r.inv.y, r.c.z, r.inv.z, col.tx_lo, col.tx_hi, z_lo, z_hi, h00, h01, h10, h11);
 }
 
 }  // namespace xp

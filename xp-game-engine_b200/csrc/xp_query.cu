@@ -762,6 +762,206 @@ k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayR
 }
 
 // ------------------------------------------------------------------------------------------
+// the same walk with the cell tests spread over the whole warp (k_broadphase_grid2, the default)
+// ------------------------------------------------------------------------------------------
+// k_broadphase_grid keeps a ray's cells on the ray's lane: ncu counts 15 of 32 lanes active, because the lanes of a
+// warp are in different phases (fetching a ray, setting up a column, skipping windows, inside a run of 1 .. 8 cells).
+// Here the lanes only FIND work -- one attempt per lane per iteration: next column if needed, then the height-range
+// test of its next window of XP_GW_WINDOW cells -- and push each window that passes as an ITEM (the four ray values
+// the cell test needs, P's x-axis interval of the column, (ix, iz0), the number of cells, the ray id) onto a ring in
+// shared memory.  Whenever the ring holds 32 cells or more, all 32 lanes take one CELL each: the items' running cell
+// numbers locate each lane's item (one OR-reduction + popc), adjacent lanes read adjacent heights, and the hits leave
+// through a staging area as runs that share the ray and name consecutive triangles, exactly as before.  The functions
+// that DECIDE are the same (grid_col_setup, grid_window_test, grid_cell_test_s): the emitted set is P, bit for bit.
+#ifndef XP_GW2
+#define XP_GW2 1
+#endif
+#ifndef XP_GW2_BLOCKS
+#define XP_GW2_BLOCKS 4
+#endif
+static constexpr int GW2_ITEMS = 64;                 // ring: < 32 items left over + at most 32 pushed per iteration
+static constexpr int GW2_FLUSH = 128;                // pairs staged before a flush
+static constexpr int GW2_OUT = GW2_FLUSH + 64;       // < GW2_FLUSH staged + at most 64 appended per chunk
+
+__global__ void __launch_bounds__(BP_THREADS, XP_GW2_BLOCKS)
+k_broadphase_grid2(const GridDesc g, const float *__restrict__ yrange, const RayRec *__restrict__ rays, uint64_t ray_base,
+                   uint64_t ray_end, float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out,
+                   uint64_t pair_cap, const unsigned *__restrict__ n_active) {
+    __shared__ float4 it_a_all[BP_WARPS][GW2_ITEMS];    // (c.y, 1/m.y, c.z, 1/m.z) of the item's ray
+    __shared__ float4 it_b_all[BP_WARPS][GW2_ITEMS];    // (tx_lo, tx_hi, bits(ix), bits(iz0))
+    __shared__ uint2 it_c_all[BP_WARPS][GW2_ITEMS];     // (the item's first cell in the warp's running cell count, ray id)
+    __shared__ uint2 out_all[BP_WARPS][GW2_OUT];
+    __shared__ float4 rpool_all[BP_WARPS][96];          // the warp's current run of rays: (c,|m|)[32], (m,|m|^2)[32], (1/m,flags)[32]
+    const int wid = threadIdx.x >> 5;
+    float4 *it_a = it_a_all[wid], *it_b = it_b_all[wid], *rpool = rpool_all[wid];
+    uint2 *it_c = it_c_all[wid], *out = out_all[wid];
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
+    if (n_active) {
+        const uint64_t live = *n_active;
+        if (ray_end > live) ray_end = live;
+        if (ray_base > ray_end) ray_base = ray_end;
+    }
+    rays += ray_base;
+    const unsigned n_rays = (unsigned)(ray_end - ray_base);
+    const unsigned ray0 = (unsigned)ray_base;
+    const float ymin = __ldg(yrange), ymax = __ldg(yrange + 1);
+    const unsigned row = g.nz + 1;
+
+    GridRay r;
+    r.ix = 0; r.ix_hi = -1;
+    GridCol col;
+    col.iz = 0; col.iz_hi = -1; col.tx_lo = 0.0f; col.tx_hi = 0.0f;
+    int cur_ix = 0;
+    unsigned my_ray = 0;
+    unsigned pool = 0, pool_end = 0, pool_base = 0;
+    bool drained = false;
+    unsigned pushed = 0, eaten = 0;          // cells pushed / consumed so far (running counts; only differences matter)
+    unsigned it_head = 0, it_tail = 0;       // ring positions (running counts, slot = position & 63)
+    unsigned n_out = 0;
+    unsigned n_cells = 0, n_irregular = 0;
+
+    for (;;) {
+        // ---- lanes that have finished their ray take the next one of the warp's run
+        const bool done = col.iz > col.iz_hi && r.ix > r.ix_hi;
+        const unsigned idle = __ballot_sync(FULL, done);
+        bool finished = false;
+        if (idle) {
+            if (pool >= pool_end && !drained) {
+                unsigned start = 0;
+                if (lane == 0) start = (unsigned)atomicAdd(&ctr->ray_cursor, 32ull);
+                start = __shfl_sync(FULL, start, 0);
+                pool = start < n_rays ? start : n_rays;
+                pool_end = pool + 32 < n_rays ? pool + 32 : n_rays;
+                drained = pool >= n_rays;
+                pool_base = pool;
+                __syncwarp();
+                if (pool + lane < pool_end) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(rays + pool + lane);
+                    rpool[lane] = __ldcs(rp + 0);
+                    rpool[32 + lane] = __ldcs(rp + 1);
+                    rpool[64 + lane] = __ldcs(rp + 3);
+                }
+                __syncwarp();
+            }
+            if (pool < pool_end) {
+                const unsigned mine = pool + __popc(idle & lt_mask);
+                if (done && mine < pool_end) {
+                    my_ray = mine;
+                    const float4 q0 = rpool[mine - pool_base], q1 = rpool[32 + mine - pool_base], q3 = rpool[64 + mine - pool_base];
+                    const unsigned flags = __float_as_uint(q3.w);
+                    if ((flags & (RAY_VALID | RAY_GRID_OK)) == (RAY_VALID | RAY_GRID_OK))
+                        grid_ray_setup(g, ymin, ymax, f4_xyz(q0), f4_xyz(q1), f4_xyz(q3), horizon, r);
+                    else if (flags & RAY_VALID) ++n_irregular;           // left to k_broadphase<3>
+                }
+                pool = min(pool + __popc(idle), pool_end);
+            } else if (idle == FULL) {
+                finished = true;
+            }
+        }
+        // ---- one attempt per lane: the next column if this one is exhausted, then the height-range test of its next window
+        bool have = false;
+        unsigned cnt = 0;
+        int item_iz = 0;
+        if (col.iz <= col.iz_hi || r.ix <= r.ix_hi) {
+            if (col.iz > col.iz_hi) {
+                cur_ix = r.ix++;
+                grid_col_setup(g, r, cur_ix, col);
+            }
+            if (col.iz <= col.iz_hi) {
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(g.mm) + (size_t)cur_ix * g.nz + col.iz);
+                if (grid_window_test(r, col, w.x, w.y)) {
+                    have = true;
+                    item_iz = col.iz;
+                    cnt = (unsigned)min(XP_GW_WINDOW, col.iz_hi - col.iz + 1);
+                }
+                col.iz += XP_GW_WINDOW;
+            }
+        }
+        // ---- push the windows that passed, in lane order
+        const unsigned hm = __ballot_sync(FULL, have);
+        if (hm) {
+            unsigned inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(FULL, inc, o); if (lane >= (unsigned)o) inc += y; }
+            if (have) {
+                const unsigned slot = (it_tail + __popc(hm & lt_mask)) & (GW2_ITEMS - 1);
+                it_a[slot] = make_float4(r.c.y, r.inv.y, r.c.z, r.inv.z);
+                it_b[slot] = make_float4(col.tx_lo, col.tx_hi, __int_as_float(cur_ix), __int_as_float(item_iz));
+                it_c[slot] = make_uint2(pushed + inc - cnt, ray0 + my_ray);
+            }
+            it_tail += __popc(hm);
+            pushed += __shfl_sync(FULL, inc, 31);
+            __syncwarp();
+        }
+        // ---- consume: one cell per lane, 32 at a time (whatever is left once no lane can find more)
+        while (pushed - eaten >= 32u || (finished && pushed != eaten)) {
+            const unsigned avail = pushed - eaten;
+            const unsigned adv = avail < 32u ? avail : 32u;
+            // which item does cell (eaten + lane) belong to?  lane i looks at item it_head + i: a chunk of 32 cells meets at
+            // most 32 items, the first of which may have started before the chunk (its offset wraps and sets no bit)
+            const unsigned off = (lane < it_tail - it_head) ? it_c[(it_head + lane) & (GW2_ITEMS - 1)].x - eaten : 0xffffffffu;
+            const unsigned starts = __reduce_or_sync(FULL, off < 32u ? (1u << off) : 0u);
+            const unsigned j = it_head + __popc(starts & le_mask) - (starts & 1u);
+            const bool valid = lane < adv;
+            unsigned m2 = 0u, tri = 0u, ray_id = 0u;
+            if (valid) {
+                const unsigned slot = j & (GW2_ITEMS - 1);
+                const float4 a = it_a[slot], b = it_b[slot];
+                const uint2 c = it_c[slot];
+                const int ix = __float_as_int(b.z), iz = __float_as_int(b.w) + (int)(eaten + lane - c.x);
+                const float *p = g.h + (size_t)ix * row + iz;
+                const float h00 = __ldg(p), h01 = __ldg(p + 1), h10 = __ldg(p + row), h11 = __ldg(p + row + 1);
+                m2 = grid_cell_test_s(a.x, a.y, a.z, a.w, b.x, b.y, grid_coord(g.z0, g.sp, iz), grid_coord(g.z0, g.sp, iz + 1),
+                                      h00, h01, h10, h11);
+                tri = 2u * ((unsigned)ix * g.nz + (unsigned)iz);
+                ray_id = c.y;
+            }
+            n_cells += valid ? 1u : 0u;
+            // the item of the chunk's last cell: finished with this chunk iff it ends where the chunk ends
+            const unsigned j_last = __shfl_sync(FULL, j, adv - 1u);
+            const unsigned end_last = (j_last + 1u != it_tail) ? it_c[(j_last + 1u) & (GW2_ITEMS - 1)].x : pushed;
+            eaten += adv;
+            it_head = (end_last == eaten) ? j_last + 1u : j_last;
+            // hits: bit 0 = triangle 2 * cell, bit 1 = triangle 2 * cell + 1; lane order = cell order
+            const unsigned b0 = __ballot_sync(FULL, m2 & 1u), b1 = __ballot_sync(FULL, m2 & 2u);
+            if (b0 | b1) {
+                unsigned pos = n_out + __popc(b0 & lt_mask) + __popc(b1 & lt_mask);
+                if (m2 & 1u) out[pos++] = make_uint2(ray_id, tri);
+                if (m2 & 2u) out[pos] = make_uint2(ray_id, tri + 1u);
+                n_out += __popc(b0) + __popc(b1);
+            }
+            __syncwarp();
+            if (n_out >= (unsigned)GW2_FLUSH || (finished && pushed == eaten && n_out)) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)n_out);
+                base = __shfl_sync(FULL, base, 0);
+                for (unsigned w = lane; w < n_out; w += 32)
+                    if (base + w < pair_cap) __stcs(&pairs_out[base + w], out[w]);
+                n_out = 0;
+                __syncwarp();
+            }
+        }
+        if (finished) break;
+    }
+    if (n_out) {                                   // (only when the last chunk produced nothing: staged pairs of earlier chunks)
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)n_out);
+        base = __shfl_sync(FULL, base, 0);
+        for (unsigned w = lane; w < n_out; w += 32)
+            if (base + w < pair_cap) __stcs(&pairs_out[base + w], out[w]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_cells += __shfl_xor_sync(FULL, n_cells, o);
+        n_irregular += __shfl_xor_sync(FULL, n_irregular, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&ctr->node_visits, (unsigned long long)n_cells);
+        if (n_irregular) atomicAdd(&ctr->irregular_rays, n_irregular);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // stage 1 over the quantised 4-wide tree (XP_METHOD_Q4_PAIRS)
 // ------------------------------------------------------------------------------------------
 // Same persistent-warp scheme as k_broadphase, but one step reads a 64 B Node4 = four child boxes:
@@ -1623,10 +1823,15 @@ static GridDesc grid_desc(const xp_scene *s) {
 static cudaError_t launch_grid_broadphase(xp_scene *s, uint64_t pos, uint64_t end, uint2 *pairs, uint64_t cap) {
     cudaStream_t st = s->stream;
     DeviceCounters *ctr = s->counters.as<DeviceCounters>();
-    const uint64_t want = (end - pos + BP_THREADS - 1) / BP_THREADS, full = (uint64_t)s->n_sm * XP_GW_BLOCKS;
+    const uint64_t want = (end - pos + BP_THREADS - 1) / BP_THREADS, full = (uint64_t)s->n_sm * (XP_GW2 ? XP_GW2_BLOCKS : XP_GW_BLOCKS);
     const unsigned grid = (unsigned)(want < full ? (want ? want : 1) : full);
+#if XP_GW2
+    k_broadphase_grid2<<<grid, BP_THREADS, 0, st>>>(grid_desc(s), s->grid_yrange.as<float>(), s->rays.as<RayRec>(), pos, end,
+                                                   s->cur_horizon, ctr, pairs, cap, s->na_dev);
+#else
     k_broadphase_grid<<<grid, BP_THREADS, 0, st>>>(grid_desc(s), s->grid_yrange.as<float>(), s->rays.as<RayRec>(), pos, end,
                                                   s->cur_horizon, ctr, pairs, cap, s->na_dev);
+#endif
     XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
     k_broadphase<3><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end, s->cur_horizon,
                                                                ctr, pairs, cap, 0.0f, INFINITY, nullptr, s->vals_a.as<uint32_t>(), s->na_dev);
