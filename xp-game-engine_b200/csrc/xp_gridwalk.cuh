@@ -44,11 +44,8 @@ XP_HD void grid_slab_axis(float c, float inv, float lo, float hi, float &tmin, f
 }
 
 XP_HD int grid_floor_clamped(float u, int lo, int hi) {
-    // floor with saturation; NaN cannot occur (finite rays only), +-inf saturate
-    const float f = floorf(u);
-    if (!(f >= (float)lo)) return lo;
-    if (!(f <= (float)hi)) return hi;
-    return (int)f;
+    // floor with saturation, branch-free; NaN cannot occur (finite rays only; fmaxf would map it to lo), +-inf saturate
+    return (int)fminf(fmaxf(floorf(u), (float)lo), (float)hi);
 }
 
 struct GridRay {

@@ -600,182 +600,21 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
 // stage 1 for heightmap scenes: the ray walks the height grid (xp_gridwalk.cuh), no tree
 // ------------------------------------------------------------------------------------------
 // Same persistent-warp frame as k_broadphase (warps claim runs of 32 Morton-consecutive rays, a lane takes its
-// next ray the moment it has finished one), but a lane's state is (column, cell) instead of a node stack, the
-// data it reads are 4 B heights at computed addresses -- consecutive along a column -- and nothing is
-// pointer-chased.  Per outer iteration a lane tests up to GW_CELLS cells (2 triangles each) with uniform control
-// flow, then the warp writes the hits out with each LANE's hits contiguous: a run of pairs that share the ray and
-// name consecutive triangles of one column, i.e. consecutive 64 B records of the upload-order record array.  That
-// is what the narrowphase wants: its gathers are bound by L1 wavefronts (one per distinct line per instruction),
-// and such runs put ~4 rays and ~16 triangle lines under a warp instead of 32 and 32.
-#ifndef XP_GW_CELLS
-#define XP_GW_CELLS 8
-#endif
-#ifndef XP_GW_BLOCKS
-#define XP_GW_BLOCKS 4
-#endif
-static constexpr int GW_CELLS = XP_GW_CELLS;
-static_assert(XP_GW_CELLS == XP_GW_WINDOW, "one outer iteration walks exactly the cells one height window covers");
-static constexpr int GW_QUEUE = 32 * 2 * GW_CELLS;
-
-__global__ void __launch_bounds__(BP_THREADS, XP_GW_BLOCKS)
-k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayRec *__restrict__ rays, uint64_t ray_base,
-                  uint64_t ray_end, float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out,
-                  uint64_t pair_cap, const unsigned *__restrict__ n_active) {
-    __shared__ uint2 queue[BP_WARPS][GW_QUEUE];
-    __shared__ float4 rpool_all[BP_WARPS][96];          // the warp's current run of rays: (c,|m|)[32], (m,|m|^2)[32], (1/m,flags)[32]
-    uint2 *q = queue[threadIdx.x >> 5];
-    float4 *rpool = rpool_all[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    if (n_active) {
-        const uint64_t live = *n_active;
-        if (ray_end > live) ray_end = live;
-        if (ray_base > ray_end) ray_base = ray_end;
-    }
-    rays += ray_base;
-    const unsigned n_rays = (unsigned)(ray_end - ray_base);
-    const unsigned ray0 = (unsigned)ray_base;
-    const float ymin = __ldg(yrange), ymax = __ldg(yrange + 1);
-    const unsigned row = g.nz + 1;
-
-    GridRay r;
-    r.ix = 0; r.ix_hi = -1;
-    GridCol col;
-    col.iz = 0; col.iz_hi = -1; col.tx_lo = 0.0f; col.tx_hi = 0.0f;
-    int cur_ix = 0;                          // the column col belongs to
-    float h00 = 0.0f, h10 = 0.0f, z_lo = 0.0f;      // carried from cell to cell along the column
-    unsigned my_ray = 0;
-    unsigned pool = 0, pool_end = 0, pool_base = 0;
-    bool drained = false;
-    unsigned n_cells = 0, n_irregular = 0;
-
-    for (;;) {
-        // ---- lanes that have finished their ray take the next one of the warp's run
-        const bool done = col.iz > col.iz_hi && r.ix > r.ix_hi;
-        const unsigned idle = __ballot_sync(FULL, done);
-        if (idle) {
-            if (pool >= pool_end && !drained) {
-                unsigned start = 0;
-                if (lane == 0) start = (unsigned)atomicAdd(&ctr->ray_cursor, 32ull);
-                start = __shfl_sync(FULL, start, 0);
-                pool = start < n_rays ? start : n_rays;
-                pool_end = pool + 32 < n_rays ? pool + 32 : n_rays;
-                drained = pool >= n_rays;
-                pool_base = pool;
-                __syncwarp();
-                if (pool + lane < pool_end) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(rays + pool + lane);
-                    rpool[lane] = __ldcs(rp + 0);
-                    rpool[32 + lane] = __ldcs(rp + 1);
-                    rpool[64 + lane] = __ldcs(rp + 3);
-                }
-                __syncwarp();
-            }
-            if (pool < pool_end) {
-                const unsigned mine = pool + __popc(idle & lt_mask);
-                if (done && mine < pool_end) {
-                    my_ray = mine;
-                    const float4 q0 = rpool[mine - pool_base], q1 = rpool[32 + mine - pool_base], q3 = rpool[64 + mine - pool_base];
-                    const unsigned flags = __float_as_uint(q3.w);
-                    if ((flags & (RAY_VALID | RAY_GRID_OK)) == (RAY_VALID | RAY_GRID_OK))
-                        grid_ray_setup(g, ymin, ymax, f4_xyz(q0), f4_xyz(q1), f4_xyz(q3), horizon, r);
-                    else if (flags & RAY_VALID) ++n_irregular;           // left to k_broadphase<3>
-                }
-                pool = min(pool + __popc(idle), pool_end);
-            } else if (idle == FULL) {
-                break;
-            }
-        }
-        // ---- lanes whose column is exhausted move to their next column that can hold a candidate
-        // ... and past the windows of GW_WINDOW cells whose height range the ray misses (the cull of this implicit
-        // hierarchy: one 8 B read decides 16 triangles)
-        bool ready = false;                    // the window at col.iz has been tested and may hold candidates
-#pragma unroll 1
-        for (int tries = 0; tries < 4; ++tries) {
-            const bool need = !ready && (col.iz <= col.iz_hi || r.ix <= r.ix_hi);
-            if (!__any_sync(FULL, need)) break;
-            if (need) {
-                if (col.iz > col.iz_hi) {
-                    cur_ix = r.ix++;
-                    grid_col_setup(g, r, cur_ix, col);
-                }
-                if (col.iz <= col.iz_hi) {
-                    const float2 w = __ldg(reinterpret_cast<const float2 *>(g.mm) + (size_t)cur_ix * g.nz + col.iz);
-                    if (grid_window_test(r, col, w.x, w.y)) ready = true;
-                    else col.iz += XP_GW_WINDOW;
-                }
-            }
-        }
-        if (ready) {
-            const float *p = g.h + (size_t)cur_ix * row + col.iz;
-            h00 = __ldg(p); h10 = __ldg(p + row);
-            z_lo = grid_coord(g.z0, g.sp, col.iz);
-        }
-        // ---- up to GW_CELLS cells of the column, two triangles each
-        unsigned mask = 0;
-        const unsigned first_tri = 2u * ((unsigned)cur_ix * g.nz + (unsigned)col.iz);
-        {
-            const float *p = g.h + (size_t)cur_ix * row + col.iz + 1;
-#pragma unroll
-            for (int k = 0; k < GW_CELLS; ++k) {
-                if (ready && col.iz <= col.iz_hi) {
-                    const float h01 = __ldg(p + k), h11 = __ldg(p + row + k);
-                    const float z_hi = grid_coord(g.z0, g.sp, col.iz + 1);
-                    mask |= grid_cell_test(r, col, z_lo, z_hi, h00, h01, h10, h11) << (2 * k);
-                    h00 = h01; h10 = h11; z_lo = z_hi;
-                    ++col.iz;
-                    ++n_cells;
-                }
-            }
-        }
-        // ---- write the hits out, each lane's as one contiguous run (same ray, consecutive triangles)
-        if (__any_sync(FULL, mask != 0u)) {
-            const unsigned cnt = __popc(mask);
-            unsigned inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += y; }
-            const unsigned total = __shfl_sync(FULL, inc, 31);
-            unsigned pos = inc - cnt;
-            const unsigned ray_id = ray0 + my_ray;
-            while (mask) {
-                const unsigned b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                q[pos++] = make_uint2(ray_id, first_tri + b);           // bit 2k+s <-> triangle 2 (cell0 + k) + s
-            }
-            __syncwarp();
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->pairs, (unsigned long long)total);
-            base = __shfl_sync(FULL, base, 0);
-            for (unsigned w = lane; w < total; w += 32)
-                if (base + w < pair_cap) __stcs(&pairs_out[base + w], q[w]);
-            __syncwarp();
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        n_cells += __shfl_xor_sync(FULL, n_cells, o);
-        n_irregular += __shfl_xor_sync(FULL, n_irregular, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&ctr->node_visits, (unsigned long long)n_cells);
-        if (n_irregular) atomicAdd(&ctr->irregular_rays, n_irregular);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// the same walk with the cell tests spread over the whole warp (k_broadphase_grid2, the default)
-// ------------------------------------------------------------------------------------------
-// k_broadphase_grid keeps a ray's cells on the ray's lane: ncu counts 15 of 32 lanes active, because the lanes of a
+// next ray the moment it has finished one), but a lane's state is (column, window of cells) instead of a node stack,
+// the data read are 4 B heights at computed addresses -- consecutive along a column -- and nothing is pointer-chased.
+// The first version kept a ray's cells on the ray's lane: ncu counted 15 of 32 lanes active, because the lanes of a
 // warp are in different phases (fetching a ray, setting up a column, skipping windows, inside a run of 1 .. 8 cells).
 // Here the lanes only FIND work -- one attempt per lane per iteration: next column if needed, then the height-range
 // test of its next window of XP_GW_WINDOW cells -- and push each window that passes as an ITEM (the four ray values
 // the cell test needs, P's x-axis interval of the column, (ix, iz0), the number of cells, the ray id) onto a ring in
 // shared memory.  Whenever the ring holds 32 cells or more, all 32 lanes take one CELL each: the items' running cell
 // numbers locate each lane's item (one OR-reduction + popc), adjacent lanes read adjacent heights, and the hits leave
-// through a staging area as runs that share the ray and name consecutive triangles, exactly as before.  The functions
-// that DECIDE are the same (grid_col_setup, grid_window_test, grid_cell_test_s): the emitted set is P, bit for bit.
-#ifndef XP_GW2
-#define XP_GW2 1
-#endif
+// through a staging area as runs of pairs that share the ray and name consecutive triangles of one column, i.e.
+// consecutive 64 B records of the upload-order record array.  That is what the narrowphase wants: its gathers are
+// bound by L1 wavefronts (one per distinct line per instruction), and such runs put ~4 rays and ~16 triangle lines
+// under a warp instead of 32 and 32.  The functions that DECIDE are those of xp_gridwalk.cuh (grid_col_setup,
+// grid_window_test, grid_cell_test_s): the emitted set is P, bit for bit.  ncu (profiles/r02l_ncu_full.txt): 27 of 32
+// lanes active, 331 M warp instructions (176 per chunk of 32 cells; 40 % are still the lane-per-ray search).
 #ifndef XP_GW2_BLOCKS
 #define XP_GW2_BLOCKS 4
 #endif
@@ -784,7 +623,7 @@ static constexpr int GW2_FLUSH = 128;                // pairs staged before a fl
 static constexpr int GW2_OUT = GW2_FLUSH + 64;       // < GW2_FLUSH staged + at most 64 appended per chunk
 
 __global__ void __launch_bounds__(BP_THREADS, XP_GW2_BLOCKS)
-k_broadphase_grid2(const GridDesc g, const float *__restrict__ yrange, const RayRec *__restrict__ rays, uint64_t ray_base,
+k_broadphase_grid(const GridDesc g, const float *__restrict__ yrange, const RayRec *__restrict__ rays, uint64_t ray_base,
                    uint64_t ray_end, float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out,
                    uint64_t pair_cap, const unsigned *__restrict__ n_active) {
     __shared__ float4 it_a_all[BP_WARPS][GW2_ITEMS];    // (c.y, 1/m.y, c.z, 1/m.z) of the item's ray
@@ -910,7 +749,7 @@ k_broadphase_grid2(const GridDesc g, const float *__restrict__ yrange, const Ray
                 const float4 a = it_a[slot], b = it_b[slot];
                 const uint2 c = it_c[slot];
                 const int ix = __float_as_int(b.z), iz = __float_as_int(b.w) + (int)(eaten + lane - c.x);
-                const float *p = g.h + (size_t)ix * row + iz;
+                const float *p = g.h + ((unsigned)ix * row + (unsigned)iz);       // (nx + 1)(nz + 1) < 2^32 (xp_scene_set_heightmap)
                 const float h00 = __ldg(p), h01 = __ldg(p + 1), h10 = __ldg(p + row), h11 = __ldg(p + row + 1);
                 m2 = grid_cell_test_s(a.x, a.y, a.z, a.w, b.x, b.y, grid_coord(g.z0, g.sp, iz), grid_coord(g.z0, g.sp, iz + 1),
                                       h00, h01, h10, h11);
@@ -1823,15 +1662,10 @@ static GridDesc grid_desc(const xp_scene *s) {
 static cudaError_t launch_grid_broadphase(xp_scene *s, uint64_t pos, uint64_t end, uint2 *pairs, uint64_t cap) {
     cudaStream_t st = s->stream;
     DeviceCounters *ctr = s->counters.as<DeviceCounters>();
-    const uint64_t want = (end - pos + BP_THREADS - 1) / BP_THREADS, full = (uint64_t)s->n_sm * (XP_GW2 ? XP_GW2_BLOCKS : XP_GW_BLOCKS);
+    const uint64_t want = (end - pos + BP_THREADS - 1) / BP_THREADS, full = (uint64_t)s->n_sm * XP_GW2_BLOCKS;
     const unsigned grid = (unsigned)(want < full ? (want ? want : 1) : full);
-#if XP_GW2
-    k_broadphase_grid2<<<grid, BP_THREADS, 0, st>>>(grid_desc(s), s->grid_yrange.as<float>(), s->rays.as<RayRec>(), pos, end,
-                                                   s->cur_horizon, ctr, pairs, cap, s->na_dev);
-#else
     k_broadphase_grid<<<grid, BP_THREADS, 0, st>>>(grid_desc(s), s->grid_yrange.as<float>(), s->rays.as<RayRec>(), pos, end,
                                                   s->cur_horizon, ctr, pairs, cap, s->na_dev);
-#endif
     XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
     k_broadphase<3><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end, s->cur_horizon,
                                                                ctr, pairs, cap, 0.0f, INFINITY, nullptr, s->vals_a.as<uint32_t>(), s->na_dev);
