@@ -83,6 +83,9 @@ struct DeviceCounters {           // one small block of device memory, zeroed pe
     unsigned int iters_done;        // response loop: iterations that had work
     unsigned int pad0;
     unsigned long long rays_swept;  // response loop: sum of the live counts over its iterations
+    unsigned long long np_cursor;   // k_narrow_pairs: next unclaimed span of the pair list (the last block to leave resets it)
+    unsigned int np_done;           // k_narrow_pairs: blocks that have left
+    unsigned int pad1;
 };
 
 }  // namespace xp

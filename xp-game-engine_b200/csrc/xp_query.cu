@@ -1137,7 +1137,29 @@ __global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == N
 #ifndef XP_NP_PREFETCH
 #define XP_NP_PREFETCH 1
 #endif
+#ifndef XP_NP_DYNAMIC
+#define XP_NP_DYNAMIC 1
+#endif
+#if XP_NP_DYNAMIC
+    // Spans are claimed from a global cursor by exactly as many blocks as are resident, so the whole grid moves through
+    // the pair list -- and with it through the triangle and ray records, which the list visits in Morton order -- ONCE,
+    // front to back.  (A static grid of two waves, block b taking spans b, b + G, ..., made two passes over the scene
+    // data: ncu counted 4.7 DRAM fetches per record sector.)  The claim for the next span is issued before the current
+    // one is processed; the last block to leave resets the cursor for the next launch.
+    __shared__ unsigned long long span_slot[2];
+    unsigned long long span_next = 0;
+    unsigned span_buf = 0;
+    if (threadIdx.x == 0) span_next = atomicAdd(&ctr->np_cursor, NP_SPAN);
+    for (;;) {
+    if (threadIdx.x == 0) span_slot[span_buf] = span_next;
+    __syncthreads();
+    const unsigned long long s0 = span_slot[span_buf];
+    span_buf ^= 1u;
+    if (s0 >= n) break;
+    if (threadIdx.x == 0) span_next = atomicAdd(&ctr->np_cursor, NP_SPAN);
+#else
     for (unsigned long long s0 = blockIdx.x * NP_SPAN; s0 < n; s0 += (unsigned long long)gridDim.x * NP_SPAN) {
+#endif
     const unsigned long long s_end = (s0 + NP_SPAN < n) ? s0 + NP_SPAN : n;
     unsigned long long p = s0 + threadIdx.x;
 #if XP_NP_PREFETCH
@@ -1197,6 +1219,12 @@ __global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == N
         }
     }
     }
+#if XP_NP_DYNAMIC
+    if (threadIdx.x == 0 && atomicAdd(&ctr->np_done, 1u) == gridDim.x - 1u) {     // every other block has made its last claim
+        ctr->np_cursor = 0ull;
+        ctr->np_done = 0u;
+    }
+#endif
     if (FILTER) {
         for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(FULL, kept, o);
         if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&ctr->tests, (unsigned long long)kept);
@@ -1844,7 +1872,7 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
         {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
             const int np_blocks = s->arith == XP_ARITH_EXACT ? XP_NP_BLOCKS_X : s->arith == XP_ARITH_FAST ? XP_NP_BLOCKS_F : XP_NP_BLOCKS;
-            const unsigned ng = (unsigned)s->n_sm * 2u * (unsigned)np_blocks;          // two waves of resident blocks
+            const unsigned ng = (unsigned)s->n_sm * (XP_NP_DYNAMIC ? 1u : 2u) * (unsigned)np_blocks;   // dynamic spans: exactly the resident blocks
 #define XP_NP_LAUNCH(M) do { if (q4) k_narrow_pairs<M, true><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
                              else k_narrow_pairs<M, false><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); } while (0)
             switch (s->arith) {
