@@ -91,8 +91,8 @@ void xp_scene_destroy(xp_scene *s) {
     cudaStreamSynchronize(s->stream);
     if (s->io_ready) { cudaStreamSynchronize(s->copy_in); cudaStreamSynchronize(s->copy_out); }   // batches still in flight
     for (auto &x : s->ex_slot) if (x.busy) cudaEventSynchronize(x.fin);
-    DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->node_box, &s->leaf_box,
-                      &s->parent_internal, &s->parent_leaf, &s->refit_flags, &s->keys_a, &s->keys_b,
+    DevBuf *bufs[] = {&s->tris_aos, &s->recs, &s->nodes, &s->leaf_box,
+                      &s->refit_flags, &s->tree_work, &s->keys_a, &s->keys_b,
                       &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->degen, &s->grid_h, &s->grid_yrange, &s->grid_mm, &s->recs_grid, &s->rays, &s->best, &s->active_a,
                       &s->active_b, &s->inv_order, &s->pairs, &s->counters, &s->rays2, &s->best2, &s->active_c, &s->io_backup, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
                       &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
@@ -846,15 +846,15 @@ int xp_scene_debug_tree(xp_scene *s, uint32_t *sorted_tri, uint32_t *morton, int
         delete[] h;
         if (e != cudaSuccess) return fail_cuda(e);
     }
-    if (node_lo || node_hi) {
-        float4 *h = new (std::nothrow) float4[2 * ni];
+    if (node_lo || node_hi) {          // a node's own box = the union of the two child boxes its record holds
+        Node *h = new (std::nothrow) Node[ni];
         if (!h) return XP_ENOMEM;
-        cudaError_t e = cudaMemcpy(h, s->node_box.p, 2 * ni * sizeof(float4), cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpy(h, s->nodes.p, ni * sizeof(Node), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { delete[] h; return fail_cuda(e); }
-        for (int pass = 0; pass < 2; ++pass) {
-            xp_vec3 *dst = pass ? node_hi : node_lo;
-            if (!dst) continue;
-            for (uint64_t i = 0; i < ni; ++i) { dst[i].x = h[2 * i + pass].x; dst[i].y = h[2 * i + pass].y; dst[i].z = h[2 * i + pass].z; }
+        for (uint64_t i = 0; i < ni; ++i) {
+            const Node &d = h[i];
+            if (node_lo) { node_lo[i].x = fminf(d.q0.x, d.q1.z); node_lo[i].y = fminf(d.q0.y, d.q1.w); node_lo[i].z = fminf(d.q0.z, d.q2.x); }
+            if (node_hi) { node_hi[i].x = fmaxf(d.q0.w, d.q2.y); node_hi[i].y = fmaxf(d.q1.x, d.q2.z); node_hi[i].z = fmaxf(d.q1.y, d.q2.w); }
         }
         delete[] h;
     }

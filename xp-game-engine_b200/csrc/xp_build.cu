@@ -447,68 +447,216 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
     leaf_box[2 * j + 1] = make_float4(hi.x, hi.y, hi.z, 0.0f);
 }
 
-// K4: Karras 2012 ------------------------------------------------------------------------------
-__device__ __forceinline__ int delta(const uint32_t *__restrict__ keys, int n, int i, int j) {
-    if (j < 0 || j >= n) return -1;
-    const uint32_t a = keys[i], b = keys[j];
-    if (a == b) return 32 + __clz((unsigned)i ^ (unsigned)j);   // tie-break on the index
-    return __clz(a ^ b);
+// K4 + K5: hierarchy and boxes in ONE bottom-up pass ----------------------------------------------------------
+// Round 1 emitted the hierarchy top-down per node (Karras 2012: two binary searches over the keys per internal node,
+// 0.23 ms for 10 M triangles) and then refitted bottom-up through parent pointers (0.87 ms: an atomic counter, a
+// fence, four box reads and two box writes per node, 2.1 GB of traffic).  The tree over sorted keys is determined by
+// the keys alone, so the bottom-up walk can FIND the parent itself (Apetrei 2014): a subtree covering leaves [l, r]
+// hangs under the split right of r or left of l, whichever separates less, i.e. has the smaller
+// metric(i) = (key[i] ^ key[i+1], i ^ (i+1)) -- the index part is Karras' tie-break for equal codes, so the topology
+// is exactly the old one.  Internal node p is the split between leaves p and p + 1.  A thread writes its box and its
+// link straight into its parent's 64 B record (left child: floats 0..5 + link.x, right child: floats 6..11 + link.y),
+// swaps its range bound into flags[p], and leaves if it came first; the second arrival reads the sibling's half of the
+// record, merges, and climbs.  One atomic per visit, no parent arrays, no per-node box array, no second kernel.
+// The root is the split whose subtree covers everything; the walks start at node 0, so k_tree_root_to_zero swaps the
+// root's record with node 0's (info[1], info[2]: who links to internal node 0, and on which side).
+//
+// Measured, the plain form (every visit a global atomic behind a __threadfence) took the same 1.1 ms as the two
+// kernels it replaced, and so did a version that let 512-thread blocks climb through shared memory first: a climb is a
+// dependent chain, the trees over Morton codes of surfaces are skewed (25 iterations per warp where a balanced tree has
+// 9), and a warp keeps running for its last climbing lane -- ncu counted 7.7 of 32 lanes active.  So:
+//   * k_tree_local: ONE WARP owns a segment of TREE_SEG consecutive leaves and all of its shared state.  Its lanes pull
+//     leaves from the segment as they become free (a lane whose subtree arrived first parks it and takes the next leaf;
+//     a lane that arrived second merges and climbs), so the lanes stay busy while the long climbers climb.  A child
+//     whose parent split p lies strictly inside the segment attaches through shared memory: exchange of the range bound
+//     in s_flag[p], the first arrival parks its box and link, the second builds the node's whole 64 B record and writes
+//     it out.  ~94 % of all nodes are finished this way, without a global atomic or fence.
+//   * What a segment cannot finish alone -- subtrees whose parent split is the segment's boundary or beyond, and parked
+//     children whose sibling reaches over the boundary and so never shows up -- goes onto a work list in global memory.
+//   * k_tree_global: one thread per work item continues through the global protocol (half-record store, fence,
+//     atomicExch(flags[p]); the second arrival merges and climbs), all items in flight at once.
+// A node's two arrivals always use the same protocol: both inside one segment's warp, or both global.
+static constexpr int TREE_SEG = 512;          // leaves per warp
+static constexpr unsigned long long METRIC_INF = ~0ull;
+struct TreeItem { int l, r, cur; float lo[3], hi[3]; };      // a subtree still to be attached: leaves [l, r], its link, its box
+
+// metric(j) = (key[j] ^ key[j+1], j ^ (j+1)); the ends of the array are walls
+__device__ __forceinline__ unsigned long long split_metric(const uint32_t *__restrict__ keys, int n, int j) {
+    if (j < 0 || j >= n - 1) return METRIC_INF;
+    return ((unsigned long long)(__ldg(keys + j) ^ __ldg(keys + j + 1)) << 32) | (unsigned)(j ^ (j + 1));
 }
 
-__global__ void __launch_bounds__(256) k_karras(const uint32_t *__restrict__ keys, int n,
-                                                Node *__restrict__ nodes, int *__restrict__ parent_internal,
-                                                int *__restrict__ parent_leaf) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-    const int dmin = delta(keys, n, i, i - d);
-    int lmax = 2;
-    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
-    int l = 0;
-    for (int t = lmax >> 1; t >= 1; t >>= 1)
-        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
-    const int j = i + l * d;
-    const int dnode = delta(keys, n, i, j);
-    int sft = 0;
-    int t = l;
-    do {
-        t = (t + 1) >> 1;
-        if (delta(keys, n, i, i + (sft + t) * d) > dnode) sft += t;
-    } while (t > 1);
-    const int gamma = i + sft * d + min(d, 0);
-    const int lo = min(i, j), hi = max(i, j);
-    int c0, c1;
-    if (lo == gamma) { c0 = ~gamma; parent_leaf[gamma] = i; } else { c0 = gamma; parent_internal[gamma] = i; }
-    if (hi == gamma + 1) { c1 = ~(gamma + 1); parent_leaf[gamma + 1] = i; } else { c1 = gamma + 1; parent_internal[gamma + 1] = i; }
-    if (i == 0) parent_internal[0] = -1;
-    nodes[i].link = make_int4(c0, c1, 0, 0);
-}
-
-// K5: refit --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_refit(int n, Node *__restrict__ nodes,
-                                               const int *__restrict__ parent_internal,
-                                               const int *__restrict__ parent_leaf,
-                                               const float4 *__restrict__ leaf_box, float4 *node_box,
-                                               unsigned *__restrict__ flags) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    int cur = parent_leaf[j];
-    while (cur >= 0) {
-        if (atomicAdd(&flags[cur], 1u) == 0u) return;     // first arrival: the sibling finishes
-        const int4 link = nodes[cur].link;
-        float4 lo0, hi0, lo1, hi1;
-        if (link.x < 0) { lo0 = leaf_box[2 * (~link.x)]; hi0 = leaf_box[2 * (~link.x) + 1]; }
-        else { lo0 = __ldcg(&node_box[2 * link.x]); hi0 = __ldcg(&node_box[2 * link.x + 1]); }
-        if (link.y < 0) { lo1 = leaf_box[2 * (~link.y)]; hi1 = leaf_box[2 * (~link.y) + 1]; }
-        else { lo1 = __ldcg(&node_box[2 * link.y]); hi1 = __ldcg(&node_box[2 * link.y + 1]); }
-        nodes[cur].q0 = make_float4(lo0.x, lo0.y, lo0.z, hi0.x);
-        nodes[cur].q1 = make_float4(hi0.y, hi0.z, lo1.x, lo1.y);
-        nodes[cur].q2 = make_float4(lo1.z, hi1.x, hi1.y, hi1.z);
-        __stcg(&node_box[2 * cur], make_float4(fminf(lo0.x, lo1.x), fminf(lo0.y, lo1.y), fminf(lo0.z, lo1.z), 0.0f));
-        __stcg(&node_box[2 * cur + 1], make_float4(fmaxf(hi0.x, hi1.x), fmaxf(hi0.y, hi1.y), fmaxf(hi0.z, hi1.z), 0.0f));
+// the global protocol: attach the subtree (l, r, cur, lo, hi) to its parent and climb while second to arrive
+__device__ void tree_climb_global(const uint32_t *__restrict__ keys, int n, Node *nodes, int *flags, int *info, int l, int r,
+                                  int cur, float4 lo, float4 hi) {
+    for (;;) {
+        const bool left_child = split_metric(keys, n, r) < split_metric(keys, n, l - 1);
+        const int p = left_child ? r : l - 1;
+        float *rec = reinterpret_cast<float *>(nodes + p);
+        if (left_child) {
+            __stcg(reinterpret_cast<float4 *>(rec), make_float4(lo.x, lo.y, lo.z, hi.x));
+            __stcg(reinterpret_cast<float2 *>(rec + 4), make_float2(hi.y, hi.z));
+            __stcg(reinterpret_cast<int *>(rec + 12), cur);
+        } else {
+            __stcg(reinterpret_cast<float2 *>(rec + 6), make_float2(lo.x, lo.y));
+            __stcg(reinterpret_cast<float4 *>(rec + 8), make_float4(lo.z, hi.x, hi.y, hi.z));
+            __stcg(reinterpret_cast<int *>(rec + 13), cur);
+        }
+        if (cur == 0) { info[1] = p; info[2] = left_child ? 0 : 1; }
         __threadfence();
-        cur = parent_internal[cur];
+        const int other = atomicExch(&flags[p], left_child ? l : r);
+        if (other == -1) return;                       // first arrival: the sibling finishes this node
+        if (left_child) {                              // the sibling is the right child: floats 6..11, its range ends at `other`
+            const float2 a = __ldcg(reinterpret_cast<const float2 *>(rec + 6));
+            const float4 b = __ldcg(reinterpret_cast<const float4 *>(rec + 8));
+            lo = make_float4(fminf(lo.x, a.x), fminf(lo.y, a.y), fminf(lo.z, b.x), 0.0f);
+            hi = make_float4(fmaxf(hi.x, b.y), fmaxf(hi.y, b.z), fmaxf(hi.z, b.w), 0.0f);
+            r = other;
+        } else {
+            const float4 a = __ldcg(reinterpret_cast<const float4 *>(rec));
+            const float2 b = __ldcg(reinterpret_cast<const float2 *>(rec + 4));
+            lo = make_float4(fminf(lo.x, a.x), fminf(lo.y, a.y), fminf(lo.z, a.z), 0.0f);
+            hi = make_float4(fmaxf(hi.x, a.w), fmaxf(hi.y, b.x), fmaxf(hi.z, b.y), 0.0f);
+            l = other;
+        }
+        cur = p;
+        if (l == 0 && r == n - 1) { info[0] = p; return; }
     }
+}
+
+// work[0 .. cap): the list; info[3]: its length.  A full list (never seen: the capacity is a quarter of the leaves,
+// real scenes need 3 - 8 %) makes the lane climb globally right here instead -- slow, still correct.
+__device__ __forceinline__ void tree_export(TreeItem *__restrict__ work, unsigned cap, unsigned slot, const uint32_t *__restrict__ keys,
+                                            int n, Node *nodes, int *flags, int *info, int l, int r, int cur, float4 lo, float4 hi) {
+    if (slot < cap) {
+        TreeItem it;
+        it.l = l; it.r = r; it.cur = cur;
+        it.lo[0] = lo.x; it.lo[1] = lo.y; it.lo[2] = lo.z; it.hi[0] = hi.x; it.hi[1] = hi.y; it.hi[2] = hi.z;
+        work[slot] = it;
+    } else {
+        tree_climb_global(keys, n, nodes, flags, info, l, r, cur, lo, hi);
+    }
+}
+
+__global__ void __launch_bounds__(32) k_tree_local(const uint32_t *__restrict__ keys, int n, const float4 *__restrict__ leaf_box,
+                                                   Node *nodes, int *flags, int *info, TreeItem *__restrict__ work, unsigned work_cap) {
+    __shared__ unsigned long long s_metric[TREE_SEG + 1];   // metric(j), j = b0 - 1 .. b1 - 1, at index j - b0 + 1
+    __shared__ int s_flag[TREE_SEG];                        // per split p = b0 + k: -1 nobody yet, >= 0 the far range bound of the parked child, -2 finished
+    __shared__ float s_box[TREE_SEG][6];                    // the parked child's box
+    __shared__ int s_link[TREE_SEG];                        // the parked child's link
+    const unsigned lane = threadIdx.x, lt_mask = (1u << lane) - 1u;
+    const int b0 = blockIdx.x * TREE_SEG, b1 = min(b0 + TREE_SEG, n), n_seg = b1 - b0;
+    for (int k = lane; k <= n_seg; k += 32) s_metric[k] = split_metric(keys, n, b0 - 1 + k);
+    for (int k = lane; k < TREE_SEG; k += 32) s_flag[k] = -1;
+    __syncwarp();
+    int next = 0;                          // next leaf of the segment nobody has taken
+    bool carry = false;
+    int l = 0, r = 0, cur = 0;
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    for (;;) {
+        // ---- free lanes take fresh leaves
+        const unsigned idle = __ballot_sync(0xffffffffu, !carry);
+        if (idle && next < n_seg) {
+            const int mine = next + __popc(idle & lt_mask);
+            if (!carry && mine < n_seg) {
+                l = r = b0 + mine; cur = ~(b0 + mine);
+                lo = __ldg(leaf_box + 2 * (b0 + mine)); hi = __ldg(leaf_box + 2 * (b0 + mine) + 1);
+                carry = true;
+            }
+            next = min(next + __popc(idle), n_seg);
+        }
+        if (!__any_sync(0xffffffffu, carry)) break;
+        // ---- one step of every carrying lane: attach to the parent
+        bool left_child = false, local = false;
+        int p = 0, other = -1;
+        if (carry) {
+            left_child = s_metric[r - b0 + 1] < s_metric[l - b0];          // metric(r) < metric(l - 1)
+            p = left_child ? r : l - 1;
+            local = p >= b0 && p + 1 < b1;
+            if (cur == 0) { info[1] = p; info[2] = left_child ? 0 : 1; }
+            if (local) other = atomicExch(&s_flag[p - b0], left_child ? l : r);
+        }
+        // subtrees whose parent split is not inside the segment leave for the work list
+        const unsigned out = __ballot_sync(0xffffffffu, carry && !local);
+        if (out) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned *>(info + 3), (unsigned)__popc(out));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (carry && !local) {
+                tree_export(work, work_cap, base + __popc(out & lt_mask), keys, n, nodes, flags, info, l, r, cur, lo, hi);
+                carry = false;
+            }
+        }
+        __syncwarp();
+        if (carry && other == -1) {                    // first arrival: park box and link, take a fresh leaf next
+            float *q = s_box[p - b0];
+            q[0] = lo.x; q[1] = lo.y; q[2] = lo.z; q[3] = hi.x; q[4] = hi.y; q[5] = hi.z;
+            s_link[p - b0] = cur;
+            carry = false;
+        }
+        __syncwarp();
+        if (carry) {                                   // second arrival: the node is complete
+            const float *q = s_box[p - b0];
+            const float4 slo = make_float4(q[0], q[1], q[2], 0.f), shi = make_float4(q[3], q[4], q[5], 0.f);
+            const int sl = s_link[p - b0];
+            s_flag[p - b0] = -2;
+            Node nd;
+            if (left_child) {
+                nd.q0 = make_float4(lo.x, lo.y, lo.z, hi.x); nd.q1 = make_float4(hi.y, hi.z, slo.x, slo.y);
+                nd.q2 = make_float4(slo.z, shi.x, shi.y, shi.z); nd.link = make_int4(cur, sl, 0, 0);
+                r = other;
+            } else {
+                nd.q0 = make_float4(slo.x, slo.y, slo.z, shi.x); nd.q1 = make_float4(shi.y, shi.z, lo.x, lo.y);
+                nd.q2 = make_float4(lo.z, hi.x, hi.y, hi.z); nd.link = make_int4(sl, cur, 0, 0);
+                l = other;
+            }
+            nodes[p] = nd;
+            lo = make_float4(fminf(lo.x, slo.x), fminf(lo.y, slo.y), fminf(lo.z, slo.z), 0.f);
+            hi = make_float4(fmaxf(hi.x, shi.x), fmaxf(hi.y, shi.y), fmaxf(hi.z, shi.z), 0.f);
+            cur = p;
+            if (l == 0 && r == n - 1) { info[0] = p; carry = false; }
+        }
+    }
+    __syncwarp();
+    // ---- parked children whose sibling never came: it reaches outside the segment, so both go global
+    for (int k0 = 0; k0 < n_seg; k0 += 32) {
+        const int k = k0 + (int)lane;
+        const int pend = k < n_seg ? s_flag[k] : -1;
+        const unsigned out = __ballot_sync(0xffffffffu, pend >= 0);
+        if (!out) continue;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned *>(info + 3), (unsigned)__popc(out));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pend >= 0) {
+            const int p = b0 + k;
+            const float *q = s_box[k];
+            // the parked child is the left one, [pend, p], if its far bound lies left of the split, else the right one, [p + 1, pend]
+            tree_export(work, work_cap, base + __popc(out & lt_mask), keys, n, nodes, flags, info, pend <= p ? pend : p + 1,
+                        pend <= p ? p : pend, s_link[k], make_float4(q[0], q[1], q[2], 0.f), make_float4(q[3], q[4], q[5], 0.f));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tree_global(const uint32_t *__restrict__ keys, int n, Node *nodes, int *flags, int *info,
+                                                     const TreeItem *__restrict__ work, unsigned work_cap) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned count = *reinterpret_cast<const unsigned *>(info + 3);
+    if (count > work_cap) count = work_cap;
+    if (i >= count) return;
+    const TreeItem it = work[i];
+    tree_climb_global(keys, n, nodes, flags, info, it.l, it.r, it.cur, make_float4(it.lo[0], it.lo[1], it.lo[2], 0.f),
+                      make_float4(it.hi[0], it.hi[1], it.hi[2], 0.f));
+}
+
+__global__ void k_tree_root_to_zero(Node *nodes, const int *__restrict__ info) {
+    const int root = info[0];
+    if (root == 0) return;
+    const Node a = nodes[0], b = nodes[root];
+    nodes[0] = b;
+    nodes[root] = a;
+    const int parent = info[1] == root ? 0 : info[1];            // whoever linked to internal node 0 now links to `root`
+    int *link = reinterpret_cast<int *>(&nodes[parent].link);
+    link[info[2]] = root;
 }
 
 // 32-wide implicit tree: one level per launch.  Thread t owns child slot t of the destination
@@ -611,14 +759,13 @@ __global__ void __launch_bounds__(256) k_collapse4(const Node *__restrict__ node
 }
 
 // a scene with one triangle: root = (leaf 0, empty); the empty box (+inf,-inf) can never be hit
-__global__ void k_single_root(Node *nodes, const float4 *leaf_box, float4 *node_box) {
+__global__ void k_single_root(Node *nodes, const float4 *leaf_box) {
     const float4 lo = leaf_box[0], hi = leaf_box[1];
     const float inf = INFINITY;
     nodes[0].q0 = make_float4(lo.x, lo.y, lo.z, hi.x);
     nodes[0].q1 = make_float4(hi.y, hi.z, inf, inf);
     nodes[0].q2 = make_float4(inf, -inf, -inf, -inf);
     nodes[0].link = make_int4(~0, ~0, 0, 0);
-    node_box[0] = lo; node_box[1] = hi;
 }
 
 // Row f2 of SURVEY.md section 8: heightmap terrain -> triangle soup ON THE DEVICE.  Emits, for every quad
@@ -769,9 +916,8 @@ cudaError_t build_lbvh(xp_scene *s) {
     XP_TRY(s->vals_a.reserve(n * 4)); XP_TRY(s->vals_b.reserve(n * 4));
     XP_TRY(s->recs.reserve(n * sizeof(TriRec)));
     XP_TRY(s->nodes.reserve((n > 1 ? n - 1 : 1) * sizeof(Node)));
-    XP_TRY(s->node_box.reserve(n * 32)); XP_TRY(s->leaf_box.reserve(n * 32));
-    XP_TRY(s->parent_internal.reserve(n * 4)); XP_TRY(s->parent_leaf.reserve(n * 4));
-    XP_TRY(s->refit_flags.reserve(n * 4));
+    XP_TRY(s->leaf_box.reserve(n * 32));
+    XP_TRY(s->refit_flags.reserve((n + 4) * 4));
     unsigned *bounds = s->bounds.as<unsigned>();
     {
         StageTimer t(s, XP_STAGE_BUILD_BOUNDS);
@@ -810,25 +956,22 @@ cudaError_t build_lbvh(xp_scene *s) {
         ++s->stats.kernel_launches;
     }
     if (n == 1) {
-        k_single_root<<<1, 1, 0, st>>>(s->nodes.as<Node>(), s->leaf_box.as<float4>(), s->node_box.as<float4>());
+        k_single_root<<<1, 1, 0, st>>>(s->nodes.as<Node>(), s->leaf_box.as<float4>());
         ++s->stats.kernel_launches;
     } else {
-        {
-            StageTimer t(s, XP_STAGE_BUILD_TREE);
-            k_karras<<<grid_for(n - 1, 256), 256, 0, st>>>(keys, (int)n, s->nodes.as<Node>(),
-                                                          s->parent_internal.as<int>(),
-                                                          s->parent_leaf.as<int>());
-            ++s->stats.kernel_launches;
-        }
-        {
-            StageTimer t(s, XP_STAGE_BUILD_REFIT);
-            XP_TRY(cudaMemsetAsync(s->refit_flags.p, 0, n * 4, st));
-            k_refit<<<grid_for(n, 256), 256, 0, st>>>((int)n, s->nodes.as<Node>(),
-                                                     s->parent_internal.as<int>(), s->parent_leaf.as<int>(),
-                                                     s->leaf_box.as<float4>(), s->node_box.as<float4>(),
-                                                     s->refit_flags.as<unsigned>());
-            ++s->stats.kernel_launches;
-        }
+        StageTimer t(s, XP_STAGE_BUILD_TREE);
+        int *flags = s->refit_flags.as<int>();                 // n - 1 arrival slots (-1 = nobody yet) + 4 ints: root, who links to node 0 (node, side), work-list length
+        const unsigned work_cap = (unsigned)(n / 4 + 4096);
+        XP_TRY(s->tree_work.reserve((size_t)work_cap * sizeof(TreeItem)));
+        XP_TRY(cudaMemsetAsync(flags, 0xFF, n * 4, st));
+        XP_TRY(cudaMemsetAsync(flags + n, 0, 4 * 4, st));
+        k_tree_local<<<grid_for(n, TREE_SEG), 32, 0, st>>>(keys, (int)n, s->leaf_box.as<float4>(), s->nodes.as<Node>(), flags,
+                                                          flags + n, s->tree_work.as<TreeItem>(), work_cap);
+        k_tree_global<<<grid_for(work_cap, 256), 256, 0, st>>>(keys, (int)n, s->nodes.as<Node>(), flags, flags + n,
+                                                              s->tree_work.as<TreeItem>(), work_cap);
+        ++s->stats.kernel_launches;
+        k_tree_root_to_zero<<<1, 1, 0, st>>>(s->nodes.as<Node>(), flags + n);
+        s->stats.kernel_launches += 2;
     }
     s->q4_built = s->wide_built = false;      // optional structures are (re)built on first use by build_aux()
     XP_TRY(cudaGetLastError());

@@ -116,8 +116,9 @@ struct xp_scene {
     xp::DevBuf tris_aos;      // xp_triangle[T], upload order
     xp::DevBuf recs;          // TriRec[T], Morton order
     xp::DevBuf nodes;         // Node[max(T-1,1)]
-    xp::DevBuf node_box, leaf_box;                   // float4 (lo, hi) pairs, 32 B per box, used by the refit
-    xp::DevBuf parent_internal, parent_leaf, refit_flags;
+    xp::DevBuf leaf_box;                             // float4 (lo, hi) pairs, 32 B per leaf: what the bottom-up tree pass starts from
+    xp::DevBuf refit_flags;                          // the tree pass's arrival slots (+ 4 ints: root info, work-list length)
+    xp::DevBuf tree_work;                            // the tree pass's work list (subtrees that continue through the global protocol)
     xp::DevBuf keys_a, keys_b, vals_a, vals_b;       // radix sort ping-pong (triangles / spheres)
     xp::DevBuf hist;          // radix histograms + scan scratch
     xp::DevBuf bounds;        // 6 ordered-int floats: scene AABB of triangle centres

@@ -366,8 +366,10 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
 #endif
     __shared__ float4 rpool_all[BP_WARPS][64];          // the warp's current run of rays: (c,|m|)[32], (1/m,flags)[32]
     __shared__ float rbest_all[BP_WARPS][32];
+#if XP_BP_LANESORT
     __shared__ unsigned bucket_all[BP_WARPS][32];       // span flush: entries per emitting lane
     unsigned *bucket = bucket_all[threadIdx.x >> 5];
+#endif
     uint2 *q = queue[threadIdx.x >> 5];
     float4 *rpool = rpool_all[threadIdx.x >> 5];
     float *rbest = rbest_all[threadIdx.x >> 5];
