@@ -553,17 +553,34 @@ __global__ void __launch_bounds__(32) k_tree_local(const uint32_t *__restrict__ 
     bool carry = false;
     int l = 0, r = 0, cur = 0;
     float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    // Leaf boxes are read a chunk of 32 ahead, one per lane, and handed to the lane that takes the leaf by shuffle: a
+    // load inside the loop would put a trip to HBM on the critical path of every iteration (measured: 2400 cycles per
+    // iteration with 11 warps per SM to hide them).  a: leaves chunk .. chunk + 31 of the segment, b: the next 32.
+    int chunk = 0;
+    float4 alo = lo, ahi = lo, blo = lo, bhi = lo;
+    if ((int)lane < n_seg) { alo = __ldg(leaf_box + 2 * (b0 + lane)); ahi = __ldg(leaf_box + 2 * (b0 + lane) + 1); }
+    if (32 + (int)lane < n_seg) { blo = __ldg(leaf_box + 2 * (b0 + 32 + lane)); bhi = __ldg(leaf_box + 2 * (b0 + 32 + lane) + 1); }
     for (;;) {
-        // ---- free lanes take fresh leaves
+        // ---- free lanes take fresh leaves (from the current chunk only; the next iteration continues in the next chunk)
         const unsigned idle = __ballot_sync(0xffffffffu, !carry);
         if (idle && next < n_seg) {
+            const int lim = min(chunk + 32, n_seg);
             const int mine = next + __popc(idle & lt_mask);
-            if (!carry && mine < n_seg) {
+            const int src = (mine - chunk) & 31;
+            const float lx = __shfl_sync(0xffffffffu, alo.x, src), ly = __shfl_sync(0xffffffffu, alo.y, src), lz = __shfl_sync(0xffffffffu, alo.z, src);
+            const float hx = __shfl_sync(0xffffffffu, ahi.x, src), hy = __shfl_sync(0xffffffffu, ahi.y, src), hz = __shfl_sync(0xffffffffu, ahi.z, src);
+            if (!carry && mine < lim) {
                 l = r = b0 + mine; cur = ~(b0 + mine);
-                lo = __ldg(leaf_box + 2 * (b0 + mine)); hi = __ldg(leaf_box + 2 * (b0 + mine) + 1);
+                lo = make_float4(lx, ly, lz, 0.f); hi = make_float4(hx, hy, hz, 0.f);
                 carry = true;
             }
-            next = min(next + __popc(idle), n_seg);
+            next = min(next + __popc(idle), lim);
+            if (next == chunk + 32 && next < n_seg) {         // chunk used up: the one read ahead becomes current, read the one after
+                chunk += 32;
+                alo = blo; ahi = bhi;
+                const int k = chunk + 32 + (int)lane;
+                if (k < n_seg) { blo = __ldg(leaf_box + 2 * (b0 + k)); bhi = __ldg(leaf_box + 2 * (b0 + k) + 1); }
+            }
         }
         if (!__any_sync(0xffffffffu, carry)) break;
         // ---- one step of every carrying lane: attach to the parent
