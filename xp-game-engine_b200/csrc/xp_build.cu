@@ -248,7 +248,30 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t *__restri
 
 // stable scatter: warp w owns keys [w*512, (w+1)*512) of the tile, processed in chunks of 32.
 // inv_out (last pass only, may be null): the inverse permutation, inv_out[value] = final position.
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__restrict__ keys_in,
+// Lanes holding the same digit are found with one ballot per digit bit (registers only) rather than MATCH.ANY, whose
+// result comes back through the shared-memory pipe: ncu showed the kernel waiting on exactly that (short scoreboard 18
+// per issue, 14 % of the issue slots used).  The rank of a key inside its warp's segment is fixed in the first pass and
+// kept in a register, so the second pass is a table lookup; values are read where they are written (no register copy).
+#ifndef XP_RS_MATCH
+#define XP_RS_MATCH 1              // 1: ballots per digit bit, 0: __match_any_sync
+#endif
+__device__ __forceinline__ unsigned rs_peers(unsigned d, unsigned vm) {
+#if XP_RS_MATCH
+    unsigned peers = vm;
+#pragma unroll
+    for (int b = 0; b < RS_BITS; ++b) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+        peers &= ((d >> b) & 1u) ? bal : ~bal;
+    }
+    return peers;
+#else
+    return __match_any_sync(vm, d);
+#endif
+}
+#ifndef XP_RS_MINB
+#define XP_RS_MINB 4
+#endif
+__global__ void __launch_bounds__(RS_THREADS, XP_RS_MINB) k_rs_scatter(const uint32_t *__restrict__ keys_in,
                                                            const uint32_t *__restrict__ vals_in,
                                                            uint32_t *__restrict__ keys_out,
                                                            uint32_t *__restrict__ vals_out, uint64_t n,
@@ -256,23 +279,30 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__res
                                                            unsigned num_tiles, uint32_t *__restrict__ inv_out) {
     __shared__ unsigned cnt[RS_WARPS][RS_BINS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)w * RS_SEG;
-    uint32_t k[RS_ITEMS], v[RS_ITEMS];
-    // pass A: per-warp digit counts
+    uint32_t k[RS_ITEMS];
+    uint16_t rank[RS_ITEMS];               // position among the keys of this warp's segment that share the digit (< 512)
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        const uint64_t idx = base + (uint64_t)c * 32 + lane;
+        k[c] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
+    }
+    // pass A: per-warp digit counts and each key's rank inside the warp's segment (original order -> stable)
 #pragma unroll
     for (int c = 0; c < RS_ITEMS; ++c) {
         const uint64_t idx = base + (uint64_t)c * 32 + lane;
         const bool valid = idx < n;
-        k[c] = valid ? keys_in[idx] : 0u;
-        v[c] = valid ? vals_in[idx] : 0u;
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned d = (k[c] >> shift) & RS_MASK;
-            const unsigned peers = __match_any_sync(vm, d);
-            if (lane == (31 - __clz(peers))) cnt[w][d] += __popc(peers);
-        }
+        const unsigned d = (k[c] >> shift) & RS_MASK;
+        const unsigned peers = rs_peers(d, vm) & vm;
+        unsigned before = 0;
+        if (valid) before = cnt[w][d];
+        __syncwarp();
+        if (valid && lane == (31 - __clz(peers))) cnt[w][d] = before + __popc(peers);
+        rank[c] = (uint16_t)(before + __popc(peers & lt_mask));
         __syncwarp();
     }
     __syncthreads();
@@ -286,24 +316,17 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t *__res
         }
     }
     __syncthreads();
-    // pass B: ranks in original order -> stable
+    // pass B: a lookup
 #pragma unroll
     for (int c = 0; c < RS_ITEMS; ++c) {
         const uint64_t idx = base + (uint64_t)c * 32 + lane;
-        const bool valid = idx < n;
-        const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        unsigned d = 0, peers = 0;
-        if (valid) {
-            d = (k[c] >> shift) & RS_MASK;
-            peers = __match_any_sync(vm, d);
-            const unsigned pos = cnt[w][d] + __popc(peers & ((1u << lane) - 1u));
+        if (idx < n) {
+            const unsigned pos = cnt[w][(k[c] >> shift) & RS_MASK] + rank[c];
+            const uint32_t v = vals_in[idx];
             keys_out[pos] = k[c];
-            vals_out[pos] = v[c];
-            if (inv_out) inv_out[v[c]] = pos;
+            vals_out[pos] = v;
+            if (inv_out) inv_out[v] = pos;
         }
-        __syncwarp();
-        if (valid && lane == (31 - __clz(peers))) cnt[w][d] += __popc(peers);
-        __syncwarp();
     }
 }
 
