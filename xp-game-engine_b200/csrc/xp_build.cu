@@ -289,6 +289,9 @@ __global__ void __launch_bounds__(RS_THREADS, XP_RS_MINB) k_rs_scatter(const uin
     for (int c = 0; c < RS_ITEMS; ++c) {
         const uint64_t idx = base + (uint64_t)c * 32 + lane;
         k[c] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
+        // the values are first touched in pass B, a whole ranking pass from here: ask for them now (L2), or the first of
+        // those loads waits for HBM at the end of the kernel (45 % of the stall samples)
+        if ((lane & 7) == 0 && idx < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals_in + idx));   // one per 32 B sector
     }
     // pass A: per-warp digit counts and each key's rank inside the warp's segment (original order -> stable)
 #pragma unroll
@@ -464,7 +467,15 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
         const float cc = c.x * c.x + c.y * c.y + c.z * c.z;
         const float l1 = e1.x * e1.x + e1.y * e1.y + e1.z * e1.z, l2 = e2.x * e2.x + e2.y * e2.y + e2.z * e2.z;
         const float m2 = fmaxf(l1, l2);
-        if (!(cc > 1e-4f * (l1 * l2)) || !(cc * 1.7e5f > m2 * m2 * m2)) degen[1 + atomicAdd(&degen[0], 1u)] = (uint32_t)j;
+        const bool ill = !(cc > 1e-4f * (l1 * l2)) || !(cc * 1.7e5f > m2 * m2 * m2);
+        const unsigned act = __activemask(), im = __ballot_sync(act, ill);
+        if (im) {                                      // one atomic per warp
+            const int lane = threadIdx.x & 31, leader = __ffs(im) - 1;
+            unsigned at = 0;
+            if (lane == leader) at = atomicAdd(&degen[0], (unsigned)__popc(im));
+            at = __shfl_sync(act, at, leader);
+            if (ill) degen[1 + at + __popc(im & ((1u << lane) - 1u))] = (uint32_t)j;
+        }
     }
     leaf_box[2 * j] = make_float4(lo.x, lo.y, lo.z, 0.0f);          // (lo, hi) side by side: one 32 B sector per box for the refit
     leaf_box[2 * j + 1] = make_float4(hi.x, hi.y, hi.z, 0.0f);

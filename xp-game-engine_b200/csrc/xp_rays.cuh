@@ -21,7 +21,7 @@ __device__ __forceinline__ RayRec make_ray_rec(V3 c, V3 m, bool valid) {
     rr.q1 = make_float4(m.x, m.y, m.z, ray.msl);
     // q2.w: the per-ray operand of the narrowphase's one vertex-root division (+inf = irregular ray, literal path)
     rr.q2 = make_float4(ray.mh.x, ray.mh.y, ray.mh.z, xp_ray_r2a<O>(ray));
-    rr.q3 = make_float4(fdiv(1.0f, m.x), fdiv(1.0f, m.y), fdiv(1.0f, m.z), __uint_as_float(flags));
+    rr.q3 = make_float4(frcp_z(m.x), frcp_z(m.y), frcp_z(m.z), __uint_as_float(flags));
     return rr;
 }
 
