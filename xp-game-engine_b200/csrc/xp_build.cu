@@ -504,13 +504,16 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
 //     a lane that arrived second merges and climbs), so the lanes stay busy while the long climbers climb.  A child
 //     whose parent split p lies strictly inside the segment attaches through shared memory: exchange of the range bound
 //     in s_flag[p], the first arrival parks its box and link, the second builds the node's whole 64 B record and writes
-//     it out.  ~94 % of all nodes are finished this way, without a global atomic or fence.
+//     it out.  ~90 % of all nodes are finished this way, without a global atomic or fence.
 //   * What a segment cannot finish alone -- subtrees whose parent split is the segment's boundary or beyond, and parked
 //     children whose sibling reaches over the boundary and so never shows up -- goes onto a work list in global memory.
 //   * k_tree_global: one thread per work item continues through the global protocol (half-record store, fence,
 //     atomicExch(flags[p]); the second arrival merges and climbs), all items in flight at once.
 // A node's two arrivals always use the same protocol: both inside one segment's warp, or both global.
-static constexpr int TREE_SEG = 512;          // leaves per warp
+#ifndef XP_TREE_SEG
+#define XP_TREE_SEG 256                   /* 10 KB of shared memory per warp: 22 warps per SM; 512: 0.58 ms, 256: 0.48, 128: 0.52 (10 M triangles) */
+#endif
+static constexpr int TREE_SEG = XP_TREE_SEG;  // leaves per warp
 static constexpr unsigned long long METRIC_INF = ~0ull;
 struct TreeItem { int l, r, cur; float lo[3], hi[3]; };      // a subtree still to be attached: leaves [l, r], its link, its box
 
