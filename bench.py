@@ -806,6 +806,34 @@ def run_config5(ctx: Ctx, args, scale: float = 1.0) -> dict:
            "device_mem_gb": (total - free) / 1e9}
     if ex is not None:
         ex.close()
+        # the same steps with 16 B records (XP_OPT_CONTACT_RECORD = 1: centre at the contact + triangle): the exchange of the
+        # 40 B records runs at NVLink line rate, so fewer bytes is the only way to make it shorter
+        ex16 = ContactExchange(s, S, dev, n_buf=1, record="compact")
+        if ex16.ok:
+            tests.clear(); stage.clear()
+
+            def step16():
+                ex16.sweep(d_in.data_ptr(), S)
+                dist.barrier()
+                st = s.stats()
+                tests.append(st["narrowphase_tests"]); stage.append(st["stage_ms"])
+            ms16 = ev_ms(ctx, step16, 3, warmup=1)
+            local16 = torch.empty((S, 4), dtype=torch.float32, device=dev)
+            s.detect_contacts_dev(d_in.data_ptr(), S, local16.data_ptr())
+            torch.cuda.synchronize()
+            ok = bool(torch.equal(ex16.view[rank][:S].view(torch.int32), local16.view(torch.int32)))
+            sums = torch.stack([ex16.view[r][:S].contiguous().view(torch.int32).to(torch.int64).sum() for r in range(world)])
+            lo_, hi_ = sums.clone(), sums.clone()
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+            flag = torch.tensor([1 if (ok and bool(torch.equal(lo_, hi_))) else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            out["compact_records"] = {"record": "xp_contact16: (position, tri_index), 16 B", "ms_per_step": ms16,
+                                      "spheres_per_sec": world * S / (ms16 * 1e-3), "gathered_bytes_per_gpu": world * S * 16,
+                                      "finalize_ms": float(np.mean([x["finalize"] for x in stage[1:]])),
+                                      "exchange_verified": bool(flag.item() == 1)}
+            del local16
+        ex16.close()
+        s.set_options(contact_record="full")
     s.close()
     del d_in, local, gathered
     torch.cuda.empty_cache()

@@ -87,6 +87,11 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                 itself (computed cell addresses, no tree; csrc/xp_gridwalk.cuh) instead of the LBVH.
                                 Same candidate set, bit for bit; applies to XP_METHOD_LBVH_PAIRS without distance
                                 windows.  0: always the LBVH. */
+#define XP_OPT_CONTACT_RECORD 9 /* what the contact entry points (xp_detect_contacts_*) write per sphere:
+                                * 0 (default) xp_contact, 40 B;  1 xp_contact16, 16 B = the sphere's centre at the contact and
+                                * the triangle -- what a PEER can use without the sphere's own Response (time_to, distance_to
+                                * and intersection are functions of the Response, collision_detect.rs:188-194, which only the
+                                * owning rank holds).  128 M spheres on 8 GPUs: 2.1 GB instead of 5.4 GB landed per GPU. */
 
 #define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical to the reference's results         */
 #define XP_ARITH_FAST     1  /* tolerance mode: FMA, hardware reciprocal / square root, reduced quadratics (<= 1e-5) */
@@ -262,6 +267,9 @@ int  xp_scene_debug_tree(xp_scene *s, uint32_t *sorted_tri, uint32_t *morton, in
 /* ---- contact record for the multi-GPU allgather ----
  * 40 B per sphere: the 32 B collision + tri_index + (hit | status << 8 | iterations << 16). */
 typedef struct { xp_collision col; uint32_t tri_index; uint32_t flags; } xp_contact;
+/* XP_OPT_CONTACT_RECORD = 1: position = c + m * time_to (all zero without a hit), tri_index = 0xFFFFFFFF without a hit.
+ * Every buffer / slot argument of the contact entry points then counts records of this size. */
+typedef struct { xp_vec3 position; uint32_t tri_index; } xp_contact16;
 /* Closest collision per sphere written as xp_contact records straight into a (send) buffer,
  * e.g. this rank's slot of the NCCL allgather buffer.  Device pointers. */
 int  xp_detect_contacts_dev(xp_scene *s, const xp_response *d_in, uint64_t n,

@@ -43,13 +43,13 @@ def _init(rank, world, port):
     return torch, dist
 
 
-def _worker(rank, world, port, n, out_dir, exchange="auto"):
+def _worker(rank, world, port, n, out_dir, exchange="auto", record="full"):
     torch, dist = _init(rank, world, port)
     from xp_physics_cuda import scenes
     from xp_physics_cuda.distributed import ShardedSweep
     tris, h = scenes.sine_terrain(40, 40, seed=15)
     resps = scenes.terrain_spheres(h, n, seed=16)
-    sw = ShardedSweep(tris, rank, exchange=exchange)
+    sw = ShardedSweep(tris, rank, exchange=exchange, record=record)
     full = sw.sweep(resps)
     full2 = sw.sweep(resps)                      # buffers are reused across sweeps
     torch.cuda.synchronize()
@@ -82,6 +82,29 @@ def test_sharded_sweep(tmp_path, oracle, exchange):
         hh = hit.astype(bool)
         for f in ("time_to", "distance_to", "position", "intersection"):
             assert np.array_equal(g[f][hh].view(np.uint32), col[f][hh].view(np.uint32)), f
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "auto"])
+def test_sharded_sweep_compact_records(tmp_path, oracle, exchange):
+    """XP_OPT_CONTACT_RECORD = 1: the 16 B record (centre at the contact, triangle) through both transports --
+    the fields a peer can use without the owner's Response, bit-identical to the oracle's on every rank."""
+    import torch.multiprocessing as mp
+    from xp_physics_cuda import CONTACT16_DTYPE, scenes
+    world = _world()
+    n = 5001
+    mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path), exchange, "compact"), nprocs=world, join=True)
+    tris, h = scenes.sine_terrain(40, 40, seed=15)
+    resps = scenes.terrain_spheres(h, n, seed=16)
+    col, hit, tri, st, _ = oracle.detect_batch(resps, tris)
+    hh = hit.astype(bool)
+    assert hh.sum() > 1000 and (~hh).sum() > 0
+    for r in range(world):
+        g = np.load(tmp_path / f"rank{r}.npy")
+        assert g.shape == (n, 4)
+        g = np.ascontiguousarray(g).view(CONTACT16_DTYPE).reshape(-1)
+        assert np.array_equal(g["tri_index"], tri)
+        assert np.array_equal(g["position"][hh].view(np.uint32), col["position"][hh].view(np.uint32))
+        assert not g["position"][~hh].any() and (g["tri_index"][~hh] == 0xFFFFFFFF).all()
 
 
 def _loop_worker(rank, world, port, out_dir, steps):

@@ -762,6 +762,51 @@ def test_async_exchange_loop_single_process(terrain, oracle):
         assert_bits_equal(rec["intersection"][hm], w[0]["intersection"][hm], f"async exchange step {k}")
 
 
+def test_compact_contact_records(terrain, oracle):
+    """XP_OPT_CONTACT_RECORD = 1: xp_contact16 = (centre at the contact, triangle), 16 B instead of 40 -- through the
+    contacts-only entry point, the synchronous exchange and the loop of steps; misses are (0, 0, 0, 0xFFFFFFFF)."""
+    import torch
+    from xp_physics_cuda import CONTACT16_DTYPE
+    from xp_physics_cuda.distributed import ContactExchange, contacts_as_records
+    tris, h, resps, want = terrain
+    n = len(resps)
+    col, hit, tri = want[0], want[1].astype(bool), want[2]
+    dev = torch.device("cuda", 0)
+    d_in = torch.from_numpy(np.ascontiguousarray(resps).view(np.float32).reshape(-1, 7)).to(dev)
+
+    def check(rec, what):
+        assert rec.dtype == CONTACT16_DTYPE and len(rec) == n, what
+        assert np.array_equal(rec["tri_index"], np.where(hit, tri, 0xFFFFFFFF).astype(np.uint32)), what
+        assert_bits_equal(rec["position"][hit], col["position"][hit], what)
+        assert not rec["position"][~hit].any(), what
+    with xp.Scene(0, tris) as s:
+        s.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        s.set_options(contact_record="compact")
+        out = torch.full((n + 1, 4), 7.0, dtype=torch.float32, device=dev)
+        s.detect_contacts_dev(d_in.data_ptr(), n, out.data_ptr())
+        torch.cuda.synchronize()
+        assert (out[n] == 7.0).all()                                       # nothing written past n records of 16 B
+        check(contacts_as_records(out[:n]), "xp_detect_contacts_dev")
+        s.detect_contacts_dev(d_in.data_ptr(), n, out.data_ptr() + 4)      # 4-byte aligned only: the per-sphere writer
+        torch.cuda.synchronize()
+        check(contacts_as_records(out.reshape(-1)[1:1 + 4 * n].reshape(n, 4).clone()), "xp_detect_contacts_dev, unaligned")
+        ex = ContactExchange(s, n, dev, record="compact")
+        assert ex.ok and ex.view.shape[-1] == 4
+        ex.sweep(d_in.data_ptr(), n)
+        torch.cuda.synchronize()
+        check(contacts_as_records(ex.view[0, :n]), "synchronous exchange")
+        t = ex.sweep_async(d_in.data_ptr(), n)
+        check(contacts_as_records(ex.wait(t)[0, :n]), "loop of steps")
+        ex.close()
+        s.set_options(contact_record="full")                               # and back: the 40 B records again
+        full = torch.zeros((n, 10), dtype=torch.float32, device=dev)
+        s.detect_contacts_dev(d_in.data_ptr(), n, full.data_ptr())
+        torch.cuda.synchronize()
+        rec = contacts_as_records(full)
+        assert np.array_equal((rec["flags"] & 1).astype(bool), hit)
+        assert_bits_equal(rec["position"][hit], col["position"][hit], "full records after compact")
+
+
 # ---- ill-conditioned triangles: the reference's face test reports hits the geometric broadphase never offers
 SLIVER = [[-0.7752354741096497, -0.6470972299575806, 5.695098400115967],
           [-0.21221216022968292, -0.4316372871398926, 5.311792373657227],

@@ -147,6 +147,9 @@ int xp_scene_set_option(xp_scene *s, int option, int64_t value) {
         s->prune = (int)value; s->cand_per_ray = 0.0; return XP_OK;
     case XP_OPT_FAR_EXACT: s->far_exact = value ? 1 : 0; return XP_OK;
     case XP_OPT_GRID_WALK: s->use_grid = value ? 1 : 0; return XP_OK;
+    case XP_OPT_CONTACT_RECORD:
+        if (value > 1) return XP_EINVAL;
+        s->contact_record = (int)value; return XP_OK;
     default: return XP_EINVAL;
     }
 }

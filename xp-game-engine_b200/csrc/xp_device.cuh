@@ -100,6 +100,7 @@ struct xp_scene {
     int prune = 2;                     // XP_OPT_PRUNE: auto (distance windows once a sweep saw > 96 candidates per sphere)
     int timing = 0;
     int sort_spheres = 1;
+    int contact_record = 0;            // XP_OPT_CONTACT_RECORD: 0 = xp_contact (40 B), 1 = xp_contact16 (16 B)
     int far_exact = 0;                 // XP_OPT_FAR_EXACT: second pass for far-range grazing noise of the reference
     uint64_t max_pairs = 1ull << 26;
     float cur_horizon = 0.0f;          // horizon of the rays currently in `rays`

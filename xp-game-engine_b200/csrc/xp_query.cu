@@ -1300,7 +1300,7 @@ __global__ void __launch_bounds__(256) k_finalize_detect(const RayRec *__restric
                                                          uint32_t *__restrict__ tri_index,
                                                          const uint32_t *__restrict__ status,
                                                          xp_contact *__restrict__ contact, int col_vec,
-                                                         xp_hit *__restrict__ compact) {
+                                                         xp_hit *__restrict__ compact, int contact16) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= na) return;
     const uint64_t k = inv_order ? inv_order[i] : i;
@@ -1331,7 +1331,10 @@ __global__ void __launch_bounds__(256) k_finalize_detect(const RayRec *__restric
             o[5] = ct.intersection.x; o[6] = ct.intersection.y; o[7] = ct.intersection.z;
         }
     }
-    if (contact) {
+    if (contact && contact16) {                      // XP_OPT_CONTACT_RECORD = 1: (position, triangle)
+        float *o = reinterpret_cast<float *>(contact) + i * 4;
+        o[0] = ct.position.x; o[1] = ct.position.y; o[2] = ct.position.z; o[3] = __uint_as_float(tri);
+    } else if (contact) {
         float *o = reinterpret_cast<float *>(contact) + i * 10;
         o[0] = ct.time_to; o[1] = ct.distance_to;
         o[2] = ct.position.x; o[3] = ct.position.y; o[4] = ct.position.z;
@@ -1351,13 +1354,15 @@ __global__ void __launch_bounds__(256) k_finalize_detect(const RayRec *__restric
 // i in input order, so the block's records are one contiguous 10 KB span) and then streams that span
 // to each peer with fully coalesced 8 B stores, so the transfer overlaps the record construction of
 // the other blocks.  The ranks only need a barrier afterwards.
-template <class O>
+// RECW: floats per record -- 10 = xp_contact, 4 = xp_contact16 (XP_OPT_CONTACT_RECORD)
+template <class O, int RECW>
 __global__ void __launch_bounds__(256) k_finalize_exchange(const RayRec *__restrict__ rays,
                                                            const unsigned long long *__restrict__ best,
                                                            const uint32_t *__restrict__ inv_order, uint64_t n,
                                                            const uint32_t *__restrict__ status, PeerBufs peers,
                                                            uint64_t slot_first) {
-    __shared__ __align__(16) float rec[256 * 10];
+    __shared__ __align__(16) float rec[256 * RECW];
+    constexpr unsigned W8 = RECW / 2;                                           // 8-byte words per record
     // grid-stride over spans of 256 records
     for (uint64_t i0 = blockIdx.x * 256ull; i0 < n; i0 += gridDim.x * 256ull) {
         const uint64_t i = i0 + threadIdx.x;
@@ -1370,21 +1375,26 @@ __global__ void __launch_bounds__(256) k_finalize_exchange(const RayRec *__restr
                 const float4 *rp = reinterpret_cast<const float4 *>(rays + k);
                 ct = xp_make_collision<O>(ray_from(rp[0], rp[1], rp[2]), __uint_as_float((unsigned)(b >> 32)));
             }
-            float *o = rec + threadIdx.x * 10;
-            o[0] = ct.time_to; o[1] = ct.distance_to;
-            o[2] = ct.position.x; o[3] = ct.position.y; o[4] = ct.position.z;
-            o[5] = ct.intersection.x; o[6] = ct.intersection.y; o[7] = ct.intersection.z;
-            o[8] = __uint_as_float(h ? ~(uint32_t)(b & 0xFFFFFFFFull) : 0xFFFFFFFFu);
-            o[9] = __uint_as_float((h ? 1u : 0u) | (((status ? status[i] : 0u) & 0xFFu) << 8));
+            float *o = rec + threadIdx.x * RECW;
+            const uint32_t tri = h ? ~(uint32_t)(b & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+            if (RECW == 4) {
+                o[0] = ct.position.x; o[1] = ct.position.y; o[2] = ct.position.z; o[3] = __uint_as_float(tri);
+            } else {
+                o[0] = ct.time_to; o[1] = ct.distance_to;
+                o[2] = ct.position.x; o[3] = ct.position.y; o[4] = ct.position.z;
+                o[5] = ct.intersection.x; o[6] = ct.intersection.y; o[7] = ct.intersection.z;
+                o[8] = __uint_as_float(tri);
+                o[9] = __uint_as_float((h ? 1u : 0u) | (((status ? status[i] : 0u) & 0xFFu) << 8));
+            }
         }
         __syncthreads();
         const unsigned cnt = (unsigned)((n - i0 < 256) ? (n - i0) : 256);       // records of this span
-        const unsigned n8 = cnt * 5;                                            // 8-byte words
+        const unsigned n8 = cnt * W8;                                           // 8-byte words
         const float2 *src = reinterpret_cast<const float2 *>(rec);
         if (peers.multicast) {
             // p[0] is a multicast address of the NVSwitch fabric: one store, every rank's buffer (this rank's
             // included) receives it -- the span leaves this GPU once instead of once per peer
-            float2 *dst = reinterpret_cast<float2 *>(peers.p[0]) + (slot_first + i0) * 5;   // 16 B aligned: both terms are even
+            float2 *dst = reinterpret_cast<float2 *>(peers.p[0]) + (slot_first + i0) * W8;  // 16 B aligned: both terms are even
             const unsigned n16 = n8 >> 1;
             for (unsigned w = threadIdx.x; w < n16; w += 256) {
                 const float4 v = reinterpret_cast<const float4 *>(rec)[w];
@@ -1401,7 +1411,7 @@ __global__ void __launch_bounds__(256) k_finalize_exchange(const RayRec *__restr
             const unsigned span = (unsigned)(i0 >> 8);
             for (int j = 0; j < peers.n; ++j) {
                 const int p = (int)((j + peers.rot + span) % (unsigned)peers.n);
-                float2 *dst = reinterpret_cast<float2 *>(peers.p[p]) + (slot_first + i0) * 5;
+                float2 *dst = reinterpret_cast<float2 *>(peers.p[p]) + (slot_first + i0) * W8;
                 for (unsigned w = threadIdx.x; w < n8; w += 256) dst[w] = src[w];
             }
         }
@@ -1977,7 +1987,7 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
             xp_collision *col = out.col ? out.col + off : nullptr;
             uint8_t *hit = out.hit ? out.hit + off : nullptr;
             uint32_t *tri = out.tri_index ? out.tri_index + off : nullptr;
-            xp_contact *ct = out.contact ? out.contact + off : nullptr;
+            xp_contact *ct = out.contact ? reinterpret_cast<xp_contact *>(reinterpret_cast<char *>(out.contact) + off * (s->contact_record == 1 ? sizeof(xp_contact16) : sizeof(xp_contact))) : nullptr;
             const int col_vec = (reinterpret_cast<uintptr_t>(col) & 15u) == 0;
             PeerBufs peers = out.peers;
             uint64_t slot = out.slot_first + off;
@@ -1991,24 +2001,29 @@ cudaError_t detect_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_
                 const int self = out.copy_self_plus1 - 1;
                 PeerBufs kp = peers;
                 if (self >= 0) { kp.n = 1; kp.rot = 0; kp.p[0] = peers.p[self]; }       // the kernel fills this rank's buffer only
-                if (arith_fast(s))
-                    k_finalize_exchange<FastOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
-                else
-                    k_finalize_exchange<ExactOps><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
+                const bool c16 = s->contact_record == 1;
+                if (arith_fast(s)) {
+                    if (c16) k_finalize_exchange<FastOps, 4><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
+                    else k_finalize_exchange<FastOps, 10><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
+                } else {
+                    if (c16) k_finalize_exchange<ExactOps, 4><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
+                    else k_finalize_exchange<ExactOps, 10><<<fgrid, 256, 0, s->stream>>>(rays, best, inv, m, status, kp, slot);
+                }
                 if (self >= 0) {
                     // ... and the copy engines carry the span to the peers.  Measured on 8 B200s: peer stores issued
                     // by SMs back-pressure the memory system while NVLink is saturated and stall the next step's
                     // sweep for as long as the exchange lasts (no gain from overlapping); DMA copies do not.
-                    const xp_contact *src = peers.p[self] + slot;
+                    const size_t recb = c16 ? sizeof(xp_contact16) : sizeof(xp_contact);
+                    const char *src = reinterpret_cast<const char *>(peers.p[self]) + slot * recb;
                     for (int j = 1; j < peers.n; ++j) {
                         const int p = (self + j) % peers.n;
-                        XP_TRY(cudaMemcpyAsync(peers.p[p] + slot, src, m * sizeof(xp_contact), cudaMemcpyDeviceToDevice, s->stream));
+                        XP_TRY(cudaMemcpyAsync(reinterpret_cast<char *>(peers.p[p]) + slot * recb, src, m * recb, cudaMemcpyDeviceToDevice, s->stream));
                     }
                 }
             } else if (arith_fast(s))
-                k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec, out.compact ? out.compact + off : nullptr);
+                k_finalize_detect<FastOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec, out.compact ? out.compact + off : nullptr, s->contact_record);
             else
-                k_finalize_detect<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec, out.compact ? out.compact + off : nullptr);
+                k_finalize_detect<ExactOps><<<grid_for(m, 256), 256, 0, s->stream>>>(rays, best, inv, m, col, hit, tri, status, ct, col_vec, out.compact ? out.compact + off : nullptr, s->contact_record);
             ++s->stats.kernel_launches;
         }
         if (out.finalize_stream) XP_TRY(cudaEventRecord(out.ev_fin, s->stream));

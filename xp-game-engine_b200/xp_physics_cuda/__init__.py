@@ -8,7 +8,7 @@ this package is the thin host-side mirror of the reference's Rust API.  There is
 """
 from . import _lib
 from ._lib import XpError, build
-from .api import (COLLISION_DTYPE, CONTACT_DTYPE, HIT_DTYPE, RESPONSE_DTYPE, Collision, collision_from_hit, Response, Scene, Sphere, Triangle,
+from .api import (COLLISION_DTYPE, CONTACT_DTYPE, CONTACT16_DTYPE, HIT_DTYPE, RESPONSE_DTYPE, Collision, collision_from_hit, Response, Scene, Sphere, Triangle,
                   as_triangles, collision_response, collision_response_non_trianulated, debug_check_arith, device_count,
                   make_responses, probe_fp32_peak, sphere_triangle_calculate_response,
                   sphere_triangle_detect_collision)
@@ -18,4 +18,4 @@ from . import clipmap, controller, distributed, fauerby, ingest, scenes   # noqa
 __all__ = ["Scene", "Sphere", "Triangle", "Response", "Collision", "collision_response",
            "collision_response_non_trianulated", "sphere_triangle_detect_collision",
            "sphere_triangle_calculate_response", "make_responses", "as_triangles", "device_count",
-           "probe_fp32_peak", "debug_check_arith", "build", "XpError", "RESPONSE_DTYPE", "COLLISION_DTYPE", "CONTACT_DTYPE", "HIT_DTYPE", "collision_from_hit"]
+           "probe_fp32_peak", "debug_check_arith", "build", "XpError", "RESPONSE_DTYPE", "COLLISION_DTYPE", "CONTACT_DTYPE", "CONTACT16_DTYPE", "HIT_DTYPE", "collision_from_hit"]

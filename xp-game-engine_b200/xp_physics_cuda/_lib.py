@@ -19,6 +19,7 @@ XP_OK, XP_EINVAL, XP_ECUDA, XP_ENOMEM, XP_ESTATE, XP_ECAP = 0, -1, -2, -3, -4, -
 ST_RADIUS_NE_1, ST_ASSERT_NEG_DISTANCE, ST_ITER_CAP = 1, 2, 4
 HORIZON_INF, HORIZON_UNIT = 0, 1
 OPT_ARITH, OPT_METHOD, OPT_TIMING, OPT_SORT_SPHERES, OPT_MAX_PAIRS, OPT_PRUNE, OPT_FAR_EXACT, OPT_GRID_WALK = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_CONTACT_RECORD = 9
 ARITH_EXACT, ARITH_FAST, ARITH_EXACT_LITERAL, ARITH_FAST_LITERAL = 0, 1, 2, 3
 ARITH = {"exact": 0, "fast": 1, "exact_literal": 2, "fast_literal": 3}
 METHODS = {"wide_fused": 0, "lbvh_fused": 1, "lbvh_pairs": 2, "brute": 3, "wide_pairs": 4, "q4_pairs": 5}

@@ -29,7 +29,10 @@ COLLISION_DTYPE = np.dtype([("time_to", "<f4"), ("distance_to", "<f4"),
 HIT_DTYPE = np.dtype([("time_to", "<f4"), ("tri_index", "<u4")])       # xp_hit: the compact result, 8 B
 CONTACT_DTYPE = np.dtype([("time_to", "<f4"), ("distance_to", "<f4"), ("position", "<f4", (3,)),
                           ("intersection", "<f4", (3,)), ("tri_index", "<u4"), ("flags", "<u4")])
+# xp_contact16 (contact_record="compact"): what a peer can use without the sphere's own Response
+CONTACT16_DTYPE = np.dtype([("position", "<f4", (3,)), ("tri_index", "<u4")])
 assert RESPONSE_DTYPE.itemsize == 28 and COLLISION_DTYPE.itemsize == 32 and CONTACT_DTYPE.itemsize == 40
+assert CONTACT16_DTYPE.itemsize == 16
 
 
 def _p(a):
@@ -137,8 +140,10 @@ class Scene:
 
     # -- options
     def set_options(self, *, arith=None, method=None, prune=None, sort_spheres=None, timing=None, max_pairs=None,
-                    far_exact=None, grid_walk=None):
+                    far_exact=None, grid_walk=None, contact_record=None):
         L, h = self._L, self._h
+        if contact_record is not None:           # "full" (xp_contact, 40 B) or "compact" (xp_contact16, 16 B)
+            check(L.xp_scene_set_option(h, _lib.OPT_CONTACT_RECORD, {"full": 0, "compact": 1}[contact_record]))
         if arith is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_ARITH, _lib.ARITH[arith]))
         if method is not None:

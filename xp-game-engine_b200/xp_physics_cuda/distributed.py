@@ -15,9 +15,10 @@ import os
 
 import numpy as np
 
-from .api import CONTACT_DTYPE, RESPONSE_DTYPE, Scene
+from .api import CONTACT16_DTYPE, CONTACT_DTYPE, RESPONSE_DTYPE, Scene
 
-CONTACT_FLOATS = 10      # 40 B
+CONTACT_FLOATS = 10      # xp_contact, 40 B
+CONTACT16_FLOATS = 4     # xp_contact16 (Scene.set_options(contact_record="compact")), 16 B: (position, tri_index)
 
 
 def shard_range(n: int, rank: int, world: int):
@@ -41,8 +42,9 @@ def gather_contacts(local, n_total: int, group=None):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     cap = shard_capacity(n_total, world)
-    assert local.shape == (cap, CONTACT_FLOATS), (local.shape, cap)
-    buf = torch.empty((world, cap, CONTACT_FLOATS), dtype=local.dtype, device=local.device)
+    width = local.shape[1]
+    assert local.shape[0] == cap and width in (CONTACT_FLOATS, CONTACT16_FLOATS), (local.shape, cap)
+    buf = torch.empty((world, cap, width), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(buf.view(-1), local.reshape(-1).contiguous(), group=group)
     parts = []
     for r in range(world):
@@ -52,9 +54,9 @@ def gather_contacts(local, n_total: int, group=None):
 
 
 def contacts_as_records(t) -> np.ndarray:
-    """[n,10] float32 tensor -> structured CONTACT_DTYPE array (host)."""
+    """[n,10] (or [n,4]) float32 tensor -> structured CONTACT_DTYPE (CONTACT16_DTYPE) array (host)."""
     a = t.detach().cpu().numpy()
-    return np.ascontiguousarray(a).view(CONTACT_DTYPE).reshape(-1)
+    return np.ascontiguousarray(a).view(CONTACT16_DTYPE if a.shape[1] == CONTACT16_FLOATS else CONTACT_DTYPE).reshape(-1)
 
 
 class _DeviceArray:
@@ -80,10 +82,14 @@ class ContactExchange:
 
     N_BUF = 4
 
-    def __init__(self, scene: Scene, cap: int, device, group=None, n_buf: int = 0):
+    def __init__(self, scene: Scene, cap: int, device, group=None, n_buf: int = 0, record: str = "full"):
         import torch
         import torch.distributed as dist
         self.scene, self.group, self.device = scene, group, device
+        # record = "compact": 16 B (position, triangle) instead of the 40 B xp_contact -- 2.5x fewer bytes over NVLink
+        self.record = record
+        self.width = CONTACT16_FLOATS if record == "compact" else CONTACT_FLOATS
+        scene.set_options(contact_record=record)
         if n_buf:
             self.N_BUF = n_buf                      # 1 is enough for synchronous steps (sweep); sweep_async needs 4
         self.solo = not (dist.is_available() and dist.is_initialized())        # one process, no peers
@@ -91,11 +97,11 @@ class ContactExchange:
         self.rank = 0 if self.solo else dist.get_rank(group)
         self.cap = cap + (cap & 1)                   # even slots: 16-byte aligned spans
         self.half = self.world * self.cap            # records per gather buffer; there are N_BUF (steps use them round robin)
-        self.nbytes = self.N_BUF * self.half * 4 * CONTACT_FLOATS
+        self.nbytes = self.N_BUF * self.half * 4 * self.width
         self.ptr, self.bufs, self.ok, self.mode = 0, [], True, "p2p"
         self.mc_ptr, self._symm = 0, None
         self._side, self._done, self._flag = None, {}, None
-        shape = (self.N_BUF, self.world, self.cap, CONTACT_FLOATS)
+        shape = (self.N_BUF, self.world, self.cap, self.width)
         if (not self.solo and os.environ.get("XP_EXCHANGE_MULTICAST", "0") == "1"
                 and self._try_multicast(torch, dist, device, shape)):
             self.mode = "multicast"
@@ -227,8 +233,9 @@ class ShardedSweep:
     exchange = "auto": p2p when the peer mapping succeeds on all ranks, else nccl.
     """
 
-    def __init__(self, triangles, device: int, exchange: str = "auto", **scene_opts):
+    def __init__(self, triangles, device: int, exchange: str = "auto", record: str = "full", **scene_opts):
         import torch
+        self.record = record
         self.torch = torch
         self.device = torch.device("cuda", device)
         self.scene = Scene(device, **scene_opts)
@@ -245,7 +252,7 @@ class ShardedSweep:
             return True
         if self._ex is not None:
             self._ex.close()
-        self._ex = ContactExchange(self.scene, cap, self.device, group)
+        self._ex = ContactExchange(self.scene, cap, self.device, group, record=self.record)
         return self._ex.ok
 
     def sweep(self, responses: np.ndarray, group=None):
@@ -273,7 +280,8 @@ class ShardedSweep:
             dist.barrier(group)                       # nobody overwrites a buffer that is still being read
             return out
         cap = shard_capacity(n, world)
-        slot = torch.zeros((cap, CONTACT_FLOATS), dtype=torch.float32, device=self.device)
+        self.scene.set_options(contact_record=self.record)
+        slot = torch.zeros((cap, CONTACT16_FLOATS if self.record == "compact" else CONTACT_FLOATS), dtype=torch.float32, device=self.device)
         if hi > lo:
             self.scene.detect_contacts_dev(d_in.data_ptr(), hi - lo, slot.data_ptr())
         return gather_contacts(slot, n, group)
