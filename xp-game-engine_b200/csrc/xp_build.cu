@@ -184,6 +184,15 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict_
                                                      unsigned long long *__restrict__ best, uint32_t *__restrict__ status,
                                                      int have_tris) {
     __shared__ unsigned group_base[CS_GROUPS];
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    // everything this thread reads is requested first: its key and (RAYS) its Response
+    const unsigned key = i < n ? __ldg(keys + i) : 0xFFFFFFFFu;
+    float in7[7] = {0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f};
+    if (RAYS && i < n) {
+        const float *p = reinterpret_cast<const float *>(in) + i * 7;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) in7[k] = __ldg(p + k);
+    }
     if (threadIdx.x < 32) {                                  // exclusive prefix of the 64 group totals
         const unsigned a = group_tot[2 * threadIdx.x], b = group_tot[2 * threadIdx.x + 1];
         unsigned inc = a + b;
@@ -193,25 +202,27 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict_
         group_base[2 * threadIdx.x + 1] = inc - b;
     }
     __syncthreads();
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const unsigned key = i < n ? keys[i] : 0xFFFFFFFFu;
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     const int leader = __ffs(peers) - 1;
     unsigned base = 0;
     if (i < n && lane == leader) base = group_base[key >> 10] + atomicAdd(&offs[key], (unsigned)__popc(peers));
+    // The slot comes back from L2 about a microsecond later (ncu: a fifth of the kernel's stall samples sat on it, and the
+    // Response was only read after it).  Nothing below needs it until the stores, so the record is built in the meantime.
+    RayRec rr;
+    bool valid = true;
+    if (RAYS && i < n) {
+        valid = in7[3] == 1.0f;
+        rr = make_ray_rec<O>(V3{in7[0], in7[1], in7[2]}, V3{in7[4], in7[5], in7[6]}, valid);
+    }
     base = __shfl_sync(0xffffffffu, base, leader);
     if (i >= n) return;
     const unsigned pos = base + __popc(peers & ((1u << lane) - 1u));
     order[pos] = (uint32_t)i;
     if (inv) inv[i] = pos;
     if (RAYS) {
-        const float *p = reinterpret_cast<const float *>(in) + i * 7;
-        const V3 c = {__ldg(p + 0), __ldg(p + 1), __ldg(p + 2)};
-        const bool valid = __ldg(p + 3) == 1.0f;
-        const V3 m = {__ldg(p + 4), __ldg(p + 5), __ldg(p + 6)};
         if (!valid && status && have_tris) status[i] |= XP_ST_RADIUS_NE_1;     // collision_detect.rs:161 (see k_ray_setup)
-        rays[pos] = make_ray_rec<O>(c, m, valid);
+        rays[pos] = rr;
         best[pos] = BEST_NONE;
     }
 }
