@@ -29,7 +29,7 @@ if [ $BRC -eq 0 ] && [ "$1" != "noncu" ] && [ "$1" != "stress" ]; then
   echo "launch list rc=$?"
   echo "== ncu full (k_traverse)"
   timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain2.log 2>&1 &&
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"k_broadphase|k_narrow_pairs" -s 6 -c 4 -f -o gpurun_out/prof_twostage \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"k_broadphase_grid|k_narrow_pairs" -s 4 -c 4 -f -o gpurun_out/prof_twostage \
       python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
   echo "full rc=$?"
 fi
