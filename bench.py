@@ -677,7 +677,7 @@ def run_config3(ctx: Ctx, args, scale: float = 1.0) -> dict:
     s = xp.Scene(ctx.local, timing=True, arith=args.arith)              # prune = auto: distance windows once a sweep saw > 96 candidates per sphere
     s.set_stream(ctx.stream.cuda_stream)
     shift = torch.tensor([0.01, 0.0, 0.01] * 3, device=dev)
-    build_ms, sweep_ms, tests, stage = [], [], [], []
+    build_ms, sweep_ms, tests, stage, sweep_stage = [], [], [], [], []
 
     def frame():
         d_tris.add_(shift)                                   # every mesh moves: the tree is stale
@@ -687,7 +687,7 @@ def run_config3(ctx: Ctx, args, scale: float = 1.0) -> dict:
         build_ms.append(sum(b.values())); stage.append(b)
         s.detect_batch_compact_dev(d_in.data_ptr(), S, hits.data_ptr())
         st = s.stats()
-        sweep_ms.append(sum(st["stage_ms"].values())); tests.append(st["narrowphase_tests"])
+        sweep_ms.append(sum(st["stage_ms"].values())); tests.append(st["narrowphase_tests"]); sweep_stage.append(st["stage_ms"])
     ms = ev_ms(ctx, frame, 3, warmup=2)
     hbm, hbm_src = measured_hbm_gbs()
     bms = float(np.mean(build_ms[2:]))
@@ -695,6 +695,7 @@ def run_config3(ctx: Ctx, args, scale: float = 1.0) -> dict:
     out = {"workload": f"config3: {S} spheres x {len(tris)}-triangle cube+icosphere field per GPU, LBVH rebuilt every frame",
            "ms_per_frame": ms, "build_ms": bms, "sweep_ms": float(np.mean(sweep_ms[2:])),
            "build_stage_ms": {k: float(np.mean([x[k] for x in stage[2:]])) for k in stage[0] if stage[0][k] > 0},
+           "sweep_stage_ms": {k: float(np.mean([x[k] for x in sweep_stage[2:]])) for k in sweep_stage[0] if sweep_stage[0][k] > 0},
            "tests_per_sec": tests_all / (ms * 1e-3), "spheres_per_sec": ctx.world * S / (ms * 1e-3),
            "candidates_per_sphere": float(np.mean(tests[2:])) / S,
            "build_hbm": {"algorithmic_bytes": 224.0 * len(tris), "achieved_gbs": 224.0 * len(tris) / (bms * 1e-3) / 1e9, "peak_gbs": hbm,

@@ -75,6 +75,11 @@ def test_tree_invariants_duplicates_and_small(oracle):
     for n in (1, 2, 3, 4, 7):
         _check_tree(tris[:n], oracle)
     _check_tree(np.repeat(tris[:1], 37, axis=0), oracle)                      # all codes equal
+    # around the 256-leaf segments of the bottom-up tree pass, with and without runs of equal codes
+    field, _, _ = scenes.mesh_field(1100, seed=11)
+    for n in (255, 256, 257, 511, 512, 513, 1025):
+        _check_tree(field[:n], oracle)
+    _check_tree(np.concatenate([np.repeat(field[:3], 200, axis=0), field[:300]]), oracle)
 
 
 def test_tree_large_sort(oracle):
@@ -86,6 +91,39 @@ def test_tree_large_sort(oracle):
     assert (np.diff(morton.astype(np.int64)) >= 0).all()
     same = morton[1:] == morton[:-1]
     assert (sorted_tri[1:][same] > sorted_tri[:-1][same]).all()
+
+
+def test_tree_work_list_overflow_path(oracle):
+    """The bottom-up tree pass hands subtrees a 256-leaf segment cannot attach alone to a work list; when the list is
+    full the lane climbs through the global protocol in place.  Forced here with a list of 4 entries (XP_TREE_WORK_CAP,
+    read once per process, hence the subprocess): same tree, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, xp_physics_cuda as xp\n"
+        "from xp_physics_cuda import scenes\n"
+        "tris, lo, hi = scenes.mesh_field(30011, seed=7)\n"
+        "with xp.Scene(0, tris) as s:\n"
+        "    t = s.debug_tree()\n"
+        "np.savez(r'%s', *t)\n")
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        outs = []
+        for cap in (None, "3"):
+            env = dict(os.environ)
+            env["PYTHONPATH"] = os.pathsep.join([os.path.dirname(os.path.dirname(xp.__file__)), env.get("PYTHONPATH", "")])
+            env.pop("XP_TREE_WORK_CAP", None)
+            if cap is not None:
+                env["XP_TREE_WORK_CAP"] = cap
+            path = os.path.join(d, f"tree_{cap}.npz")
+            subprocess.run([sys.executable, "-c", code % path], check=True, env=env, timeout=300)
+            z = np.load(path)
+            outs.append([z[k] for k in z.files])
+    for a, b in zip(*outs):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    tris, _, _ = scenes.mesh_field(30011, seed=7)
+    _check_tree(tris, oracle)
 
 
 def test_device_heightmap_emission_equals_host_soup(oracle):

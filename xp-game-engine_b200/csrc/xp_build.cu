@@ -1026,7 +1026,9 @@ cudaError_t build_lbvh(xp_scene *s) {
     } else {
         StageTimer t(s, XP_STAGE_BUILD_TREE);
         int *flags = s->refit_flags.as<int>();                 // n - 1 arrival slots (-1 = nobody yet) + 4 ints: root, who links to node 0 (node, side), work-list length
-        const unsigned work_cap = (unsigned)(n / 4 + 4096);
+        // XP_TREE_WORK_CAP (tests): a tiny list forces the overflow path -- lanes that find the list full climb globally in place
+        static const long cap_env = getenv("XP_TREE_WORK_CAP") ? atol(getenv("XP_TREE_WORK_CAP")) : -1;
+        const unsigned work_cap = cap_env >= 0 ? (unsigned)cap_env + 1u : (unsigned)(n / 4 + 4096);
         XP_TRY(s->tree_work.reserve((size_t)work_cap * sizeof(TreeItem)));
         XP_TRY(cudaMemsetAsync(flags, 0xFF, n * 4, st));
         XP_TRY(cudaMemsetAsync(flags + n, 0, 4 * 4, st));
