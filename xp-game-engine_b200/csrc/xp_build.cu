@@ -282,26 +282,42 @@ __device__ __forceinline__ unsigned rs_peers(unsigned d, unsigned vm) {
 #ifndef XP_RS_MINB
 #define XP_RS_MINB 4
 #endif
+#ifndef XP_RS_LOCALSORT
+#define XP_RS_LOCALSORT 1          // 1: the tile is put in digit order in shared memory first, so that global stores go out in runs
+#endif
+// With 10-bit digits a tile of 4096 keys holds ~4 keys per digit: written straight from the ranking pass, every lane of
+// a store instruction lands in a different 32 B sector -- 2 x 10 M sector requests per pass, and the request rate, not the
+// bytes, is what the kernel waits for (ncu: lts 52 %, DRAM 13 %).  So the keys (and the tile-local index of their value)
+// are first placed at their position inside the tile's own digit order in shared memory; thread j then stores sorted
+// element j, and consecutive elements of a digit go to consecutive addresses: a warp's store touches ~9 sectors, not 32.
 __global__ void __launch_bounds__(RS_THREADS, XP_RS_MINB) k_rs_scatter(const uint32_t *__restrict__ keys_in,
                                                            const uint32_t *__restrict__ vals_in,
                                                            uint32_t *__restrict__ keys_out,
                                                            uint32_t *__restrict__ vals_out, uint64_t n,
                                                            int shift, const uint32_t *__restrict__ scanned,
                                                            unsigned num_tiles, uint32_t *__restrict__ inv_out) {
+#if XP_RS_LOCALSORT
+    __shared__ uint16_t cnt[RS_WARPS][RS_BINS];        // per (warp, digit): count, then the tile-local position of the warp's first such key
+    __shared__ uint32_t s_key[RS_TILE];                // the tile in digit order
+    __shared__ uint16_t s_src[RS_TILE];                // ... and where in the tile each key came from (its value is fetched from there)
+    __shared__ uint32_t delta[RS_BINS];                // global position of a digit's first key of this tile - its tile-local position
+    __shared__ unsigned warp_tot[RS_WARPS];
+#else
     __shared__ unsigned cnt[RS_WARPS][RS_BINS];
+#endif
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
-    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE + (uint64_t)w * RS_SEG;
+    const uint64_t tile_base = (uint64_t)blockIdx.x * RS_TILE;
+    const uint64_t base = tile_base + (uint64_t)w * RS_SEG;
     uint32_t k[RS_ITEMS];
     uint16_t rank[RS_ITEMS];               // position among the keys of this warp's segment that share the digit (< 512)
 #pragma unroll
     for (int c = 0; c < RS_ITEMS; ++c) {
         const uint64_t idx = base + (uint64_t)c * 32 + lane;
         k[c] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
-        // the values are first touched in pass B, a whole ranking pass from here: ask for them now (L2), or the first of
-        // those loads waits for HBM at the end of the kernel (45 % of the stall samples)
+        // the values are first touched in pass B, a whole ranking pass from here: ask for them now (L2)
         if ((lane & 7) == 0 && idx < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals_in + idx));   // one per 32 B sector
     }
     // pass A: per-warp digit counts and each key's rank inside the warp's segment (original order -> stable)
@@ -320,6 +336,61 @@ __global__ void __launch_bounds__(RS_THREADS, XP_RS_MINB) k_rs_scatter(const uin
         __syncwarp();
     }
     __syncthreads();
+#if XP_RS_LOCALSORT
+    {
+        // thread t owns digits 4t .. 4t+3: exclusive prefix over the warps, then over all 1024 digits of the tile
+        constexpr int DPT = RS_BINS / RS_THREADS;
+        unsigned tot[DPT], sum = 0;
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            const unsigned d = threadIdx.x * DPT + q;
+            unsigned run = 0;
+#pragma unroll
+            for (int ww = 0; ww < RS_WARPS; ++ww) { const unsigned t = cnt[ww][d]; cnt[ww][d] = (uint16_t)run; run += t; }
+            tot[q] = run; sum += run;
+        }
+        unsigned inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        unsigned before_warp = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) before_warp += ww < w ? warp_tot[ww] : 0u;
+        unsigned lb = before_warp + inc - sum;           // tile-local position of this thread's first digit
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) {
+            const unsigned d = threadIdx.x * DPT + q;
+#pragma unroll
+            for (int ww = 0; ww < RS_WARPS; ++ww) cnt[ww][d] = (uint16_t)(cnt[ww][d] + lb);
+            delta[d] = scanned[(uint64_t)d * num_tiles + blockIdx.x] - lb;
+            lb += tot[q];
+        }
+    }
+    __syncthreads();
+    // pass B: into the tile's digit order
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; ++c) {
+        const uint64_t idx = base + (uint64_t)c * 32 + lane;
+        if (idx < n) {
+            const unsigned lpos = cnt[w][(k[c] >> shift) & RS_MASK] + rank[c];
+            s_key[lpos] = k[c];
+            s_src[lpos] = (uint16_t)(w * RS_SEG + c * 32 + lane);
+        }
+    }
+    __syncthreads();
+    // pass C: out, element j of the sorted tile from thread j
+    const unsigned nv = (unsigned)((n - tile_base < (uint64_t)RS_TILE) ? (n - tile_base) : (uint64_t)RS_TILE);
+#pragma unroll 4
+    for (unsigned j = threadIdx.x; j < nv; j += RS_THREADS) {
+        const uint32_t key = s_key[j];
+        const unsigned pos = j + delta[(key >> shift) & RS_MASK];
+        const uint32_t v = vals_in[tile_base + s_src[j]];
+        keys_out[pos] = key;
+        vals_out[pos] = v;
+        if (inv_out) inv_out[v] = pos;
+    }
+#else
     for (unsigned d = threadIdx.x; d < (unsigned)RS_BINS; d += RS_THREADS) {   // exclusive prefix over warps, seeded with this tile's global base for the digit
         unsigned run = scanned[(uint64_t)d * num_tiles + blockIdx.x];
 #pragma unroll
@@ -342,6 +413,7 @@ __global__ void __launch_bounds__(RS_THREADS, XP_RS_MINB) k_rs_scatter(const uin
             if (inv_out) inv_out[v] = pos;
         }
     }
+#endif
 }
 
 // exclusive scan of a uint32 array (hierarchical: 2048 elements per block) -------------------
