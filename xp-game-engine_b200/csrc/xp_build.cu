@@ -107,17 +107,36 @@ __device__ __forceinline__ unsigned morton30(V3 c, const unsigned *__restrict__ 
     return code;
 }
 
+// One block = one tile of the radix sort (RS_TILE triangles): besides codes and indices it leaves the tile's histogram
+// of the FIRST digit (hist, digit-major like k_rs_hist's; may be null), so the sort's first pass starts at its scan.
+static constexpr int MT_TILE = 4096, MT_BINS = 1024;           // == RS_TILE, RS_BINS (asserted where those are defined)
 __global__ void __launch_bounds__(256) k_morton_tris(const float *__restrict__ aos, uint64_t n,
                                                      const unsigned *__restrict__ bounds,
                                                      uint32_t *__restrict__ keys,
-                                                     uint32_t *__restrict__ vals) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    V3 v0, v1, v2, lo, hi;
-    load_tri(aos, i, v0, v1, v2);
-    xp_tri_aabb(v0, v1, v2, lo, hi);
-    keys[i] = morton30(box_centre(lo, hi), bounds);
-    vals[i] = (uint32_t)i;
+                                                     uint32_t *__restrict__ vals, uint32_t *__restrict__ hist, unsigned num_tiles) {
+    __shared__ unsigned h[MT_BINS];
+    if (hist) {
+        for (int b = threadIdx.x; b < MT_BINS; b += 256) h[b] = 0;
+        __syncthreads();
+    }
+    const uint64_t base = (uint64_t)blockIdx.x * MT_TILE;
+#pragma unroll 4
+    for (int c = 0; c < MT_TILE / 256; ++c) {
+        const uint64_t i = base + (uint64_t)c * 256 + threadIdx.x;
+        if (i < n) {
+            V3 v0, v1, v2, lo, hi;
+            load_tri(aos, i, v0, v1, v2);
+            xp_tri_aabb(v0, v1, v2, lo, hi);
+            const uint32_t key = morton30(box_centre(lo, hi), bounds);
+            keys[i] = key;
+            vals[i] = (uint32_t)i;
+            if (hist) atomicAdd(&h[key & (MT_BINS - 1)], 1u);
+        }
+    }
+    if (hist) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < MT_BINS; b += 256) hist[(uint64_t)b * num_tiles + blockIdx.x] = h[b];
+    }
 }
 
 __global__ void __launch_bounds__(256) k_morton_spheres(const xp_response *__restrict__ in, uint64_t n,
@@ -239,6 +258,7 @@ static constexpr int RS_SEG = RS_TILE / RS_WARPS;       // 512 consecutive keys 
 static constexpr int RS_BITS = XP_RS_BITS;              // digit width: 10 bits = three passes over the 30-bit Morton codes
 static constexpr int RS_BINS = 1 << RS_BITS;
 static constexpr unsigned RS_MASK = RS_BINS - 1;
+static_assert(RS_TILE == MT_TILE && RS_BINS == MT_BINS, "k_morton_tris leaves the first pass's histogram in the sort's tile layout");
 
 // per-tile digit histogram, stored digit-major so one flat exclusive scan yields the bases
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t *__restrict__ keys, uint64_t n,
@@ -279,6 +299,10 @@ __device__ __forceinline__ unsigned rs_peers(unsigned d, unsigned vm) {
     return __match_any_sync(vm, d);
 #endif
 }
+// the scan of the tiles x bins table works on blocks of SC_TILE entries (k_scan_local)
+static constexpr int SC_THREADS = 256;
+static constexpr int SC_ITEMS = 8;
+static constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
 #ifndef XP_RS_MINB
 #define XP_RS_MINB 4
 #endif
@@ -295,6 +319,7 @@ __global__ void __launch_bounds__(RS_THREADS, XP_RS_MINB) k_rs_scatter(const uin
                                                            uint32_t *__restrict__ keys_out,
                                                            uint32_t *__restrict__ vals_out, uint64_t n,
                                                            int shift, const uint32_t *__restrict__ scanned,
+                                                           const uint32_t *__restrict__ block_sums,
                                                            unsigned num_tiles, uint32_t *__restrict__ inv_out) {
 #if XP_RS_LOCALSORT
     __shared__ uint16_t cnt[RS_WARPS][RS_BINS];        // per (warp, digit): count, then the tile-local position of the warp's first such key
@@ -363,7 +388,8 @@ __global__ void __launch_bounds__(RS_THREADS, XP_RS_MINB) k_rs_scatter(const uin
             const unsigned d = threadIdx.x * DPT + q;
 #pragma unroll
             for (int ww = 0; ww < RS_WARPS; ++ww) cnt[ww][d] = (uint16_t)(cnt[ww][d] + lb);
-            delta[d] = scanned[(uint64_t)d * num_tiles + blockIdx.x] - lb;
+            const uint64_t at = (uint64_t)d * num_tiles + blockIdx.x;          // the table was scanned per block of SC_TILE entries:
+            delta[d] = scanned[at] + block_sums[at / SC_TILE] - lb;             // the block's base is added here, not by a k_scan_add pass
             lb += tot[q];
         }
     }
@@ -392,7 +418,8 @@ __global__ void __launch_bounds__(RS_THREADS, XP_RS_MINB) k_rs_scatter(const uin
     }
 #else
     for (unsigned d = threadIdx.x; d < (unsigned)RS_BINS; d += RS_THREADS) {   // exclusive prefix over warps, seeded with this tile's global base for the digit
-        unsigned run = scanned[(uint64_t)d * num_tiles + blockIdx.x];
+        const uint64_t at = (uint64_t)d * num_tiles + blockIdx.x;
+        unsigned run = scanned[at] + block_sums[at / SC_TILE];
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ++ww) {
             unsigned t = cnt[ww][d];
@@ -417,9 +444,6 @@ __global__ void __launch_bounds__(RS_THREADS, XP_RS_MINB) k_rs_scatter(const uin
 }
 
 // exclusive scan of a uint32 array (hierarchical: 2048 elements per block) -------------------
-static constexpr int SC_THREADS = 256;
-static constexpr int SC_ITEMS = 8;
-static constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
 
 __global__ void __launch_bounds__(SC_THREADS) k_scan_local(uint32_t *__restrict__ data, uint64_t n,
                                                            uint32_t *__restrict__ sums) {
@@ -470,39 +494,54 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_add(uint32_t *__restrict__ 
 }
 
 // scratch must hold ceil(n/2048) + ceil(that/2048) + ... uint32
+// histogram table + scan scratch (geometric series of block sums: < hist_n/2047 + 64)
+static cudaError_t radix_sort_reserve(xp_scene *s, uint64_t n) {
+    const uint64_t hist_n = (uint64_t)grid_for(n, RS_TILE) * RS_BINS;
+    return s->hist.reserve((hist_n + hist_n / 1024 + 4096) * sizeof(uint32_t));
+}
+
+// defer_add: the top level's k_scan_add is left to the consumer, which adds scratch[i / SC_TILE] (the fully scanned
+// block sums) to data[i] itself -- one launch and one pass over the table less per radix pass
 static cudaError_t exclusive_scan_u32(uint32_t *data, uint64_t n, uint32_t *scratch, cudaStream_t st,
-                                      unsigned *launches) {
+                                      unsigned *launches, bool defer_add = false) {
     if (n == 0) return cudaSuccess;
     const unsigned blocks = grid_for(n, SC_TILE);
-    k_scan_local<<<blocks, SC_THREADS, 0, st>>>(data, n, blocks > 1 ? scratch : nullptr);
+    k_scan_local<<<blocks, SC_THREADS, 0, st>>>(data, n, (blocks > 1 || defer_add) ? scratch : nullptr);
     ++*launches;
     if (blocks > 1) {
         cudaError_t e = exclusive_scan_u32(scratch, blocks, scratch + blocks, st, launches);
         if (e != cudaSuccess) return e;
-        k_scan_add<<<blocks, SC_THREADS, 0, st>>>(data, n, scratch);
-        ++*launches;
+        if (!defer_add) {
+            k_scan_add<<<blocks, SC_THREADS, 0, st>>>(data, n, scratch);
+            ++*launches;
+        }
+    } else if (defer_add) {
+        cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(uint32_t), st);      // a single block: its base is 0
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
 
+// first_hist_done: the caller has already left the first pass's per-tile histogram in s->hist (k_morton_tris)
 cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb,
-                             uint64_t n, int bits, bool *in_a, uint32_t *inv_out) {
+                             uint64_t n, int bits, bool *in_a, uint32_t *inv_out, bool first_hist_done) {
     *in_a = true;
     if (n == 0) return cudaSuccess;
     const unsigned tiles = grid_for(n, RS_TILE);
     const uint64_t hist_n = (uint64_t)tiles * RS_BINS;
-    // histogram + scan scratch (geometric series of block sums: < hist_n/2047 + 64)
-    cudaError_t e = s->hist.reserve((hist_n + hist_n / 1024 + 4096) * sizeof(uint32_t));
+    cudaError_t e = radix_sort_reserve(s, n);
     if (e != cudaSuccess) return e;
     uint32_t *hist = s->hist.as<uint32_t>();
     uint32_t *scratch = hist + hist_n;
     uint32_t *ki = ka, *ko = kb, *vi = va, *vo = vb;
     for (int shift = 0; shift < bits; shift += RS_BITS) {
-        k_rs_hist<<<tiles, RS_THREADS, 0, s->stream>>>(ki, n, shift, hist, tiles);
-        ++s->stats.kernel_launches;
-        e = exclusive_scan_u32(hist, hist_n, scratch, s->stream, &s->stats.kernel_launches);
+        if (!(shift == 0 && first_hist_done)) {
+            k_rs_hist<<<tiles, RS_THREADS, 0, s->stream>>>(ki, n, shift, hist, tiles);
+            ++s->stats.kernel_launches;
+        }
+        e = exclusive_scan_u32(hist, hist_n, scratch, s->stream, &s->stats.kernel_launches, /*defer_add=*/true);
         if (e != cudaSuccess) return e;
-        k_rs_scatter<<<tiles, RS_THREADS, 0, s->stream>>>(ki, vi, ko, vo, n, shift, hist, tiles,
+        k_rs_scatter<<<tiles, RS_THREADS, 0, s->stream>>>(ki, vi, ko, vo, n, shift, hist, scratch, tiles,
                                                           shift + RS_BITS >= bits ? inv_out : nullptr);
         ++s->stats.kernel_launches;
         uint32_t *t = ki; ki = ko; ko = t;
@@ -1066,15 +1105,16 @@ cudaError_t build_lbvh(xp_scene *s) {
     }
     {
         StageTimer t(s, XP_STAGE_BUILD_MORTON);
-        k_morton_tris<<<grid_for(n, 256), 256, 0, st>>>(aos, n, bounds, s->keys_a.as<uint32_t>(),
-                                                       s->vals_a.as<uint32_t>());
+        XP_TRY(radix_sort_reserve(s, n));
+        k_morton_tris<<<grid_for(n, MT_TILE), 256, 0, st>>>(aos, n, bounds, s->keys_a.as<uint32_t>(),
+                                                           s->vals_a.as<uint32_t>(), s->hist.as<uint32_t>(), grid_for(n, MT_TILE));
         ++s->stats.kernel_launches;
     }
     bool in_a = true;
     {
         StageTimer t(s, XP_STAGE_BUILD_SORT);
         XP_TRY(radix_sort_pairs(s, s->keys_a.as<uint32_t>(), s->keys_b.as<uint32_t>(),
-                                s->vals_a.as<uint32_t>(), s->vals_b.as<uint32_t>(), n, 30, &in_a));   // 30-bit Morton codes
+                                s->vals_a.as<uint32_t>(), s->vals_b.as<uint32_t>(), n, 30, &in_a, nullptr, /*first_hist_done=*/true));   // 30-bit Morton codes
     }
     if (!in_a) {   // keep the sorted arrays in *_a (scene invariant used by debug_tree and queries)
         xp::DevBuf t = s->keys_a; s->keys_a = s->keys_b; s->keys_b = t;

@@ -18,11 +18,12 @@ void resolve_stage_timers(xp_scene *s);
 inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 // ---- xp_build.cu ----
-// LSD radix sort of (key, value) pairs on `bits` key bits, 8 bits per pass, CUB-free.
+// LSD radix sort of (key, value) pairs on `bits` key bits, 10 bits per pass, CUB-free.
 // Ping-pongs between (ka,va) and (kb,vb); *in_a tells where the sorted result ended up.
 // inv_out (optional): the last pass also writes the inverse permutation, inv_out[value] = position.
+// first_hist_done: the first pass's per-tile digit histogram already sits in s->hist (k_morton_tris leaves it there).
 cudaError_t radix_sort_pairs(xp_scene *s, uint32_t *ka, uint32_t *kb, uint32_t *va, uint32_t *vb,
-                             uint64_t n, int bits, bool *in_a, uint32_t *inv_out = nullptr);
+                             uint64_t n, int bits, bool *in_a, uint32_t *inv_out = nullptr, bool first_hist_done = false);
 cudaError_t build_lbvh(xp_scene *s);
 cudaError_t emit_heightmap(xp_scene *s, const float *d_heights, unsigned nx, unsigned nz, float x0, float z0, float spacing);
 cudaError_t height_range(xp_scene *s, const float *d_heights, uint64_t n);     // -> s->grid_yrange
