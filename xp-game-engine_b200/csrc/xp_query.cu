@@ -2122,11 +2122,201 @@ static cudaError_t response_chunk_device(xp_scene *s, xp_response *cur, uint64_t
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// collision_response for a HANDFUL of spheres: the whole loop in one launch, one warp per sphere
+// ------------------------------------------------------------------------------------------
+// The game calls collision_response for one player sphere per frame (game/src/simulation.rs:45-48; BASELINE config 1).
+// Through the batch machinery that is ~16 launches per iteration of kernels built for a million rays -- 0.3 ms of
+// launch latency for microseconds of work.  Here a warp owns the sphere for the whole loop (lib.rs:29-62): it walks the
+// LBVH with all 32 lanes (each round pops up to 32 nodes from a shared work list, tests both child boxes of each with
+// predicate P's slab test, pushes the children that pass), collects the leaves that pass, runs the same narrowphase on
+// them 32 at a time (xp_detect_x, literal form for operands outside the guarded range), sweeps the ill-conditioned
+// list, takes the minimum key, applies the reference's response step and goes round again.  Same candidate set, same
+// arithmetic, same tie-break as the two-stage sweep: bit-identical results (the whole small-batch test tier runs on it).
+// A work list that would overflow (never seen: it is LIFO, so it holds a few levels of the tree) raises *fallback and the
+// host redoes the call with the batch kernels.
+static constexpr int SMALL_WARPS = 4;
+static constexpr int SMALL_QUEUE = 2048;
+static constexpr int SMALL_CAND = 512;
+static constexpr uint64_t SMALL_MAX_SPHERES = 512;
+
+template <class O>
+__device__ __forceinline__ unsigned long long small_narrow(const TriRec *__restrict__ recs, const uint32_t *cand, unsigned cn,
+                                                           const Ray &ray, float r2a, unsigned lane) {
+    unsigned long long mine = BEST_NONE;
+    for (unsigned j = lane; j < cn; j += 32) {
+        const float4 *tp = reinterpret_cast<const float4 *>(recs + cand[j]);
+        const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
+        const V3 v0 = f4_xyz(t0), v1 = f4_xyz(t1), v2 = f4_xyz(t2), nrm = {t0.w, t1.w, t2.w};
+        float t;
+        bool bad;
+        bool hit = xp_detect_x(ray, r2a, v0, v1, v2, nrm, t3.x, t3.y, t3.z, t, bad);
+        if (bad) {
+            const float els01[2] = {t3.y, t3.z};
+            hit = xp_detect<O>(ray, v0, v1, v2, nrm, t3.x, t, nullptr, t3.y <= XP_ELS_HI ? els01 : nullptr);
+        }
+        if (hit) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(~__float_as_uint(t3.w));
+            mine = key < mine ? key : mine;
+        }
+    }
+    return mine;
+}
+
+template <class O>
+__global__ void __launch_bounds__(32 * SMALL_WARPS) k_small_response(const Node *__restrict__ nodes, const TriRec *__restrict__ recs,
+                                                                   uint64_t n_tris, const uint32_t *__restrict__ degen, uint32_t n_degen,
+                                                                   const xp_response *__restrict__ d_in, xp_response *__restrict__ d_out,
+                                                                   uint64_t n, uint32_t cap_iter, float horizon,
+                                                                   uint32_t *__restrict__ iter_out, uint32_t *__restrict__ status_out,
+                                                                   xp_vec3 *__restrict__ normal_out, DeviceCounters *__restrict__ ctr,
+                                                                   unsigned *__restrict__ fallback) {
+    __shared__ int q_all[SMALL_WARPS][SMALL_QUEUE];
+    __shared__ uint32_t cand_all[SMALL_WARPS][SMALL_CAND];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
+    const uint64_t i = (uint64_t)blockIdx.x * SMALL_WARPS + wid;
+    if (i >= n) return;
+    int *q = q_all[wid];
+    uint32_t *cand = cand_all[wid];
+    const float *p = reinterpret_cast<const float *>(d_in) + i * 7;
+    V3 c = {__ldg(p + 0), __ldg(p + 1), __ldg(p + 2)};
+    float r = __ldg(p + 3);
+    V3 m = {__ldg(p + 4), __ldg(p + 5), __ldg(p + 6)};
+    V3 sn = {0.0f, 0.0f, 0.0f};
+    uint32_t status = 0, iters = 0, sweeps = 0;
+    unsigned long long tests = 0, visits = 0;
+    bool overflow = false;
+    for (uint32_t it = 0;; ++it) {
+        if (it >= cap_iter) { status |= XP_ST_ITER_CAP; break; }
+        ++sweeps;
+        tests += n_degen;                                                  // (k_sweep_degenerate's accounting: per swept ray)
+        if (!(r == 1.0f)) { if (n_tris > 0) status |= XP_ST_RADIUS_NE_1; break; }       // collision_detect.rs:161 (see k_ray_setup)
+        if (n_tris == 0) break;
+        const RayRec rr = make_ray_rec<O>(c, m, true);
+        const Ray ray = ray_from(rr.q0, rr.q1, rr.q2);
+        const V3 inv = f4_xyz(rr.q3);
+        unsigned long long best = BEST_NONE;
+        // ---- the walk: 32 nodes per round from a LIFO work list
+        unsigned qn = 1, cn = 0;
+        if (lane == 0) q[0] = 0;
+        __syncwarp();
+        while (qn > 0) {
+            const unsigned take = qn < 32u ? qn : 32u;
+            const int node = lane < take ? q[qn - 1u - lane] : -1;
+            qn -= take;
+            __syncwarp();
+            int push_a = -1, push_b = -1, leaf_a = -1, leaf_b = -1;
+            if (node >= 0) {
+                const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+                const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+                const int2 link = make_int2(__float_as_int(n3.x), __float_as_int(n3.y));
+                float ta, tb;
+                const bool hit_a = slab(c, inv, horizon, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ta);
+                const bool hit_b = slab(c, inv, horizon, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tb);
+                if (hit_a) { if (link.x < 0) leaf_a = ~link.x; else push_a = link.x; }
+                if (hit_b) { if (link.y < 0) leaf_b = ~link.y; else push_b = link.y; }
+            }
+            visits += take;
+            const unsigned pa = __ballot_sync(FULL, push_a >= 0), pb = __ballot_sync(FULL, push_b >= 0);
+            const unsigned la = __ballot_sync(FULL, leaf_a >= 0), lb = __ballot_sync(FULL, leaf_b >= 0);
+            if (qn + __popc(pa) + __popc(pb) > (unsigned)SMALL_QUEUE) { overflow = true; break; }
+            if (push_a >= 0) q[qn + __popc(pa & lt_mask)] = push_a;
+            if (push_b >= 0) q[qn + __popc(pa) + __popc(pb & lt_mask)] = push_b;
+            qn += __popc(pa) + __popc(pb);
+            if (leaf_a >= 0) cand[cn + __popc(la & lt_mask)] = (uint32_t)leaf_a;
+            if (leaf_b >= 0) cand[cn + __popc(la) + __popc(lb & lt_mask)] = (uint32_t)leaf_b;
+            cn += __popc(la) + __popc(lb);
+            __syncwarp();
+            if (cn > (unsigned)SMALL_CAND - 64u) {                          // no room for another round's leaves: test what is there
+                const unsigned long long k = small_narrow<O>(recs, cand, cn, ray, rr.q2.w, lane);
+                best = k < best ? k : best;
+                tests += cn;
+                cn = 0;
+                __syncwarp();
+            }
+        }
+        if (overflow) break;
+        {
+            const unsigned long long k = small_narrow<O>(recs, cand, cn, ray, rr.q2.w, lane);
+            best = k < best ? k : best;
+            tests += cn;
+        }
+        // ---- ill-conditioned triangles are swept exhaustively (k_sweep_degenerate), literal form
+        for (uint32_t e = lane; e < n_degen; e += 32) {
+            const float4 *tp = reinterpret_cast<const float4 *>(recs + __ldg(&degen[1 + e]));
+            const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3);
+            float t;
+            if (xp_detect<O>(ray, f4_xyz(t0), f4_xyz(t1), f4_xyz(t2), V3{t0.w, t1.w, t2.w}, t3.x, t)) {
+                const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(~__float_as_uint(t3.w));
+                best = key < best ? key : best;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long y = __shfl_xor_sync(FULL, best, o);
+            best = y < best ? y : best;
+        }
+        __syncwarp();
+        if (best == BEST_NONE) break;                                       // lib.rs:44: None -> done
+        // ---- the response step (k_respond), every lane the same values
+        const Contact ct = xp_make_collision<O>(ray, __uint_as_float((unsigned)(best >> 32)));
+        V3 nc, nm;
+        const bool ok = xp_respond<O>(ray.c, ray.m, ct.position, ct.intersection, nc, nm, sn);
+        if (!ok) { status |= XP_ST_ASSERT_NEG_DISTANCE; break; }             // collision_response.rs:22
+        c = nc; r = 1.0f; m = nm;                                           // collision_response.rs:29-32
+        ++iters;                                                            // lib.rs:45
+        if (len<O>(nm) < 0.001f) break;                                     // lib.rs:55, collision.rs:3
+    }
+    if (overflow) { if (lane == 0) atomicExch(fallback, 1u); return; }
+    if (lane == 0) {
+        float *o = reinterpret_cast<float *>(d_out) + i * 7;
+        o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = r; o[4] = m.x; o[5] = m.y; o[6] = m.z;
+        if (iter_out) iter_out[i] = iters;
+        if (status_out) status_out[i] = status;
+        if (normal_out) { normal_out[i].x = sn.x; normal_out[i].y = sn.y; normal_out[i].z = sn.z; }
+        atomicAdd(&ctr->tests, tests);
+        atomicAdd(&ctr->pairs_total, tests - (unsigned long long)sweeps * n_degen);
+        atomicAdd(&ctr->node_visits, visits);
+        atomicAdd(&ctr->rays_swept, (unsigned long long)sweeps);
+        atomicMax(&ctr->iters_done, sweeps);
+    }
+}
+
 cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t max_iter,
                          uint32_t horizon_mode, xp_response *d_out, uint32_t *d_iter,
                          uint32_t *d_status, xp_vec3 *d_normal) {
     cudaStream_t st = s->stream;
     XP_TRY(zero_counters(s));
+    // a handful of spheres: the whole loop in one launch (k_small_response); anything it cannot take falls through
+    static const bool no_small = getenv("XP_NO_SMALL_PATH") != nullptr;
+    if (n <= SMALL_MAX_SPHERES && !no_small && s->method == XP_METHOD_LBVH_PAIRS && !s->far_exact && !s->safe_pairs &&
+        (s->arith == XP_ARITH_EXACT || s->arith == XP_ARITH_EXACT_LITERAL) && !s->timing) {
+        const xp_response *src = d_in;
+        if (d_out == d_in) {                    // in place: keep the input for a fallback
+            XP_TRY(s->io_backup.reserve(n * sizeof(xp_response)));
+            XP_TRY(cudaMemcpyAsync(s->io_backup.p, d_in, n * sizeof(xp_response), cudaMemcpyDeviceToDevice, st));
+            src = s->io_backup.as<xp_response>();
+        }
+        XP_TRY(build_aux(s));
+        DeviceCounters *c0 = s->counters.as<DeviceCounters>();
+        unsigned *fb = &c0->stack_overflow;     // (zeroed with the counters; reused as this kernel's fallback flag)
+        k_small_response<ExactOps><<<(unsigned)((n + SMALL_WARPS - 1) / SMALL_WARPS), 32 * SMALL_WARPS, 0, st>>>(
+            s->nodes.as<Node>(), s->recs.as<TriRec>(), s->n_tris, s->degen.as<uint32_t>(), (uint32_t)s->n_degen, src, d_out, n,
+            max_iter ? max_iter : HARD_ITER_CAP, horizon_of(horizon_mode), d_iter, d_status, d_normal, c0, fb);
+        ++s->stats.kernel_launches;
+        DeviceCounters h;
+        XP_TRY(fetch_counters(s, &h));
+        if (!h.stack_overflow) {
+            s->stats.narrowphase_tests += h.tests;
+            s->stats.broadphase_pairs += h.pairs_total;
+            s->stats.node_visits += h.node_visits;
+            if (h.iters_done > s->stats.iterations_run) s->stats.iterations_run = h.iters_done;
+            s->swept_rays += h.rays_swept;
+            return cudaSuccess;
+        }
+        XP_TRY(zero_counters(s));               // the work list overflowed somewhere: the batch kernels redo the call
+        d_in = src;
+    }
     // One host read-back per iteration: the next active count and the overflow flag of the optimistic pair
     // buffer travel together (k_respond applies nothing when the flag is up); only an iteration that did
     // overflow is redone in the synchronous chunk-halving mode.
