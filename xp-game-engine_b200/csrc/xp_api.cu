@@ -95,8 +95,9 @@ void xp_scene_destroy(xp_scene *s) {
                       &s->refit_flags, &s->tree_work, &s->keys_a, &s->keys_b,
                       &s->vals_a, &s->vals_b, &s->hist, &s->bounds, &s->wide, &s->wide_lo, &s->wide_hi, &s->nodes4, &s->degen, &s->grid_h, &s->grid_yrange, &s->grid_mm, &s->recs_grid, &s->rays, &s->best, &s->active_a,
                       &s->active_b, &s->inv_order, &s->pairs, &s->counters, &s->rays2, &s->best2, &s->active_c, &s->io_backup, &s->sort_ka, &s->sort_kb, &s->io_in, &s->io_out,
-                      &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col};
+                      &s->io_hit, &s->io_tri, &s->io_status, &s->io_iter, &s->io_normal, &s->io_col, &s->small_dev};
     for (DevBuf *b : bufs) b->release();
+    if (s->small_pin) cudaFreeHost(s->small_pin);
     for (auto &a : s->async_slot) {
         DevBuf *ab[] = {&a.in, &a.col, &a.hit, &a.tri, &a.status, &a.compact};
         for (DevBuf *b : ab) b->release();
@@ -737,6 +738,11 @@ int xp_collision_response_batch(xp_scene *s, const xp_response *in, uint64_t n, 
     XP_BIND(s);
     reset_stats(s);
     if (n == 0) return XP_OK;
+    {
+        bool taken = false;
+        XP_API_TRY(response_small_host(s, in, n, max_iter, horizon_mode, out, iterations, status, last_slide_normal, &taken));
+        if (taken) return XP_OK;
+    }
     cudaStream_t st = s->stream;
     XP_API_TRY(s->io_out.reserve(n * sizeof(xp_response)));
     XP_API_TRY(s->io_iter.reserve(n * 4));

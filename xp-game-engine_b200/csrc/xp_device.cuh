@@ -143,6 +143,8 @@ struct xp_scene {
     xp::DevBuf rays2, best2, active_c, io_backup;       // response loop: next iteration's rays / keys / list, and the input kept for a redo
     xp::DevBuf sort_ka, sort_kb;   // sphere Morton keys (ping-pong)
     xp::DevBuf io_in, io_out, io_hit, io_tri, io_status, io_iter, io_normal, io_col;
+    xp::DevBuf small_dev;          // the small-batch response path's one block each way: counters | in | out | iterations | status | normals
+    void *small_pin = nullptr;     // ... and its pinned mirror
     // stats
     xp_stats stats;
     // XP_OPT_TIMING: a pool of event pairs recorded without synchronising; resolved into

@@ -62,6 +62,10 @@ cudaError_t collect_stats(xp_scene *s);
 cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t max_iter,
                          uint32_t horizon_mode, xp_response *d_out, uint32_t *d_iter,
                          uint32_t *d_status, xp_vec3 *d_normal);
+// collision_response for a handful of spheres from and to HOST memory: one copy in, one launch, one copy out.
+// *taken = false: not eligible (options, size) or the kernel gave up -- nothing was written, use the batch path.
+cudaError_t response_small_host(xp_scene *s, const xp_response *in, uint64_t n, uint32_t max_iter, uint32_t horizon_mode,
+                                xp_response *out, uint32_t *iterations, uint32_t *status, xp_vec3 *normal, bool *taken);
 cudaError_t slide_dev(xp_scene *s, const xp_vec3 *d_pos, const xp_vec3 *d_vel, uint64_t n, uint32_t max_iter, const float *radii,
                       xp_vec3 *d_out_pos, xp_vec3 *d_out_vel, uint32_t *d_handled);
 cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t horizon_mode,

@@ -2282,15 +2282,64 @@ __global__ void __launch_bounds__(32 * SMALL_WARPS) k_small_response(const Node 
     }
 }
 
+static bool small_path_ok(const xp_scene *s, uint64_t n) {
+    static const bool no_small = getenv("XP_NO_SMALL_PATH") != nullptr;
+    return n > 0 && n <= SMALL_MAX_SPHERES && !no_small && s->method == XP_METHOD_LBVH_PAIRS && !s->far_exact && !s->safe_pairs &&
+           (s->arith == XP_ARITH_EXACT || s->arith == XP_ARITH_EXACT_LITERAL) && !s->timing;
+}
+
+// The host-pointer call of the small path.  Both directions go through ONE block, pinned on the host side:
+//   [DeviceCounters | Response in | Response out | iterations | status | slide normals]
+// the prefix (zeroed counters + inputs) goes up in one copy, the whole block comes back in one copy: two copies, one
+// launch and one synchronisation per call instead of five copies and a counter read-back.
+cudaError_t response_small_host(xp_scene *s, const xp_response *in, uint64_t n, uint32_t max_iter, uint32_t horizon_mode,
+                                xp_response *out, uint32_t *iterations, uint32_t *status, xp_vec3 *normal, bool *taken) {
+    *taken = false;
+    if (!small_path_ok(s, n)) return cudaSuccess;
+    constexpr size_t CTR = (sizeof(DeviceCounters) + 255) & ~size_t(255);
+    const size_t o_in = CTR, o_out = o_in + SMALL_MAX_SPHERES * sizeof(xp_response), o_it = o_out + SMALL_MAX_SPHERES * sizeof(xp_response);
+    const size_t o_st = o_it + SMALL_MAX_SPHERES * 4, o_nm = o_st + SMALL_MAX_SPHERES * 4, total = o_nm + SMALL_MAX_SPHERES * sizeof(xp_vec3);
+    XP_TRY(s->small_dev.reserve(total));
+    if (!s->small_pin) XP_TRY(cudaHostAlloc(&s->small_pin, total, cudaHostAllocDefault));
+    char *pin = static_cast<char *>(s->small_pin), *dev = s->small_dev.as<char>();
+    cudaStream_t st = s->stream;
+    XP_TRY(build_aux(s));
+    memset(pin, 0, CTR);
+    memcpy(pin + o_in, in, n * sizeof(xp_response));
+    XP_TRY(cudaMemcpyAsync(dev, pin, o_in + n * sizeof(xp_response), cudaMemcpyHostToDevice, st));
+    DeviceCounters *ctr = reinterpret_cast<DeviceCounters *>(dev);
+    k_small_response<ExactOps><<<(unsigned)((n + SMALL_WARPS - 1) / SMALL_WARPS), 32 * SMALL_WARPS, 0, st>>>(
+        s->nodes.as<Node>(), s->recs.as<TriRec>(), s->n_tris, s->degen.as<uint32_t>(), (uint32_t)s->n_degen,
+        reinterpret_cast<const xp_response *>(dev + o_in), reinterpret_cast<xp_response *>(dev + o_out), n,
+        max_iter ? max_iter : HARD_ITER_CAP, horizon_of(horizon_mode), reinterpret_cast<uint32_t *>(dev + o_it),
+        reinterpret_cast<uint32_t *>(dev + o_st), reinterpret_cast<xp_vec3 *>(dev + o_nm), ctr, &ctr->stack_overflow);
+    ++s->stats.kernel_launches;
+    // one copy back: the block up to the last array the caller wants
+    const size_t back = normal ? o_nm + n * sizeof(xp_vec3) : o_st + n * 4;
+    XP_TRY(cudaMemcpyAsync(pin, dev, back, cudaMemcpyDeviceToHost, st));
+    XP_TRY(cudaStreamSynchronize(st));
+    const DeviceCounters *h = reinterpret_cast<const DeviceCounters *>(pin);
+    if (h->stack_overflow) return cudaSuccess;                  // gave up: the caller takes the batch path
+    memcpy(out, pin + o_out, n * sizeof(xp_response));
+    if (iterations) memcpy(iterations, pin + o_it, n * 4);
+    if (status) memcpy(status, pin + o_st, n * 4);
+    if (normal) memcpy(normal, pin + o_nm, n * sizeof(xp_vec3));
+    s->stats.narrowphase_tests += h->tests;
+    s->stats.broadphase_pairs += h->pairs_total;
+    s->stats.node_visits += h->node_visits;
+    if (h->iters_done > s->stats.iterations_run) s->stats.iterations_run = h->iters_done;
+    s->swept_rays += h->rays_swept;
+    *taken = true;
+    return cudaSuccess;
+}
+
 cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t max_iter,
                          uint32_t horizon_mode, xp_response *d_out, uint32_t *d_iter,
                          uint32_t *d_status, xp_vec3 *d_normal) {
     cudaStream_t st = s->stream;
     XP_TRY(zero_counters(s));
     // a handful of spheres: the whole loop in one launch (k_small_response); anything it cannot take falls through
-    static const bool no_small = getenv("XP_NO_SMALL_PATH") != nullptr;
-    if (n <= SMALL_MAX_SPHERES && !no_small && s->method == XP_METHOD_LBVH_PAIRS && !s->far_exact && !s->safe_pairs &&
-        (s->arith == XP_ARITH_EXACT || s->arith == XP_ARITH_EXACT_LITERAL) && !s->timing) {
+    if (small_path_ok(s, n)) {
         const xp_response *src = d_in;
         if (d_out == d_in) {                    // in place: keep the input for a fallback
             XP_TRY(s->io_backup.reserve(n * sizeof(xp_response)));
