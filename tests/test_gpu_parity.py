@@ -483,6 +483,56 @@ def test_config1_player_vs_heightmap(oracle):
         assert_bits_equal(resp_fields(out), resp_fields(w[0]), f"config1 response {method}")
 
 
+def test_small_batch_path_and_its_fall_through(oracle):
+    """collision_response for a handful of spheres runs as ONE launch (k_small_response: a warp per sphere).  The same
+    batch through that path, through the batch kernels (XP_NO_SMALL_PATH) and through the small path giving up (a work
+    list of one entry, XP_SMALL_QUEUE: the call falls through) must agree bit for bit with each other and with the
+    oracle -- host call and device-pointer call in place, stats included.  The switches are read once per process."""
+    import subprocess
+    import sys
+    import tempfile
+    code = (
+        "import numpy as np, torch, xp_physics_cuda as xp\n"
+        "from xp_physics_cuda import scenes\n"
+        "tris, h = scenes.sine_terrain(48, 48, seed=21)\n"
+        "resps = scenes.terrain_spheres(h, 300, seed=22)\n"
+        "resps['r'][7] = 2.0\n"
+        "with xp.Scene(0, tris) as s:\n"
+        "    out, it, st, ln = s.collision_response_batch(resps, max_iter=6)\n"
+        "    stats = s.stats()\n"
+        "    d = torch.from_numpy(np.ascontiguousarray(resps).view(np.float32).reshape(-1, 7)).cuda()\n"
+        "    di = torch.zeros(len(resps), dtype=torch.int32, device='cuda'); ds = torch.zeros_like(di)\n"
+        "    s.collision_response_batch_dev(d.data_ptr(), len(resps), d.data_ptr(), 6, di.data_ptr(), ds.data_ptr())\n"
+        "    torch.cuda.synchronize()\n"
+        "np.savez(r'%s', out=out.view(np.float32), it=it, st=st, ln=ln.view(np.float32), dev=d.cpu().numpy(), di=di.cpu().numpy(),\n"
+        "         ds=ds.cpu().numpy(), launches=stats['kernel_launches'], tests=stats['narrowphase_tests'])\n")
+    res = {}
+    with tempfile.TemporaryDirectory() as dd:
+        for tag, env_add in (("small", {}), ("batch", {"XP_NO_SMALL_PATH": "1"}), ("giveup", {"XP_SMALL_QUEUE": "1"})):
+            env = dict(os.environ)
+            env["PYTHONPATH"] = os.pathsep.join([os.path.dirname(os.path.dirname(xp.__file__)), env.get("PYTHONPATH", "")])
+            for k in ("XP_NO_SMALL_PATH", "XP_SMALL_QUEUE"):
+                env.pop(k, None)
+            env.update(env_add)
+            path = os.path.join(dd, tag + ".npz")
+            subprocess.run([sys.executable, "-c", code % path], check=True, env=env, timeout=300)
+            z = np.load(path)
+            res[tag] = {k: z[k] for k in z.files}
+    assert res["small"]["launches"] == 1 and res["batch"]["launches"] > 5 and res["giveup"]["launches"] > 5
+    for tag in ("batch", "giveup"):
+        for k in ("out", "it", "st", "ln", "dev", "di", "ds"):
+            assert np.array_equal(res["small"][k].view(np.uint32), res[tag][k].view(np.uint32)), (tag, k)
+    assert res["small"]["tests"] == res["batch"]["tests"]                     # the same candidate sets were tested
+    assert np.array_equal(res["small"]["out"].view(np.uint32), res["small"]["dev"].view(np.uint32).reshape(res["small"]["out"].shape))
+    tris, h = scenes.sine_terrain(48, 48, seed=21)
+    resps = scenes.terrain_spheres(h, 300, seed=22)
+    resps["r"][7] = 2.0
+    w = oracle.collision_response_batch(resps, tris, max_iter=6)
+    assert np.array_equal(res["small"]["it"], w[1]) and np.array_equal(res["small"]["st"], w[2])
+    assert_bits_equal(res["small"]["out"].reshape(-1, 7), resp_fields(w[0]).reshape(-1, 7), "small path vs oracle")
+    assert (res["small"]["st"] & 4).any() or (res["small"]["it"] >= 1).any()
+
+
 def test_config3_mesh_field_with_rebuild(oracle):
     """config 3 (scaled down): cubes + icospheres, LBVH rebuilt for every frame's translated meshes."""
     with xp.Scene(0) as s:

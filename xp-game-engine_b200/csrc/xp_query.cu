@@ -2170,7 +2170,7 @@ __global__ void __launch_bounds__(32 * SMALL_WARPS) k_small_response(const Node 
                                                                    uint64_t n, uint32_t cap_iter, float horizon,
                                                                    uint32_t *__restrict__ iter_out, uint32_t *__restrict__ status_out,
                                                                    xp_vec3 *__restrict__ normal_out, DeviceCounters *__restrict__ ctr,
-                                                                   unsigned *__restrict__ fallback) {
+                                                                   unsigned *__restrict__ fallback, unsigned queue_cap) {
     __shared__ int q_all[SMALL_WARPS][SMALL_QUEUE];
     __shared__ uint32_t cand_all[SMALL_WARPS][SMALL_CAND];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
@@ -2219,7 +2219,7 @@ __global__ void __launch_bounds__(32 * SMALL_WARPS) k_small_response(const Node 
             visits += take;
             const unsigned pa = __ballot_sync(FULL, push_a >= 0), pb = __ballot_sync(FULL, push_b >= 0);
             const unsigned la = __ballot_sync(FULL, leaf_a >= 0), lb = __ballot_sync(FULL, leaf_b >= 0);
-            if (qn + __popc(pa) + __popc(pb) > (unsigned)SMALL_QUEUE) { overflow = true; break; }
+            if (qn + __popc(pa) + __popc(pb) > queue_cap) { overflow = true; break; }      // (queue_cap = SMALL_QUEUE; tests shrink it)
             if (push_a >= 0) q[qn + __popc(pa & lt_mask)] = push_a;
             if (push_b >= 0) q[qn + __popc(pa) + __popc(pb & lt_mask)] = push_b;
             qn += __popc(pa) + __popc(pb);
@@ -2282,6 +2282,11 @@ __global__ void __launch_bounds__(32 * SMALL_WARPS) k_small_response(const Node 
     }
 }
 
+// XP_SMALL_QUEUE (tests): a work list of a few entries makes the kernel give up, which exercises the fall-through
+static unsigned small_queue_cap() {
+    static const unsigned cap = getenv("XP_SMALL_QUEUE") ? (unsigned)atoi(getenv("XP_SMALL_QUEUE")) : (unsigned)SMALL_QUEUE;
+    return cap < (unsigned)SMALL_QUEUE ? cap : (unsigned)SMALL_QUEUE;
+}
 static bool small_path_ok(const xp_scene *s, uint64_t n) {
     static const bool no_small = getenv("XP_NO_SMALL_PATH") != nullptr;
     return n > 0 && n <= SMALL_MAX_SPHERES && !no_small && s->method == XP_METHOD_LBVH_PAIRS && !s->far_exact && !s->safe_pairs &&
@@ -2312,7 +2317,7 @@ cudaError_t response_small_host(xp_scene *s, const xp_response *in, uint64_t n, 
         s->nodes.as<Node>(), s->recs.as<TriRec>(), s->n_tris, s->degen.as<uint32_t>(), (uint32_t)s->n_degen,
         reinterpret_cast<const xp_response *>(dev + o_in), reinterpret_cast<xp_response *>(dev + o_out), n,
         max_iter ? max_iter : HARD_ITER_CAP, horizon_of(horizon_mode), reinterpret_cast<uint32_t *>(dev + o_it),
-        reinterpret_cast<uint32_t *>(dev + o_st), reinterpret_cast<xp_vec3 *>(dev + o_nm), ctr, &ctr->stack_overflow);
+        reinterpret_cast<uint32_t *>(dev + o_st), reinterpret_cast<xp_vec3 *>(dev + o_nm), ctr, &ctr->stack_overflow, small_queue_cap());
     ++s->stats.kernel_launches;
     // one copy back: the block up to the last array the caller wants
     const size_t back = normal ? o_nm + n * sizeof(xp_vec3) : o_st + n * 4;
@@ -2351,7 +2356,7 @@ cudaError_t response_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint3
         unsigned *fb = &c0->stack_overflow;     // (zeroed with the counters; reused as this kernel's fallback flag)
         k_small_response<ExactOps><<<(unsigned)((n + SMALL_WARPS - 1) / SMALL_WARPS), 32 * SMALL_WARPS, 0, st>>>(
             s->nodes.as<Node>(), s->recs.as<TriRec>(), s->n_tris, s->degen.as<uint32_t>(), (uint32_t)s->n_degen, src, d_out, n,
-            max_iter ? max_iter : HARD_ITER_CAP, horizon_of(horizon_mode), d_iter, d_status, d_normal, c0, fb);
+            max_iter ? max_iter : HARD_ITER_CAP, horizon_of(horizon_mode), d_iter, d_status, d_normal, c0, fb, small_queue_cap());
         ++s->stats.kernel_launches;
         DeviceCounters h;
         XP_TRY(fetch_counters(s, &h));
