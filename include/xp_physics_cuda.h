@@ -102,7 +102,7 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                    sphere: the 32 lanes test a node's 32 child boxes (six coalesced 128 B loads),
                                    leaf hits go to a warp-shared queue in shared memory that is drained 32 pairs at
                                    a time through the narrowphase */
-#define XP_METHOD_LBVH_FUSED  1  /* binary Karras LBVH, one LANE per sphere with a private stack, same warp queue */
+#define XP_METHOD_LBVH_FUSED  1  /* binary LBVH, one LANE per sphere with a private stack, same warp queue */
 #define XP_METHOD_LBVH_PAIRS  2  /* default. Persistent-warp binary LBVH traversal (4 blocks of 256 per SM, 60 registers) emits every pair passing P to HBM; narrowphase over the pairs */
 #define XP_METHOD_BRUTE       3  /* the reference's literal algorithm: every triangle for every sphere (lib.rs:33-35) */
 #define XP_METHOD_WIDE_PAIRS  4  /* 32-wide tree traversal emits the pairs to HBM; narrowphase over the pairs */
@@ -167,7 +167,8 @@ int  xp_scene_set_heightmap(xp_scene *s, const float *heights, uint32_t nx, uint
 int  xp_scene_set_clipmap(xp_scene *s, const float *heights, uint32_t levels, uint32_t size,
                           const int32_t *parts, uint32_t n_parts, float unit0);
 /* (Re)build the device LBVH: per-triangle normal / plane constant / inflated AABB, 30-bit
- * Morton codes, radix sort, Karras hierarchy, bottom-up refit.  New: the reference has no
+ * Morton codes, radix sort, hierarchy and boxes in one bottom-up pass (the binary radix tree of
+ * Karras 2012, built the way of Apetrei 2014).  New: the reference has no
  * broadphase (lib.rs:33-35 walks every triangle). */
 int  xp_scene_build(xp_scene *s);
 uint64_t xp_scene_triangle_count(const xp_scene *s);

@@ -5,13 +5,14 @@
 // quantities cached here are the ones collision_detect.rs:162,171 recomputes on every test
 // (Triangle::normal, triangle.rs:44-46; Triangle::plane_constant, triangle.rs:47-50).
 //
-// Stages (all HBM-bound; bytes per triangle in DESIGN.md):
+// Stages (bytes per triangle and measured times in DESIGN.md section 4):
 //   K0 bounds   AABB of the triangle-box centres (ordered-int atomics, block-reduced)
-//   K2 morton   30-bit Morton code of each centre
-//   K3 sort     CUB-free LSD radix sort, 8 bits x 4 passes, stable (histogram / scan / scatter)
-//   K1 pack     TriRec + inflated leaf AABB written in Morton order
-//   K4 tree     Karras 2012 hierarchy emission (one thread per internal node)
-//   K5 refit    bottom-up AABB refit with per-node arrival counters; writes the 64 B nodes
+//   K2 morton   30-bit Morton code of each centre (+ the per-tile histogram of the sort's first digit)
+//   K3 sort     CUB-free stable LSD radix sort, 10 bits x 3 passes (histogram / scan / scatter through the tile's
+//               own digit order in shared memory)
+//   K1 pack     TriRec + inflated leaf AABB written in Morton order, the ill-conditioned list
+//   K4+K5 tree  hierarchy AND child boxes in one bottom-up pass (k_tree_local: a warp per 256 leaves in shared
+//               memory; k_tree_global: what crosses segments), writes the 64 B nodes; node 0 = root
 #include <cstdio>
 #include <cstdlib>
 
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
             if (ill) degen[1 + at + __popc(im & ((1u << lane) - 1u))] = (uint32_t)j;
         }
     }
-    leaf_box[2 * j] = make_float4(lo.x, lo.y, lo.z, 0.0f);          // (lo, hi) side by side: one 32 B sector per box for the refit
+    leaf_box[2 * j] = make_float4(lo.x, lo.y, lo.z, 0.0f);          // (lo, hi) side by side: one 32 B sector per box for the tree pass
     leaf_box[2 * j + 1] = make_float4(hi.x, hi.y, hi.z, 0.0f);
 }
 
