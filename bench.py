@@ -426,7 +426,7 @@ def run_config2(ctx: Ctx, args) -> dict:
                 "algorithmic_flops_per_launch": flops, "flops_per_test_by_path": PATH_FLOPS, "path_mix": paths,
                 "traffic": TRAFFIC_NARROW, "traffic_source": TRAFFIC_SOURCE,
                 "note": "231 algorithmic flops per full test; the exact kernel issues ~423 thread instructions per test "
-                        "(round 1: 577), the fast one ~230; ncu (profiles/r02r_ncu_full.txt): issue slots 84% busy, "
+                        "(round 1: 577), the fast one ~230; ncu (profiles/r02x_ncu_full.txt): issue slots 84% busy, "
                         "FMA pipe 54%, 30 of 32 lanes active; exact arithmetic may not contract (the reference does not), so "
                         "one flop costs one issue slot where the FFMA peak counts two"}
     tests_step = float(np.mean([s["narrowphase_tests"] for s in stats]))
@@ -439,7 +439,7 @@ def run_config2(ctx: Ctx, args) -> dict:
                     "frac": (bp_bytes / (bp_ms * 1e-3) / 1e9) / hbm_peak if (two_stage and bp_ms > 0) else None,
                     "algorithmic_bytes_per_launch": bp_bytes, "traffic": TRAFFIC_BROADPHASE, "traffic_source": TRAFFIC_SOURCE,
                     "note": "64 B ray record per sphere + 8 B per candidate pair; the walk itself reads L1/L2-resident heights "
-                            "(grid) or nodes (LBVH) and is bound by instruction issue (grid: 27 of 32 lanes active, issue slots 80% "
+                            "(grid) or nodes (LBVH) and is bound by instruction issue (grid: 29 of 32 lanes active, issue slots 80% "
                             "busy, DRAM 11%) or by L1 wavefronts (LBVH), not by HBM"}
 
     # ---- e2e: host pointers, pinned buffers, every step's H2D + D2H inside the timed region, two batches in flight
@@ -608,10 +608,10 @@ def run_config2(ctx: Ctx, args) -> dict:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
-# same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r02r_ncu_full.txt
+# same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r02x_ncu_full.txt
 TRAFFIC_NARROW = 475.5e6         # k_narrow_pairs: 466 MB read (315 MB of it the pair list) + 9 MB written (round 1: 610 MB; 956 MB before the spans were claimed dynamically)
-TRAFFIC_BROADPHASE = 333.5e6     # k_broadphase_grid: 73 MB read + 260 MB written (the pair list)
-TRAFFIC_SOURCE = "profiles/r02r_ncu_full.txt"
+TRAFFIC_BROADPHASE = 331.5e6     # k_broadphase_grid: 73 MB read + 258 MB written (the pair list)
+TRAFFIC_SOURCE = "profiles/r02x_ncu_full.txt"
 
 
 # ---------------------------------------------------------------------------------------------
