@@ -346,23 +346,24 @@ def run_config2(ctx: Ctx, args) -> dict:
 
     last_view = [None]
 
-    def loop_device(k):
+    def loop_device(k, ex=None):
         """k steps as a loop: submit step i, then complete step i-1 -- step i's sweep runs while step i-1's records
         cross NVLink (copy engines, second stream) and its barrier completes.  Returns the per-step stats."""
+        ex = ex or exchange
         pending, out = [], []
         for _ in range(k):
             if len(pending) == 2:
-                last_view[0] = exchange.wait(pending.pop(0))
+                last_view[0] = ex.wait(pending.pop(0))
                 out.append(scene.stats())
-            pending.append(exchange.sweep_async(d_in.data_ptr(), n))
+            pending.append(ex.sweep_async(d_in.data_ptr(), n))
         while pending:
-            last_view[0] = exchange.wait(pending.pop(0))
+            last_view[0] = ex.wait(pending.pop(0))
             out.append(scene.stats())
         return out
 
-    def timed_loop(steps, warmup):
-        loop_device(warmup)
-        ms, stats = ctx.timed_region(lambda: loop_device(steps))
+    def timed_loop(steps, warmup, ex=None):
+        loop_device(warmup, ex)
+        ms, stats = ctx.timed_region(lambda: loop_device(steps, ex))
         return ms, stats
 
     W = max(args.warmup, 3)
@@ -394,6 +395,21 @@ def run_config2(ctx: Ctx, args) -> dict:
         exchange_verified = bool(flag.item() == 1)
 
     last_records = (last_view[0][rank][:n] if pipelined else mine).clone()
+    # ---- N > 1: the same loop shipping 16 B records (XP_OPT_CONTACT_RECORD = 1: centre at the contact + triangle) instead
+    # of the 40 B xp_contact: what the exchange's bytes cost the sweep they run under
+    exchange_compact = None
+    if world > 1 and pipelined and not args.no_extras:
+        ex16 = ContactExchange(scene, n, dev, record="compact")
+        if ex16.ok:
+            keep = last_view[0]
+            ms16, st16 = timed_loop(args.steps, W, ex16)
+            (t16,) = ctx.sum_over_ranks(sum(x["narrowphase_tests"] for x in st16))
+            exchange_compact = {"record": "xp_contact16: (position, tri_index), 16 B instead of 40 B per sphere",
+                                "ms_per_step": ms16 / args.steps, "value": t16 / (ms16 * 1e-3), "unit": "tests/s"}
+            last_view[0] = keep
+        ex16.close()
+        scene.set_options(contact_record="full")
+
     tests_local = sum(s["narrowphase_tests"] for s in stats)
     launches = sum(s["kernel_launches"] for s in stats)
     (tests_all,) = ctx.sum_over_ranks(tests_local)
@@ -589,7 +605,7 @@ def run_config2(ctx: Ctx, args) -> dict:
             "walk_visits_per_step": float(np.mean([s["node_visits"] for s in stats])),
             "stage_ms": st_ms,
             "hit_fraction": float((last_records[:, 9].contiguous().view(torch.int32) & 1).float().mean().item()),
-            "exchange_verified": exchange_verified,
+            "exchange_verified": exchange_verified, "exchange_compact": exchange_compact,
             "single_step": {"ms_per_step": sync_ms / args.steps,
                             "value": sum(s_["narrowphase_tests"] for s_ in sync_stats) * world / (sync_ms * 1e-3),
                             "note": "one synchronous call per step (host waits for the result), L2 flushed between steps"},
