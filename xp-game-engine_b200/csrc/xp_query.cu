@@ -1124,7 +1124,10 @@ __device__ __noinline__ bool detect_literal_call(const RayRec *__restrict__ rays
 #define XP_NP_BLOCKS_F 4
 #endif
 template <int MODE, bool FILTER>
-__global__ void __launch_bounds__(256, MODE == NP_X ? XP_NP_BLOCKS_X : MODE == NP_F ? XP_NP_BLOCKS_F : XP_NP_BLOCKS) k_narrow_pairs(const TriRec *__restrict__ recs,
+#ifndef XP_NP_THREADS
+#define XP_NP_THREADS 128            /* 256: 0.551 ms, 128: 0.545, 64 (spans of 512): 0.542 */
+#endif
+__global__ void __launch_bounds__(XP_NP_THREADS, (256 / XP_NP_THREADS) * (MODE == NP_X ? XP_NP_BLOCKS_X : MODE == NP_F ? XP_NP_BLOCKS_F : XP_NP_BLOCKS)) k_narrow_pairs(const TriRec *__restrict__ recs,
                                                       const RayRec *__restrict__ rays,
                                                       const uint2 *__restrict__ pairs,
                                                       DeviceCounters *__restrict__ ctr,
@@ -1910,9 +1913,9 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
         {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
             const int np_blocks = s->arith == XP_ARITH_EXACT ? XP_NP_BLOCKS_X : s->arith == XP_ARITH_FAST ? XP_NP_BLOCKS_F : XP_NP_BLOCKS;
-            const unsigned ng = (unsigned)s->n_sm * (XP_NP_DYNAMIC ? 1u : 2u) * (unsigned)np_blocks;   // dynamic spans: exactly the resident blocks
-#define XP_NP_LAUNCH(M) do { if (q4) k_narrow_pairs<M, true><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
-                             else k_narrow_pairs<M, false><<<ng, 256, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); } while (0)
+            const unsigned ng = (unsigned)s->n_sm * (XP_NP_DYNAMIC ? 1u : 2u) * (unsigned)np_blocks * (256u / XP_NP_THREADS);   // dynamic spans: exactly the resident blocks
+#define XP_NP_LAUNCH(M) do { if (q4) k_narrow_pairs<M, true><<<ng, XP_NP_THREADS, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
+                             else k_narrow_pairs<M, false><<<ng, XP_NP_THREADS, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); } while (0)
             switch (s->arith) {
             case XP_ARITH_FAST: XP_NP_LAUNCH(NP_F); break;
             case XP_ARITH_EXACT_LITERAL: XP_NP_LAUNCH(NP_LITERAL_EXACT); break;
