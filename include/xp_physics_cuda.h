@@ -93,6 +93,13 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                 * and intersection are functions of the Response, collision_detect.rs:188-194, which only the
                                 * owning rank holds).  128 M spheres on 8 GPUs: 2.1 GB instead of 5.4 GB landed per GPU. */
 
+#define XP_OPT_LEAF_RUNS 10  /* 1 (default): the LBVH walk of XP_METHOD_LBVH_PAIRS does not visit an internal node over exactly two
+                                leaves (Morton neighbours; usually the two triangles of a quad): when the ray hits their union
+                                box it emits both, and the narrowphase kernel applies P to each triangle's own box before testing
+                                it.  The tested set stays P bit for bit (narrowphase_tests == |P|; broadphase_pairs counts what
+                                was emitted, a few per cent more); a fifth of the node visits disappear.  Exhaustive sweeps only: the
+                                windowed passes of XP_OPT_PRUNE and xp_broadphase_pairs walk without runs.  0: off. */
+
 #define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical to the reference's results         */
 #define XP_ARITH_FAST     1  /* tolerance mode: FMA, hardware reciprocal / square root, reduced quadratics (<= 1e-5) */
 #define XP_ARITH_EXACT_LITERAL 2 /* same results as 0 through the compiler's IEEE div / sqrt (the round-1 kernel; A/B)  */
@@ -264,6 +271,9 @@ int  xp_broadphase_pairs(xp_scene *s, const xp_response *in, uint64_t n, uint32_
  * node_lo/hi[i]  = AABB of internal node i. */
 int  xp_scene_debug_tree(xp_scene *s, uint32_t *sorted_tri, uint32_t *morton, int32_t *node_child,
                          xp_vec3 *node_lo, xp_vec3 *node_hi);
+/* node_run[2i], node_run[2i+1] = leaf run of the left / right child of internal node i (XP_OPT_LEAF_RUNS): l + 1 when that
+ * child is an internal node over exactly the leaves l and l + 1, else 0. */
+int  xp_scene_debug_leaf_runs(xp_scene *s, int32_t *node_run);
 
 /* ---- contact record for the multi-GPU allgather ----
  * 40 B per sphere: the 32 B collision + tri_index + (hit | status << 8 | iterations << 16). */

@@ -20,6 +20,7 @@ def _check_tree(tris, oracle):
     n = len(tris)
     with xp.Scene(0, tris) as s:
         sorted_tri, morton, child, nlo, nhi = s.debug_tree()
+        run = s.debug_leaf_runs()
     assert np.array_equal(np.sort(sorted_tri), np.arange(n))                 # a permutation
     assert (np.diff(morton.astype(np.int64)) >= 0).all()                     # sorted
     assert (morton < (1 << 30)).all()
@@ -51,6 +52,15 @@ def _check_tree(tris, oracle):
                 blo, bhi = nlo[c_], nhi[c_]
             assert (nlo[i] <= blo).all() and (nhi[i] >= bhi).all()
     assert (seen_leaf == 1).all() and seen_node[0] == 0 and (seen_node[1:] == 1).all()
+    # leaf runs (XP_OPT_LEAF_RUNS): marked on exactly the children that are internal nodes over two leaves, with the first leaf
+    kid = child.astype(np.int64)
+    internal = kid >= 0
+    grand = child[np.where(internal, kid, 0)]                               # (n-1, 2, 2): the children's own links
+    two_leaves = internal & (grand < 0).all(axis=2)
+    assert np.array_equal(run > 0, two_leaves)
+    assert np.array_equal(run[two_leaves] - 1, ~grand[two_leaves][:, 0])
+    assert np.array_equal(~grand[two_leaves][:, 1], run[two_leaves])
+    assert two_leaves.sum() > 0 or n < 3
     # leaf ranges: an in-order walk visits leaves 0..n-1 in order
     order = []
     stack = [0]

@@ -163,7 +163,7 @@ def test_pair_buffer_overflow_is_recovered(terrain):
             check_detect_exact(got, want, f"overflow recovery {method}")
             st_ = s.stats()
             assert st_["narrowphase_tests"] <= st_["broadphase_pairs"]
-            if method != "q4_pairs":
+            if method == "wide_pairs":                     # (q4 and the leaf runs of lbvh_pairs emit a superset and filter it)
                 assert st_["narrowphase_tests"] == st_["broadphase_pairs"]
             out, it, st, ln = s.collision_response_batch(resps[:300], max_iter=2)
             assert it.max() == 2
@@ -223,7 +223,7 @@ def test_host_pipeline_chunks(terrain, monkeypatch):
             monkeypatch.setenv("XP_IO_CHUNKS", k)
             got = s.detect_batch(resps)
             check_detect_exact(got, want, f"{k} pipeline chunks")
-            assert s.stats()["narrowphase_tests"] == s.stats()["broadphase_pairs"] > 0
+            assert 0 < s.stats()["narrowphase_tests"] <= s.stats()["broadphase_pairs"]
     monkeypatch.delenv("XP_IO_CHUNKS")
 
 
@@ -936,3 +936,38 @@ def test_far_exact_reproduces_the_references_far_grazing_noise(oracle):
         b = s.detect_batch(resps2)
     for x, y in zip(a, b):
         assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+
+
+def test_leaf_runs_change_nothing_but_the_visits(terrain, oracle):
+    """XP_OPT_LEAF_RUNS: two-leaf children of the LBVH are emitted unvisited and stage 2 applies P per triangle -- same
+    tested set (|P|), same contacts bit for bit, fewer node visits; with and without the option, both horizons, through
+    the response loop, and in a pruned sweep (whose windowed passes walk without runs: nothing may change there)."""
+    tris, h, resps, want = terrain
+    n_p = {hz: len(oracle.broadphase_pairs(resps, tris, np.inf if hz == "inf" else 1.0)[0]) for hz in ("inf", "unit")}
+    for prune in (False, True):
+        res = {}
+        for runs in (False, True):
+            with xp.Scene(0, tris, prune=prune) as s:
+                s.set_options(leaf_runs=runs)
+                got = s.detect_batch(resps)
+                st_ = s.stats()
+                unit = s.detect_batch(resps, horizon="unit")
+                st_u = s.stats()
+                out = s.collision_response_batch(resps[:600], max_iter=3)
+            res[runs] = (got, st_, unit, st_u, out)
+            check_detect_exact(got, want, f"leaf runs {runs} prune {prune}", tri_index=not prune)
+            if not prune:
+                assert st_["narrowphase_tests"] == n_p["inf"] and st_u["narrowphase_tests"] == n_p["unit"]
+                assert (st_["broadphase_pairs"] == n_p["inf"]) == (not runs) and st_["broadphase_pairs"] >= n_p["inf"]
+        (a, sa, ua, sua, oa), (b, sb, ub, sub_, ob) = res[False], res[True]
+        check_detect_exact(b, a, f"runs on vs off (prune {prune})")
+        check_detect_exact(ub, ua, f"runs on vs off, unit horizon (prune {prune})")
+        assert sa["narrowphase_tests"] == sb["narrowphase_tests"] and sua["narrowphase_tests"] == sub_["narrowphase_tests"]
+        if prune:
+            assert sb["node_visits"] == sa["node_visits"] and sb["broadphase_pairs"] == sa["broadphase_pairs"]
+        else:
+            assert sb["node_visits"] < 0.9 * sa["node_visits"]
+            assert sb["broadphase_pairs"] < 1.25 * sa["broadphase_pairs"]
+            print(f"leaf runs: {sa['node_visits']} -> {sb['node_visits']} node visits, {sb['broadphase_pairs']} pairs emitted for |P| = {n_p['inf']}")
+        for x, y in zip(oa, ob):
+            assert np.array_equal(np.ascontiguousarray(x).view(np.uint8), np.ascontiguousarray(y).view(np.uint8))

@@ -80,6 +80,7 @@ int xp_scene_create(int device, xp_scene **out) {
     s->device = device;
     int n_sm = 0;
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n_sm > 0) s->n_sm = n_sm;
+    if (const char *e = getenv("XP_LEAF_RUNS")) s->leaf_runs = atoi(e) ? 1 : 0;     // A/B hook: the option's initial value
     reset_stats(s);
     *out = s;
     return XP_OK;
@@ -148,6 +149,7 @@ int xp_scene_set_option(xp_scene *s, int option, int64_t value) {
         s->prune = (int)value; s->cand_per_ray = 0.0; return XP_OK;
     case XP_OPT_FAR_EXACT: s->far_exact = value ? 1 : 0; return XP_OK;
     case XP_OPT_GRID_WALK: s->use_grid = value ? 1 : 0; return XP_OK;
+    case XP_OPT_LEAF_RUNS: s->leaf_runs = value ? 1 : 0; return XP_OK;
     case XP_OPT_CONTACT_RECORD:
         if (value > 1) return XP_EINVAL;
         s->contact_record = (int)value; return XP_OK;
@@ -867,6 +869,24 @@ int xp_scene_debug_tree(xp_scene *s, uint32_t *sorted_tri, uint32_t *morton, int
         }
         delete[] h;
     }
+    return XP_OK;
+}
+
+int xp_scene_debug_leaf_runs(xp_scene *s, int32_t *node_run) {
+    if (!s || !node_run) return XP_EINVAL;
+    if (!s->built) return XP_ESTATE;
+    XP_BIND(s);
+    const uint64_t n = s->n_tris;
+    if (n == 0) return XP_OK;
+    XP_API_TRY(cudaStreamSynchronize(s->stream));
+    const uint64_t ni = n > 1 ? n - 1 : 1;
+    Node *h = new (std::nothrow) Node[ni];
+    if (!h) return XP_ENOMEM;
+    const cudaError_t e = cudaMemcpy(h, s->nodes.p, ni * sizeof(Node), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        for (uint64_t i = 0; i < ni; ++i) { node_run[2 * i] = h[i].link.z; node_run[2 * i + 1] = h[i].link.w; }
+    delete[] h;
+    if (e != cudaSuccess) return fail_cuda(e);
     return XP_OK;
 }
 

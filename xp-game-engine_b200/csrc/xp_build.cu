@@ -657,10 +657,12 @@ __device__ void tree_climb_global(const uint32_t *__restrict__ keys, int n, Node
             __stcg(reinterpret_cast<float4 *>(rec), make_float4(lo.x, lo.y, lo.z, hi.x));
             __stcg(reinterpret_cast<float2 *>(rec + 4), make_float2(hi.y, hi.z));
             __stcg(reinterpret_cast<int *>(rec + 12), cur);
+            __stcg(reinterpret_cast<int *>(rec + 14), r - l == 1 ? l + 1 : 0);     // leaf run (see Node)
         } else {
             __stcg(reinterpret_cast<float2 *>(rec + 6), make_float2(lo.x, lo.y));
             __stcg(reinterpret_cast<float4 *>(rec + 8), make_float4(lo.z, hi.x, hi.y, hi.z));
             __stcg(reinterpret_cast<int *>(rec + 13), cur);
+            __stcg(reinterpret_cast<int *>(rec + 15), r - l == 1 ? l + 1 : 0);
         }
         if (cur == 0) { info[1] = p; info[2] = left_child ? 0 : 1; }
         __threadfence();
@@ -780,11 +782,13 @@ __global__ void __launch_bounds__(32) k_tree_local(const uint32_t *__restrict__ 
             Node nd;
             if (left_child) {
                 nd.q0 = make_float4(lo.x, lo.y, lo.z, hi.x); nd.q1 = make_float4(hi.y, hi.z, slo.x, slo.y);
-                nd.q2 = make_float4(slo.z, shi.x, shi.y, shi.z); nd.link = make_int4(cur, sl, 0, 0);
+                nd.q2 = make_float4(slo.z, shi.x, shi.y, shi.z);
+                nd.link = make_int4(cur, sl, p - l == 1 ? l + 1 : 0, other - p == 2 ? p + 2 : 0);     // children [l, p], [p + 1, other]
                 r = other;
             } else {
                 nd.q0 = make_float4(slo.x, slo.y, slo.z, shi.x); nd.q1 = make_float4(shi.y, shi.z, lo.x, lo.y);
-                nd.q2 = make_float4(lo.z, hi.x, hi.y, hi.z); nd.link = make_int4(sl, cur, 0, 0);
+                nd.q2 = make_float4(lo.z, hi.x, hi.y, hi.z);
+                nd.link = make_int4(sl, cur, p - other == 1 ? other + 1 : 0, r - p == 2 ? p + 2 : 0);  // children [other, p], [p + 1, r]
                 l = other;
             }
             nodes[p] = nd;

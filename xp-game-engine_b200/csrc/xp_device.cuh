@@ -4,7 +4,9 @@
 //   TriRec[T]  64 B  leaf j (Morton order): q0=(v0, n.x) q1=(v1, n.y) q2=(v2, n.z)
 //                    q3=(plane_constant, |v1-v0|^2, |v2-v1|^2, bits(upload index))
 //   Node[T-1]  64 B  internal node i: both child AABBs (already inflated by 1+1e-4) and the two
-//                    child links (>= 0 internal, < 0 leaf ~c); node 0 is the root
+//                    child links (>= 0 internal, < 0 leaf ~c); node 0 is the root.  link.z / link.w: leaf run of the
+//                    left / right child -- l + 1 when that child is an internal node over exactly the leaves l, l + 1,
+//                    else 0 (XP_OPT_LEAF_RUNS; written by the tree pass, read by k_broadphase only)
 //   RayRec[S]  64 B  per sphere per sweep: q0=(c, |m|) q1=(m, |m|^2) q2=(m/|m|, horizon)
 //                    q3=(1/m.x, 1/m.y, 1/m.z, bits(flags))
 //   best[S]     8 B  (bits(t) << 32) | ~upload_index, all ones = no hit; atomicMin gives the
@@ -101,6 +103,7 @@ struct xp_scene {
     int timing = 0;
     int sort_spheres = 1;
     int contact_record = 0;            // XP_OPT_CONTACT_RECORD: 0 = xp_contact (40 B), 1 = xp_contact16 (16 B)
+    int leaf_runs = 1;                 // XP_OPT_LEAF_RUNS: two-leaf children are emitted, not visited (stage 2 filters with P)
     int far_exact = 0;                 // XP_OPT_FAR_EXACT: second pass for far-range grazing noise of the reference
     uint64_t max_pairs = 1ull << 26;
     float cur_horizon = 0.0f;          // horizon of the rays currently in `rays`

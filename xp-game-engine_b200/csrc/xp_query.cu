@@ -347,7 +347,15 @@ static constexpr int BP_BLOCKS_PER_SM = XP_BP_BLOCKS;
 // by XP_FAR_K * D^2 with D the farthest a closer hit could be, every leaf the ray is inside of after d_lo and
 // before its best hit (see closest_t).
 static constexpr float XP_FAR_K = 8e-7f;
-template <int MODE>
+// RUNS (MODE 0 only): leaf runs.  A child that is an internal node over exactly two leaves -- Morton neighbours l, l + 1;
+// the tree pass leaves l + 1 in link.z / link.w of the PARENT's record -- is not visited: when the ray hits the box the
+// parent holds for it (the union of the two leaf boxes), both leaves are emitted and stage 2 applies P to each
+// triangle's own box (k_narrow_pairs<.., FILTER>), so exactly the pairs of P are still tested.  Config 2 handed over as
+// a soup: 82.7 M -> 65.1 M node visits, walk 0.73 -> 0.62 ms, narrowphase 0.59 -> 0.64 ms (the filter's ~45 instructions
+// per pair and the lanes it idles), step 1.45 -> 1.40 ms.  Not used in the windowed passes of a pruned sweep:
+// a run has to be offered to every pass its union box overlaps and is filtered out of all but one -- measured on
+// config 3: walk 38.6 -> 33.4 ms, narrowphase 21.2 -> 27.1 ms, a net loss (profiles/r02_leaf_runs_ab.log).
+template <int MODE, bool RUNS>
 __global__ void __launch_bounds__(BP_THREADS, BP_BLOCKS_PER_SM)
 k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
              float horizon, DeviceCounters *__restrict__ ctr, uint2 *__restrict__ pairs_out, uint64_t pair_cap,
@@ -359,7 +367,8 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     // Distance window [d_lo, d_hi) of this pass (pruned sweeps, see closest_t): only leaves whose box the
     // ray ENTERS inside the window are emitted, and spheres whose best hit so far lies before the window
     // are skipped.  The exhaustive sweep is the single window [0, +inf) with best == nullptr.
-    __shared__ uint2 queue[BP_WARPS][BP_QUEUE];
+    static_assert(!RUNS || MODE == 0, "leaf runs: the exhaustive sweep only");
+    __shared__ uint2 queue[BP_WARPS][BP_QUEUE + (RUNS ? 64 : 0)];     // with runs a step appends at most 128
 #if XP_BP_GATHER == 1
     __shared__ float4 stage_all[BP_WARPS][32 * GATHER_STRIDE];
     float4 *stage = stage_all[threadIdx.x >> 5];
@@ -505,6 +514,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
 #endif
         n_nodes += __popc(__ballot_sync(FULL, node >= 0));
         int leaf_a = -1, leaf_b = -1;
+        bool run_a = false, run_b = false;
         if (node >= 0) {
             const int2 link = make_int2(__float_as_int(n3.x), __float_as_int(n3.y));
             float ta, tb, fa, fb;
@@ -524,6 +534,12 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
             }
             if (hit_a && link.x < 0) { if (MODE != 1 || ta >= t_lo) leaf_a = ~link.x; hit_a = false; }
             if (hit_b && link.y < 0) { if (MODE != 1 || tb >= t_lo) leaf_b = ~link.y; hit_b = false; }
+            if (RUNS) {
+                // a two-leaf child: emit both leaves instead of visiting it
+                const int ra = __float_as_int(n3.z), rb = __float_as_int(n3.w);
+                if (hit_a && ra > 0) { leaf_a = ra - 1; run_a = true; hit_a = false; }
+                if (hit_b && rb > 0) { leaf_b = rb - 1; run_b = true; hit_b = false; }
+            }
             if (hit_a && hit_b) {
                 node = link.x;
                 if (sp < STACK_DEPTH) stack[sp++] = link.y;
@@ -542,11 +558,28 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
                 if (leaf_b >= 0) leaf_b = (int)__ldg(&leaf_to_tri[leaf_b]);
             }
             // (the emitting lane rides in the top 5 bits of the leaf word until the span is written out)
-            if (leaf_a >= 0) q[count + __popc(ma & lt_mask)] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)leaf_a);
-            if (leaf_b >= 0) q[count + na + __popc(mb & lt_mask)] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)leaf_b);
-            count += na + __popc(mb);
+            if (!RUNS) {
+                if (leaf_a >= 0) q[count + __popc(ma & lt_mask)] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)leaf_a);
+                if (leaf_b >= 0) q[count + na + __popc(mb & lt_mask)] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)leaf_b);
+                count += na + __popc(mb);
+            } else {
+                // the two leaves of a run go side by side: adjacent 64 B records of the same ray for the narrowphase
+                const unsigned xa = __ballot_sync(FULL, run_a), xb = __ballot_sync(FULL, run_b);
+                const unsigned ta_n = na + __popc(xa);
+                if (leaf_a >= 0) {
+                    const unsigned at = count + __popc(ma & lt_mask) + __popc(xa & lt_mask);
+                    q[at] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)leaf_a);
+                    if (run_a) q[at + 1] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)(leaf_a + 1));
+                }
+                if (leaf_b >= 0) {
+                    const unsigned at = count + ta_n + __popc(mb & lt_mask) + __popc(xb & lt_mask);
+                    q[at] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)leaf_b);
+                    if (run_b) q[at + 1] = make_uint2(ray0 + my_ray, ((uint32_t)lane << 27) | (uint32_t)(leaf_b + 1));
+                }
+                count += ta_n + __popc(mb) + __popc(xb);
+            }
             __syncwarp();
-            if (count >= BP_SPAN) {
+            while (count >= BP_SPAN) {
                 // Flush a whole span, GROUPED BY EMITTING LANE (a counting sort of the 128 entries on the 5-bit lane id):
                 // a step appends one entry per lane, so the queue interleaves up to 32 rays; grouped, a warp of the
                 // narrowphase sees runs of pairs that share the ray and name leaves adjacent in Morton order -- its
@@ -1123,6 +1156,7 @@ __device__ __noinline__ bool detect_literal_call(const RayRec *__restrict__ rays
 #ifndef XP_NP_BLOCKS_F
 #define XP_NP_BLOCKS_F 4
 #endif
+// FILTER: stage 1 emitted a superset of P (quantised boxes, leaf runs): apply P to the triangle's own box first
 template <int MODE, bool FILTER>
 #ifndef XP_NP_THREADS
 #define XP_NP_THREADS 128            /* 256: 0.551 ms, 128: 0.545, 64 (spans of 512): 0.542 */
@@ -1718,7 +1752,7 @@ static cudaError_t launch_grid_broadphase(xp_scene *s, uint64_t pos, uint64_t en
     k_broadphase_grid<<<grid, BP_THREADS, 0, st>>>(grid_desc(s), s->grid_yrange.as<float>(), s->rays.as<RayRec>(), pos, end,
                                                   s->cur_horizon, ctr, pairs, cap, s->na_dev);
     XP_TRY(cudaMemsetAsync(&ctr->ray_cursor, 0, sizeof(unsigned long long), st));
-    k_broadphase<3><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end, s->cur_horizon,
+    k_broadphase<3, false><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end, s->cur_horizon,
                                                                ctr, pairs, cap, 0.0f, INFINITY, nullptr, s->vals_a.as<uint32_t>(), s->na_dev);
     s->stats.kernel_launches += 2;
     return cudaGetLastError();
@@ -1874,6 +1908,8 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
     const bool windows = !far && s->method == XP_METHOD_LBVH_PAIRS && (s->prune == 1 || (s->prune == 2 && s->cand_per_ray > 96.0));
     const int n_pass = windows ? kWinN : 1;
     const bool grid = !far && !windows && grid_walk_on(s);
+    // XP_OPT_LEAF_RUNS: the LBVH walk emits two-leaf children unvisited, stage 2 filters with P (k_broadphase<0, RUNS>)
+    const bool runs = !far && !grid && !windows && s->leaf_runs && s->method == XP_METHOD_LBVH_PAIRS;
     if (grid) recs = s->recs_grid.as<TriRec>();      // the grid walk names triangles by upload index
     uint64_t pos = 0;
     unsigned long long snap_tests = 0, snap_pairs = 0;   // synchronous mode: accounting before the current chunk
@@ -1899,22 +1935,25 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
             else if (grid)
                 XP_TRY(launch_grid_broadphase(s, pos, end, pairs, cap));
             else if (far)
-                k_broadphase<2><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                k_broadphase<2, false><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
                                                                            XP_FAR_D0, INFINITY, best, nullptr, s->na_dev);
             else
-                if (windows)
-                    k_broadphase<1><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                                  d_lo, d_hi, best, nullptr, s->na_dev);
-                else
-                    k_broadphase<0><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                               0.0f, INFINITY, nullptr, nullptr, s->na_dev);
+                if (windows) {
+                    k_broadphase<1, false><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                                                                                      d_lo, d_hi, best, nullptr, s->na_dev);
+                } else {
+                    if (runs) k_broadphase<0, true><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                                                                                               0.0f, INFINITY, nullptr, nullptr, s->na_dev);
+                    else k_broadphase<0, false><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                                                                                           0.0f, INFINITY, nullptr, nullptr, s->na_dev);
+                }
             if (!grid) ++s->stats.kernel_launches;
         }
         {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
             const int np_blocks = s->arith == XP_ARITH_EXACT ? XP_NP_BLOCKS_X : s->arith == XP_ARITH_FAST ? XP_NP_BLOCKS_F : XP_NP_BLOCKS;
             const unsigned ng = (unsigned)s->n_sm * (XP_NP_DYNAMIC ? 1u : 2u) * (unsigned)np_blocks * (256u / XP_NP_THREADS);   // dynamic spans: exactly the resident blocks
-#define XP_NP_LAUNCH(M) do { if (q4) k_narrow_pairs<M, true><<<ng, XP_NP_THREADS, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
+#define XP_NP_LAUNCH(M) do { if (q4 || runs) k_narrow_pairs<M, true><<<ng, XP_NP_THREADS, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
                              else k_narrow_pairs<M, false><<<ng, XP_NP_THREADS, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); } while (0)
             switch (s->arith) {
             case XP_ARITH_FAST: XP_NP_LAUNCH(NP_F); break;
@@ -2540,7 +2579,7 @@ cudaError_t pairs_dev(xp_scene *s, const xp_response *d_in, uint64_t n, uint32_t
             XP_TRY(launch_grid_broadphase(s, pos, end, pairs, buf_cap));
             --s->stats.kernel_launches;
         } else if (s->method != XP_METHOD_WIDE_FUSED && s->method != XP_METHOD_WIDE_PAIRS)
-            k_broadphase<0><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
+            k_broadphase<0, false><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(s->nodes.as<Node>(), s->rays.as<RayRec>(), pos, end,
                                                                   s->cur_horizon, ctr, pairs, buf_cap, 0.0f, INFINITY, nullptr, nullptr, nullptr);
         else
             k_sweep<ExactOps, false, true><<<grid_for(end - pos, SWEEP_THREADS), SWEEP_THREADS, 0, st>>>(

@@ -20,6 +20,7 @@ ST_RADIUS_NE_1, ST_ASSERT_NEG_DISTANCE, ST_ITER_CAP = 1, 2, 4
 HORIZON_INF, HORIZON_UNIT = 0, 1
 OPT_ARITH, OPT_METHOD, OPT_TIMING, OPT_SORT_SPHERES, OPT_MAX_PAIRS, OPT_PRUNE, OPT_FAR_EXACT, OPT_GRID_WALK = 1, 2, 3, 4, 5, 6, 7, 8
 OPT_CONTACT_RECORD = 9
+OPT_LEAF_RUNS = 10
 ARITH_EXACT, ARITH_FAST, ARITH_EXACT_LITERAL, ARITH_FAST_LITERAL = 0, 1, 2, 3
 ARITH = {"exact": 0, "fast": 1, "exact_literal": 2, "fast_literal": 3}
 METHODS = {"wide_fused": 0, "lbvh_fused": 1, "lbvh_pairs": 2, "brute": 3, "wide_pairs": 4, "q4_pairs": 5}
@@ -92,6 +93,7 @@ def lib() -> C.CDLL:
         "xp_sphere_triangle_calculate_response": ([i32, vp, vp, vp], i32),
         "xp_broadphase_pairs": ([vp, vp, u64, u32, u64, vp, vp, vp], i32),
         "xp_scene_debug_tree": ([vp, vp, vp, vp, vp, vp], i32),
+        "xp_scene_debug_leaf_runs": ([vp, vp], i32),
         "xp_detect_contacts_dev": ([vp, vp, u64, u32, vp], i32),
         "xp_exchange_alloc": ([vp, u64, vp, vp], i32),
         "xp_exchange_free": ([vp, vp], i32),
@@ -122,7 +124,7 @@ EXPORTED_SYMBOLS = [
     "xp_scene_build", "xp_scene_triangle_count", "xp_detect_batch", "xp_detect_batch_dev",
     "xp_detect_batch_submit", "xp_detect_batch_wait", "xp_detect_batch_compact", "xp_detect_batch_compact_dev", "xp_detect_batch_compact_submit",
     "xp_collision_response_batch", "xp_collision_response_batch_dev", "xp_collide_and_slide_batch", "xp_collide_and_slide_batch_dev", "xp_sphere_triangle_detect_collision",
-    "xp_sphere_triangle_calculate_response", "xp_broadphase_pairs", "xp_scene_debug_tree",
+    "xp_sphere_triangle_calculate_response", "xp_broadphase_pairs", "xp_scene_debug_tree", "xp_scene_debug_leaf_runs",
     "xp_detect_contacts_dev", "xp_exchange_alloc", "xp_exchange_free", "xp_exchange_open", "xp_exchange_close",
     "xp_detect_contacts_exchange_dev", "xp_detect_contacts_multicast_dev", "xp_scene_set_exchange_stream",
     "xp_detect_contacts_exchange_submit", "xp_detect_contacts_exchange_wait", "xp_probe_fp32_peak", "xp_debug_check_arith", "xp_strerror", "xp_last_cuda_error", "xp_version",

@@ -140,7 +140,7 @@ class Scene:
 
     # -- options
     def set_options(self, *, arith=None, method=None, prune=None, sort_spheres=None, timing=None, max_pairs=None,
-                    far_exact=None, grid_walk=None, contact_record=None):
+                    far_exact=None, grid_walk=None, contact_record=None, leaf_runs=None):
         L, h = self._L, self._h
         if contact_record is not None:           # "full" (xp_contact, 40 B) or "compact" (xp_contact16, 16 B)
             check(L.xp_scene_set_option(h, _lib.OPT_CONTACT_RECORD, {"full": 0, "compact": 1}[contact_record]))
@@ -160,6 +160,8 @@ class Scene:
             check(L.xp_scene_set_option(h, _lib.OPT_FAR_EXACT, int(bool(far_exact))))
         if grid_walk is not None:
             check(L.xp_scene_set_option(h, _lib.OPT_GRID_WALK, int(bool(grid_walk))))
+        if leaf_runs is not None:
+            check(L.xp_scene_set_option(h, _lib.OPT_LEAF_RUNS, int(bool(leaf_runs))))
 
     def set_stream(self, cuda_stream_ptr: int):
         check(self._L.xp_scene_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
@@ -317,6 +319,11 @@ class Scene:
         hi = np.zeros((ni, 3), np.float32)
         check(self._L.xp_scene_debug_tree(self._h, _p(sorted_tri), _p(morton), _p(child), _p(lo), _p(hi)))
         return sorted_tri, morton, child, lo, hi
+
+    def debug_leaf_runs(self):
+        run = np.zeros((max(self.triangle_count - 1, 1), 2), np.int32)
+        check(self._L.xp_scene_debug_leaf_runs(self._h, _p(run)))
+        return run
 
     # -- sweeps, device pointers (ints, e.g. torch.Tensor.data_ptr())
     def detect_batch_dev(self, d_in: int, n: int, d_col: int = 0, d_hit: int = 0, d_tri: int = 0,
