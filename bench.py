@@ -62,10 +62,15 @@ def build_workload(seed: int, n_spheres: int = N_SPHERES, with_heights: bool = F
 
 
 def workload_config(n_gpus: int) -> dict:
+    """The `config` of the JSON line: the SAME dict in both arms (the reference arm runs on this arm's config), so it
+    names the workload only; how the B200 arm ran it (arithmetic mode, method, exchange transport ...) is the `arm` key."""
     return {"workload": "config2: 2^20 swept unit spheres x 1001112-triangle sine+noise heightmap terrain, "
                         "single sweep per step, horizon=inf (reference-faithful)",
             "spheres_per_gpu": N_SPHERES, "triangles": 2 * NX * NZ,
-            "parallelism": f"spheres sharded over {n_gpus} GPU(s), scene replicated"}
+            "parallelism": f"spheres sharded over {n_gpus} GPU(s), scene replicated",
+            "l2": ("B200 arm: inputs larger than L2 -- one step's inputs (scene records + 29 MB of spheres) exceed the 126 MB "
+                   "L2 and a step streams ~0.5 GB through it; no flush inside the loop of steps (they overlap); "
+                   "single_step is the same step with an explicit 256 MiB L2 flush between steps.  Reference arm: CPU, n/a")}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -591,15 +596,15 @@ def run_config2(ctx: Ctx, args) -> dict:
     line = {"metric": "narrowphase_tests_per_sec", "value": value, "unit": "tests/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), arith=args.arith, method=args.method, scene=args.scene,
-                           broadphase="height-grid walk (k_broadphase_grid)" if grid_walk else "LBVH walk",
-                           prune=args.prune, far_exact=bool(args.far_exact),
-                           l2=("not flushed inside the loop (steps overlap): one step's inputs -- scene records + 29 MB of spheres "
-                               "-- exceed the 126 MB L2 and a step streams ~0.5 GB through it; single_step is the same step with "
-                               "an explicit L2 flush" if pipelined else "flushed (256 MiB write) between timed steps"),
-                           step=("loop of steps, two in flight: step i's record build + exchange runs on a second stream under "
-                                 "step i+1's sweep" if pipelined else "one synchronous call per step"),
-                           exchange=exch),
+            "config": workload_config(world),
+            "arm": dict(arith=args.arith, method=args.method, scene=args.scene,
+                        broadphase="height-grid walk (k_broadphase_grid)" if grid_walk else "LBVH walk (leaf runs)",
+                        prune=args.prune, far_exact=bool(args.far_exact),
+                        l2=("not flushed inside the loop (steps overlap): inputs larger than L2" if pipelined
+                            else "flushed (256 MiB write) between timed steps"),
+                        step=("loop of steps, two in flight: step i's record build + exchange runs on a second stream under "
+                              "step i+1's sweep" if pipelined else "one synchronous call per step"),
+                        exchange=exch),
             "spheres_per_sec": spheres_per_sec, "tests_per_step": tests_all / args.steps,
             "candidates_per_sphere": tests_all / args.steps / (world * n),
             "walk_visits_per_step": float(np.mean([s["node_visits"] for s in stats])),

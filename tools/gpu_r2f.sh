@@ -14,7 +14,7 @@ import json, sys
 n=sys.argv[1]
 d=json.loads(open(f"gpurun_out/bench_n{n}.json").read().strip().splitlines()[-1])
 print("N", d["n_gpus"], "value %.4g ms/step %.4f e2e %.4g (%.3f ms, frac of pcie ceiling %.3f) resolved %.4g verified %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["frac_of_pcie_ceiling"], d["resolved"]["value"], d["exchange_verified"]))
-print("exchange:", d["config"]["exchange"][:120])
+print("exchange:", d["arm"]["exchange"][:120])
 print("ceiling", {k:(round(v,3) if isinstance(v,float) else v) for k,v in d["e2e"]["pcie_ceiling"].items() if k!="note"}, "full_records %.4g" % d["e2e"]["full_records"]["value"])
 print("sustained", d.get("sustained"))
 for k,v in d.get("configs",{}).items(): print("config",k, json.dumps(v)[:600])
