@@ -97,8 +97,10 @@ typedef struct xp_scene xp_scene;   /* opaque: device triangle records + LBVH + 
                                 leaves (Morton neighbours; usually the two triangles of a quad): when the ray hits their union
                                 box it emits both, and the narrowphase kernel applies P to each triangle's own box before testing
                                 it.  The tested set stays P bit for bit (narrowphase_tests == |P|; broadphase_pairs counts what
-                                was emitted, a few per cent more); a fifth of the node visits disappear.  Exhaustive sweeps only: the
-                                windowed passes of XP_OPT_PRUNE and xp_broadphase_pairs walk without runs.  0: off. */
+                                was emitted, a few per cent more); a fifth of the node visits disappear.  In the windowed passes of
+                                XP_OPT_PRUNE a run belongs to the pass that holds its union box's entry time (never later than
+                                either triangle's own pass: the closest hit cannot change) and, with the infinite horizon, both
+                                triangles are tested unfiltered.  xp_broadphase_pairs always walks without runs.  0: off. */
 
 #define XP_ARITH_EXACT    0  /* no FMA, reference operation order: bit-identical to the reference's results         */
 #define XP_ARITH_FAST     1  /* tolerance mode: FMA, hardware reciprocal / square root, reduced quadratics (<= 1e-5) */

@@ -347,14 +347,15 @@ static constexpr int BP_BLOCKS_PER_SM = XP_BP_BLOCKS;
 // by XP_FAR_K * D^2 with D the farthest a closer hit could be, every leaf the ray is inside of after d_lo and
 // before its best hit (see closest_t).
 static constexpr float XP_FAR_K = 8e-7f;
-// RUNS (MODE 0 only): leaf runs.  A child that is an internal node over exactly two leaves -- Morton neighbours l, l + 1;
+// RUNS (MODE 0 and 1): leaf runs.  A child that is an internal node over exactly two leaves -- Morton neighbours l, l + 1;
 // the tree pass leaves l + 1 in link.z / link.w of the PARENT's record -- is not visited: when the ray hits the box the
 // parent holds for it (the union of the two leaf boxes), both leaves are emitted and stage 2 applies P to each
 // triangle's own box (k_narrow_pairs<.., FILTER>), so exactly the pairs of P are still tested.  Config 2 handed over as
 // a soup: 82.7 M -> 65.1 M node visits, walk 0.73 -> 0.62 ms, narrowphase 0.59 -> 0.64 ms (the filter's ~45 instructions
-// per pair and the lanes it idles), step 1.45 -> 1.40 ms.  Not used in the windowed passes of a pruned sweep:
-// a run has to be offered to every pass its union box overlaps and is filtered out of all but one -- measured on
-// config 3: walk 38.6 -> 33.4 ms, narrowphase 21.2 -> 27.1 ms, a net loss (profiles/r02_leaf_runs_ab.log).
+// per pair and the lanes it idles), step 1.45 -> 1.40 ms.  In the windowed passes of a pruned sweep a run counts as one
+// leaf with the union box (see below); config 3: walk 38.5 -> 33.5 ms, frame 65.5 -> 61.0 ms (profiles/r02_leaf_runs_ab.log;
+// the first form, a run offered to every pass its union box overlaps and filtered per triangle by P and by the window,
+// lost: narrowphase 21.2 -> 27.1 ms).
 template <int MODE, bool RUNS>
 __global__ void __launch_bounds__(BP_THREADS, BP_BLOCKS_PER_SM)
 k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, uint64_t ray_base, uint64_t ray_end,
@@ -367,7 +368,7 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
     // Distance window [d_lo, d_hi) of this pass (pruned sweeps, see closest_t): only leaves whose box the
     // ray ENTERS inside the window are emitted, and spheres whose best hit so far lies before the window
     // are skipped.  The exhaustive sweep is the single window [0, +inf) with best == nullptr.
-    static_assert(!RUNS || MODE == 0, "leaf runs: the exhaustive sweep only");
+    static_assert(!RUNS || MODE == 0 || MODE == 1, "leaf runs: exhaustive and windowed passes only");
     __shared__ uint2 queue[BP_WARPS][BP_QUEUE + (RUNS ? 64 : 0)];     // with runs a step appends at most 128
 #if XP_BP_GATHER == 1
     __shared__ float4 stage_all[BP_WARPS][32 * GATHER_STRIDE];
@@ -535,10 +536,13 @@ k_broadphase(const Node *__restrict__ nodes, const RayRec *__restrict__ rays, ui
             if (hit_a && link.x < 0) { if (MODE != 1 || ta >= t_lo) leaf_a = ~link.x; hit_a = false; }
             if (hit_b && link.y < 0) { if (MODE != 1 || tb >= t_lo) leaf_b = ~link.y; hit_b = false; }
             if (RUNS) {
-                // a two-leaf child: emit both leaves instead of visiting it
+                // a two-leaf child: emit both leaves instead of visiting it.  In a windowed pass the run is treated like ONE
+                // leaf with the union box: it belongs to the pass that holds the union's entry time, which is no later than
+                // either leaf's own -- a triangle is tested in the same pass as without runs or in an earlier one, never
+                // after its sphere has been declared finished, so the closest hit cannot change
                 const int ra = __float_as_int(n3.z), rb = __float_as_int(n3.w);
-                if (hit_a && ra > 0) { leaf_a = ra - 1; run_a = true; hit_a = false; }
-                if (hit_b && rb > 0) { leaf_b = rb - 1; run_b = true; hit_b = false; }
+                if (hit_a && ra > 0) { if (MODE != 1 || ta >= t_lo) { leaf_a = ra - 1; run_a = true; } hit_a = false; }
+                if (hit_b && rb > 0) { if (MODE != 1 || tb >= t_lo) { leaf_b = rb - 1; run_b = true; } hit_b = false; }
             }
             if (hit_a && hit_b) {
                 node = link.x;
@@ -1908,8 +1912,14 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
     const bool windows = !far && s->method == XP_METHOD_LBVH_PAIRS && (s->prune == 1 || (s->prune == 2 && s->cand_per_ray > 96.0));
     const int n_pass = windows ? kWinN : 1;
     const bool grid = !far && !windows && grid_walk_on(s);
-    // XP_OPT_LEAF_RUNS: the LBVH walk emits two-leaf children unvisited, stage 2 filters with P (k_broadphase<0, RUNS>)
-    const bool runs = !far && !grid && !windows && s->leaf_runs && s->method == XP_METHOD_LBVH_PAIRS;
+    // XP_OPT_LEAF_RUNS: the LBVH walk emits two-leaf children unvisited (k_broadphase<.., RUNS>).  In an exhaustive sweep stage 2
+    // filters with P, so the tested set stays P.  In a pruned sweep with the infinite horizon it does not: the tested set is a
+    // subset of the scene chosen for speed there anyway, a filtered-out lane would only idle inside its warp, and whatever a
+    // triangle outside P could contribute the reference's loop over ALL triangles sees too -- the filter would cost its ~45
+    // instructions per pair and save nothing (config 3: narrowphase 24.3 ms with it, 21.7 without).  With a finite horizon the
+    // filter is what keeps triangles entered after the horizon out of the result, so it stays.
+    const bool runs = !far && !grid && s->leaf_runs && s->method == XP_METHOD_LBVH_PAIRS;
+    const bool run_filter = runs && (!windows || s->cur_horizon < 3.402823466e+38f);
     if (grid) recs = s->recs_grid.as<TriRec>();      // the grid walk names triangles by upload index
     uint64_t pos = 0;
     unsigned long long snap_tests = 0, snap_pairs = 0;   // synchronous mode: accounting before the current chunk
@@ -1939,8 +1949,10 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
                                                                            XP_FAR_D0, INFINITY, best, nullptr, s->na_dev);
             else
                 if (windows) {
-                    k_broadphase<1, false><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
-                                                                                      d_lo, d_hi, best, nullptr, s->na_dev);
+                    if (runs) k_broadphase<1, true><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                                                                                               d_lo, d_hi, best, nullptr, s->na_dev);
+                    else k_broadphase<1, false><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
+                                                                                           d_lo, d_hi, best, nullptr, s->na_dev);
                 } else {
                     if (runs) k_broadphase<0, true><<<bp_grid(s, end - pos), BP_THREADS, 0, st>>>(nodes, rays, pos, end, s->cur_horizon, ctr, pairs, cap,
                                                                                                0.0f, INFINITY, nullptr, nullptr, s->na_dev);
@@ -1953,7 +1965,7 @@ static cudaError_t closest_main_t(xp_scene *s, uint64_t na, bool far) {
             StageTimer t(s, XP_STAGE_NARROWPHASE);
             const int np_blocks = s->arith == XP_ARITH_EXACT ? XP_NP_BLOCKS_X : s->arith == XP_ARITH_FAST ? XP_NP_BLOCKS_F : XP_NP_BLOCKS;
             const unsigned ng = (unsigned)s->n_sm * (XP_NP_DYNAMIC ? 1u : 2u) * (unsigned)np_blocks * (256u / XP_NP_THREADS);   // dynamic spans: exactly the resident blocks
-#define XP_NP_LAUNCH(M) do { if (q4 || runs) k_narrow_pairs<M, true><<<ng, XP_NP_THREADS, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
+#define XP_NP_LAUNCH(M) do { if (q4 || run_filter) k_narrow_pairs<M, true><<<ng, XP_NP_THREADS, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); \
                              else k_narrow_pairs<M, false><<<ng, XP_NP_THREADS, 0, st>>>(recs, rays, pairs, ctr, cap, s->cur_horizon, best); } while (0)
             switch (s->arith) {
             case XP_ARITH_FAST: XP_NP_LAUNCH(NP_F); break;
