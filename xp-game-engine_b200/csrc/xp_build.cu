@@ -194,8 +194,13 @@ __global__ void __launch_bounds__(1024) k_bin_offsets(uint32_t *__restrict__ bin
     if (threadIdx.x == 1023) group_tot[blockIdx.x] = ti;
 }
 
-// RAYS: the scatter also writes the sphere's ray record and an empty best key at its slot -- the ray setup of the
-// sweep that follows, fused (one launch and one gather of the Response less).
+// RAYS: the scatter also writes the sphere's ray record at its slot -- the ray setup of the sweep that follows, fused
+// (one launch and one gather of the Response less); the empty best keys are a memset before the launch.
+// XP_SCATTER_COOP: the 64 B record leaves through shared memory, four lanes per record, so one store instruction of a
+// warp writes 8 whole records (16 full 32 B sectors) instead of a 16 B quarter of 32 different records.
+#ifndef XP_SCATTER_COOP
+#define XP_SCATTER_COOP 1
+#endif
 template <class O, bool RAYS>
 __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict__ keys, uint64_t n,
                                                      uint32_t *__restrict__ offs, const uint32_t *__restrict__ group_tot,
@@ -204,6 +209,9 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict_
                                                      unsigned long long *__restrict__ best, uint32_t *__restrict__ status,
                                                      int have_tris) {
     __shared__ unsigned group_base[CS_GROUPS];
+#if XP_SCATTER_COOP
+    __shared__ float4 stage_all[RAYS ? 256 / 32 : 1][RAYS ? 32 * 5 : 1];    // a record every 80 B: the 16 B accesses of a quarter-warp fall into distinct banks
+#endif
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     // everything this thread reads is requested first: its key and (RAYS) its Response
     const unsigned key = i < n ? __ldg(keys + i) : 0xFFFFFFFFu;
@@ -236,14 +244,32 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict_
         rr = make_ray_rec<O>(V3{in7[0], in7[1], in7[2]}, V3{in7[4], in7[5], in7[6]}, valid);
     }
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (i >= n) return;
     const unsigned pos = base + __popc(peers & ((1u << lane) - 1u));
+#if XP_SCATTER_COOP
+    if (RAYS) {
+        float4 *stage = stage_all[threadIdx.x >> 5];
+        if (i < n) {
+            stage[lane * 5 + 0] = rr.q0; stage[lane * 5 + 1] = rr.q1; stage[lane * 5 + 2] = rr.q2; stage[lane * 5 + 3] = rr.q3;
+        }
+        __syncwarp();
+        const uint64_t warp_first = i - lane;                               // the warp's lanes are consecutive spheres
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int src = r * 8 + (lane >> 2), part = lane & 3;
+            const unsigned dst = __shfl_sync(0xffffffffu, pos, src);
+            if (warp_first + src < n) reinterpret_cast<float4 *>(rays + dst)[part] = stage[src * 5 + part];
+        }
+    }
+#endif
+    if (i >= n) return;
     order[pos] = (uint32_t)i;
     if (inv) inv[i] = pos;
     if (RAYS) {
         if (!valid && status && have_tris) status[i] |= XP_ST_RADIUS_NE_1;     // collision_detect.rs:161 (see k_ray_setup)
+#if !XP_SCATTER_COOP
         rays[pos] = rr;
         best[pos] = BEST_NONE;
+#endif
     }
 }
 
@@ -1238,6 +1264,9 @@ cudaError_t sphere_morton_order(xp_scene *s, const xp_response *d_in, uint64_t n
             RayRec *rays = s->rays.as<RayRec>();
             unsigned long long *best = s->best.as<unsigned long long>();
             const bool fast = s->arith == XP_ARITH_FAST || s->arith == XP_ARITH_FAST_LITERAL;
+#if XP_SCATTER_COOP
+            XP_TRY(cudaMemsetAsync(best, 0xFF, n * sizeof(unsigned long long), s->stream));      // BEST_NONE everywhere
+#endif
             if (fast) k_bin_scatter<FastOps, true><<<grid_for(n, 256), 256, 0, s->stream>>>(ka, n, bins, bins + CS_BINS, va, inv, d_in, rays, best, status_for_rays, s->n_tris > 0);
             else k_bin_scatter<ExactOps, true><<<grid_for(n, 256), 256, 0, s->stream>>>(ka, n, bins, bins + CS_BINS, va, inv, d_in, rays, best, status_for_rays, s->n_tris > 0);
             *rays_done = true;
