@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict_
                                                      unsigned long long *__restrict__ best, uint32_t *__restrict__ status,
                                                      int have_tris) {
     __shared__ unsigned group_base[CS_GROUPS];
-#if XP_SCATTER_COOP
+#if XP_SCATTER_COOP == 1
     __shared__ float4 stage_all[RAYS ? 256 / 32 : 1][RAYS ? 32 * 5 : 1];    // a record every 80 B: the 16 B accesses of a quarter-warp fall into distinct banks
 #endif
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict_
     }
     base = __shfl_sync(0xffffffffu, base, leader);
     const unsigned pos = base + __popc(peers & ((1u << lane) - 1u));
-#if XP_SCATTER_COOP
+#if XP_SCATTER_COOP == 1
     if (RAYS) {
         float4 *stage = stage_all[threadIdx.x >> 5];
         if (i < n) {
@@ -266,8 +266,10 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t *__restrict_
     if (inv) inv[i] = pos;
     if (RAYS) {
         if (!valid && status && have_tris) status[i] |= XP_ST_RADIUS_NE_1;     // collision_detect.rs:161 (see k_ray_setup)
-#if !XP_SCATTER_COOP
-        rays[pos] = rr;
+#if XP_SCATTER_COOP == 2
+        store_rec64(rays + pos, rr);
+#elif !XP_SCATTER_COOP
+        store_rec64(rays + pos, rr);
         best[pos] = BEST_NONE;
 #endif
     }
@@ -598,8 +600,8 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
     // (+inf instead of the first one marks a triangle outside the narrowphase's regular domain: literal path)
     r.q3 = make_float4(d.pc, xp_tri_regular(v0, v1, v2) ? xp_edge_len2<ExactOps>(v0, v1) : INFINITY,
                        xp_edge_len2<ExactOps>(v1, v2), __uint_as_float(i));
-    recs[j] = r;
-    if (recs_upload) recs_upload[i] = r;          // heightmap scenes: a second copy in upload (cell-major) order for the grid walk
+    store_rec64(recs + j, r);
+    if (recs_upload) store_rec64(recs_upload + i, r);          // heightmap scenes: a second copy in upload (cell-major) order for the grid walk
     // Ill-conditioned triangles.  When the edges at v0 are (nearly) parallel -- sin^2 of their angle <= 1e-4 --
     // the reference's normal and the denominator of its point-in-triangle test (triangle.rs:11-32) are
     // dominated by rounding, and its face test can report a "collision" arbitrarily far from the triangle;
@@ -626,8 +628,7 @@ __global__ void __launch_bounds__(256) k_pack(const float *__restrict__ aos, uin
             if (ill) degen[1 + at + __popc(im & ((1u << lane) - 1u))] = (uint32_t)j;
         }
     }
-    leaf_box[2 * j] = make_float4(lo.x, lo.y, lo.z, 0.0f);          // (lo, hi) side by side: one 32 B sector per box for the tree pass
-    leaf_box[2 * j + 1] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    stg256(leaf_box + 2 * j, make_float4(lo.x, lo.y, lo.z, 0.0f), make_float4(hi.x, hi.y, hi.z, 0.0f));   // (lo, hi) side by side: one 32 B sector per box for the tree pass
 }
 
 // K4 + K5: hierarchy and boxes in ONE bottom-up pass ----------------------------------------------------------
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(32) k_tree_local(const uint32_t *__restrict__ 
                 nd.link = make_int4(sl, cur, p - other == 1 ? other + 1 : 0, r - p == 2 ? p + 2 : 0);  // children [other, p], [p + 1, r]
                 l = other;
             }
-            nodes[p] = nd;
+            store_rec64(nodes + p, nd);
             lo = make_float4(fminf(lo.x, slo.x), fminf(lo.y, slo.y), fminf(lo.z, slo.z), 0.f);
             hi = make_float4(fmaxf(hi.x, shi.x), fmaxf(hi.y, shi.y), fmaxf(hi.z, shi.z), 0.f);
             cur = p;

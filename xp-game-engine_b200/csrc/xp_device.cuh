@@ -34,6 +34,29 @@ struct __align__(16) RayRec { float4 q0, q1, q2, q3; };
 struct __align__(16) Node4 { uint4 w0, w1, w2, w3; };
 static constexpr int Q4_EMPTY = (int)0x80000000;
 
+// A 64 B record (TriRec, Node, RayRec) or a 32 B box leaves its lane as 256-bit stores (STG.E.256, sm_100+): each writes one
+// whole 32 B sector, where the four 16 B stores the compiler makes of a struct assignment write half-sectors that L2 has to
+// merge.  p must be 32 B aligned.
+#ifndef XP_STG256
+#define XP_STG256 1
+#endif
+#if defined(__CUDACC__)
+__device__ __forceinline__ void stg256(void *p, float4 a, float4 b) {
+#if XP_STG256
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+#else
+    reinterpret_cast<float4 *>(p)[0] = a; reinterpret_cast<float4 *>(p)[1] = b;
+#endif
+}
+template <class R> __device__ __forceinline__ void store_rec64(R *dst, const R &r) {     // R = {float4 q0, q1, q2; 16 B}
+    static_assert(sizeof(R) == 64, "64 B records only");
+    const float4 *q = reinterpret_cast<const float4 *>(&r);
+    stg256(dst, q[0], q[1]);
+    stg256(reinterpret_cast<char *>(dst) + 32, q[2], q[3]);
+}
+#endif
+
 static constexpr unsigned long long BEST_NONE = 0xFFFFFFFFFFFFFFFFull;
 static constexpr uint32_t RAY_VALID = 1u;
 static constexpr uint32_t RAY_GRID_OK = 2u;      // centre and movement finite: the height-grid walk may take this ray

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) k_ray_setup(const xp_response *__restrict
     // the assert sits inside sphere_triangle_detect_collision (collision_detect.rs:161), which the loop over an
     // EMPTY triangle slice (lib.rs:33-35) never calls: no triangles, no panic
     if (!valid && status && have_tris) status[i] |= XP_ST_RADIUS_NE_1;
-    rays[k] = make_ray_rec<O>(c, m, valid);
+    store_rec64(rays + k, make_ray_rec<O>(c, m, valid));
     best[k] = BEST_NONE;
 }
 
@@ -1571,7 +1571,7 @@ __global__ void __launch_bounds__(256) k_respond_setup(const RayRec *__restrict_
         if (again) {
             const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
             next_active[pos] = i;
-            next_rays[pos] = make_ray_rec<O>(nc, nm, true);                   // r = 1.0 by construction
+            store_rec64(next_rays + pos, make_ray_rec<O>(nc, nm, true));      // r = 1.0 by construction
             next_best[pos] = BEST_NONE;
         }
     }
@@ -1679,7 +1679,7 @@ __global__ void __launch_bounds__(256) k_slide_setup(const RayRec *__restrict__ 
         if (again) {
             const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
             next_active[pos] = i;
-            next_rays[pos] = make_ray_rec<O>(np_, nv, true);
+            store_rec64(next_rays + pos, make_ray_rec<O>(np_, nv, true));
             next_best[pos] = BEST_NONE;
         }
     }
