@@ -114,3 +114,20 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".rs", "Makefile")):
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "xp_oracle" not in text and "xpo_" not in text and "libxp_oracle" not in text, os.path.join(dp, f)
+
+
+def test_python_constants_match_the_header():
+    """the ctypes mirror restates the header's numeric constants: options, arithmetic modes, methods, status bits, errors"""
+    src = open(_lib.HEADER).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(XP_[A-Z0-9_]+)\s+(-?\d+)u?\b", src)}
+    for name, value in defs.items():
+        if name.startswith("XP_OPT_"):
+            assert getattr(_lib, name[3:]) == value, name
+    assert len([k for k in defs if k.startswith("XP_OPT_")]) == 10
+    assert {k: defs["XP_ARITH_" + k.upper()] for k in _lib.ARITH} == _lib.ARITH
+    assert {k: defs["XP_METHOD_" + k.upper()] for k in _lib.METHODS} == _lib.METHODS
+    assert (defs["XP_ST_RADIUS_NE_1"], defs["XP_ST_ASSERT_NEG_DISTANCE"], defs["XP_ST_ITER_CAP"]) == (
+        _lib.ST_RADIUS_NE_1, _lib.ST_ASSERT_NEG_DISTANCE, _lib.ST_ITER_CAP)
+    for e in ("XP_OK", "XP_EINVAL", "XP_ECUDA", "XP_ENOMEM", "XP_ESTATE", "XP_ECAP"):
+        assert defs[e] == getattr(_lib, e), e
+    assert (defs["XP_HORIZON_INF"], defs["XP_HORIZON_UNIT"]) == (_lib.HORIZON_INF, _lib.HORIZON_UNIT)
