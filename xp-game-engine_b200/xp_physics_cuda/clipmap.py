@@ -63,31 +63,30 @@ def snap_down_to_index(val, level: int) -> int:
 
 
 def calculate_update_range_1d(first: int, second: int, size: int) -> range:
-    """clipmap.rs:988-996: the texel rows that scroll in when the base index moves first -> second."""
-    if abs(second - first) > size:
-        return range(second, second + size)
-    if first < second:
-        return range(first + size, second + size)
-    return range(second, first)
+    """The rows that scroll in when a window of `size` rows moves from base `first` to base `second`: the new window
+    [second, second + size) minus the old one [first, first + size), which is one interval because both have the same
+    length (what clipmap.rs:988-996 computes; its known answers are checked in tests/test_clipmap.py)."""
+    moved_up = second > first
+    lo = max(second, first + size) if moved_up else second
+    hi = second + size if moved_up else min(first, second + size)
+    return range(lo, max(lo, hi))
 
 
 def calculate_copy_ranges_1d(rng: range, size: int) -> list[range]:
-    """clipmap.rs:998-1019: the same rows as at most two ranges of texture coordinates (u32 `%`)."""
-    assert rng.start <= rng.stop
-    out: list[range] = []
-    if rng.start != rng.stop:
-        start = (rng.start & 0xFFFFFFFF) % size
-        end = (rng.stop & 0xFFFFFFFF) % size
-        if abs(rng.stop - rng.start) >= size:
-            out.append(range(0, size))
-        elif start < end:
-            out.append(range(start, end))
-        else:
-            if end != 0:
-                out.append(range(0, end))
-            if start != size:
-                out.append(range(start, size))
-    return out
+    """The same rows as texture coordinates: rows live at `row mod size` (the reference casts to u32 first,
+    clipmap.rs:998-1019), so an interval becomes the whole texture, one piece, or -- when it crosses the seam -- the piece
+    after the seam followed by the piece before it (the reference's order)."""
+    count = rng.stop - rng.start
+    assert count >= 0
+    if count == 0:
+        return []
+    if count >= size:
+        return [range(0, size)]
+    start = (rng.start & 0xFFFFFFFF) % size
+    over = start + count - size                      # rows that wrap past the seam
+    if over <= 0:
+        return [range(start, start + count)] if over < 0 else [range(start, size)]
+    return [range(0, over), range(start, size)]
 
 
 @dataclass
