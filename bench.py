@@ -630,9 +630,9 @@ def run_config2(ctx: Ctx, args) -> dict:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
 # same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r02x_ncu_full.txt
-TRAFFIC_NARROW = 475.5e6         # k_narrow_pairs: 466 MB read (315 MB of it the pair list) + 9 MB written (round 1: 610 MB; 956 MB before the spans were claimed dynamically)
-TRAFFIC_BROADPHASE = 331.5e6     # k_broadphase_grid: 73 MB read + 258 MB written (the pair list)
-TRAFFIC_SOURCE = "profiles/r02x_ncu_full.txt"
+TRAFFIC_NARROW = 482.9e6         # k_narrow_pairs: 473 MB read (315 MB of it the pair list) + 10 MB written (round 1: 610 MB; 956 MB before the spans were claimed dynamically)
+TRAFFIC_BROADPHASE = 332.8e6     # k_broadphase_grid: 74 MB read + 259 MB written (the pair list)
+TRAFFIC_SOURCE = "profiles/r02zz_ncu_full.txt"
 
 
 # ---------------------------------------------------------------------------------------------
