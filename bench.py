@@ -447,7 +447,7 @@ def run_config2(ctx: Ctx, args) -> dict:
                 "algorithmic_flops_per_launch": flops, "flops_per_test_by_path": PATH_FLOPS, "path_mix": paths,
                 "traffic": TRAFFIC_NARROW, "traffic_source": TRAFFIC_SOURCE,
                 "note": "231 algorithmic flops per full test; the exact kernel issues ~423 thread instructions per test "
-                        "(round 1: 577), the fast one ~230; ncu (profiles/r02x_ncu_full.txt): issue slots 84% busy, "
+                        "(round 1: 577), the fast one ~230; ncu (profiles/r02zz_ncu_full.txt): issue slots 85% busy, "
                         "FMA pipe 54%, 30 of 32 lanes active; exact arithmetic may not contract (the reference does not), so "
                         "one flop costs one issue slot where the FFMA peak counts two"}
     tests_step = float(np.mean([s["narrowphase_tests"] for s in stats]))
@@ -629,7 +629,7 @@ def run_config2(ctx: Ctx, args) -> dict:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the
-# same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r02x_ncu_full.txt
+# same command (bench.py --steps 2 --warmup 3 --no-cpu), profiles/r02zz_ncu_full.txt
 TRAFFIC_NARROW = 482.9e6         # k_narrow_pairs: 473 MB read (315 MB of it the pair list) + 10 MB written (round 1: 610 MB; 956 MB before the spans were claimed dynamically)
 TRAFFIC_BROADPHASE = 332.8e6     # k_broadphase_grid: 74 MB read + 259 MB written (the pair list)
 TRAFFIC_SOURCE = "profiles/r02zz_ncu_full.txt"
