@@ -12,7 +12,8 @@
 //               own digit order in shared memory)
 //   K1 pack     TriRec + inflated leaf AABB written in Morton order, the ill-conditioned list
 //   K4+K5 tree  hierarchy AND child boxes in one bottom-up pass (k_tree_local: a warp per 256 leaves in shared
-//               memory; k_tree_global: what crosses segments), writes the 64 B nodes; node 0 = root
+//               memory; k_tree_global: what crosses segments), writes the 64 B nodes (child boxes, links and the leaf-run
+//               words of XP_OPT_LEAF_RUNS); node 0 = root
 #include <cstdio>
 #include <cstdlib>
 

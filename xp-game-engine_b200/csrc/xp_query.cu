@@ -8,8 +8,9 @@
 //
 // closest() implementations selected by XP_OPT_METHOD:
 //   WIDE_FUSED k_sweep: one WARP per sphere over the 32-wide implicit tree (see k_sweep)
-//   LBVH_PAIRS k_broadphase (persistent warps over the binary LBVH) writes the pairs of P to HBM,
-//              k_narrow_pairs tests them (default; see k_broadphase)
+//   LBVH_PAIRS k_broadphase (persistent warps over the binary LBVH; two-leaf children are emitted unvisited, "leaf runs")
+//              or, for a heightmap scene, k_broadphase_grid (the ray walks the height grid, no tree) writes the pairs
+//              of P to HBM, k_narrow_pairs tests them (default; see k_broadphase / k_broadphase_grid)
 //   Q4_PAIRS   k_broadphase4 over the quantised 4-wide collapse, k_narrow_pairs<FILTER> re-checks P
 //   WIDE_PAIRS k_sweep<.., EMIT=true> writes the pairs to HBM, k_narrow_pairs tests them
 //   LBVH_FUSED k_traverse: one lane per sphere walks the LBVH with a private
