@@ -26,6 +26,8 @@ def read(path):
     return tot
 a, b = read(f"gpurun_out/nvlink_before_{n}.txt"), read(f"gpurun_out/nvlink_after_{n}.txt")
 print("# nvidia-smi nvlink -gt d, summed over a GPU's links, after - before the whole `bench.py --gpus N` run (all blocks of the line)")
+if "N/A" in open(f"gpurun_out/nvlink_after_{n}.txt", errors="ignore").read() and not any(sum(v) for v in b.values()):
+    print("the per-link data counters read N/A in this container (see the raw file)")
 for g in sorted(b):
     tx, rx = b[g][0] - a.get(g, [0, 0])[0], b[g][1] - a.get(g, [0, 0])[1]
     print(f"GPU {g}: NVLink data Tx {tx / 1048576:.2f} GiB, Rx {rx / 1048576:.2f} GiB")
