@@ -79,3 +79,22 @@ def test_incremental_toroidal_update_equals_regeneration():
     c2.update_heightmap((5.0, 5.0), scenes.sine_height)
     c2.update_heightmap((5.5, 5.5), scenes.sine_height)                       # same base index on every level
     assert c2.texels_generated == 0
+
+
+def test_range_helpers_against_a_set_model():
+    """The two 1-D helpers against what they mean: the rows of the new window that the old window did not hold, and the
+    same rows as texture coordinates (row mod size), for every small move and window size."""
+    from xp_physics_cuda.clipmap import calculate_copy_ranges_1d, calculate_update_range_1d
+    for size in (1, 2, 5, 8, 128):
+        for first in range(-2 * size - 3, 2 * size + 4, max(1, size // 5)):
+            for second in range(first - 2 * size - 2, first + 2 * size + 3):
+                rows = calculate_update_range_1d(first, second, size)
+                new, old = set(range(second, second + size)), set(range(first, first + size))
+                assert set(rows) == new - old, (first, second, size)
+                if first >= 0 and second >= 0:                                  # (u32 cast: non-negative rows only)
+                    pieces = calculate_copy_ranges_1d(rows, size)
+                    assert len(pieces) <= 2
+                    texels = [t for p in pieces for t in p]
+                    assert len(texels) == len(set(texels)) == len(rows)
+                    assert set(texels) == {r % size for r in rows}
+                    assert all(0 <= p.start < p.stop <= size for p in pieces)
